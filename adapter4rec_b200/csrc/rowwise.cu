@@ -1,0 +1,532 @@
+// rowwise.cu — HBM-bound row kernels: K1 (embedding gather + LayerNorm), K6 (LayerNorm fwd/bwd with an
+// optional residual), activation gradients and small utility reductions.  All use 128-bit global access,
+// fp32 statistics, bf16 activations; a row is owned by G = 8/16/32 lanes so that H = 64 (SASRec) does not
+// waste 3/4 of a warp.
+#include <type_traits>
+
+#include "a4r_common.cuh"
+
+namespace {
+
+constexpr int ROW_THREADS = 256;
+
+template <int G>
+A4R_DEVICE float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+A4R_DEVICE void unpack8(const uint4& r, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(r.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(r.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(r.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(r.w); f[6] = t.x; f[7] = t.y;
+}
+A4R_DEVICE uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward:  z = x (+ res[row % res_rows]);  y = (z - mean) * rstd * gamma + beta
+// ------------------------------------------------------------------------------------------------
+template <int G, int CPL>
+__global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ res, int64_t res_rows,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            __nv_bfloat16* __restrict__ y,
+                                                            __nv_bfloat16* __restrict__ z_out,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int64_t M, int H) {
+  const int nchunks = H >> 3;
+  const int sub = threadIdx.x % G;
+  const int64_t rows_per_block = ROW_THREADS / G;
+  const float invH = 1.0f / static_cast<float>(H);
+  // the loop trip count is uniform across the warp (group shuffles use the full mask): out-of-range row
+  // slots recompute row M-1 and skip their stores.
+  for (int64_t base = blockIdx.x * rows_per_block; base < M; base += gridDim.x * rows_per_block) {
+    const int64_t row_raw = base + threadIdx.x / G;
+    const bool valid = row_raw < M;
+    const int64_t row = valid ? row_raw : M - 1;
+    float v[CPL][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
+      if (ch < nchunks) {
+        unpack8(ld_nc_v4(x + row * H + ch * 8), v[c]);
+        if (res != nullptr) {
+          float r[8];
+          unpack8(ld_nc_v4(res + (row % res_rows) * H + ch * 8), r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[c][e] += r[e];
+        }
+        if (z_out != nullptr) {
+          const uint4 zz = pack8(v[c]);
+          if (valid) st_na_v4(z_out + row * H + ch * 8, zz);
+          unpack8(zz, v[c]);  // normalise exactly what the backward will read
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[c][e];
+      }
+    }
+    const float mean = group_sum<G>(s) * invH;
+    float q = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
+      if (ch < nchunks) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[c][e] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(group_sum<G>(q) * invH + eps);
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
+      if (ch < nchunks) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * gg[e] + bb[e];
+        if (valid) st_na_v4(y + row * H + ch * 8, pack8(o));
+      }
+    }
+    if (sub == 0 && valid) {
+      if (mean_out != nullptr) mean_out[row] = mean;
+      if (rstd_out != nullptr) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward: dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  optional dgamma/dbeta partials
+// ------------------------------------------------------------------------------------------------
+template <int G, int CPL>
+__global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const __nv_bfloat16* __restrict__ z,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ gamma,
+                                                            __nv_bfloat16* __restrict__ dz,
+                                                            float* __restrict__ partial /* [grid,2,H] or NULL */,
+                                                            int64_t M, int H) {
+  const int nchunks = H >> 3;
+  const int sub = threadIdx.x % G;
+  const int64_t rows_per_block = ROW_THREADS / G;
+  const float invH = 1.0f / static_cast<float>(H);
+  float dg[CPL][8], db[CPL][8];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dg[c][e] = db[c][e] = 0.0f;
+  float gg[CPL][8];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int ch = sub + c * G;
+    if (ch < nchunks) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
+      gg[c][0] = g0.x; gg[c][1] = g0.y; gg[c][2] = g0.z; gg[c][3] = g0.w;
+      gg[c][4] = g1.x; gg[c][5] = g1.y; gg[c][6] = g1.z; gg[c][7] = g1.w;
+    }
+  }
+  // the loop trip count is uniform across the warp (group shuffles use the full mask): out-of-range row
+  // slots recompute row M-1 and skip their stores.
+  for (int64_t base = blockIdx.x * rows_per_block; base < M; base += gridDim.x * rows_per_block) {
+    const int64_t row_raw = base + threadIdx.x / G;
+    const bool valid = row_raw < M;
+    const int64_t row = valid ? row_raw : M - 1;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[CPL][8], gy[CPL][8];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
+      if (ch < nchunks) {
+        float a[8], b[8];
+        unpack8(ld_nc_v4(dy + row * H + ch * 8), a);
+        unpack8(ld_nc_v4(z + row * H + ch * 8), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[c][e] = (b[e] - mean) * rstd;
+          gy[c][e] = a[e] * gg[c][e];
+          s1 += gy[c][e];
+          s2 += gy[c][e] * xh[c][e];
+          if (valid) {
+            dg[c][e] += a[e] * xh[c][e];
+            db[c][e] += a[e];
+          }
+        }
+      }
+    }
+    s1 = group_sum<G>(s1) * invH;
+    s2 = group_sum<G>(s2) * invH;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
+      if (ch < nchunks) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (gy[c][e] - s1 - xh[c][e] * s2);
+        if (valid) st_na_v4(dz + row * H + ch * 8, pack8(o));
+      }
+    }
+  }
+  if (partial != nullptr) {
+    // block-level reduction of the per-thread column sums over the ROW_THREADS/G row slots (fixed order =>
+    // deterministic), one pass for dgamma and one for dbeta through the same shared buffer.
+    __shared__ float buf[8192];  // (ROW_THREADS/G) * H <= 8192 floats for every supported (G, H)
+    const int slot = threadIdx.x / G;
+    for (int which = 0; which < 2; ++which) {
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int ch = sub + c * G;
+        if (ch < nchunks) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) buf[slot * H + ch * 8 + e] = which == 0 ? dg[c][e] : db[c][e];
+        }
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < H; j += ROW_THREADS) {
+        float acc = 0.0f;
+        for (int r = 0; r < ROW_THREADS / G; ++r) acc += buf[r * H + j];
+        partial[(static_cast<int64_t>(blockIdx.x) * 2 + which) * H + j] = acc;
+      }
+    }
+  }
+}
+
+// dgamma[j] = sum_b partial[b,0,j], dbeta[j] = sum_b partial[b,1,j]  (fixed order => deterministic)
+__global__ void ln_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
+                                 float* __restrict__ dbeta, int nblocks, int H, int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * H) return;
+  const int which = j / H, col = j % H;
+  float acc = 0.0f;
+  for (int b = 0; b < nblocks; ++b) acc += partial[(static_cast<int64_t>(b) * 2 + which) * H + col];
+  float* out = which == 0 ? dgamma : dbeta;
+  out[col] = accumulate ? out[col] + acc : acc;
+}
+
+// out[j] = sum_b partial[b, j]  (fixed order => deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks,
+                                       int width, int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= width) return;
+  float acc = 0.0f;
+  for (int b = 0; b < nblocks; ++b) acc += partial[static_cast<int64_t>(b) * width + j];
+  out[j] = accumulate ? out[j] + acc : acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: token + position + token-type embedding gather, LayerNorm.  One warp per token.
+// ------------------------------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(ROW_THREADS) embed_ln_kernel(const a4r_embed_args a) {
+  const int H = static_cast<int>(a.H);
+  const int L = static_cast<int>(a.L);
+  const int nchunks = H >> 3;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_per_block = ROW_THREADS / 32;
+  const int64_t total = a.N * a.L;
+  const float invH = 1.0f / static_cast<float>(H);
+  const __nv_bfloat16* word = static_cast<const __nv_bfloat16*>(a.word_emb);
+  const __nv_bfloat16* pos = static_cast<const __nv_bfloat16*>(a.pos_emb);
+  const __nv_bfloat16* type0 = static_cast<const __nv_bfloat16*>(a.type_emb);
+  const __nv_bfloat16* prompt = static_cast<const __nv_bfloat16*>(a.prompt);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out);
+  __nv_bfloat16* z_out = static_cast<__nv_bfloat16*>(a.z_out);
+  for (int64_t tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < total;
+       tok += gridDim.x * warps_per_block) {
+    const int64_t n = tok / L;
+    const int t = static_cast<int>(tok % L);
+    const int64_t* ids = a.ids + n * a.ld_ids;
+    int64_t id = ids[t];
+    int64_t pid = t + a.pos_offset;
+    if (a.roberta_pad_id >= 0) {
+      // RoBERTa: position = pad + (#non-pad tokens up to and including t) for non-pad tokens, pad otherwise
+      const int64_t mine = lane < L ? ids[lane] : a.roberta_pad_id;
+      const uint32_t nonpad = __ballot_sync(0xffffffffu, mine != a.roberta_pad_id);
+      const uint32_t upto = t >= 31 ? 0xffffffffu : ((2u << t) - 1u);
+      pid = (id != a.roberta_pad_id) ? a.roberta_pad_id + __popc(nonpad & upto) : a.roberta_pad_id;
+    }
+    const bool use_prompt = prompt != nullptr && t < a.n_prompt;
+    const __nv_bfloat16* wrow = use_prompt ? prompt + static_cast<int64_t>(t) * H : word + id * H;
+    float v[CPL][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = lane + c * 32;
+      if (ch < nchunks) {
+        float w[8], p[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(wrow + ch * 8)), w);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pos + pid * H + ch * 8)), p);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[c][e] = w[e] + p[e];
+        if (type0 != nullptr) {
+          float ty[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(type0 + ch * 8)), ty);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[c][e] += ty[e];
+        }
+        if (z_out != nullptr) {
+          const uint4 zz = pack8(v[c]);
+          st_na_v4(z_out + tok * H + ch * 8, zz);
+          unpack8(zz, v[c]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[c][e];
+      }
+    }
+    const float mean = warp_sum(s) * invH;
+    float q = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = lane + c * 32;
+      if (ch < nchunks) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[c][e] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invH + a.eps);
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = lane + c * 32;
+      if (ch < nchunks) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + ch * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + ch * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + ch * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + ch * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * gg[e] + bb[e];
+        st_na_v4(out + tok * H + ch * 8, pack8(o));
+      }
+    }
+    if (lane == 0) {
+      if (a.mean_out != nullptr) a.mean_out[tok] = mean;
+      if (a.rstd_out != nullptr) a.rstd_out[tok] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise activation gradient: out = dy * act'(u)   (u = saved pre-activation for GELU, output for ReLU)
+// ------------------------------------------------------------------------------------------------
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ u,
+                               __nv_bfloat16* __restrict__ out, int64_t nvec, int kind) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[8], b[8], o[8];
+    unpack8(ld_nc_v4(dy + i * 8), a);
+    unpack8(ld_nc_v4(u + i * 8), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = kind == 0 ? a[e] * gelu_erf_grad(b[e]) : (b[e] > 0.0f ? a[e] : 0.0f);
+    st_na_v4(out + i * 8, pack8(o));
+  }
+}
+
+// column sums of a bf16 [M, ld] matrix over `width` columns: out[j] (+)= sum_m x[m, j].  Two-stage.
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t M, int width,
+                                      float* __restrict__ partial) {
+  // block handles a strided set of rows; thread j handles 8-column chunk(s)
+  const int nchunks = width >> 3;
+  for (int ch = threadIdx.x; ch < nchunks; ch += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t r = blockIdx.x; r < M; r += gridDim.x) {
+      float a[8];
+      unpack8(ld_nc_v4(x + r * ld + ch * 8), a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += a[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) partial[static_cast<int64_t>(blockIdx.x) * width + ch * 8 + e] = acc[e];
+  }
+}
+
+template <typename F>
+int dispatch_ln(int H, F&& f) {
+  // (G lanes per row, chunks per lane)
+  if (H <= 64) return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+  if (H <= 128) return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 1>{});
+  if (H <= 256) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 1>{});
+  if (H <= 512) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 2>{});
+  if (H <= 768) return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 3>{});
+  return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 4>{});
+}
+
+constexpr int LN_BWD_MAX_BLOCKS = 592;  // 4 x 148
+
+}  // namespace
+
+extern "C" int a4r_layernorm_fwd(const void* x, const void* res, int64_t res_rows, const float* gamma,
+                                 const float* beta, float eps, void* y, void* z_out, float* mean, float* rstd,
+                                 int64_t M, int64_t H, a4r_stream_t stream_) {
+  A4R_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: NULL pointer");
+  A4R_CHECK_ARG(H >= 8 && H <= 1024 && H % 8 == 0, "layernorm: H must be a multiple of 8 in [8,1024] (got %lld)",
+                (long long)H);
+  A4R_CHECK_ARG(M >= 0, "layernorm: bad M");
+  A4R_CHECK_ARG(a4r_aligned16(x) && a4r_aligned16(y) && a4r_aligned16(gamma) && a4r_aligned16(beta) &&
+                    a4r_aligned16(res) && a4r_aligned16(z_out),
+                "layernorm: pointers must be 16B aligned");
+  if (res != nullptr) A4R_CHECK_ARG(res_rows > 0, "layernorm: res_rows must be > 0 when res is given");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  if (M == 0) return A4R_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return dispatch_ln(static_cast<int>(H), [&](auto G, auto CPL) -> int {
+    const int64_t rows_per_block = ROW_THREADS / G.value;
+    int64_t blocks = (M + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    ln_fwd_kernel<G.value, CPL.value><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(res), res_rows, gamma, beta, eps,
+        static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(z_out), mean, rstd, M, static_cast<int>(H));
+    A4R_LAUNCH_OK();
+    a4r_count_launch(1);
+    return A4R_OK;
+  });
+}
+
+extern "C" size_t a4r_layernorm_bwd_workspace_bytes(int64_t H) {
+  return static_cast<size_t>(LN_BWD_MAX_BLOCKS) * 2 * static_cast<size_t>(H) * sizeof(float);
+}
+
+extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd,
+                                 const float* gamma, void* dz, float* dgamma, float* dbeta, int32_t accumulate,
+                                 void* workspace, size_t workspace_bytes, int64_t M, int64_t H,
+                                 a4r_stream_t stream_) {
+  A4R_CHECK_ARG(dy && z && mean && rstd && gamma && dz, "layernorm_bwd: NULL pointer");
+  A4R_CHECK_ARG(H >= 8 && H <= 1024 && H % 8 == 0, "layernorm: H must be a multiple of 8 in [8,1024]");
+  A4R_CHECK_ARG(a4r_aligned16(dy) && a4r_aligned16(z) && a4r_aligned16(dz) && a4r_aligned16(gamma),
+                "layernorm_bwd: pointers must be 16B aligned");
+  const bool want_wgrad = dgamma != nullptr || dbeta != nullptr;
+  if (want_wgrad) {
+    A4R_CHECK_ARG(dgamma && dbeta, "layernorm_bwd: dgamma and dbeta must be given together");
+    if (workspace == nullptr || workspace_bytes < a4r_layernorm_bwd_workspace_bytes(H))
+      return a4r_set_error(A4R_EWORKSPACE, "layernorm_bwd: workspace too small (%zu < %zu)", workspace_bytes,
+                           a4r_layernorm_bwd_workspace_bytes(H));
+  }
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  if (M == 0) return A4R_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return dispatch_ln(static_cast<int>(H), [&](auto G, auto CPL) -> int {
+    const int64_t rows_per_block = ROW_THREADS / G.value;
+    int64_t blocks = (M + rows_per_block - 1) / rows_per_block;
+    if (blocks > LN_BWD_MAX_BLOCKS) blocks = LN_BWD_MAX_BLOCKS;
+    float* partial = want_wgrad ? static_cast<float*>(workspace) : nullptr;
+    ln_bwd_kernel<G.value, CPL.value><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
+        static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H));
+    A4R_LAUNCH_OK();
+    a4r_count_launch(1);
+    if (want_wgrad) {
+      ln_reduce_kernel<<<(2 * static_cast<int>(H) + 255) / 256, 256, 0, stream>>>(
+          partial, dgamma, dbeta, static_cast<int>(blocks), static_cast<int>(H), accumulate);
+      A4R_LAUNCH_OK();
+      a4r_count_launch(1);
+    }
+    return A4R_OK;
+  });
+}
+
+extern "C" int a4r_embed_ln_fwd(const a4r_embed_args* a, a4r_stream_t stream_) {
+  A4R_CHECK_ARG(a != nullptr, "embed_ln: args is NULL");
+  A4R_CHECK_ARG(a->ids && a->word_emb && a->pos_emb && a->gamma && a->beta && a->out, "embed_ln: NULL pointer");
+  A4R_CHECK_ARG(a->H >= 8 && a->H <= 1024 && a->H % 8 == 0, "embed_ln: H must be a multiple of 8 in [8,1024]");
+  A4R_CHECK_ARG(a->N >= 0 && a->L >= 1 && a->ld_ids >= a->L, "embed_ln: bad N/L/ld_ids");
+  A4R_CHECK_ARG(a->roberta_pad_id < 0 || a->L <= 32, "embed_ln: RoBERTa position rule supports L <= 32");
+  A4R_CHECK_ARG(a->n_prompt >= 0 && a->n_prompt <= a->L, "embed_ln: bad n_prompt");
+  A4R_CHECK_ARG(a4r_aligned16(a->word_emb) && a4r_aligned16(a->pos_emb) && a4r_aligned16(a->type_emb) &&
+                    a4r_aligned16(a->prompt) && a4r_aligned16(a->out) && a4r_aligned16(a->z_out) &&
+                    a4r_aligned16(a->gamma) && a4r_aligned16(a->beta),
+                "embed_ln: pointers must be 16B aligned");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  if (a->N == 0) return A4R_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t total = a->N * a->L;
+  int64_t blocks = (total + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  const int cpl = static_cast<int>((a->H / 8 + 31) / 32);
+  switch (cpl) {
+    case 1: embed_ln_kernel<1><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(*a); break;
+    case 2: embed_ln_kernel<2><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(*a); break;
+    case 3: embed_ln_kernel<3><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(*a); break;
+    default: embed_ln_kernel<4><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(*a); break;
+  }
+  A4R_LAUNCH_OK();
+  a4r_count_launch(1);
+  return A4R_OK;
+}
+
+extern "C" int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream_) {
+  A4R_CHECK_ARG(dy && u && out, "act_bwd: NULL pointer");
+  A4R_CHECK_ARG(n >= 0 && n % 8 == 0, "act_bwd: n must be a multiple of 8");
+  A4R_CHECK_ARG(kind == 0 || kind == 1, "act_bwd: kind must be 0 (gelu) or 1 (relu)");
+  A4R_CHECK_ARG(a4r_aligned16(dy) && a4r_aligned16(u) && a4r_aligned16(out), "act_bwd: pointers must be 16B aligned");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  if (n == 0) return A4R_OK;
+  const int64_t nvec = n / 8;
+  int64_t blocks = (nvec + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  act_bwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
+      nvec, kind);
+  A4R_LAUNCH_OK();
+  a4r_count_launch(1);
+  return A4R_OK;
+}
+
+constexpr int COLSUM_BLOCKS = 592;
+
+extern "C" size_t a4r_colsum_workspace_bytes(int64_t width) {
+  return static_cast<size_t>(COLSUM_BLOCKS) * static_cast<size_t>(width) * sizeof(float);
+}
+
+extern "C" int a4r_colsum(const void* x, int64_t ld, int64_t M, int64_t width, float* out, int32_t accumulate,
+                          void* workspace, size_t workspace_bytes, a4r_stream_t stream_) {
+  A4R_CHECK_ARG(x && out, "colsum: NULL pointer");
+  A4R_CHECK_ARG(width >= 8 && width % 8 == 0 && ld >= width && ld % 8 == 0, "colsum: bad width/ld");
+  A4R_CHECK_ARG(a4r_aligned16(x), "colsum: x must be 16B aligned");
+  if (workspace == nullptr || workspace_bytes < a4r_colsum_workspace_bytes(width))
+    return a4r_set_error(A4R_EWORKSPACE, "colsum: workspace too small");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int blocks = static_cast<int>(M < COLSUM_BLOCKS ? (M > 0 ? M : 1) : COLSUM_BLOCKS);
+  int threads = static_cast<int>(width / 8);
+  threads = threads < 32 ? 32 : (threads > 256 ? 256 : ((threads + 31) / 32) * 32);
+  colsum_partial_kernel<<<blocks, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, M,
+                                                        static_cast<int>(width), static_cast<float*>(workspace));
+  A4R_LAUNCH_OK();
+  reduce_partials_kernel<<<(static_cast<int>(width) + 255) / 256, 256, 0, stream>>>(
+      static_cast<const float*>(workspace), out, blocks, static_cast<int>(width), accumulate);
+  A4R_LAUNCH_OK();
+  a4r_count_launch(2);
+  return A4R_OK;
+}

@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C ABI: every function takes CUDA torch tensors, passes raw device pointers and
+the current CUDA stream to libadapter4rec_sm100.so, and returns torch tensors.  PyTorch is only the owner of
+device memory and streams here — no arithmetic of the hot path is done by torch ops."""
+import ctypes
+
+import torch
+
+from . import lib as _l
+from .lib import EPI_DGELU, EPI_DRELU, EPI_GELU, EPI_LINEAR, EPI_RELU  # noqa: F401
+
+BF16 = torch.bfloat16
+F32_MIN = -3.4028234663852886e38  # torch.finfo(torch.float32).min: the transformers additive attention mask value
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _rows2d(t, name):
+    """[rows, cols] view requirements of the ABI: unit column stride, row stride in elements."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("%s must be 2-D with unit column stride, got shape %s stride %s" % (name, tuple(t.shape), t.stride()))
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per (device, stream); owned by torch's allocator, handed to the library per call."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, aux=None, a2=None, b2=None,
+         alpha=1.0, out=None, out_dtype=BF16, block_n=0):
+    """C[M,N] = epi(alpha * (a @ b.T + a2 @ b2.T) + bias)  — see a4r_gemm_bf16_tn in include/adapter4rec.h."""
+    assert a.dtype == BF16 and b.dtype == BF16, "gemm operands must be bf16"
+    M, K = a.shape
+    N, Kb = b.shape
+    assert K == Kb, "gemm: K mismatch %d vs %d" % (K, Kb)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    g = _l.GemmArgs()
+    g.A, g.lda = _p(a), _rows2d(a, "a")
+    g.B, g.ldb = _p(b), _rows2d(b, "b")
+    if a2 is not None:
+        assert a2.dtype == BF16 and b2.dtype == BF16 and a2.shape[0] == M and b2.shape[0] == N and a2.shape[1] == b2.shape[1]
+        g.A2, g.lda2, g.B2, g.ldb2, g.K2 = _p(a2), _rows2d(a2, "a2"), _p(b2), _rows2d(b2, "b2"), a2.shape[1]
+    g.C, g.ldc = _p(out), _rows2d(out, "out")
+    if aux is not None:
+        assert aux.dtype == BF16 and tuple(aux.shape) == (M, N)
+        g.aux, g.ldaux = _p(aux), _rows2d(aux, "aux")
+    if residual is not None:
+        assert residual.dtype == BF16 and tuple(residual.shape) == (M, N)
+        g.residual, g.ldr = _p(residual), _rows2d(residual, "residual")
+    if residual2 is not None:
+        assert residual2.dtype == BF16 and tuple(residual2.shape) == (M, N)
+        g.residual2, g.ldr2 = _p(residual2), _rows2d(residual2, "residual2")
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+        g.bias = _p(bias)
+    g.M, g.N, g.K = M, N, K
+    g.alpha, g.epilogue, g.out_f32, g.block_n = float(alpha), int(epilogue), int(out.dtype == torch.float32), int(block_n)
+    assert out.dtype in (BF16, torch.float32)
+    _l.check(_l.get_lib().a4r_gemm_bf16_tn(ctypes.byref(g), _stream()), "a4r_gemm_bf16_tn")
+    return out
+
+
+def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg):
+    a = _l.AttnArgs()
+    a.qkv, a.ld_qkv = _p(qkv), _rows2d(qkv, "qkv")
+    a.N, a.L, a.heads, a.head_dim = N, L, heads, head_dim
+    if mask is None:
+        a.mask_dtype = 0
+    else:
+        assert mask.dim() == 2 and mask.shape[0] == N and mask.shape[1] >= L and mask.stride(1) == 1
+        a.mask, a.mask_ld = _p(mask), mask.stride(0)
+        a.mask_dtype = {torch.int64: 1, torch.float32: 2}[mask.dtype]
+    a.causal, a.scale, a.mask_neg = int(causal), float(head_dim) ** -0.5, float(mask_neg)
+    return a
+
+
+def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN):
+    assert qkv.dtype == BF16 and qkv.shape[0] == N * L
+    out = torch.empty((N * L, heads * head_dim), dtype=BF16, device=qkv.device)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg)
+    a.out, a.ld_out = _p(out), out.stride(0)
+    _l.check(_l.get_lib().a4r_attn_small_fwd(ctypes.byref(a), _stream()), "a4r_attn_small_fwd")
+    return out
+
+
+def attn_small_bwd(qkv, dctx, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN):
+    assert qkv.dtype == BF16 and dctx.dtype == BF16 and dctx.shape[0] == N * L
+    dqkv = torch.empty((N * L, 3 * heads * head_dim), dtype=BF16, device=qkv.device)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg)
+    assert _rows2d(qkv, "qkv") == dqkv.stride(0), "attention bwd expects a contiguous qkv"
+    a.out, a.dout, a.ld_out = _p(dqkv), _p(dctx), _rows2d(dctx, "dctx")
+    _l.check(_l.get_lib().a4r_attn_small_bwd(ctypes.byref(a), _stream()), "a4r_attn_small_bwd")
+    return dqkv
+
+
+def layernorm_fwd(x, gamma, beta, eps, res=None, want_z=False, want_stats=True):
+    """y = LN(x + res[row % res_rows]); returns (y, z or None, mean or None, rstd or None)."""
+    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 2
+    M, H = x.shape
+    y = torch.empty_like(x)
+    z = torch.empty_like(x) if want_z else None
+    mean = torch.empty(M, dtype=torch.float32, device=x.device) if want_stats else None
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device) if want_stats else None
+    res_rows = 0
+    if res is not None:
+        assert res.dtype == BF16 and res.is_contiguous() and res.shape[-1] == H
+        res_rows = res.numel() // H
+    _l.check(_l.get_lib().a4r_layernorm_fwd(_p(x), _p(res), res_rows, _p(gamma), _p(beta), float(eps), _p(y), _p(z),
+                                            _p(mean), _p(rstd), M, H, _stream()), "a4r_layernorm_fwd")
+    return y, z, mean, rstd
+
+
+def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma=None, dbeta=None, accumulate=False):
+    assert dy.dtype == BF16 and z.dtype == BF16 and dy.is_contiguous() and z.is_contiguous()
+    M, H = z.shape
+    dz = torch.empty_like(z)
+    ws, wsb = None, 0
+    if dgamma is not None:
+        wsb = _l.get_lib().a4r_layernorm_bwd_workspace_bytes(H)
+        ws = workspace(wsb, z.device)
+    _l.check(_l.get_lib().a4r_layernorm_bwd(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(dgamma), _p(dbeta),
+                                            int(accumulate), _p(ws), wsb, M, H, _stream()), "a4r_layernorm_bwd")
+    return dz
+
+
+def embed_ln_fwd(ids, L, word_emb, pos_emb, type_emb, gamma, beta, eps, pos_offset=0, roberta_pad_id=-1, prompt=None,
+                 want_z=False):
+    """ids: int64 [N, >=L] (row stride arbitrary); returns (out [N*L,H], z, mean, rstd)."""
+    assert ids.dtype == torch.int64 and ids.dim() == 2 and ids.stride(1) == 1
+    N, H = ids.shape[0], word_emb.shape[1]
+    out = torch.empty((N * L, H), dtype=BF16, device=ids.device)
+    z = torch.empty_like(out) if want_z else None
+    mean = torch.empty(N * L, dtype=torch.float32, device=ids.device) if want_z else None
+    rstd = torch.empty(N * L, dtype=torch.float32, device=ids.device) if want_z else None
+    a = _l.EmbedArgs()
+    a.ids, a.ld_ids = _p(ids), ids.stride(0)
+    a.word_emb, a.pos_emb, a.type_emb, a.prompt = _p(word_emb), _p(pos_emb), _p(type_emb), _p(prompt)
+    a.gamma, a.beta, a.out, a.z_out, a.mean_out, a.rstd_out = _p(gamma), _p(beta), _p(out), _p(z), _p(mean), _p(rstd)
+    a.N, a.L, a.H, a.pos_offset, a.roberta_pad_id = N, L, H, pos_offset, roberta_pad_id
+    a.n_prompt = 0 if prompt is None else prompt.shape[0]
+    a.eps = float(eps)
+    _l.check(_l.get_lib().a4r_embed_ln_fwd(ctypes.byref(a), _stream()), "a4r_embed_ln_fwd")
+    return out, z, mean, rstd
+
+
+def act_bwd(dy, u, kind):
+    """dy * act'(u): kind 'gelu' (u = pre-activation) or 'relu' (u = activation output)."""
+    assert dy.dtype == BF16 and u.dtype == BF16 and dy.is_contiguous() and u.is_contiguous() and dy.shape == u.shape
+    out = torch.empty_like(dy)
+    _l.check(_l.get_lib().a4r_act_bwd(_p(dy), _p(u), _p(out), dy.numel(), {"gelu": 0, "relu": 1}[kind], _stream()),
+             "a4r_act_bwd")
+    return out
+
+
+def colsum(x, width=None, out=None, accumulate=False):
+    assert x.dtype == BF16 and x.dim() == 2
+    M = x.shape[0]
+    width = x.shape[1] if width is None else width
+    if out is None:
+        out = torch.empty(width, dtype=torch.float32, device=x.device)
+        accumulate = False
+    wsb = _l.get_lib().a4r_colsum_workspace_bytes(width)
+    ws = workspace(wsb, x.device)
+    _l.check(_l.get_lib().a4r_colsum(_p(x), _rows2d(x, "x"), M, width, _p(out), int(accumulate), _p(ws), wsb, _stream()),
+             "a4r_colsum")
+    return out
+
+
+def wgrad(a, b, alpha=1.0, out=None, accumulate=False, n=None, k=None):
+    """dW[N,K] (+)= alpha * a[:, :N].T @ b[:, :K]   (a = dY [M,>=N], b = X [M,>=K]; fp32 result)."""
+    assert a.dtype == BF16 and b.dtype == BF16 and a.shape[0] == b.shape[0]
+    M = a.shape[0]
+    N = a.shape[1] if n is None else n
+    K = b.shape[1] if k is None else k
+    if out is None:
+        out = torch.empty((N, K), dtype=torch.float32, device=a.device)
+        accumulate = False
+    assert out.dtype == torch.float32 and tuple(out.shape) == (N, K) and out.stride(1) == 1
+    wsb = _l.get_lib().a4r_wgrad_workspace_bytes(M, N, K)
+    ws = workspace(wsb, a.device)
+    _l.check(_l.get_lib().a4r_wgrad_bf16(_p(a), _rows2d(a, "a"), _p(b), _rows2d(b, "b"), _p(out), out.stride(0), M, N, K,
+                                         float(alpha), int(accumulate), _p(ws), wsb, _stream()), "a4r_wgrad_bf16")
+    return out
+
+
+def _bce_args(prec, emb, log_mask, pos, neg, loss, count, cpc):
+    B, S, D = prec.shape
+    assert prec.dtype == BF16 and emb.dtype == BF16 and prec.is_contiguous() and emb.is_contiguous()
+    assert emb.numel() == B * (S + 1) * 2 * D
+    a = _l.BceArgs()
+    a.prec, a.emb, a.log_mask = _p(prec), _p(emb), _p(log_mask)
+    a.pos_score, a.neg_score, a.loss, a.count = _p(pos), _p(neg), _p(loss), _p(count)
+    a.B, a.S, a.D, a.cpc = B, S, D, int(cpc)
+    return a
+
+
+def bce_loss_fwd(prec, emb, log_mask, cpc=False):
+    """returns (loss [1] f32, count [1] f32, pos_score [B,S], neg_score [B,S])."""
+    B, S, _ = prec.shape
+    dev = prec.device
+    pos = torch.empty((B, S), dtype=torch.float32, device=dev)
+    neg = torch.empty((B, S), dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.float32, device=dev)
+    if log_mask is not None:
+        assert log_mask.dtype == torch.float32 and log_mask.is_contiguous() and tuple(log_mask.shape) == (B, S)
+    a = _bce_args(prec, emb, log_mask, pos, neg, loss, count, cpc)
+    wsb = _l.get_lib().a4r_bce_workspace_bytes()
+    ws = workspace(wsb, dev)
+    _l.check(_l.get_lib().a4r_bce_loss_fwd(ctypes.byref(a), _p(ws), wsb, _stream()), "a4r_bce_loss_fwd")
+    return loss, count, pos, neg
+
+
+def bce_loss_bwd(prec, emb, log_mask, pos, neg, count, grad_out=None, cpc=False):
+    d_prec = torch.empty_like(prec)
+    d_emb = torch.empty_like(emb)
+    loss = torch.empty(1, dtype=torch.float32, device=prec.device)
+    a = _bce_args(prec, emb, log_mask, pos, neg, loss, count, cpc)
+    if grad_out is not None:
+        assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
+    _l.check(_l.get_lib().a4r_bce_loss_bwd(ctypes.byref(a), _p(grad_out), _p(d_prec), _p(d_emb), _stream()),
+             "a4r_bce_loss_bwd")
+    return d_prec, d_emb
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    _l.check(_l.get_lib().a4r_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+                                        float(eps), float(weight_decay), int(step), float(grad_scale), _stream()),
+             "a4r_adam_step")

@@ -1,0 +1,246 @@
+/*
+ * adapter4rec.h — C ABI of libadapter4rec_sm100.so
+ *
+ * B200 (sm_100a) kernels for the TransRec train + full-ranking-eval hot path of
+ * westlake-repl/Adapter4Rec.  The reference is pure Python/PyTorch and has no FFI of its own
+ * ("no native components"), so each entry point cites the reference Python
+ * symbol (file:line under /root/reference) whose arithmetic it replaces; INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add at each of those call sites.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer into caller-owned memory (the library never allocates
+ *     or frees device memory and keeps no global state besides a per-process attribute cache);
+ *   - tensors are contiguous row-major unless a leading dimension (`ld*`, in ELEMENTS) is given;
+ *   - "bf16" = __nv_bfloat16, "f32" = float, ids are int64 (the reference passes LongTensor);
+ *   - 16-byte alignment of every base pointer and of every row (ld * sizeof(elem) % 16 == 0);
+ *   - kernels are enqueued asynchronously on `stream` (a cudaStream_t); no implicit sync;
+ *   - return 0 on success, a negative A4R_E* code otherwise; a4r_last_error_string() gives the
+ *     message (thread-local).  No exceptions cross the ABI.  There is NO CPU fallback and no
+ *     dispatch to other architectures: on a device that is not sm_100 every call fails with
+ *     A4R_EARCH.
+ */
+#ifndef ADAPTER4REC_H_
+#define ADAPTER4REC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A4R_OK 0
+#define A4R_EINVAL (-1)     /* bad shape / alignment / null pointer / unsupported flag */
+#define A4R_ECUDA (-2)      /* a CUDA runtime/driver call failed */
+#define A4R_EARCH (-3)      /* current device is not compute capability 10.x */
+#define A4R_EWORKSPACE (-4) /* workspace too small */
+
+typedef void* a4r_stream_t; /* cudaStream_t */
+
+#define A4R_API __attribute__((visibility("default")))
+
+/* library version: major*10000 + minor*100 + patch */
+A4R_API int a4r_version(void);
+/* message of the last failing call on this thread ("" if none) */
+A4R_API const char* a4r_last_error_string(void);
+/* 0 if the current CUDA device can run this library (sm_100), A4R_EARCH otherwise */
+A4R_API int a4r_device_check(void);
+/* number of kernels this library has launched in this process (monotonic; bench.py's gpu_launches) */
+A4R_API int64_t a4r_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 / K4 / K7 / K11-dense: tcgen05 + TMA GEMM   C[M,N] = epi(alpha * (A·Bᵀ + A2·B2ᵀ) + bias)
+ *
+ * Replaces every nn.Linear on the path: BertSelfAttention.query/key/value (fused, N=2304),
+ * BertSelfOutput.dense, BertIntermediate.dense(+GELU), BertOutput.dense (transformers, called from
+ * Downstream/Text/model/encoders.py:53), Text_Encoder.fc(+GELU) (encoders.py:55-57), the SASRec
+ * w_Q/w_K/w_V/fc/w_1/w_2 (modules.py:54-57,19-20), AdapterBlock.fc_down/fc_up (modules.py:131-134),
+ * loralib.Linear (run.py:414-428: the rank-r term enters as the K-extension A2·B2ᵀ), and — with
+ * B = Wᵀ stored [K_out, N_in] — their data gradients dX = dY·W.
+ *
+ * A [M,K] bf16 (lda), B [N,K] bf16 (ldb)  — both "K-major", i.e. nn.Linear's native [out,in].
+ * Optional K-extension A2 [M,K2], B2 [N,K2] (K2 % 8 == 0) accumulated into the same tile.
+ * Epilogue, with v = alpha*acc + bias[n] (bias f32 [N] or NULL):
+ *   A4R_EPI_LINEAR : C = v + residual + residual2           (either may be NULL)
+ *   A4R_EPI_GELU   : aux = v (if aux != NULL), C = gelu_erf(v)
+ *   A4R_EPI_RELU   : C = max(v, 0)
+ *   A4R_EPI_DGELU  : C = v * gelu_erf'(aux)                 (aux = saved pre-activation, bf16 [M,N])
+ *   A4R_EPI_DRELU  : C = aux > 0 ? v : 0                    (aux = saved ReLU output,   bf16 [M,N])
+ * C is bf16 (out_f32 = 0) or f32 (out_f32 = 1).  K % 8 == 0, N % 8 == 0; M, N, K tails are handled.
+ * ------------------------------------------------------------------------------------------------ */
+enum {
+  A4R_EPI_LINEAR = 0,
+  A4R_EPI_GELU = 1,
+  A4R_EPI_RELU = 2,
+  A4R_EPI_DGELU = 3,
+  A4R_EPI_DRELU = 4
+};
+
+typedef struct a4r_gemm_args {
+  const void* A;
+  int64_t lda;
+  const void* B;
+  int64_t ldb;
+  const void* A2;
+  int64_t lda2;
+  const void* B2;
+  int64_t ldb2;
+  int64_t K2;
+  void* C;
+  int64_t ldc;
+  void* aux;
+  int64_t ldaux;
+  const void* residual;
+  int64_t ldr;
+  const void* residual2;
+  int64_t ldr2;
+  const float* bias;
+  int64_t M, N, K;
+  float alpha;
+  int32_t epilogue;
+  int32_t out_f32;
+  int32_t block_n; /* 0 = auto; else 64, 128 or 256 */
+} a4r_gemm_args;
+
+A4R_API int a4r_gemm_bf16_tn(const a4r_gemm_args* args, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3: whole-sequence attention for short sequences (L <= 32; head_dim 32 or 64), forward / backward.
+ *
+ * Replaces BertSelfAttention's softmax(q·kᵀ/√d + mask)·v (transformers, reached from
+ * Downstream/Text/model/encoders.py:53) and SASRec's SelfAttention.forward
+ * (Downstream/Text/model/modules.py:38-42) with the mask of User_Encoder.forward (encoders.py:25-28).
+ *
+ * qkv  [N*L, ld_qkv] bf16, columns q | k | v each heads*head_dim wide (the fused-QKV GEMM output).
+ * mask [N, mask_ld]: non-zero = valid key; mask_dtype 0 none / 1 int64 / 2 f32.  The mask is ADDITIVE:
+ *      score += mask_neg once if the key is masked or (causal and key index > query index).
+ * fwd: out = ctx  [N*L, ld_out] bf16.
+ * bwd: dout = dctx [N*L, ld_out] bf16, out = dqkv [N*L, ld_qkv] bf16 (dq | dk | dv); probabilities are
+ *      recomputed from qkv, nothing else is saved by the forward.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct a4r_attn_args {
+  const void* qkv;
+  void* out;
+  const void* dout;
+  const void* mask;
+  int64_t ld_qkv, ld_out, mask_ld;
+  int64_t N, L, heads, head_dim;
+  int32_t mask_dtype;
+  int32_t causal;
+  float scale;
+  float mask_neg;
+} a4r_attn_args;
+
+A4R_API int a4r_attn_small_fwd(const a4r_attn_args* args, a4r_stream_t stream);
+A4R_API int a4r_attn_small_bwd(const a4r_attn_args* args, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6: LayerNorm (biased variance, fp32 statistics) with an optional fused residual, forward / backward.
+ *
+ * Replaces nn.LayerNorm in BertSelfOutput/BertOutput (eps 1e-12; RoBERTa 1e-5), in the SASRec blocks and
+ * TransformerEncoder (eps 1e-6; Downstream/Text/model/modules.py:21,61,96 and :105 where the residual is the
+ * position embedding broadcast over users: res_rows = S).
+ *
+ * fwd: z = x + res[row % res_rows] (res may be NULL); y = LN(z).  x, res, y, z_out bf16 [M,H]; gamma/beta f32.
+ *      z_out (optional) receives z rounded to bf16 — the tensor the backward reads; mean/rstd f32 [M] optional.
+ * bwd: dz from dy, z, mean, rstd, gamma.  If dgamma/dbeta are non-NULL (finetune_layernorm,
+ *      Downstream/Text/run.py:496-501) they receive (accumulate=0) or accumulate (=1) the parameter
+ *      gradients via a deterministic two-stage reduction through `workspace`.
+ * ------------------------------------------------------------------------------------------------ */
+A4R_API int a4r_layernorm_fwd(const void* x, const void* res, int64_t res_rows, const float* gamma, const float* beta,
+                      float eps, void* y, void* z_out, float* mean, float* rstd, int64_t M, int64_t H,
+                      a4r_stream_t stream);
+A4R_API size_t a4r_layernorm_bwd_workspace_bytes(int64_t H);
+A4R_API int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                      void* dz, float* dgamma, float* dbeta, int32_t accumulate, void* workspace,
+                      size_t workspace_bytes, int64_t M, int64_t H, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1: token + position + token-type embedding gather fused with LayerNorm (BertEmbeddings /
+ * RobertaEmbeddings, reached from Downstream/Text/model/encoders.py:53), with the soft-prompt
+ * substitution of SoftEmbedding.forward (Downstream/Text/model/model.py:620-630).
+ *
+ * ids [N, ld_ids] int64 (the first L columns of the reference's [ids | mask] item rows).
+ * word_emb [V,H], pos_emb [P,H], type_emb [H] (row 0; may be NULL) bf16.  Position id = t + pos_offset, or
+ * — if roberta_pad_id >= 0 — pad + cumsum(ids != pad) for non-pad tokens and pad otherwise (L <= 32).
+ * prompt [n_prompt,H] bf16 (may be NULL) replaces the word embedding of the first n_prompt positions.
+ * out [N*L,H] bf16; z_out (pre-LN sum), mean_out, rstd_out optional (needed for the prompt gradient).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct a4r_embed_args {
+  const int64_t* ids;
+  int64_t ld_ids;
+  const void* word_emb;
+  const void* pos_emb;
+  const void* type_emb;
+  const void* prompt;
+  const float* gamma;
+  const float* beta;
+  void* out;
+  void* z_out;
+  float* mean_out;
+  float* rstd_out;
+  int64_t N, L, H;
+  int64_t pos_offset;
+  int64_t roberta_pad_id;
+  int64_t n_prompt;
+  float eps;
+} a4r_embed_args;
+A4R_API int a4r_embed_ln_fwd(const a4r_embed_args* args, a4r_stream_t stream);
+
+/* out = dy * act'(u) elementwise over n bf16 values; kind 0: erf-GELU with u = pre-activation
+ * (Text_Encoder.activate, encoders.py:46,57), kind 1: ReLU with u = activation output. */
+A4R_API int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
+
+/* out[j] (+)= sum_m x[m, j] for a bf16 [M, ld] matrix, j < width: bias gradients of trainable biases
+ * (lora.Linear bias, AdapterBlock biases).  Deterministic two-stage reduction through `workspace`. */
+A4R_API size_t a4r_colsum_workspace_bytes(int64_t width);
+A4R_API int a4r_colsum(const void* x, int64_t ld, int64_t M, int64_t width, float* out, int32_t accumulate,
+               void* workspace, size_t workspace_bytes, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight gradient of a TRAINABLE low-rank module:  dW[N,K] (+)= alpha * A[M,N]ᵀ · B[M,K]   (f32 out)
+ *
+ * A = dY (bf16 [M,lda]), B = X (bf16 [M,ldb]) gives nn.Linear's dW[out,in]: AdapterBlock.fc_down / fc_up
+ * (Downstream/Text/model/modules.py:117-127) and loralib's lora_B = dYᵀ·(x·Aᵀ), lora_A = (dY·B)ᵀ·x
+ * (Downstream/Text/run.py:414-428).  One of N, K is small (<= 64): HBM-bound, deterministic split-M.
+ * ------------------------------------------------------------------------------------------------ */
+A4R_API size_t a4r_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+A4R_API int a4r_wgrad_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, int64_t M,
+                   int64_t N, int64_t K, float alpha, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                   a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9: fused masked dot + BCE-with-logits + mean, forward / backward.
+ * Replaces Model.forward's loss (Downstream/Text/model/model.py:53-68) and, with cpc = 1,
+ * ModelCPC.forward's (model.py:120-133).
+ *
+ * prec [B,S,D] bf16 (user-encoder output), emb [B,S+1,2,D] bf16 (encoder output; [:,:,0] history item,
+ * [:,:,1] sampled negative), log_mask [B,S] f32.  fwd writes pos_score/neg_score [B,S] f32, loss [1] f32 and
+ * count [1] f32 (= |valid positions|).  bwd (grad_out: device f32 scalar or NULL = 1) writes d_prec [B,S,D]
+ * and the LOSS part of d_emb [B,S+1,2,D] (bf16); the gradient through the user-encoder input is separate.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct a4r_bce_args {
+  const void* prec;
+  const void* emb;
+  const float* log_mask;
+  float* pos_score;
+  float* neg_score;
+  float* loss;
+  float* count;
+  int64_t B, S, D;
+  int32_t cpc;
+} a4r_bce_args;
+A4R_API size_t a4r_bce_workspace_bytes(void);
+A4R_API int a4r_bce_loss_fwd(const a4r_bce_args* args, void* workspace, size_t workspace_bytes, a4r_stream_t stream);
+A4R_API int a4r_bce_loss_bwd(const a4r_bce_args* args, const float* grad_out, void* d_prec, void* d_emb,
+                     a4r_stream_t stream);
+
+/* K14: torch.optim.Adam semantics (Downstream/Text/run.py:524-529) over one flat f32 segment.
+ * step is 1-based; the gradient is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+A4R_API int a4r_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int64_t step, float grad_scale, a4r_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAPTER4REC_H_ */

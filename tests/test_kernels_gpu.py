@@ -1,0 +1,266 @@
+"""-m gpu: each sm_100a kernel, called through the C ABI (adapter4rec_b200.ops -> ctypes -> .so), against a plain
+PyTorch fp32 reference of the same op on the same seeded inputs.  Tolerances are stated per test: inputs are
+bf16-exact, accumulation is fp32, so the only error is the final bf16 rounding (2^-8 relative) unless noted."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _ops():
+    from adapter4rec_b200 import ops
+    return ops
+
+
+def _rand(shape, scale=1.0, seed=0, dtype=BF16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda", dtype=torch.float32) * scale).to(dtype)
+
+
+def _close(got, ref, rtol, atol, what):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), "%s: %d/%d mismatches, max abs err %.4g (ref max %.4g)" % (
+        what, int(bad.sum()), bad.numel(), float(err.max()), float(ref.abs().max()))
+
+
+GEMM_SHAPES = [
+    # M, N, K, block_n
+    (128, 256, 64, 0), (128, 64, 64, 0), (128, 128, 128, 0),
+    (256, 768, 768, 0), (1000, 2304, 768, 0), (300, 3072, 768, 0), (515, 768, 3072, 0),
+    (77, 64, 768, 0), (4096, 768, 768, 128), (2048, 256, 64, 64), (130, 72, 40, 0),
+    (10240, 64, 256, 0), (148 * 128 * 2 + 5, 768, 768, 0),
+]
+
+
+@pytest.mark.parametrize("M,N,K,bn", GEMM_SHAPES)
+def test_gemm_linear(M, N, K, bn):
+    ops = _ops()
+    a, b = _rand((M, K), 1.0, 1), _rand((N, K), K ** -0.5, 2)
+    bias = _rand((N,), 1.0, 3, torch.float32)
+    ref = a.float() @ b.float().t() + bias
+    got = ops.gemm(a, b, bias=bias, block_n=bn)
+    _close(got, ref, 2 ** -7, 1e-2, "gemm bf16 out")
+    got32 = ops.gemm(a, b, bias=bias, block_n=bn, out_dtype=torch.float32)
+    _close(got32, ref, 1e-4, 1e-3, "gemm f32 out")
+
+
+def test_gemm_epilogues():
+    ops = _ops()
+    M, N, K = 700, 768, 256
+    a, b = _rand((M, K), 1.0, 1), _rand((N, K), K ** -0.5, 2)
+    bias = _rand((N,), 0.5, 3, torch.float32)
+    r1, r2 = _rand((M, N), 1.0, 4), _rand((M, N), 1.0, 5)
+    v = a.float() @ b.float().t() + bias
+    _close(ops.gemm(a, b, bias=bias, residual=r1, residual2=r2), v + r1.float() + r2.float(), 2 ** -7, 2e-2, "linear+res")
+    aux = torch.empty((M, N), dtype=BF16, device="cuda")
+    got = ops.gemm(a, b, bias=bias, epilogue=ops.EPI_GELU, aux=aux)
+    _close(aux, v, 2 ** -7, 1e-2, "gelu aux (pre-activation)")
+    _close(got, torch.nn.functional.gelu(v), 2 ** -7, 1e-2, "gelu")
+    _close(ops.gemm(a, b, bias=bias, epilogue=ops.EPI_RELU), torch.relu(v), 2 ** -7, 1e-2, "relu")
+    u = _rand((M, N), 1.5, 6)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf).sum().backward()
+    _close(ops.gemm(a, b, epilogue=ops.EPI_DGELU, aux=u), (v - bias) * uf.grad, 2 ** -6, 2e-2, "dgelu")
+    _close(ops.gemm(a, b, epilogue=ops.EPI_DRELU, aux=u), (v - bias) * (u.float() > 0), 2 ** -7, 1e-2, "drelu")
+    _close(ops.gemm(a, b, alpha=0.125), (v - bias) * 0.125, 2 ** -7, 1e-2, "alpha")
+
+
+def test_gemm_k_extension_and_strided_a():
+    ops = _ops()
+    M, N, K, K2 = 900, 2304, 768, 64
+    a, b = _rand((M, K), 1.0, 1), _rand((N, K), K ** -0.5, 2)
+    a2, b2 = _rand((M, K2), 1.0, 3), _rand((N, K2), 0.1, 4)
+    ref = a.float() @ b.float().t() + a2.float() @ b2.float().t()
+    _close(ops.gemm(a, b, a2=a2, b2=b2), ref, 2 ** -7, 2e-2, "k-extension")
+    # strided A: the CLS rows (row 0 of every 30-token item) of a [N_items*30, 768] activation
+    items, L = 333, 30
+    h = _rand((items * L, K), 1.0, 5)
+    w = _rand((64, K), K ** -0.5, 6)
+    cls = h.view(items, L, K)[:, 0]
+    assert cls.stride(0) == L * K
+    _close(ops.gemm(cls, w), cls.float() @ w.float().t(), 2 ** -7, 1e-2, "strided A")
+    # strided C: write into column block of a wider buffer
+    wide = torch.zeros((M, 1024), dtype=BF16, device="cuda")
+    ops.gemm(a, b[:256], out=wide[:, 512:768])
+    _close(wide[:, 512:768], a.float() @ b[:256].float().t(), 2 ** -7, 1e-2, "strided C")
+    assert float(wide[:, :512].abs().max()) == 0.0 and float(wide[:, 768:].abs().max()) == 0.0
+
+
+def test_gemm_rejects_bad_args():
+    ops = _ops()
+    a, b = _rand((64, 60), 1, 1), _rand((64, 60), 1, 2)  # K % 8 != 0
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.gemm(a, b)
+
+
+def _attn_ref(qkv, N, L, heads, dh, mask, causal, mask_neg):
+    H = heads * dh
+    q, k, v = [t.view(N, L, heads, dh).transpose(1, 2) for t in qkv.float().view(N * L, 3, H).unbind(1)]
+    s = (q @ k.transpose(-1, -2)) * dh ** -0.5
+    ok = torch.ones(N, 1, L, L, dtype=torch.bool, device=qkv.device)
+    if mask is not None:
+        ok = ok & (mask[:, :L] != 0).view(N, 1, 1, L)
+    if causal:
+        ok = ok & torch.tril(torch.ones(L, L, dtype=torch.bool, device=qkv.device))
+    s = s + torch.where(ok, 0.0, mask_neg)
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(N * L, H)
+
+
+@pytest.mark.parametrize("N,L,heads,dh,mask_kind,causal", [
+    (37, 30, 12, 64, "int64", False), (5, 30, 12, 64, None, False), (64, 20, 2, 32, "f32", True),
+    (9, 10, 2, 32, "f32", True), (3, 32, 4, 64, "int64", True), (2, 1, 2, 32, None, False),
+])
+def test_attention_small_fwd_bwd(N, L, heads, dh, mask_kind, causal):
+    ops = _ops()
+    H = heads * dh
+    qkv = _rand((N * L, 3 * H), 1.0, 7)
+    mask = None
+    if mask_kind is not None:
+        g = torch.Generator(device="cuda").manual_seed(11)
+        lens = torch.randint(0, L + 1, (N,), generator=g, device="cuda")  # includes fully masked rows (len 0)
+        m = (torch.arange(L, device="cuda")[None, :] < lens[:, None])
+        if causal:  # SASRec: left padding
+            m = m.flip(1)
+        mask = m.to(torch.int64 if mask_kind == "int64" else torch.float32)
+        if mask_kind == "int64":  # the reference's [ids | mask] rows: pass the strided right half
+            both = torch.zeros((N, 2 * L), dtype=torch.int64, device="cuda")
+            both[:, L:] = mask
+            mask = both[:, L:]
+    mask_neg = -1e9 if causal else ops.F32_MIN
+    qf = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qf, N, L, heads, dh, mask, causal, mask_neg)
+    got = ops.attn_small_fwd(qkv, N, L, heads, dh, mask=mask, causal=causal, mask_neg=mask_neg)
+    _close(got, ref.detach(), 2 ** -6, 2e-2, "attention fwd")
+    dctx = _rand((N * L, H), 1.0, 8)
+    ref.backward(dctx.float())
+    dqkv = ops.attn_small_bwd(qkv, dctx, N, L, heads, dh, mask=mask, causal=causal, mask_neg=mask_neg)
+    # probabilities and dS are rounded to bf16 before the second contraction: 2^-6 relative + small absolute
+    _close(dqkv, qf.grad, 2 ** -5, 6e-2, "attention bwd")
+
+
+@pytest.mark.parametrize("M,H", [(1000, 768), (515, 64), (33, 256), (7, 128), (4099, 1024), (64, 512)])
+def test_layernorm_fwd_bwd(M, H):
+    ops = _ops()
+    x, res = _rand((M, H), 1.0, 1), _rand((M, H), 1.0, 2)
+    gamma, beta = 1 + 0.1 * _rand((H,), 1, 3, torch.float32), 0.1 * _rand((H,), 1, 4, torch.float32)
+    y, z, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-12, res=res, want_z=True)
+    zr = (x.float() + res.float())
+    _close(z, zr, 2 ** -8, 1e-6, "z")
+    zf = z.float().requires_grad_(True)
+    gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(zf, (H,), gf, bf, 1e-12)
+    _close(y, ref.detach(), 2 ** -7, 1e-2, "ln fwd")
+    dy = _rand((M, H), 1.0, 5)
+    ref.backward(dy.float())
+    dg, db = torch.empty(H, device="cuda"), torch.empty(H, device="cuda")
+    dz = ops.layernorm_bwd(dy, z, mean, rstd, gamma, dgamma=dg, dbeta=db)
+    _close(dz, zf.grad, 2 ** -6, 2e-2, "ln bwd dz")
+    _close(dg, gf.grad, 1e-3, 1e-2 * math.sqrt(M), "ln bwd dgamma")
+    _close(db, bf.grad, 1e-3, 1e-2 * math.sqrt(M), "ln bwd dbeta")
+    # broadcast residual (SASRec position embedding): res_rows = S
+    S = 5 if M % 5 == 0 else 1
+    pos = _rand((S, H), 1.0, 6)
+    y2, _, _, _ = ops.layernorm_fwd(x, gamma, beta, 1e-6, res=pos)
+    ref2 = torch.nn.functional.layer_norm(x.float() + pos.float().repeat(M // S, 1), (H,), gamma, beta, 1e-6)
+    _close(y2, ref2, 2 ** -7, 1e-2, "ln fwd broadcast residual")
+
+
+@pytest.mark.parametrize("roberta,prompt", [(False, 0), (True, 0), (False, 10), (True, 7)])
+def test_embed_ln(roberta, prompt):
+    ops = _ops()
+    N, L, H, V, P = 50, 30, 768, 1000, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    pad = 1 if roberta else 0
+    ids = torch.randint(3, V, (N, L), generator=g, device="cuda")
+    lens = torch.randint(2, L + 1, (N,), generator=g, device="cuda")
+    ids = torch.where(torch.arange(L, device="cuda")[None] < lens[:, None], ids, torch.full_like(ids, pad))
+    rows = torch.cat([ids, (ids != pad).long()], 1)  # the reference's [ids | mask] layout
+    word, pos, typ = _rand((V, H), 0.02, 1), _rand((P, H), 0.02, 2), _rand((1, H), 0.02, 3)
+    gamma, beta = 1 + 0.1 * _rand((H,), 1, 4, torch.float32), 0.1 * _rand((H,), 1, 5, torch.float32)
+    pr = _rand((prompt, H), 0.02, 6) if prompt else None
+    out, z, mean, rstd = ops.embed_ln_fwd(rows[:, :L], L, word, pos, typ[0], gamma, beta, 1e-5,
+                                          roberta_pad_id=(1 if roberta else -1), prompt=pr, want_z=True)
+    w = word.float()[ids]
+    if prompt:
+        w = torch.cat([pr.float()[None].expand(N, -1, -1), w[:, prompt:]], 1)
+    if roberta:
+        m = (ids != pad).long()
+        pid = torch.cumsum(m, 1) * m + pad
+    else:
+        pid = torch.arange(L, device="cuda")[None].expand(N, -1)
+    zr = w + pos.float()[pid] + typ.float()[0]
+    ref = torch.nn.functional.layer_norm(zr, (H,), gamma, beta, 1e-5).view(N * L, H)
+    _close(out, ref, 2 ** -6, 3e-2, "embed+ln")
+
+
+def test_act_bwd_colsum_wgrad():
+    ops = _ops()
+    dy, u = _rand((1000, 64), 1, 1), _rand((1000, 64), 1.5, 2)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf).sum().backward()
+    _close(ops.act_bwd(dy, u, "gelu"), dy.float() * uf.grad, 2 ** -6, 1e-2, "act_bwd gelu")
+    _close(ops.act_bwd(dy, u, "relu"), dy.float() * (u.float() > 0), 2 ** -8, 1e-6, "act_bwd relu")
+    x = _rand((5000, 2304), 1, 3)
+    _close(ops.colsum(x), x.float().sum(0), 1e-4, 2e-2, "colsum")
+    _close(ops.colsum(x[:, 768:1536]), x[:, 768:1536].float().sum(0), 1e-4, 2e-2, "colsum strided")
+    for (M, N, K) in [(5000, 768, 8), (3001, 8, 768), (4096, 768, 64), (777, 64, 768), (10240, 64, 16), (100, 16, 64)]:
+        a, b = _rand((M, N), 1, 4), _rand((M, K), 1, 5)
+        ref = a.float().t() @ b.float()
+        got = ops.wgrad(a, b, alpha=0.5)
+        _close(got, 0.5 * ref, 1e-3, 2e-3 * math.sqrt(M), "wgrad %dx%dx%d" % (M, N, K))
+        got2 = ops.wgrad(a, b, alpha=0.5, out=got.clone(), accumulate=True)
+        _close(got2, ref, 1e-3, 4e-3 * math.sqrt(M), "wgrad accumulate")
+    # operands that are column slices of wider buffers (T = x·Aᵀ padded to 64 columns)
+    t = _rand((3000, 64), 1, 6)
+    dq = _rand((3000, 2304), 1, 7)
+    _close(ops.wgrad(dq[:, :768], t, k=8), dq[:, :768].float().t() @ t[:, :8].float(), 1e-3, 0.2, "wgrad sliced")
+
+
+@pytest.mark.parametrize("B,S,D,cpc", [(64, 20, 64, False), (7, 10, 256, False), (33, 20, 768, False), (16, 20, 64, True)])
+def test_bce_loss(B, S, D, cpc):
+    ops = _ops()
+    prec = _rand((B, S, D), D ** -0.5, 1)
+    emb = _rand((B, S + 1, 2, D), 1.0, 2)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lens = torch.randint(1, S + 1, (B,), generator=g, device="cuda")
+    log_mask = (torch.arange(S, device="cuda")[None] >= (S - lens)[:, None]).float()
+    pf, ef = prec.float().requires_grad_(True), emb.float().requires_grad_(True)
+    pos, neg = ef[:, :, 0], ef[:, :, 1]
+    ps, ns = (pf * pos[:, 1:]).sum(-1), (pf * neg[:, :-1]).sum(-1)
+    bce = torch.nn.BCEWithLogitsLoss()
+    if cpc:
+        ref = bce(ps[:, -1], torch.ones(B, device="cuda")) + bce(ns[:, -1], torch.zeros(B, device="cuda"))
+    else:
+        idx = torch.where(log_mask != 0)
+        ref = bce(ps[idx], torch.ones_like(ps[idx])) + bce(ns[idx], torch.zeros_like(ns[idx]))
+    loss, count, p, n = ops.bce_loss_fwd(prec, emb.view(B, S + 1, 2, D), None if cpc else log_mask, cpc=cpc)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref))), (float(loss), float(ref))
+    assert float(count) == (B if cpc else float(log_mask.sum()))
+    ref.backward()
+    go = torch.full((1,), 2.0, device="cuda")
+    d_prec, d_emb = ops.bce_loss_bwd(prec, emb, None if cpc else log_mask, p, n, count, grad_out=go, cpc=cpc)
+    _close(d_prec, 2 * pf.grad, 2 ** -7, 1e-6, "d_prec")
+    _close(d_emb, 2 * ef.grad, 2 ** -7, 1e-6, "d_emb")
+
+
+def test_adam_matches_torch():
+    ops = _ops()
+    n = 100003
+    p0 = _rand((n,), 1, 1, torch.float32)
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    for step in range(1, 4):
+        g = _rand((n,), 1, 10 + step, torch.float32)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g * 4, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.0, step, grad_scale=0.25)
+    _close(p, ref.detach(), 1e-6, 1e-6, "adam")
