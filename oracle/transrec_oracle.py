@@ -1,0 +1,256 @@
+"""CPU oracle for the TransRec train + full-ranking-eval hot path of westlake-repl/Adapter4Rec.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under adapter4rec_b200/ imports this module; it may be imported by tests/,
+by __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs, and only as the checker or the
+timed CPU baseline — never as the product path.
+
+What it is: a plain fp32 restatement, in functional PyTorch-on-CPU form, of the arithmetic the reference executes
+for this path.  The reference itself is PyTorch, and the transformer bodies live in `transformers` (pinned 4.20.1 in
+/root/reference/README.md:64; installed here: 5.5.0), so the restatement follows the reference's own call sites and
+module code (cited per function, paths relative to /root/reference) and the published BERT/RoBERTa layer algebra.
+loralib (pinned 0.1.1, README.md:65) is NOT installed: `lora_linear` restates its published Linear.forward.
+
+Pinned: tests/golden/*.pt hold outputs of the UNMODIFIED reference modules (imported from /root/reference by
+tests/golden/make_golden.py in the build container, with transformers' own BertModel/RobertaModel bodies) on seeded
+weights and inputs; tests/test_oracle.py checks every function here against them.
+
+Every function takes a `state_dict`-style mapping whose KEYS ARE THE REFERENCE'S, so the same
+checkpoint dictionary drives the oracle and the CUDA path.  All functions are differentiable (torch autograd) so
+gradient parity of the trainable adapter / LoRA / prompt parameters can be checked too.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BERT_PREFIX = "bert_encoder.text_encoders.title.bert_model."
+FC_PREFIX = "bert_encoder.text_encoders.title.fc."
+USER_PREFIX = "user_encoder.transformer_encoder."
+
+
+class TextConfig:
+    """The few numbers of the transformers config the path depends on."""
+
+    def __init__(self, hidden=768, layers=12, heads=12, eps=1e-12, roberta=False, pad_token_id=0):
+        self.hidden, self.layers, self.heads, self.eps = hidden, layers, heads, eps
+        self.roberta, self.pad_token_id = roberta, pad_token_id
+
+
+class RecConfig:
+    """argparse fields read by the path (Downstream/Text/parameters.py:25-31,55,62,65,76)."""
+
+    def __init__(self, max_seq_len=20, embedding_dim=64, heads=2, blocks=2, num_words_title=30,
+                 adapter_activation="RELU", n_tokens=0):
+        self.max_seq_len, self.embedding_dim, self.heads, self.blocks = max_seq_len, embedding_dim, heads, blocks
+        self.num_words_title, self.adapter_activation, self.n_tokens = num_words_title, adapter_activation, n_tokens
+
+
+def layer_norm(x, sd, prefix, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], eps)
+
+
+def adapter_block(x, sd, prefix, activation="RELU"):
+    """AdapterBlock.forward, Downstream/Text/model/modules.py:131-134: fc_up(act(fc_down(x))) + x.
+    (self.dropout is constructed at :129 but never applied.)  act = GELU iff args.adapter_activation == "GELU"
+    (modules.py:122-125)."""
+    h = F.linear(x, sd[prefix + "fc_down.weight"], sd[prefix + "fc_down.bias"])
+    h = F.gelu(h) if activation == "GELU" else F.relu(h)
+    return F.linear(h, sd[prefix + "fc_up.weight"], sd[prefix + "fc_up.bias"]) + x
+
+
+def lora_linear(x, sd, prefix):
+    """loralib 0.1.1 Linear.forward as used at Downstream/Text/run.py:414-428 (r > 0, lora_alpha = 1, lora_dropout = 0,
+    not merged): F.linear(x, W, b) + (x @ lora_A.T @ lora_B.T) * (lora_alpha / r)."""
+    y = F.linear(x, sd[prefix + "weight"], sd.get(prefix + "bias"))
+    if prefix + "lora_A" in sd:
+        a, b = sd[prefix + "lora_A"], sd[prefix + "lora_B"]
+        y = y + (x @ a.t() @ b.t()) * (1.0 / a.shape[0])
+    return y
+
+
+def linear_or_lora(x, sd, prefix):
+    return lora_linear(x, sd, prefix)
+
+
+def self_output(hidden, input_tensor, sd, prefix, eps, activation):
+    """BertSelfOutput / BertOutput (transformers) or, if the Houlsby wrapper keys are present,
+    BertAdaptedSelfOutput.forward, Downstream/Text/model/model.py:292-297:
+    dense -> dropout (eval: identity) -> adapter -> LayerNorm(h + input)."""
+    if prefix + "self_output.dense.weight" in sd:
+        h = F.linear(hidden, sd[prefix + "self_output.dense.weight"], sd[prefix + "self_output.dense.bias"])
+        h = adapter_block(h, sd, prefix + "adapter.", activation)
+        return layer_norm(h + input_tensor, sd, prefix + "self_output.LayerNorm.", eps)
+    h = F.linear(hidden, sd[prefix + "dense.weight"], sd[prefix + "dense.bias"])
+    return layer_norm(h + input_tensor, sd, prefix + "LayerNorm.", eps)
+
+
+def bert_embeddings(ids, sd, cfg, n_tokens=0):
+    """BertEmbeddings / RobertaEmbeddings.forward (transformers) with the SoftEmbedding substitution of
+    Downstream/Text/model/model.py:620-630 when `embeddings.word_embeddings.learned_embedding` is present."""
+    p = BERT_PREFIX + "embeddings."
+    L = ids.shape[1]
+    if p + "word_embeddings.learned_embedding" in sd:
+        learned = sd[p + "word_embeddings.learned_embedding"]
+        n = learned.shape[0]
+        w = torch.cat([learned.unsqueeze(0).expand(ids.shape[0], -1, -1), sd[p + "word_embeddings.wte.weight"][ids[:, n:]]], 1)
+    else:
+        w = sd[p + "word_embeddings.weight"][ids]
+    if cfg.roberta:
+        m = (ids != cfg.pad_token_id).long()
+        pos_ids = torch.cumsum(m, 1) * m + cfg.pad_token_id
+    else:
+        pos_ids = torch.arange(L).unsqueeze(0).expand_as(ids)
+    x = w + sd[p + "token_type_embeddings.weight"][0] + sd[p + "position_embeddings.weight"][pos_ids]
+    return layer_norm(x, sd, p + "LayerNorm.", cfg.eps)
+
+
+def bert_layer(x, add_mask, sd, i, cfg, activation):
+    """One BertLayer (post-LN).  q/k/v may be loralib Linears (run.py:416-421); attention.output / output may be
+    Houlsby-wrapped (run.py:456-460).  Attention: softmax(q kᵀ / sqrt(d) + mask) v with the transformers additive
+    mask (1 - m) * finfo(float32).min."""
+    p = BERT_PREFIX + "encoder.layer.%d." % i
+    N, L, H = x.shape
+    dh = H // cfg.heads
+    q = linear_or_lora(x, sd, p + "attention.self.query.").view(N, L, cfg.heads, dh).transpose(1, 2)
+    k = linear_or_lora(x, sd, p + "attention.self.key.").view(N, L, cfg.heads, dh).transpose(1, 2)
+    v = linear_or_lora(x, sd, p + "attention.self.value.").view(N, L, cfg.heads, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) / math.sqrt(dh) + add_mask
+    ctx = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(N, L, H)
+    y = self_output(ctx, x, sd, p + "attention.output.", cfg.eps, activation)
+    f = F.gelu(F.linear(y, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
+    return self_output(f, y, sd, p + "output.", cfg.eps, activation)
+
+
+def bert_encoder(text, sd, cfg, rec):
+    """Bert_Encoder.forward + Text_Encoder.forward, Downstream/Text/model/encoders.py:48-57,89-99:
+    text [N, 2L] = ids | attention mask; returns GELU(fc(hidden[:, 0])) [N, D]."""
+    L = text.shape[1] // 2
+    ids, mask = text[:, :L], text[:, L:]
+    x = bert_embeddings(ids, sd, cfg, rec.n_tokens)
+    add_mask = (1.0 - mask.float()).view(-1, 1, 1, L) * torch.finfo(torch.float32).min
+    for i in range(cfg.layers):
+        x = bert_layer(x, add_mask, sd, i, cfg, rec.adapter_activation)
+    cls = F.linear(x[:, 0], sd[FC_PREFIX + "weight"], sd[FC_PREFIX + "bias"])
+    return F.gelu(cls)
+
+
+def sasrec_block(x, att_mask, sd, p, rec):
+    """TransformerBlock.forward (Downstream/Text/model/modules.py:45-87) or, when the wrapper keys are present,
+    SASRecAdaptedSelfOutput.forward (model.py:341-376): adapter1 after fc, adapter2 after the FFN, both before the
+    LayerNorms.  w_Q / w_V may be loralib Linears with a bias (run.py:425-428)."""
+    wrapped = p + "transformer_block.multi_head_attention.w_Q.weight" in sd
+    tb = p + ("transformer_block." if wrapped else "")
+    a = tb + "multi_head_attention."
+    B, S, D = x.shape
+    dk = D // rec.heads
+    q = linear_or_lora(x, sd, a + "w_Q.").view(B, S, rec.heads, dk).transpose(1, 2)
+    k = linear_or_lora(x, sd, a + "w_K.").view(B, S, rec.heads, dk).transpose(1, 2)
+    v = linear_or_lora(x, sd, a + "w_V.").view(B, S, rec.heads, dk).transpose(1, 2)
+    attn = q @ k.transpose(-2, -1) / (dk ** 0.5) + att_mask
+    h = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(B, S, D)
+    h = F.linear(h, sd[a + "fc.weight"])
+    if wrapped:
+        h = adapter_block(h, sd, p + "adapter1.", rec.adapter_activation)
+    y = layer_norm(x + h, sd, a + "layer_norm.", 1e-6)
+    f = tb + "feed_forward."
+    h = F.linear(F.relu(F.linear(y, sd[f + "w_1.weight"], sd[f + "w_1.bias"])), sd[f + "w_2.weight"], sd[f + "w_2.bias"])
+    if wrapped:
+        h = adapter_block(h, sd, p + "adapter2.", rec.adapter_activation)
+    return layer_norm(y + h, sd, f + "layer_norm.", 1e-6)
+
+
+def user_encoder(input_embs, log_mask, sd, rec):
+    """User_Encoder.forward (encoders.py:24-29) + TransformerEncoder.forward (modules.py:101-113).
+    Mask: 0 where (key j <= query i and log_mask[b, j] != 0) else -1e9, shape [B,1,S,S]."""
+    B, S, D = input_embs.shape
+    valid = (log_mask != 0).view(B, 1, 1, S).expand(-1, -1, S, -1)
+    att_mask = torch.where(torch.tril(valid), 0.0, -1e9)
+    x = input_embs + sd[USER_PREFIX + "position_embedding.weight"][:S].unsqueeze(0)
+    x = layer_norm(x, sd, USER_PREFIX + "layer_norm.", 1e-6)
+    for j in range(rec.blocks):
+        x = sasrec_block(x, att_mask, sd, USER_PREFIX + "transformer_blocks.%d." % j, rec)
+    return x
+
+
+def bce_with_logits_mean(x, target_one):
+    """nn.BCEWithLogitsLoss (mean) against an all-ones / all-zeros target: mean softplus(-x) / mean softplus(x)."""
+    return F.softplus(-x).mean() if target_one else F.softplus(x).mean()
+
+
+def loss_from_embeddings(embs_all, log_mask, sd, rec, cpc=False):
+    """Model.forward lines 53-68 / ModelCPC.forward lines 120-133 (Downstream/Text/model/model.py), given the item
+    embeddings [B*(S+1)*2, D]."""
+    S1 = rec.max_seq_len + 1
+    e = embs_all.view(-1, S1, 2, rec.embedding_dim)
+    pos, neg = e[:, :, 0], e[:, :, 1]
+    prec = user_encoder(pos[:, :-1], log_mask, sd, rec)
+    ps = (prec * pos[:, 1:]).sum(-1)
+    ns = (prec * neg[:, :-1]).sum(-1)
+    if cpc:
+        return bce_with_logits_mean(ps[:, -1], True) + bce_with_logits_mean(ns[:, -1], False)
+    idx = torch.where(log_mask != 0)
+    return bce_with_logits_mean(ps[idx], True) + bce_with_logits_mean(ns[idx], False)
+
+
+def model_forward(sample_items, log_mask, sd, cfg, rec, cpc=False):
+    """Model.forward / ModelCPC.forward: sample_items [B*(S+1)*2, 2L] int64, log_mask [B,S] -> scalar loss."""
+    return loss_from_embeddings(bert_encoder(sample_items, sd, cfg, rec), log_mask, sd, rec, cpc)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# evaluation (Downstream/Text/data_utils/metrics.py:51-116, dataset.py:65-78)
+# ------------------------------------------------------------------------------------------------------------------
+def item_embeddings(item_content, sd, cfg, rec, batch=512):
+    """get_item_embeddings, metrics.py:62-79: encoder over all I+1 item rows (row 0 = all-zero ids and mask)."""
+    with torch.no_grad():
+        return torch.cat([bert_encoder(item_content[i:i + batch], sd, cfg, rec) for i in range(0, len(item_content), batch)])
+
+
+def eval_user_vectors(seqs, item_emb, sd, rec):
+    """BuildEvalDataset.__getitem__ (dataset.py:65-78) + eval_model's user-encoder call (metrics.py:102-104):
+    tokens = seq[:-1] left-padded with item 0 to max_seq_len, gather item embeddings, last-position output."""
+    S = rec.max_seq_len
+    B = len(seqs)
+    tok = torch.zeros((B, S), dtype=torch.long)
+    mask = torch.zeros((B, S))
+    for b, seq in enumerate(seqs):
+        t = seq[:-1]
+        tok[b, S - len(t):] = torch.tensor(t)
+        mask[b, S - len(t):] = 1.0
+    with torch.no_grad():
+        return user_encoder(item_emb[tok], mask, sd, rec)[:, -1], tok, mask
+
+
+def rank_metrics(scores, history, target, topk=10):
+    """metrics.py:105-111 + metrics_topK (:51-59) for ONE user.  scores [I+1] over ids 0..I; history ids are set to
+    -inf; id 0 is dropped; rank = 1 + #{j : s_j > s_t} (the reference's argsort leaves ties unspecified; the
+    tie-break fixed here and in the CUDA path is (score desc, id asc), i.e. equal scores with a smaller id rank
+    ahead).  Returns (hit, ndcg)."""
+    s = scores.clone()
+    s[torch.as_tensor(history, dtype=torch.long)] = -float("inf")
+    st = s[target]
+    ids = torch.arange(s.shape[0])
+    ahead = ((s > st) | ((s == st) & (ids < target)))[1:].sum().item()
+    rank = 1 + ahead
+    if rank <= topk:
+        return 1.0, 1.0 / math.log2(rank + 1)
+    return 0.0, 0.0
+
+
+def topk_ids(scores, history, k=10):
+    """Top-k item ids for one user under the total order (score desc, id asc), history masked, id 0 excluded."""
+    s = scores.clone().double()
+    s[torch.as_tensor(history, dtype=torch.long)] = -float("inf")
+    s[0] = -float("inf")
+    order = sorted(range(s.shape[0]), key=lambda j: (-s[j].item(), j))
+    return order[:k]
+
+
+def eval_model(seqs, histories, item_emb, sd, rec, topk=10):
+    """eval_model, metrics.py:82-116 (single process): per-user (hit, ndcg) and their means."""
+    u, _, _ = eval_user_vectors(seqs, item_emb, sd, rec)
+    scores = u @ item_emb.t()
+    res = [rank_metrics(scores[b], histories[b], seqs[b][-1], topk) for b in range(len(seqs))]
+    hit = torch.tensor([r[0] for r in res])
+    ndcg = torch.tensor([r[1] for r in res])
+    return hit, ndcg

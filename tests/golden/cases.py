@@ -1,0 +1,190 @@
+"""Seeded weights and inputs shared by tests/golden/make_golden.py (which feeds them to the UNMODIFIED reference
+modules) and by the tests (which feed the same tensors to the oracle and to the CUDA path).
+
+State-dict keys are the reference's.  Everything is generated from torch CPU generators, so
+the build container and the GPU box (same image) produce bit-identical tensors."""
+import types
+
+import torch
+
+BERT = "bert_encoder.text_encoders.title.bert_model."
+FC = "bert_encoder.text_encoders.title.fc."
+USER = "user_encoder.transformer_encoder."
+
+
+def tiny_case(kind):
+    """kind: 'base' | 'houlsby' | 'lora' | 'prompt_cpc' (RoBERTa + SoftEmbedding + ModelCPC) | 'houlsby_gelu'."""
+    c = types.SimpleNamespace()
+    c.kind = kind
+    c.roberta = kind == "prompt_cpc"
+    c.cpc = kind == "prompt_cpc"
+    c.hidden, c.layers, c.heads, c.inter = 128, 2, 2, 512
+    c.vocab, c.max_pos = 200, 40
+    c.eps = 1e-5 if c.roberta else 1e-12
+    c.pad = 1 if c.roberta else 0
+    c.L = 8                    # num_words_title
+    c.S = 5                    # max_seq_len
+    c.D = 64                   # embedding_dim
+    c.rec_heads, c.blocks = 2, 2
+    c.bert_r = 16 if kind.startswith("houlsby") else 8   # bert_adapter_down_size (LoRA rank for kind == 'lora')
+    c.rec_r = 16 if kind.startswith("houlsby") else 8    # adapter_down_size
+    c.n_tokens = 3 if kind == "prompt_cpc" else 0
+    c.activation = "GELU" if kind == "houlsby_gelu" else "RELU"
+    c.B = 6
+    c.item_num = 40
+    c.seed = {"base": 11, "houlsby": 12, "lora": 13, "prompt_cpc": 14, "houlsby_gelu": 15}[kind]
+    return c
+
+
+def reference_args(c):
+    """The argparse namespace the reference modules read (Downstream/Text/parameters.py)."""
+    return types.SimpleNamespace(
+        max_seq_len=c.S, min_seq_len=2, l2_weight=0, embedding_dim=c.D, num_attention_heads=c.rec_heads,
+        drop_rate=0.1, transformer_block=c.blocks, num_words_title=c.L, num_words_abstract=50, num_words_body=50,
+        news_attributes=["title"], word_embedding_dim=c.hidden, bert_model_load="bert_tiny",
+        bert_adapter_down_size=c.bert_r, adapter_down_size=c.rec_r, adapter_dropout_rate=0.1,
+        adapter_activation=c.activation, num_workers=0, adapter_type={"houlsby": "houslby", "houlsby_gelu": "houslby",
+                                                                      "lora": "lora", "prompt_cpc": "prompt",
+                                                                      "base": "None"}[c.kind],
+        n_tokens=c.n_tokens)
+
+
+def _n(g, shape, std):
+    return torch.randn(shape, generator=g) * std
+
+
+def _linear(sd, g, name, out_f, in_f, bias=True, std=0.05):
+    sd[name + "weight"] = _n(g, (out_f, in_f), std)
+    if bias:
+        sd[name + "bias"] = _n(g, (out_f,), 0.05)
+
+
+def _ln(sd, g, name, dim):
+    sd[name + "weight"] = 1.0 + _n(g, (dim,), 0.1)
+    sd[name + "bias"] = _n(g, (dim,), 0.1)
+
+
+def _adapter(sd, g, name, dim, r):
+    _linear(sd, g, name + "fc_down.", r, dim)
+    _linear(sd, g, name + "fc_up.", dim, r)
+
+
+def _lora(sd, g, name, dim, r):
+    _linear(sd, g, name, dim, dim, bias=True)
+    sd[name + "lora_A"] = _n(g, (r, dim), 0.1)
+    sd[name + "lora_B"] = _n(g, (dim, r), 0.1)   # loralib initialises B to zero; non-zero here so the path is exercised
+
+
+def build_state_dict(c):
+    """Full model state dict (after adapter surgery) with the reference's key names."""
+    g = torch.Generator().manual_seed(c.seed)
+    sd = {}
+    H = c.hidden
+    e = BERT + "embeddings."
+    if c.kind == "prompt_cpc":
+        sd[e + "word_embeddings.wte.weight"] = _n(g, (c.vocab, H), 0.05)
+        sd[e + "word_embeddings.learned_embedding"] = _n(g, (c.n_tokens, H), 0.05)
+    else:
+        sd[e + "word_embeddings.weight"] = _n(g, (c.vocab, H), 0.05)
+    sd[e + "position_embeddings.weight"] = _n(g, (c.max_pos, H), 0.05)
+    sd[e + "token_type_embeddings.weight"] = _n(g, (1 if c.roberta else 2, H), 0.05)
+    _ln(sd, g, e + "LayerNorm.", H)
+    for i in range(c.layers):
+        p = BERT + "encoder.layer.%d." % i
+        for nm in ("query", "key", "value"):
+            if c.kind == "lora" and nm != "key":
+                _lora(sd, g, p + "attention.self.%s." % nm, H, c.bert_r)
+            else:
+                _linear(sd, g, p + "attention.self.%s." % nm, H, H)
+        for out_name, in_f in (("attention.output.", H), ("output.", c.inter)):
+            if c.kind.startswith("houlsby"):
+                _linear(sd, g, p + out_name + "self_output.dense.", H, in_f)
+                _ln(sd, g, p + out_name + "self_output.LayerNorm.", H)
+                _adapter(sd, g, p + out_name + "adapter.", H, c.bert_r)
+            else:
+                _linear(sd, g, p + out_name + "dense.", H, in_f)
+                _ln(sd, g, p + out_name + "LayerNorm.", H)
+            if out_name == "attention.output.":
+                _linear(sd, g, p + "intermediate.dense.", c.inter, H)
+    _linear(sd, g, BERT + "pooler.dense.", H, H)
+    _linear(sd, g, FC, c.D, H)
+    D = c.D
+    sd[USER + "position_embedding.weight"] = _n(g, (c.S, D), 0.1)
+    _ln(sd, g, USER + "layer_norm.", D)
+    for j in range(c.blocks):
+        p = USER + "transformer_blocks.%d." % j
+        tb = p + ("transformer_block." if c.kind.startswith("houlsby") else "")
+        for nm in ("w_Q", "w_K", "w_V", "fc"):
+            if c.kind == "lora" and nm in ("w_Q", "w_V"):
+                _lora(sd, g, tb + "multi_head_attention.%s." % nm, D, c.rec_r)
+            else:
+                _linear(sd, g, tb + "multi_head_attention.%s." % nm, D, D, bias=False, std=0.1)
+        _ln(sd, g, tb + "multi_head_attention.layer_norm.", D)
+        _linear(sd, g, tb + "feed_forward.w_1.", 4 * D, D, std=0.1)
+        _linear(sd, g, tb + "feed_forward.w_2.", D, 4 * D, std=0.1)
+        _ln(sd, g, tb + "feed_forward.layer_norm.", D)
+        if c.kind.startswith("houlsby"):
+            _adapter(sd, g, p + "adapter1.", D, c.rec_r)
+            _adapter(sd, g, p + "adapter2.", D, c.rec_r)
+    return sd
+
+
+def trainable_keys(c, sd):
+    """Parameters left trainable by Downstream/Text/run.py:367-479 with fine_tune_to=None."""
+    if c.kind.startswith("houlsby"):
+        return [k for k in sd if "adapter" in k]
+    if c.kind == "lora":
+        return [k for k in sd if "lora_" in k or (k.endswith("bias") and (
+            ".query." in k or ".value." in k or ".w_Q." in k or ".w_V." in k))]
+    if c.kind == "prompt_cpc":
+        return [k for k in sd if k.endswith("learned_embedding")]
+    return []
+
+
+def build_item_content(c):
+    """[item_num+1, 2L] int64 rows of ids | attention mask, as get_doc_input_bert builds them
+    (Downstream/Text/data_utils/preprocess.py:114-151): row 0 all zeros; BERT: [CLS]=101->here 2, [SEP]->3, pad 0;
+    RoBERTa: <s>=0, </s>=2, pad id 1 with mask 0."""
+    g = torch.Generator().manual_seed(c.seed + 1000)
+    rows = torch.zeros((c.item_num + 1, 2 * c.L), dtype=torch.long)
+    for i in range(1, c.item_num + 1):
+        n = int(torch.randint(3, c.L + 1, (1,), generator=g))
+        ids = torch.randint(5, c.vocab, (n,), generator=g)
+        if c.roberta:
+            ids[0], ids[-1] = 0, 2
+            rows[i, :c.L] = c.pad
+        else:
+            ids[0], ids[-1] = 2, 3
+        rows[i, :n] = ids
+        rows[i, c.L:c.L + n] = 1
+    return rows
+
+
+def build_batch(c, item_content):
+    """A training batch as BuildTrainDataset.__getitem__ returns it (Downstream/Text/data_utils/dataset.py:24-49):
+    sample_items [B, S+1, 2, 2L] int64, log_mask [B, S] float32 (left padded).  Also returns the id-level tensor."""
+    g = torch.Generator().manual_seed(c.seed + 2000)
+    S1 = c.S + 1
+    ids = torch.zeros((c.B, S1, 2), dtype=torch.long)
+    log_mask = torch.zeros((c.B, c.S))
+    for b in range(c.B):
+        n = int(torch.randint(2, S1 + 1, (1,), generator=g))   # sequence length incl. the last target
+        seq = (torch.randperm(c.item_num, generator=g)[:n] + 1)
+        ids[b, S1 - n:, 0] = seq
+        neg = torch.randint(1, c.item_num + 1, (n - 1,), generator=g)
+        ids[b, S1 - n:S1 - 1, 1] = neg
+        log_mask[b, c.S - (n - 1):] = 1.0
+    return item_content[ids], log_mask, ids
+
+
+def build_eval_users(c):
+    """Eval sequences (history + target) and the ids to mask, as read_behaviors builds them
+    (Downstream/Text/data_utils/preprocess.py:51-59)."""
+    g = torch.Generator().manual_seed(c.seed + 3000)
+    seqs, hist = [], []
+    for _ in range(9):
+        n = int(torch.randint(2, c.S + 2, (1,), generator=g))
+        seq = (torch.randperm(c.item_num, generator=g)[:n] + 1).tolist()
+        seqs.append(seq)
+        hist.append(seq[:-1])
+    return seqs, hist
