@@ -1,0 +1,319 @@
+"""Autograd glue: torch.autograd.Function wrappers that call the sm_100a kernels (adapter4rec_b200.ops) for both
+directions.  No arithmetic of the path is done by torch here — torch tracks the graph, owns memory and streams.
+
+Backward policy: a frozen weight never gets a weight gradient (only dX = dY·W through a cached bf16
+transpose); trainable adapter / LoRA / bias / LayerNorm parameters get theirs from the skinny wgrad, column-sum and
+LayerNorm-backward kernels, in fp32."""
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+PARAM_EPOCH = [0]   # bumped by the trainer after every optimizer step (the Adam kernel writes through raw pointers,
+                    # which torch's version counters cannot see)
+
+
+def bump_param_epoch():
+    PARAM_EPOCH[0] += 1
+
+
+class WeightCache:
+    """bf16 copies of an fp32 master weight: W [N,K] for the forward GEMM and Wᵀ [K,N] for the data-gradient GEMM.
+    Rebuilt when the parameter is modified in place (optimizer step, load_state_dict) or moved."""
+
+    def __init__(self):
+        self.key = None
+        self.w = None
+        self.wt = None
+
+    def get(self, weight, need_t=False):
+        key = (weight.data_ptr(), weight._version, weight.device, PARAM_EPOCH[0] if weight.requires_grad else -1)
+        if key != self.key:
+            self.key = key
+            self.w = weight.detach().to(BF16).contiguous()
+            self.wt = None
+        if need_t and self.wt is None:
+            self.wt = self.w.t().contiguous()
+        return self.w, self.wt
+
+
+def _as2d(x):
+    return x.reshape(-1, x.shape[-1])
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = act(x Wᵀ + b) + residual + residual2, act in {none, gelu, relu}."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, residual2, cache, act):
+        w, _ = cache.get(weight)
+        epi = {None: ops.EPI_LINEAR, "gelu": ops.EPI_GELU, "relu": ops.EPI_RELU}[act]
+        b = None if bias is None else bias.detach().float().contiguous()
+        need_grad = any(ctx.needs_input_grad[:5])
+        aux = None
+        if act == "gelu" and need_grad:
+            aux = torch.empty((x.shape[0], w.shape[0]), dtype=BF16, device=x.device)
+        y = ops.gemm(x, w, bias=b, epilogue=epi, residual=residual, residual2=residual2, aux=aux)
+        ctx.cache, ctx.act = cache, act
+        ctx.has_bias, ctx.has_r1, ctx.has_r2 = bias is not None, residual is not None, residual2 is not None
+        save_x = x if ctx.needs_input_grad[1] else None
+        act_saved = aux if act == "gelu" else (y if act == "relu" else None)
+        ctx.save_for_backward(save_x, act_saved, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, act_saved, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.act is not None:
+            dy = ops.act_bwd(dy, act_saved, ctx.act)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            _, wt = ctx.cache.get(weight, need_t=True)
+            dx = ops.gemm(dy, wt)
+        if ctx.needs_input_grad[1]:
+            dw = ops.wgrad(dy, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dy)
+        # the residuals enter after the activation only when act is None (enforced by the callers)
+        dr1 = dy if ctx.has_r1 and ctx.needs_input_grad[3] else None
+        dr2 = dy if ctx.has_r2 and ctx.needs_input_grad[4] else None
+        return dx, dw, db, dr1, dr2, None, None
+
+
+def linear(x, weight, bias, cache, act=None, residual=None, residual2=None):
+    assert act is None or (residual is None and residual2 is None)
+    return LinearFunction.apply(x, weight, bias, residual, residual2, cache, act)
+
+
+class FFNFunction(torch.autograd.Function):
+    """Frozen BERT feed-forward: h = GELU(y Wiᵀ + bi) Wfᵀ + bf (+ residual).  The backward fuses GELU' into the epilogue
+    of the first data-gradient GEMM and the residual gradient into the second, and keeps only the pre-activation."""
+
+    @staticmethod
+    def forward(ctx, y, wi, bi, wf, bf, residual, cache_i, cache_f):
+        w1, _ = cache_i.get(wi)
+        w2, _ = cache_f.get(wf)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[5]
+        u = torch.empty((y.shape[0], w1.shape[0]), dtype=BF16, device=y.device) if need else None
+        f = ops.gemm(y, w1, bias=bi.detach(), epilogue=ops.EPI_GELU, aux=u)
+        h = ops.gemm(f, w2, bias=bf.detach(), residual=residual)
+        ctx.caches = (cache_i, cache_f)
+        ctx.has_res = residual is not None
+        ctx.res_is_input = residual is y
+        ctx.save_for_backward(u, wi, wf)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        u, wi, wf = ctx.saved_tensors
+        dh = dh.contiguous()
+        _, w2t = ctx.caches[1].get(wf, need_t=True)
+        _, w1t = ctx.caches[0].get(wi, need_t=True)
+        du = ops.gemm(dh, w2t, epilogue=ops.EPI_DGELU, aux=u)
+        # when the residual IS the input (post-LN BERT: h = FFN(y) + y) its gradient is folded into the epilogue of the
+        # last data-gradient GEMM and nothing is returned for the residual slot (autograd would add them otherwise).
+        fold = ctx.has_res and ctx.res_is_input
+        dy = ops.gemm(du, w1t, residual=dh if fold else None) if ctx.needs_input_grad[0] else None
+        dres = dh if (ctx.has_res and not fold and ctx.needs_input_grad[5]) else None
+        return dy, None, None, None, None, dres, None, None
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """y = LN(x + res[row % res_rows]).  res is a constant (the frozen SASRec position table) or None."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, res):
+        need = any(ctx.needs_input_grad[:3])
+        g, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        if res is not None:
+            y, z, mean, rstd = ops.layernorm_fwd(x, g, b, eps, res=res, want_z=need, want_stats=need)
+        else:
+            y, _, mean, rstd = ops.layernorm_fwd(x, g, b, eps, want_stats=need)
+            z = x
+        if need:
+            ctx.save_for_backward(z, mean, rstd, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, rstd, g = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dg, db = torch.empty_like(g), torch.empty_like(g)
+            dz = ops.layernorm_bwd(dy, z, mean, rstd, g, dgamma=dg, dbeta=db)
+            return dz, dg, db, None, None
+        return ops.layernorm_bwd(dy, z, mean, rstd, g), None, None, None, None
+
+
+def layer_norm(x, weight, bias, eps, res=None):
+    return LayerNormFunction.apply(x, weight, bias, eps, res)
+
+
+class AttentionFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, mask, N, L, heads, head_dim, causal, mask_neg):
+        ctx.cfg = (N, L, heads, head_dim, causal, mask_neg)
+        ctx.mask = mask
+        ctx.save_for_backward(qkv)
+        return ops.attn_small_fwd(qkv, N, L, heads, head_dim, mask=mask, causal=causal, mask_neg=mask_neg)
+
+    @staticmethod
+    def backward(ctx, dctx):
+        (qkv,) = ctx.saved_tensors
+        N, L, heads, head_dim, causal, mask_neg = ctx.cfg
+        dqkv = ops.attn_small_bwd(qkv, dctx.contiguous(), N, L, heads, head_dim, mask=ctx.mask, causal=causal,
+                                  mask_neg=mask_neg)
+        return dqkv, None, None, None, None, None, None, None
+
+
+def attention(qkv, mask, N, L, heads, head_dim, causal=False, mask_neg=ops.F32_MIN):
+    return AttentionFunction.apply(qkv, mask, N, L, heads, head_dim, causal, mask_neg)
+
+
+LORA_PAD = 64  # the rank-r intermediates of all LoRA'd projections of one fused QKV share one 64-column k-block
+
+
+class QKVFunction(torch.autograd.Function):
+    """Fused q|k|v projection of one attention module:  qkv = x·[Wq;Wk;Wv]ᵀ + [bq;bk;bv]  (one GEMM, N = 3H), where any
+    of the three may be a loralib Linear (Downstream/Text/run.py:414-428):  + (x·Aᵀ)·Bᵀ / r.  The low-rank term rides in
+    the same tcgen05 tile as a K-extension: T = x·A_catᵀ  [M,64]  is one skinny GEMM, then
+    qkv = [x | T]·[W_cat | B_ext]ᵀ with B_ext the block matrix of the (scaled) lora_B factors.
+
+    params = (W, b, lora_A, lora_B) per fused projection (3 for q|k|v, 1 for a stand-alone loralib Linear), None where absent."""
+
+    @staticmethod
+    def forward(ctx, x, cache, *params):
+        assert len(params) % 4 == 0
+        n = len(params) // 4
+        H = params[0].shape[0]
+        K = params[0].shape[1]
+        dev = x.device
+        frozen_w = not any(p is not None and p.requires_grad for p in [params[4 * j] for j in range(n)])
+        key = tuple((p.data_ptr(), p._version) for p in [params[4 * j] for j in range(n)]) + (PARAM_EPOCH[0] if not frozen_w else -1,)
+        if cache.get("key") != key or not frozen_w:
+            cache["key"] = key
+            cache["w"] = torch.cat([params[i].detach().to(BF16) for i in range(0, 4 * n, 4)], 0).contiguous()
+            cache["wt"] = None
+        w = cache["w"]
+        bias = torch.zeros(n * H, dtype=torch.float32, device=dev)
+        for j in range(n):
+            if params[4 * j + 1] is not None:
+                bias[j * H:(j + 1) * H] = params[4 * j + 1].detach()
+        # LoRA bookkeeping: slot j occupies columns [off_j, off_j + r_j) of the 64-wide T
+        slots, off = [], 0
+        for j in range(n):
+            A = params[4 * j + 2]
+            if A is not None:
+                r = A.shape[0]
+                slots.append((j, off, r))
+                off += r
+        assert off <= LORA_PAD, "sum of LoRA ranks of one fused projection must be <= 64"
+        T = a_cat = b_ext = None
+        if slots:
+            a_cat = torch.zeros((LORA_PAD, K), dtype=BF16, device=dev)
+            b_ext = torch.zeros((n * H, LORA_PAD), dtype=BF16, device=dev)
+            for j, o, r in slots:
+                a_cat[o:o + r] = params[4 * j + 2].detach().to(BF16)
+                b_ext[j * H:(j + 1) * H, o:o + r] = (params[4 * j + 3].detach() * (1.0 / r)).to(BF16)
+            T = ops.gemm(x, a_cat)
+            qkv = ops.gemm(x, w, bias=bias, a2=T, b2=b_ext)
+        else:
+            qkv = ops.gemm(x, w, bias=bias)
+        ctx.cache, ctx.slots, ctx.H, ctx.n = cache, slots, H, n
+        ctx.n_params = len(params)
+        ctx.param_needs = [p is not None and p.requires_grad for p in params]
+        need_x = any(ctx.param_needs[4 * j + 2] for j in range(n)) or any(ctx.param_needs[4 * j] for j in range(n))
+        ctx.save_for_backward(x if need_x else None, T, a_cat, b_ext)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        x, T, a_cat, b_ext = ctx.saved_tensors
+        dqkv = dqkv.contiguous()
+        H, cache, n = ctx.H, ctx.cache, ctx.n
+        if cache.get("wt") is None:
+            cache["wt"] = cache["w"].t().contiguous()
+        grads = [None] * ctx.n_params
+        dT = None
+        if ctx.slots:
+            # dT = dqkv·B_ext  [M,64];  dx = [dqkv | dT]·[W_catᵀ | A_catᵀ]ᵀ
+            dT = ops.gemm(dqkv, b_ext.t().contiguous())
+            dx = ops.gemm(dqkv, cache["wt"], a2=dT, b2=a_cat.t().contiguous()) if ctx.needs_input_grad[0] else None
+        else:
+            dx = ops.gemm(dqkv, cache["wt"]) if ctx.needs_input_grad[0] else None
+        for j in range(n):
+            dq = dqkv[:, j * H:(j + 1) * H]
+            if ctx.param_needs[4 * j]:
+                grads[4 * j] = ops.wgrad(dq, x)
+            if ctx.param_needs[4 * j + 1]:
+                grads[4 * j + 1] = ops.colsum(dq)
+        for j, o, r in ctx.slots:
+            dq = dqkv[:, j * H:(j + 1) * H]
+            if ctx.param_needs[4 * j + 3]:   # lora_B [H, r] = (1/r) dqᵀ · T_j
+                grads[4 * j + 3] = _pad_cols_wgrad(dq, T, o, r, 1.0 / r, transpose=False)
+            if ctx.param_needs[4 * j + 2]:   # lora_A [r, K] = dT_jᵀ · x   (dT already carries the 1/r of B_ext)
+                grads[4 * j + 2] = _pad_cols_wgrad(dT, x, o, r, 1.0, transpose=True)
+        return (dx, None) + tuple(grads)
+
+
+def _pad_cols_wgrad(a, b, off, r, alpha, transpose):
+    """Skinny wgrad where the rank-r operand is columns [off, off+r) of a 64-wide buffer.  The kernel wants 16-byte
+    aligned column windows, so compute over the aligned window and slice."""
+    lo = (off // 8) * 8
+    hi = ((off + r + 7) // 8) * 8
+    if transpose:      # result [r, K] from a = dT [M,64] (window), b = x [M,K]
+        full = ops.wgrad(a[:, lo:hi], b, alpha=alpha)
+        return full[off - lo:off - lo + r].contiguous()
+    full = ops.wgrad(a, b[:, lo:hi], alpha=alpha)   # result [H, window]
+    return full[:, off - lo:off - lo + r].contiguous()
+
+
+class EmbedLNFunction(torch.autograd.Function):
+    """K1 with the soft-prompt substitution; only the prompt rows are trainable (everything else is a frozen table)."""
+
+    @staticmethod
+    def forward(ctx, ids, L, tables, gamma, beta, eps, roberta_pad_id, prompt):
+        word, pos, typ = tables
+        need = prompt is not None and prompt.requires_grad
+        p16 = None if prompt is None else prompt.detach().to(BF16).contiguous()
+        out, z, mean, rstd = ops.embed_ln_fwd(ids, L, word, pos, typ, gamma, beta, eps, roberta_pad_id=roberta_pad_id,
+                                              prompt=p16, want_z=need)
+        ctx.L = L
+        if need:
+            ctx.save_for_backward(z, mean, rstd, gamma)
+            ctx.n_prompt = prompt.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, mean, rstd, gamma = ctx.saved_tensors
+        dz = ops.layernorm_bwd(dout.contiguous(), z, mean, rstd, gamma)
+        H = dz.shape[1]
+        L, n = ctx.L, ctx.n_prompt
+        # d prompt[t] = sum over items of dz[item, t]: view [N, L*H] and column-sum the first n*H columns
+        dp = ops.colsum(dz.view(-1, L * H), width=n * H).view(n, H)
+        return None, None, None, None, None, None, None, dp
+
+
+class BceLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prec, emb, log_mask, cpc):
+        loss, count, pos, neg = ops.bce_loss_fwd(prec, emb, log_mask, cpc=cpc)
+        ctx.cpc = cpc
+        ctx.log_mask = log_mask
+        ctx.save_for_backward(prec, emb, pos, neg, count)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        prec, emb, pos, neg, count = ctx.saved_tensors
+        go = grad_out.reshape(1).float().contiguous()
+        d_prec, d_emb = ops.bce_loss_bwd(prec, emb, ctx.log_mask, pos, neg, count, grad_out=go, cpc=ctx.cpc)
+        return d_prec, d_emb, None, None
+
+
+def bce_loss(prec, emb, log_mask, cpc=False):
+    return BceLossFunction.apply(prec, emb, log_mask, cpc)

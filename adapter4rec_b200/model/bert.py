@@ -1,0 +1,201 @@
+"""BERT / RoBERTa encoder body with the module tree and parameter names of transformers' BertModel / RobertaModel
+(so `model.bert_encoder.text_encoders.title.bert_model.encoder.layer[i].attention.output = ...` surgery from
+Downstream/Text/run.py:414-465 and reference checkpoints work unchanged), executing on the sm_100a kernels.
+
+Numerics follow the layer algebra of SURVEY.md Appendix A2: bf16 activations, fp32 accumulation/statistics.
+Dropout: the modules keep a `dropout` attribute for structural compatibility; this path implements the
+deterministic (eval / p = 0) arithmetic the parity tests are defined on."""
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .. import ops
+from .layers import BF16, Embedding, LayerNorm, Linear, LoRALinear, to_2d_bf16
+
+
+class TextConfigLite:
+    """Subset of transformers' BertConfig / RobertaConfig used by the path.  Accepts a transformers config object
+    (duck-typed) or keyword arguments."""
+
+    def __init__(self, hf_config=None, **kw):
+        src = {} if hf_config is None else {k: getattr(hf_config, k) for k in dir(hf_config) if not k.startswith("_")
+                                            and isinstance(getattr(hf_config, k, None), (int, float, str, bool, type(None)))}
+        src.update(kw)
+        self.vocab_size = src.get("vocab_size", 30522)
+        self.hidden_size = src.get("hidden_size", 768)
+        self.num_hidden_layers = src.get("num_hidden_layers", 12)
+        self.num_attention_heads = src.get("num_attention_heads", 12)
+        self.intermediate_size = src.get("intermediate_size", 3072)
+        self.max_position_embeddings = src.get("max_position_embeddings", 512)
+        self.type_vocab_size = src.get("type_vocab_size", 2)
+        self.layer_norm_eps = src.get("layer_norm_eps", 1e-12)
+        self.pad_token_id = src.get("pad_token_id", 0)
+        self.model_type = src.get("model_type", "bert")
+        self.hidden_dropout_prob = src.get("hidden_dropout_prob", 0.1)
+        self.initializer_range = src.get("initializer_range", 0.02)
+
+
+class BertEmbeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.word_embeddings = Embedding(config.vocab_size, config.hidden_size, padding_idx=config.pad_token_id)
+        self.position_embeddings = Embedding(config.max_position_embeddings, config.hidden_size)
+        self.token_type_embeddings = Embedding(config.type_vocab_size, config.hidden_size)
+        self.LayerNorm = LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self._typ_cache = Fn.WeightCache()
+
+    def forward(self, input_ids):
+        """input_ids: int64 [N, L] (may be a strided view of the reference's [ids | mask] rows) -> bf16 [N*L, H]."""
+        N, L = input_ids.shape
+        we = self.word_embeddings
+        prompt = None
+        if hasattr(we, "learned_embedding"):          # SoftEmbedding (Downstream/Text/model/model.py:586-630)
+            prompt, table = we.learned_embedding, we.wte.table_bf16()
+            assert we.n_tokens <= L
+        else:
+            table = we.table_bf16()
+        roberta_pad = self.config.pad_token_id if self.config.model_type == "roberta" else -1
+        typ = self._typ_cache.get(self.token_type_embeddings.weight)[0][0]
+        tables = (table, self.position_embeddings.table_bf16(), typ)
+        g, b = self.LayerNorm.weight.detach().float(), self.LayerNorm.bias.detach().float()
+        return Fn.EmbedLNFunction.apply(input_ids, L, tables, g, b, self.LayerNorm.eps, roberta_pad, prompt)
+
+
+class BertSelfAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = config.hidden_size // config.num_attention_heads
+        self.all_head_size = config.hidden_size
+        self.query = Linear(config.hidden_size, config.hidden_size)
+        self.key = Linear(config.hidden_size, config.hidden_size)
+        self.value = Linear(config.hidden_size, config.hidden_size)
+        self.dropout = nn.Dropout(0.1)
+        self._qkv_cache = {}
+
+    def forward(self, x2d, attention_mask, N, L):
+        """x2d bf16 [N*L, H]; attention_mask int64/f32 [N, L] (non-zero = attend) or None -> context [N*L, H]."""
+        params = []
+        for m in (self.query, self.key, self.value):     # any of them may have been replaced by a loralib Linear
+            params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
+        qkv = Fn.QKVFunction.apply(x2d, self._qkv_cache, *params)
+        return Fn.attention(qkv, attention_mask, N, L, self.num_attention_heads, self.attention_head_size,
+                            causal=False, mask_neg=ops.F32_MIN)
+
+
+class BertSelfOutput(nn.Module):
+    """dense -> dropout -> LayerNorm(h + input).  Used for attention.output and (as BertOutput) for output."""
+
+    def __init__(self, config, in_features=None):
+        super().__init__()
+        self.dense = Linear(in_features or config.hidden_size, config.hidden_size)
+        self.LayerNorm = LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, hidden_states, input_tensor):
+        shape = input_tensor.shape
+        z = self.dense(to_2d_bf16(hidden_states), residual=to_2d_bf16(input_tensor))   # residual fused in the epilogue
+        return self.LayerNorm(z).view(shape)
+
+
+class BertOutput(BertSelfOutput):
+    def __init__(self, config):
+        super().__init__(config, in_features=config.intermediate_size)
+
+
+class BertAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.self = BertSelfAttention(config)
+        self.output = BertSelfOutput(config)
+
+    def forward(self, x2d, attention_mask, N, L):
+        ctx = self.self(x2d, attention_mask, N, L)
+        return self.output(ctx, x2d)
+
+
+class BertIntermediate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = Linear(config.hidden_size, config.intermediate_size)
+
+    def forward(self, x):
+        return self.dense(x, act="gelu")
+
+
+class BertLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.attention = BertAttention(config)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+
+    def forward(self, x2d, attention_mask, N, L):
+        y = self.attention(x2d, attention_mask, N, L)
+        out = self.output
+        wi, wf = self.intermediate.dense, getattr(out, "dense", None)
+        if type(out) is BertOutput and not (wi.weight.requires_grad or wi.bias.requires_grad or
+                                            wf.weight.requires_grad or wf.bias.requires_grad):
+            # frozen feed-forward: one fused function (GELU' and the residual gradient live in GEMM epilogues)
+            z = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, y, wi._cache, wf._cache)
+            return out.LayerNorm(z)
+        return out(self.intermediate(y), y)                 # adapter-wrapped or trainable output module
+
+
+class BertEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.layer = nn.ModuleList([BertLayer(config) for _ in range(config.num_hidden_layers)])
+
+
+class BertPooler(nn.Module):
+    """Kept for state_dict compatibility; the reference computes it and discards the result
+    (SURVEY.md Appendix B-5), so it is never evaluated here."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.dense = Linear(config.hidden_size, config.hidden_size)
+
+
+class BertModel(nn.Module):
+    """forward(input_ids=, attention_mask=) -> (last_hidden_state [N, L, H] bf16,) like transformers' BertModel[0]."""
+
+    def __init__(self, config, add_pooling_layer=True):
+        super().__init__()
+        self.config = config if isinstance(config, TextConfigLite) else TextConfigLite(config)
+        self.embeddings = BertEmbeddings(self.config)
+        self.encoder = BertEncoder(self.config)
+        self.pooler = BertPooler(self.config) if add_pooling_layer else None
+        self.apply(self._init_weights)
+
+    def _init_weights(self, module):
+        std = self.config.initializer_range
+        if isinstance(module, (Linear, Embedding)):
+            nn.init.normal_(module.weight, mean=0.0, std=std)
+            if getattr(module, "bias", None) is not None:
+                nn.init.zeros_(module.bias)
+        elif isinstance(module, LayerNorm):
+            nn.init.ones_(module.weight)
+            nn.init.zeros_(module.bias)
+
+    def get_input_embeddings(self):
+        return self.embeddings.word_embeddings
+
+    def set_input_embeddings(self, value):
+        self.embeddings.word_embeddings = value
+
+    def forward(self, input_ids=None, attention_mask=None, **unused):
+        N, L = input_ids.shape
+        x = self.embeddings(input_ids)
+        for layer in self.encoder.layer:
+            x = layer(x, attention_mask, N, L)
+        return (x.view(N, L, -1),)
+
+
+class RobertaModel(BertModel):
+    def __init__(self, config, add_pooling_layer=True):
+        cfg = config if isinstance(config, TextConfigLite) else TextConfigLite(config)
+        cfg.model_type = "roberta"
+        super().__init__(cfg, add_pooling_layer)

@@ -1,0 +1,75 @@
+"""Item and user encoders, mirroring Downstream/Text/model/encoders.py."""
+import torch
+import torch.nn as nn
+from torch.nn.init import constant_, xavier_normal_
+
+from .layers import BF16, Embedding, Linear, to_2d_bf16
+from .modules import TransformerEncoder
+
+
+class User_Encoder(nn.Module):
+    """encoders.py:8-29.  forward(input_embs [B,S,D], log_mask [B,S], local_rank) -> [B,S,D] (bf16)."""
+
+    def __init__(self, item_num, max_seq_len, item_dim, num_attention_heads, dropout, n_layers):
+        super().__init__()
+        self.transformer_encoder = TransformerEncoder(n_vocab=item_num, n_position=max_seq_len, d_model=item_dim,
+                                                      n_heads=num_attention_heads, dropout=dropout, n_layers=n_layers)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, module):
+        if isinstance(module, (Embedding, Linear)):
+            xavier_normal_(module.weight.data)
+            if getattr(module, "bias", None) is not None:
+                constant_(module.bias.data, 0)
+
+    def forward(self, input_embs, log_mask, local_rank=None):
+        # The reference materialises a [B,1,S,S] additive mask (0 / -1e9) from tril(log_mask != 0); the attention
+        # kernel rebuilds exactly that mask from log_mask, so the float mask itself is what travels.
+        key_mask = log_mask.to(device=input_embs.device, dtype=torch.float32).contiguous()
+        return self.transformer_encoder(input_embs, log_mask, key_mask)
+
+
+class Text_Encoder(nn.Module):
+    """encoders.py:38-57: BERT body -> fc(hidden[:, 0]) -> GELU."""
+
+    def __init__(self, bert_model, item_embedding_dim, word_embedding_dim):
+        super().__init__()
+        self.bert_model = bert_model
+        self.fc = Linear(word_embedding_dim, item_embedding_dim)
+        self.activate = nn.GELU()
+
+    def forward(self, text):
+        batch_size, num_words = text.shape
+        num_words = num_words // 2
+        text_ids = torch.narrow(text, 1, 0, num_words)
+        text_attmask = torch.narrow(text, 1, num_words, num_words)
+        hidden_states = self.bert_model(input_ids=text_ids, attention_mask=text_attmask)[0]
+        # CLS rows are read in place by the GEMM's TMA descriptor (row stride = L*H); GELU is its epilogue
+        return self.fc(hidden_states[:, 0], act="gelu")
+
+
+class Bert_Encoder(nn.Module):
+    """encoders.py:60-99 (only news_attributes = ['title'] is functional in the reference)."""
+
+    def __init__(self, args, bert_model):
+        super().__init__()
+        self.args = args
+        self.attributes2length = {'title': args.num_words_title * 2, 'abstract': args.num_words_abstract * 2,
+                                  'body': args.num_words_body * 2}
+        for key in list(self.attributes2length.keys()):
+            if key not in args.news_attributes:
+                self.attributes2length[key] = 0
+        self.attributes2start = {
+            key: sum(list(self.attributes2length.values())[:list(self.attributes2length.keys()).index(key)])
+            for key in self.attributes2length.keys()}
+        assert len(args.news_attributes) > 0
+        self.text_encoders = nn.ModuleDict({'title': Text_Encoder(bert_model, args.embedding_dim, args.word_embedding_dim)})
+        self.newsname = [name for name in set(args.news_attributes) & {'title', 'abstract', 'body'}]
+
+    def forward(self, news):
+        text_vectors = [
+            self.text_encoders['title'](torch.narrow(news, 1, self.attributes2start[name], self.attributes2length[name]))
+            for name in self.newsname]
+        if len(text_vectors) == 1:
+            return text_vectors[0]
+        return torch.mean(torch.stack(text_vectors, dim=1), dim=1)

@@ -1,0 +1,129 @@
+"""Model / ModelCPC and the adapter wrapper classes, mirroring Downstream/Text/model/model.py (names, constructor and
+forward signatures, state_dict keys).  The loss is the reference's BCE-with-logits over one sampled negative per
+position (model.py:30,62-68), computed by the fused K9 kernel."""
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .encoders import Bert_Encoder, User_Encoder
+from .layers import BF16, Embedding, to_2d_bf16
+from .modules import AdapterBlock
+
+
+def _word_dim(args):
+    """The reference sizes BERT adapters from the model NAME (model.py:275-286)."""
+    name = args.bert_model_load
+    for key, dim in (("tiny", 128), ("mini", 256), ("medium", 512), ("base", 768), ("large", 1024)):
+        if key in name:
+            return dim
+    raise AssertionError("The pretrained model name should be defined correctly. such as bert-base-uncased so on")
+
+
+_UNSUPPORTED_TRAINABLE = ("word_embeddings.weight", "word_embeddings.wte.weight", "position_embeddings.weight",
+                          "token_type_embeddings.weight", "position_embedding.weight", "pooler.")
+
+
+def check_trainable_supported(module):
+    """Fail loudly instead of silently leaving a gradient at zero: the path differentiates adapters, LoRA factors,
+    biases, LayerNorms, prompt embeddings and any Linear weight, but not embedding tables (full fine-tuning of the
+    backbone embeddings is outside the adapter-tuning hot path)."""
+    bad = [n for n, p in module.named_parameters() if p.requires_grad and any(k in n for k in _UNSUPPORTED_TRAINABLE)]
+    if bad:
+        raise NotImplementedError(
+            "adapter4rec_b200: gradients for these parameters are not implemented on the sm_100a path (freeze them as "
+            "Downstream/Text/run.py:369-371 does with fine_tune_to=None): %s" % bad[:6])
+
+
+class _ModelBase(nn.Module):
+    cpc = False
+
+    def __init__(self, args, item_num, use_modal, bert_model):
+        super().__init__()
+        self.args = args
+        self.use_modal = use_modal
+        self.max_seq_len = args.max_seq_len + 1
+        self.l2_weight = args.l2_weight / 2
+        if self.use_modal:
+            self.bert_encoder = Bert_Encoder(args=args, bert_model=bert_model)
+        else:
+            raise NotImplementedError("item_tower='id' (nn.Embedding item table) is outside the modality-encoder hot path")
+        self.user_encoder = User_Encoder(item_num=item_num, max_seq_len=args.max_seq_len, item_dim=args.embedding_dim,
+                                         num_attention_heads=args.num_attention_heads, dropout=args.drop_rate,
+                                         n_layers=args.transformer_block)
+        self.criterion = nn.BCEWithLogitsLoss()   # structural parity only; the fused kernel computes the loss
+        self._checked = None
+
+    def forward(self, sample_items, log_mask, local_rank=None):
+        """sample_items int64 [B*(S+1)*2, 2L] (ids | mask rows), log_mask f32 [B,S] -> scalar loss."""
+        if self.training:
+            sig = tuple(p.requires_grad for p in self.parameters())
+            if sig != self._checked:
+                check_trainable_supported(self)
+                self._checked = sig
+        input_embs_all = self.bert_encoder(sample_items)                       # [N, D] bf16
+        D = self.args.embedding_dim
+        input_embs = input_embs_all.view(-1, self.max_seq_len, 2, D)
+        input_logs_embs = input_embs[:, :-1, 0, :].contiguous()                # history items 0..S-1 as user-encoder input
+        log_mask = log_mask.to(device=input_embs_all.device, dtype=torch.float32).contiguous()
+        prec_vec = self.user_encoder(input_logs_embs, log_mask, local_rank)
+        return Fn.bce_loss(prec_vec.contiguous(), input_embs.contiguous(), None if self.cpc else log_mask, cpc=self.cpc)
+
+
+class Model(_ModelBase):
+    """Downstream/Text/model/model.py:9-70."""
+    cpc = False
+
+
+class ModelCPC(_ModelBase):
+    """Downstream/Text/model/model.py:73-135: the loss uses the last position only, without a validity mask."""
+    cpc = True
+
+
+class BertAdaptedSelfOutput(nn.Module):
+    """model.py:273-297 (Houlsby serial; wraps BOTH attention.output and output, run.py:456-460):
+    dense -> dropout -> adapter -> LayerNorm(h + input)."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = AdapterBlock(args, _word_dim(args), args.bert_adapter_down_size, args.adapter_dropout_rate)
+
+    def forward(self, hidden_states, input_tensor):
+        shape = input_tensor.shape
+        h = self.self_output.dense(to_2d_bf16(hidden_states))
+        z = self.adapter(h, extra_residual=to_2d_bf16(input_tensor))
+        return self.self_output.LayerNorm(z).view(shape)
+
+
+class SASRecAdaptedSelfOutput(nn.Module):
+    """model.py:332-376: the SASRec block with adapter1 after fc and adapter2 after the feed-forward, both before the
+    LayerNorms."""
+
+    def __init__(self, transformer_block, args):
+        super().__init__()
+        self.transformer_block = transformer_block
+        self.adapter1 = AdapterBlock(args, args.embedding_dim, args.adapter_down_size, args.adapter_dropout_rate)
+        self.adapter2 = AdapterBlock(args, args.embedding_dim, args.adapter_down_size, args.adapter_dropout_rate)
+
+    def forward(self, block_input, mask):
+        tb = self.transformer_block
+        h = tb.multi_head_attention(block_input, block_input, block_input, mask, adapter=self.adapter1)
+        return tb.feed_forward(h, adapter=self.adapter2)
+
+
+class SoftEmbedding(nn.Module):
+    """model.py:586-630: the first n_tokens word embeddings of every item are REPLACED by learned vectors
+    (tokens[:, n_tokens:] keeps the rest).  The substitution happens inside the fused embedding kernel; this module
+    owns the parameters (`wte.weight`, `learned_embedding`)."""
+
+    def __init__(self, wte, n_tokens=100, random_range=0.5, initialize_from_vocab=True):
+        super().__init__()
+        self.wte = wte
+        self.n_tokens = n_tokens
+        self.learned_embedding = nn.parameter.Parameter(
+            self.initialize_embedding(wte, n_tokens, random_range, initialize_from_vocab))
+
+    def initialize_embedding(self, wte, n_tokens=100, random_range=0.5, initialize_from_vocab=True):
+        if initialize_from_vocab:
+            return self.wte.weight[:n_tokens].clone().detach()
+        return torch.FloatTensor(n_tokens, wte.weight.size(1)).uniform_(-random_range, random_range)

@@ -1,0 +1,131 @@
+"""SASRec user-encoder building blocks and the adapter bottleneck, mirroring Downstream/Text/model/modules.py
+(class names, constructor signatures, attribute and parameter names), running on the sm_100a kernels."""
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .layers import BF16, Embedding, LayerNorm, Linear, to_2d_bf16
+
+SASREC_MASK_NEG = -1e9   # encoders.py:28
+
+
+class PositionwiseFeedForward(nn.Module):
+    """modules.py:16-28: LayerNorm(x + w_2(relu(w_1(x)))), eps 1e-6."""
+
+    def __init__(self, d_model, d_inner, dropout):
+        super().__init__()
+        self.w_1 = Linear(d_model, d_inner)
+        self.w_2 = Linear(d_inner, d_model)
+        self.layer_norm = LayerNorm(d_model, eps=1e-6)
+        self.dropout = nn.Dropout(dropout)
+        self.activate = nn.ReLU()
+
+    def forward(self, x, adapter=None):
+        x2 = to_2d_bf16(x)
+        h = self.w_1(x2, act="relu")
+        if adapter is None:
+            z = self.w_2(h, residual=x2)
+        else:
+            z = adapter(self.w_2(h), extra_residual=x2)
+        return self.layer_norm(z).view(x.shape)
+
+
+class SelfAttention(nn.Module):
+    """modules.py:31-42; the arithmetic runs inside the fused attention kernel."""
+
+    def __init__(self, temperature, dropout):
+        super().__init__()
+        self.temperature = temperature
+        self.dropout = nn.Dropout(dropout)
+
+
+class MultiHeadedAttention(nn.Module):
+    """modules.py:45-74: bias-free w_Q/w_K/w_V/fc (w_Q / w_V may be swapped for loralib Linears), LayerNorm eps 1e-6."""
+
+    def __init__(self, n_heads, d_model, dropout):
+        super().__init__()
+        assert d_model % n_heads == 0
+        self.d_model, self.d_k, self.n_heads = d_model, d_model // n_heads, n_heads
+        self.d_v = self.d_k
+        self.w_Q = Linear(d_model, n_heads * self.d_k, bias=False)
+        self.w_K = Linear(d_model, n_heads * self.d_k, bias=False)
+        self.w_V = Linear(d_model, n_heads * self.d_v, bias=False)
+        self.fc = Linear(n_heads * self.d_v, d_model, bias=False)
+        self.self_attention = SelfAttention(temperature=self.d_k ** 0.5, dropout=dropout)
+        self.dropout = nn.Dropout(p=dropout)
+        self.layer_norm = LayerNorm(d_model, eps=1e-6)
+        self._qkv_cache = {}
+
+    def forward(self, query, key, value, mask, adapter=None):
+        """query is key is value = block input [B,S,D]; mask = the [B,S] float log_mask (non-zero = valid key); the
+        causal structure of User_Encoder.forward's additive mask is applied inside the kernel."""
+        assert query is key and key is value, "SASRec self-attention only"
+        B, S, D = query.shape
+        x2 = to_2d_bf16(query)
+        params = []
+        for m in (self.w_Q, self.w_K, self.w_V):
+            params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
+        qkv = Fn.QKVFunction.apply(x2, self._qkv_cache, *params)
+        ctx = Fn.attention(qkv, mask, B, S, self.n_heads, self.d_k, causal=True, mask_neg=SASREC_MASK_NEG)
+        if adapter is None:
+            z = self.fc(ctx, residual=x2)
+        else:
+            z = adapter(self.fc(ctx), extra_residual=x2)
+        return self.layer_norm(z).view(B, S, D)
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, d_model, n_heads, d_inner, dropout):
+        super().__init__()
+        self.multi_head_attention = MultiHeadedAttention(n_heads=n_heads, d_model=d_model, dropout=dropout)
+        self.feed_forward = PositionwiseFeedForward(d_model=d_model, d_inner=d_inner, dropout=dropout)
+
+    def forward(self, block_input, mask):
+        output = self.multi_head_attention(block_input, block_input, block_input, mask)
+        return self.feed_forward(output)
+
+
+class TransformerEncoder(nn.Module):
+    """modules.py:90-113: LayerNorm(input + position_embedding) then the blocks."""
+
+    def __init__(self, n_vocab, n_position, d_model, n_heads, dropout, n_layers):
+        super().__init__()
+        self.position_embedding = Embedding(n_position, d_model)
+        self.dropout = nn.Dropout(p=dropout)
+        self.layer_norm = LayerNorm(d_model, eps=1e-6)
+        self.transformer_blocks = nn.ModuleList(
+            [TransformerBlock(d_model=d_model, n_heads=n_heads, d_inner=d_model * 4, dropout=dropout)
+             for _ in range(n_layers)])
+
+    def forward(self, input_embs, log_mask, att_mask):
+        B, S, D = input_embs.shape
+        pos = self.position_embedding.table_bf16()[:S].contiguous()
+        output = self.layer_norm(to_2d_bf16(input_embs).contiguous(), res=pos).view(B, S, D)
+        for transformer in self.transformer_blocks:
+            output = transformer.forward(output, att_mask)
+        return output
+
+
+class AdapterBlock(nn.Module):
+    """modules.py:116-134: fc_up(act(fc_down(x))) + x; N(0, 0.01²) weights, zero biases; `dropout` is constructed but
+    never applied by the reference."""
+
+    def __init__(self, args, input_size, down_size, dropout=0.1):
+        super().__init__()
+        self.fc_down = Linear(input_size, down_size)
+        nn.init.normal_(self.fc_down.weight, std=1e-2)
+        nn.init.zeros_(self.fc_down.bias)
+        self.act = "gelu" if args.adapter_activation == "GELU" else "relu"
+        self.activate = nn.GELU() if self.act == "gelu" else nn.ReLU()
+        self.fc_up = Linear(down_size, input_size)
+        nn.init.normal_(self.fc_up.weight, std=1e-2)
+        nn.init.zeros_(self.fc_up.bias)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, input_embs, extra_residual=None):
+        """Returns fc_up(act(fc_down(x))) + x (+ extra_residual: the enclosing block's skip connection, fused into
+        the same GEMM epilogue)."""
+        x2 = to_2d_bf16(input_embs)
+        s = self.fc_down(x2, act=self.act)
+        out = self.fc_up(s, residual=x2, residual2=extra_residual)
+        return out.view(input_embs.shape)

@@ -40,6 +40,25 @@ def workspace(nbytes, device):
     return ws
 
 
+_gemm_profile = None
+
+
+def gemm_profile_start():
+    """bench.py: bracket every GEMM launch with CUDA events on the launching stream (roofline.achieved)."""
+    global _gemm_profile
+    _gemm_profile = []
+
+
+def gemm_profile_stop():
+    """returns (total algorithmic FLOPs, total device milliseconds, launches) since gemm_profile_start()."""
+    global _gemm_profile
+    prof, _gemm_profile = _gemm_profile, None
+    torch.cuda.synchronize()
+    flops = sum(f for f, _, _ in prof)
+    ms = sum(e0.elapsed_time(e1) for _, e0, e1 in prof)
+    return flops, ms, len(prof)
+
+
 def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, aux=None, a2=None, b2=None,
          alpha=1.0, out=None, out_dtype=BF16, block_n=0):
     """C[M,N] = epi(alpha * (a @ b.T + a2 @ b2.T) + bias)  — see a4r_gemm_bf16_tn in include/adapter4rec.h."""
@@ -71,6 +90,13 @@ def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, au
     g.M, g.N, g.K = M, N, K
     g.alpha, g.epilogue, g.out_f32, g.block_n = float(alpha), int(epilogue), int(out.dtype == torch.float32), int(block_n)
     assert out.dtype in (BF16, torch.float32)
+    if _gemm_profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _l.check(_l.get_lib().a4r_gemm_bf16_tn(ctypes.byref(g), _stream()), "a4r_gemm_bf16_tn")
+        e1.record()
+        _gemm_profile.append((2.0 * M * N * (K + (a2.shape[1] if a2 is not None else 0)), e0, e1))
+        return out
     _l.check(_l.get_lib().a4r_gemm_bf16_tn(ctypes.byref(g), _stream()), "a4r_gemm_bf16_tn")
     return out
 

@@ -1,0 +1,56 @@
+"""Adapter insertion, mirroring the in-place module surgery of Downstream/Text/run.py:367-479 (which lives inside
+train() in the reference and is therefore restated here as a function with the same flag semantics)."""
+from .model.layers import LoRALinear
+from .model.model import BertAdaptedSelfOutput, SASRecAdaptedSelfOutput, SoftEmbedding
+
+
+def freeze_all(model):
+    """fine_tune_to = 'None' (run.py:368-371)."""
+    for _, param in model.named_parameters():
+        param.requires_grad = False
+
+
+def insert_adapters(model, args, log=None):
+    """Dispatch on args.adapter_type by SUBSTRING, in the reference's order and with its spelling 'houslby'
+    (run.py:389-452).  New modules are trainable by default."""
+    if 'None' in getattr(args, "adding_adapter_to", "bert"):
+        return model
+    bert = model.bert_encoder.text_encoders.title.bert_model
+    layers = bert.encoder.layer
+    blocks = model.user_encoder.transformer_encoder.transformer_blocks
+    t = args.adapter_type
+    dev = next(model.parameters()).device
+    if "pfeiffer" in t or "kadapter" in t or "compacter" in t:
+        raise NotImplementedError("adapter_type %r is a 'next' row (SURVEY.md §8f-4); implemented: houslby (serial), "
+                                  "lora, prompt" % t)
+    if "lora" in t:                                                    # run.py:414-428
+        for lm in layers:
+            lm.attention.self.query = LoRALinear(args.word_embedding_dim, args.word_embedding_dim,
+                                                 r=args.bert_adapter_down_size).to(dev)
+            lm.attention.self.value = LoRALinear(args.word_embedding_dim, args.word_embedding_dim,
+                                                 r=args.bert_adapter_down_size).to(dev)
+        for i in range(len(blocks)):
+            blocks[i].multi_head_attention.w_Q = LoRALinear(args.embedding_dim, args.embedding_dim,
+                                                            r=args.adapter_down_size).to(dev)
+            blocks[i].multi_head_attention.w_V = LoRALinear(args.embedding_dim, args.embedding_dim,
+                                                            r=args.adapter_down_size).to(dev)
+    elif "prompt" in t:                                                # run.py:429-434
+        s_wte = SoftEmbedding(bert.get_input_embeddings(), n_tokens=args.n_tokens, initialize_from_vocab=True)
+        bert.set_input_embeddings(s_wte.to(dev))
+    elif "houslby" in t:                                               # run.py:452-465
+        if "None" in getattr(args, "is_serial", "True"):
+            raise NotImplementedError("parallel Houlsby adapters are a 'next' row (SURVEY.md §8f-4)")
+        for lm in layers:
+            lm.attention.output = BertAdaptedSelfOutput(lm.attention.output, args).to(dev)
+            lm.output = BertAdaptedSelfOutput(lm.output, args).to(dev)
+        for i in range(len(blocks)):
+            blocks[i] = SASRecAdaptedSelfOutput(blocks[i], args).to(dev)
+    return model
+
+
+def unfreeze_layernorm(model, args):
+    """finetune_layernorm (run.py:494-501)."""
+    if "None" not in getattr(args, "adding_adapter_to", "bert") and 'None' not in getattr(args, "finetune_layernorm", "None"):
+        for name, param in model.named_parameters():
+            if "adapter" not in name and ("LayerNorm" in name or "layer_norm" in name):
+                param.requires_grad = True

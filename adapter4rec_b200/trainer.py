@@ -1,0 +1,116 @@
+"""Data-parallel adapter-tuning step: forward + backward through the sm_100a kernels, ONE all-reduce of the flat
+trainable-gradient buffer over NCCL, fused flat Adam.  Mirrors the optimisation set-up of
+Downstream/Text/run.py:503-529,595-600 (4 learning-rate groups chosen by parameter NAME, torch.optim.Adam defaults,
+DistributedDataParallel's gradient averaging)."""
+import torch
+import torch.distributed as dist
+
+from . import functional as Fn
+from . import ops
+
+
+def group_parameters(model):
+    """run.py:505-523: ('bert_encoder' in name) x ('adapter' in name or 'lora' in name)."""
+    groups = {"bert": [], "recsys": [], "adapter_bert": [], "adapter_recsys": []}
+    for name, param in model.named_parameters():
+        if not param.requires_grad:
+            continue
+        is_adapter = "adapter" in name or "lora" in name
+        if "bert_encoder" in name:
+            groups["adapter_bert" if is_adapter else "bert"].append((name, param))
+        else:
+            groups["adapter_recsys" if is_adapter else "recsys"].append((name, param))
+    return groups
+
+
+class FlatAdamTrainer:
+    """Owns one contiguous fp32 buffer each for trainable parameters, gradients and Adam moments.
+
+    Each trainable nn.Parameter becomes a view into the flat parameter buffer and its .grad a view into the flat
+    gradient buffer, so the per-step communication is exactly one all-reduce and the optimizer is one
+    kernel launch per learning-rate group."""
+
+    def __init__(self, model, lr, fine_tune_lr, adapter_bert_lr, adapter_sasrec_lr, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, users_per_pass=128, process_group=None):
+        self.model = model
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.users_per_pass = users_per_pass
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        groups = group_parameters(model)
+        lrs = {"bert": fine_tune_lr, "recsys": lr, "adapter_bert": adapter_bert_lr, "adapter_recsys": adapter_sasrec_lr}
+        plist = [(g, n, p) for g in ("bert", "recsys", "adapter_bert", "adapter_recsys") for n, p in groups[g]]
+        if not plist:
+            raise ValueError("no trainable parameters")
+        dev = plist[0][2].device
+        total = sum(p.numel() for _, _, p in plist)
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.segments = []   # (group, lr, offset, numel)
+        self.names = []
+        off = 0
+        for g in ("bert", "recsys", "adapter_bert", "adapter_recsys"):
+            start = off
+            for n, p in groups[g]:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_param[off:off + k].view(p.shape)
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                self.names.append((n, off, k))
+                off += k
+            if off > start:
+                self.segments.append((g, lrs[g], start, off - start))
+        self.step_count = 0
+        self.num_trainable = total
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def forward_backward(self, sample_items, log_mask):
+        """sample_items int64 [B*(S+1)*2, 2L], log_mask f32 [B,S] (both on the device).  The batch is processed in
+        passes of users_per_pass users to bound activation memory; pass c is weighted count_c / count so that the
+        accumulated gradient is exactly that of the batch loss (a mean over ALL valid positions)."""
+        model = self.model
+        B, S = log_mask.shape
+        rows_per_user = sample_items.shape[0] // B
+        upp = min(self.users_per_pass, B)
+        cpc = getattr(model, "cpc", False)
+        total = None
+        if not cpc:
+            count_all = (log_mask != 0).sum().float()
+        for b0 in range(0, B, upp):
+            b1 = min(B, b0 + upp)
+            lm = log_mask[b0:b1]
+            loss_c = model(sample_items[b0 * rows_per_user:b1 * rows_per_user], lm, sample_items.device)
+            w = (float(b1 - b0) / B) if cpc else (lm != 0).sum().float() / count_all
+            weighted = loss_c * w
+            weighted.backward()
+            total = weighted.detach() if total is None else total + weighted.detach()
+        return total
+
+    def optimizer_step(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        self.step_count += 1
+        for _, lr, off, n in self.segments:
+            ops.adam_step(self.flat_param[off:off + n], self.flat_grad[off:off + n], self.exp_avg[off:off + n],
+                          self.exp_avg_sq[off:off + n], lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                          self.step_count, grad_scale=1.0 / self.world)
+        Fn.bump_param_epoch()
+
+    def train_step(self, sample_items, log_mask):
+        self.zero_grad()
+        loss = self.forward_backward(sample_items, log_mask)
+        self.optimizer_step()
+        return loss
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "names": list(self.names)}
+
+    def load_state_dict(self, sd):
+        self.step_count = sd["step"]
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native TransRec hot path.
+
+Workload (BASELINE.json configs[1], "C2" in SURVEY.md §8): SASRec + BERT-base, LoRA r=8 on query/value (and on the
+SASRec w_Q/w_V), synthetic MIND-shape data (30-token titles, 20-item histories), bf16 activations with fp32
+accumulation, 512 users per GPU per optimizer step, data-parallel.  One "step" = forward + backward + gradient
+all-reduce + Adam over one batch of 512 users (= 21,504 item sequences = 645,120 tokens) per GPU.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # the reference's CPU arithmetic (oracle port) on the host cores
+
+Prints ONE JSON line on rank 0 (contract in the task statement: metric/value/unit/n_gpus/.../roofline/cpu_baseline).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train user-sequences/s (SASRec + BERT-base LoRA r=8 adapter-tuning step: fwd+bwd+allreduce+Adam)"
+UNIT = "user-seqs/s"
+S, L, D = 20, 30, 64
+ITEMS = 80000
+FLOP_FWD_PER_TOKEN = 12 * (14155776 + 92160 + 49152)   # GEMMs + attention + LoRA r=8, per token, forward
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--users", type=int, default=512, help="users per GPU per step (C2: 512)")
+    ap.add_argument("--users-per-pass", type=int, default=128, help="activation-memory pass size (exact accumulation)")
+    ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_args(r=8):
+    import types
+    return types.SimpleNamespace(
+        max_seq_len=S, min_seq_len=5, l2_weight=0, embedding_dim=D, num_attention_heads=2, drop_rate=0.1,
+        transformer_block=2, num_words_title=L, num_words_abstract=50, num_words_body=50, news_attributes=["title"],
+        word_embedding_dim=768, bert_model_load="bert_base_uncased", bert_adapter_down_size=r, adapter_down_size=r,
+        adapter_dropout_rate=0.1, adapter_activation="RELU", num_workers=0, adapter_type="lora", n_tokens=0,
+        adding_adapter_to="all", is_serial="True", finetune_layernorm="None", fine_tune_to="None",
+        lr=1e-4, fine_tune_lr=1e-5, adapter_bert_lr=5e-4, adapter_sasrec_lr=1e-4)
+
+
+def synth_catalogue(gen):
+    """I rows of ids(30) | mask(30); [CLS]=101 at 0, [SEP]=102 at len-1, zeros beyond; row 0 all zero."""
+    import torch
+    ids = torch.randint(1000, 30522, (ITEMS + 1, L), generator=gen)
+    lens = torch.randint(8, L + 1, (ITEMS + 1,), generator=gen)
+    pos = torch.arange(L).unsqueeze(0)
+    mask = (pos < lens.unsqueeze(1)).long()
+    ids = ids * mask
+    ids[:, 0] = 101
+    ids[torch.arange(ITEMS + 1), lens - 1] = 102
+    rows = torch.cat([ids, mask], 1)
+    rows[0] = 0
+    return rows
+
+
+def synth_batch(catalogue, users, gen):
+    """users x (S+1) distinct items + one sampled negative per position (not in the user's sequence), last negative
+    slot = item 0 (dataset.py:24-49); log_mask all ones (no padding: executed work = algorithmic work)."""
+    import torch
+    seq = torch.stack([torch.randperm(ITEMS, generator=gen)[:S + 1] + 1 for _ in range(users)])
+    neg = torch.randint(1, ITEMS + 1, (users, S + 1), generator=gen)
+    for _ in range(4):   # rejection: resample negatives that hit the user's own sequence
+        clash = (neg.unsqueeze(2) == seq.unsqueeze(1)).any(2)
+        if not clash.any():
+            break
+        neg = torch.where(clash, torch.randint(1, ITEMS + 1, neg.shape, generator=gen), neg)
+    neg[:, S] = 0
+    ids = torch.stack([seq, neg], 2)                                  # [users, S+1, 2]
+    sample_items = catalogue[ids].view(users * (S + 1) * 2, 2 * L)     # int64 ids | mask rows
+    log_mask = torch.ones(users, S)
+    return sample_items, log_mask
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx = float(p[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def oracle_step_factory(model_sd, users, seed=7):
+    """One adapter-tuning step of the reference's arithmetic on the CPU (oracle port, fp32, torch CPU threads):
+    forward + backward + torch.optim.Adam over `users` users of the same workload."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import transrec_oracle as O
+    cfg = O.TextConfig(hidden=768, layers=12, heads=12, eps=1e-12)
+    rec = O.RecConfig(max_seq_len=S, embedding_dim=D, heads=2, blocks=2, num_words_title=L)
+    sd = {k: v.detach().float().cpu().clone() for k, v in model_sd.items()}
+    train = [k for k in sd if "lora_" in k or (k.endswith("bias") and any(t in k for t in (".query.", ".value.", ".w_Q.", ".w_V.")))]
+    for k in train:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in train], lr=1e-4)
+    gen = torch.Generator().manual_seed(seed)
+    cat = synth_catalogue(gen)
+
+    def step():
+        items, mask = synth_batch(cat, users, gen)
+        opt.zero_grad()
+        loss = O.model_forward(items, mask, sd, cfg, rec)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step
+
+
+def reference_sd():
+    """Random-init C2 model on the CPU, only to obtain a state dict with the reference's key names for the oracle."""
+    import torch
+    from adapter4rec_b200 import surgery
+    from adapter4rec_b200.model import BertModel, Model, TextConfigLite
+    torch.manual_seed(123456)
+    args = make_args()
+    model = Model(args, ITEMS, True, BertModel(TextConfigLite()))
+    surgery.freeze_all(model)
+    surgery.insert_adapters(model, args)
+    return model.state_dict()
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU path (oracle port; the reference is Python and /root/reference does not
+    exist on the GPU box) on all host threads, each step a bounded sample of C2 (a.cpu_users users)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step = oracle_step_factory(reference_sd(), a.cpu_users)
+    for _ in range(min(a.warmup, 1)):
+        step()
+    t0 = time.time()
+    steps = max(1, min(a.steps, 3))
+    for _ in range(steps):
+        step()
+    dt = (time.time() - t0) / steps
+    v = a.cpu_users / dt
+    sample = "%d users (= %d sequences x %d tokens) per step, fp32, torch CPU" % (a.cpu_users, a.cpu_users * 42, L)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: SASRec+BERT-base LoRA r=8 train step, S=20, 30 tokens (bounded CPU sample)",
+                   "users_per_step": a.cpu_users},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    from adapter4rec_b200 import lib, ops, surgery
+    from adapter4rec_b200.model import BertModel, Model, TextConfigLite
+    from adapter4rec_b200.trainer import FlatAdamTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib.get_lib()   # fail loudly if the CUDA library is missing
+
+    torch.manual_seed(123456)
+    args = make_args()
+    model = Model(args, ITEMS, True, BertModel(TextConfigLite())).to(dev)
+    surgery.freeze_all(model)
+    surgery.insert_adapters(model, args)
+    model.train()
+    trainer = FlatAdamTrainer(model, args.lr, args.fine_tune_lr, args.adapter_bert_lr, args.adapter_sasrec_lr,
+                              users_per_pass=a.users_per_pass)
+
+    gen = torch.Generator().manual_seed(123456 + rank)
+    cat = synth_catalogue(gen)
+    n_pool = 3
+    host = [synth_batch(cat, a.users, gen) for _ in range(n_pool)]
+    host = [(x.pin_memory(), m.pin_memory()) for x, m in host]
+    resident = [(x.to(dev), m.to(dev)) for x, m in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernel-resident timing: inputs already in HBM ----------------
+    for i in range(a.warmup):
+        trainer.train_step(*resident[i % n_pool])
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ops.gemm_profile_start()
+    launches0 = lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(a.steps):
+        loss = trainer.train_step(*resident[i % n_pool])
+    ev1.record()
+    barrier()
+    launches = lib.launch_count() - launches0
+    gemm_flops, gemm_ms, gemm_calls = ops.gemm_profile_stop()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    ms_per_step = ms / a.steps
+    value = a.users * world / (ms_per_step / 1e3)
+
+    # ---------------- end-to-end: host (pinned) -> device copy of the batch + loss read-back every step ----------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        x, m = host[i % n_pool]
+        xd, md = x.to(dev, non_blocking=True), m.to(dev, non_blocking=True)
+        loss_val = trainer.train_step(xd, md).item()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / a.steps
+    h2d = host[0][0].numel() * 8 + host[0][1].numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    tokens = a.users * 42 * L
+    algo_flops_step = 2 * FLOP_FWD_PER_TOKEN * tokens            # forward + data-gradient backward (frozen backbone)
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C2: SASRec(D=64,2 blocks)+BERT-base, LoRA r=8 on q/v, S=20, 30 tokens, bf16",
+                   "users_per_gpu_per_step": a.users, "sequences_per_gpu_per_step": a.users * 42,
+                   "tokens_per_gpu_per_step": tokens, "users_per_pass": a.users_per_pass, "parallelism": "dp%d" % world,
+                   "l2": "inputs larger than L2 (>= 1 GB activations per layer per pass); %d rotating batches" % n_pool,
+                   "dropout": "off (deterministic path; see DESIGN.md)"},
+        "model_tflops_per_gpu": algo_flops_step / (ms_per_step / 1e3) / 1e12,
+        "loss": loss_val,
+        "gpu_launches": int(launches),
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        "e2e": {"value": a.users * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "kernel": "gemm_tn_kernel (tcgen05+TMA, all %d launches in the timed region; share of step %.1f%%)"
+                               % (gemm_calls, 100.0 * gemm_ms / ms), "peak_source": pk_kind + " bf16_tflops_sustained"},
+    }
+    if not a.no_cpu_baseline:
+        import torch as _t
+        step = oracle_step_factory({k: v for k, v in model.state_dict().items()}, a.cpu_users)
+        t0 = time.time()
+        step()
+        dt = time.time() - t0
+        out["cpu_baseline"] = {"value": a.cpu_users / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                               "sample": "1 step over %d users (= %d sequences x %d tokens), fp32 oracle port, %.1f s"
+                                         % (a.cpu_users, a.cpu_users * 42, L, dt)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,112 @@
+"""-m gpu: the full train path (item encoder -> user encoder -> loss, forward AND backward) through the drop-in
+model classes and the C ABI, against (a) the CPU oracle on the same seeded weights/inputs and (b) the golden outputs
+of the unmodified reference.  bf16 activations with fp32 accumulation vs an fp32 oracle: tolerances stated inline."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+
+import cases  # noqa: E402
+import transrec_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+KINDS = ["base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc"]
+
+LOSS_RTOL = 2e-2        # |loss - oracle| <= 2e-2 * |oracle|   (bf16 activations through 2 BERT + 2 SASRec layers)
+EMB_ATOL = 3e-2         # item embeddings are O(0.1-1): absolute 3e-2
+GRAD_REL_L2 = 0.12      # per trainable tensor: ||g - g_oracle|| <= 0.12 * ||g_oracle|| and cosine >= 0.99 (the smallest
+                        # tensors — rank-8 factors behind a softmax, 6 users x 5 positions — carry ~10% bf16 noise)
+GRAD_ALL_REL_L2 = 5e-2  # all trainable gradients concatenated: relative L2 error <= 5e-2
+
+
+def build_gpu_model(c, sd):
+    from adapter4rec_b200 import surgery
+    from adapter4rec_b200.model import BertModel, Model, ModelCPC, RobertaModel, TextConfigLite
+    args = cases.reference_args(c)
+    args.adding_adapter_to, args.is_serial, args.finetune_layernorm = "all", "True", "None"
+    cfg = TextConfigLite(vocab_size=c.vocab, hidden_size=c.hidden, num_hidden_layers=c.layers,
+                         num_attention_heads=c.heads, intermediate_size=c.inter, max_position_embeddings=c.max_pos,
+                         layer_norm_eps=c.eps, type_vocab_size=1 if c.roberta else 2, pad_token_id=c.pad)
+    bert = (RobertaModel if c.roberta else BertModel)(cfg)
+    model = (ModelCPC if c.cpc else Model)(args, c.item_num, True, bert).cuda()
+    surgery.freeze_all(model)
+    if c.kind != "base":
+        surgery.insert_adapters(model, args)
+    assert set(model.state_dict().keys()) == set(sd.keys()), "state_dict keys must equal the reference's"
+    model.load_state_dict(sd)
+    got_train = sorted(n for n, p in model.named_parameters() if p.requires_grad)
+    assert got_train == sorted(cases.trainable_keys(c, sd))
+    return model, args
+
+
+def oracle_setup(c):
+    cfg = O.TextConfig(hidden=c.hidden, layers=c.layers, heads=c.heads, eps=c.eps, roberta=c.roberta, pad_token_id=c.pad)
+    rec = O.RecConfig(max_seq_len=c.S, embedding_dim=c.D, heads=c.rec_heads, blocks=c.blocks, num_words_title=c.L,
+                      adapter_activation=c.activation, n_tokens=c.n_tokens)
+    return cfg, rec
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_train_step_matches_oracle_and_reference(kind):
+    c = cases.tiny_case(kind)
+    sd = cases.build_state_dict(c)
+    gold = torch.load(os.path.join(HERE, "golden", "transrec_%s.pt" % kind), weights_only=False)
+    model, args = build_gpu_model(c, sd)
+    items = cases.build_item_content(c)
+    sample_items, log_mask, _ = cases.build_batch(c, items)
+    rows = sample_items.view(-1, 2 * c.L)
+
+    # oracle (CPU fp32) on the same tensors
+    cfg, rec = oracle_setup(c)
+    osd = {k: v.clone() for k, v in sd.items()}
+    train = cases.trainable_keys(c, sd)
+    for k in train:
+        osd[k].requires_grad_(True)
+    oloss = O.model_forward(rows, log_mask, osd, cfg, rec, cpc=c.cpc)
+    if train:
+        oloss.backward()
+
+    model.train()   # the path has no stochastic op; train() only enables the trainable-parameter check
+    loss = model(rows.cuda(), log_mask.cuda(), 0)
+    assert loss.dim() == 0
+    lv, ov, gv = float(loss), float(oloss), float(gold["loss"])
+    assert abs(ov - gv) <= 2e-5 * abs(gv)
+    assert abs(lv - ov) <= LOSS_RTOL * abs(ov), "loss %.6f vs oracle %.6f" % (lv, ov)
+    if train:
+        loss.backward()
+        params = dict(model.named_parameters())
+        for k in train:
+            g, og = params[k].grad, osd[k].grad
+            assert g is not None, "no gradient for " + k
+            g = g.float().cpu()
+            rel = float((g - og).norm() / (og.norm() + 1e-12))
+            cos = float((g * og).sum() / (g.norm() * og.norm() + 1e-20))
+            assert rel <= GRAD_REL_L2 and cos >= 0.99, "%s: rel L2 %.4f cos %.5f" % (k, rel, cos)
+            ref_g = gold["grads"][k]
+            assert float((og - ref_g).norm() / (ref_g.norm() + 1e-12)) < 1e-3
+        allg = torch.cat([params[k].grad.float().cpu().flatten() for k in train])
+        allo = torch.cat([osd[k].grad.flatten() for k in train])
+        assert float((allg - allo).norm() / allo.norm()) <= GRAD_ALL_REL_L2
+        # frozen parameters must not have received gradients
+        assert all(p.grad is None for n, p in params.items() if n not in train)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_item_encoder_matches_reference(kind):
+    c = cases.tiny_case(kind)
+    sd = cases.build_state_dict(c)
+    gold = torch.load(os.path.join(HERE, "golden", "transrec_%s.pt" % kind), weights_only=False)
+    model, args = build_gpu_model(c, sd)
+    model.eval()
+    items = cases.build_item_content(c)
+    with torch.no_grad():
+        emb = model.bert_encoder(items.cuda()).float().cpu()
+    ref = gold["item_emb"]
+    err = (emb[1:] - ref[1:]).abs().max()
+    assert float(err) <= EMB_ATOL, "max abs err %.4f" % float(err)
+    assert torch.isfinite(emb).all()   # incl. the all-masked padding item (row 0)
