@@ -19,7 +19,7 @@ KINDS = ["base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc"]
 
 LOSS_RTOL = 2e-2        # |loss - oracle| <= 2e-2 * |oracle|   (bf16 activations through 2 BERT + 2 SASRec layers)
 EMB_ATOL = 3e-2         # item embeddings are O(0.1-1): absolute 3e-2
-GRAD_REL_L2 = 0.12      # per trainable tensor: ||g - g_oracle|| <= 0.12 * ||g_oracle|| and cosine >= 0.99 (the smallest
+GRAD_REL_L2 = 0.15      # per trainable tensor: ||g - g_oracle|| <= 0.15 * ||g_oracle|| and cosine >= 0.99 (the smallest
                         # tensors — rank-8 factors behind a softmax, 6 users x 5 positions — carry ~10% bf16 noise)
 GRAD_ALL_REL_L2 = 5e-2  # all trainable gradients concatenated: relative L2 error <= 5e-2
 
