@@ -77,6 +77,12 @@ PROTOTYPES = {
     "a4r_bce_loss_bwd": (c_int32, [POINTER(BceArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
     "a4r_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_int64, c_float, c_void_p]),
+    "a4r_gather_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "a4r_score_topk_partials": (c_int32, [c_int64, c_int64]),
+    "a4r_score_topk": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                 c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "a4r_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
 }
 
 _lib = None

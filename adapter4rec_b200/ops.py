@@ -270,3 +270,47 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     _l.check(_l.get_lib().a4r_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
                                         float(eps), float(weight_decay), int(step), float(grad_scale), _stream()),
              "a4r_adam_step")
+
+
+def gather_rows(table, ids):
+    """out[..., :] = table[ids[...], :]  (bf16 table [R, D], int64 ids of any shape)."""
+    assert table.dtype == BF16 and table.is_contiguous() and ids.dtype == torch.int64
+    ids_c = ids.contiguous()
+    out = torch.empty(tuple(ids.shape) + (table.shape[1],), dtype=BF16, device=table.device)
+    _l.check(_l.get_lib().a4r_gather_rows(_p(table), _p(ids_c), _p(out), ids_c.numel(), table.shape[1], _stream()),
+             "a4r_gather_rows")
+    return out
+
+
+def score_topk(users, items, id_base=0, history=None, k=10):
+    """Partial top-k lists of users @ items.T over one item shard: returns (scores [P,U,k] f32, ids [P,U,k] i32)."""
+    assert users.dtype == BF16 and items.dtype == BF16 and users.shape[1] == items.shape[1]
+    U, d = users.shape
+    I = items.shape[0]
+    P = _l.get_lib().a4r_score_topk_partials(U, I)
+    sc = torch.empty((P, U, k), dtype=torch.float32, device=users.device)
+    ids = torch.empty((P, U, k), dtype=torch.int32, device=users.device)
+    hl = 0
+    if history is not None:
+        assert history.dtype == torch.int32 and history.is_contiguous() and history.shape[0] == U
+        hl = history.shape[1]
+    _l.check(_l.get_lib().a4r_score_topk(_p(users), _rows2d(users, "users"), _p(items), _rows2d(items, "items"), U, I, d,
+                                         int(id_base), _p(history), hl, int(k), _p(sc), _p(ids), _stream()),
+             "a4r_score_topk")
+    return sc, ids
+
+
+def topk_merge(scores, ids, target=None):
+    """Merge [P,U,k] partial lists -> (scores [U,k], ids [U,k], hit [U] or None, ndcg [U] or None)."""
+    P, U, k = scores.shape
+    assert scores.dtype == torch.float32 and ids.dtype == torch.int32 and scores.is_contiguous() and ids.is_contiguous()
+    osc = torch.empty((U, k), dtype=torch.float32, device=scores.device)
+    oid = torch.empty((U, k), dtype=torch.int32, device=scores.device)
+    hit = ndcg = None
+    if target is not None:
+        assert target.dtype == torch.int32 and target.numel() == U and target.is_contiguous()
+        hit = torch.empty(U, dtype=torch.float32, device=scores.device)
+        ndcg = torch.empty(U, dtype=torch.float32, device=scores.device)
+    _l.check(_l.get_lib().a4r_topk_merge(_p(scores), _p(ids), P, U, k, _p(osc), _p(oid), _p(target), _p(hit), _p(ndcg),
+                                         _stream()), "a4r_topk_merge")
+    return osc, oid, hit, ndcg

@@ -240,6 +240,37 @@ A4R_API int a4r_bce_loss_bwd(const a4r_bce_args* args, const float* grad_out, vo
 A4R_API int a4r_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int64_t step, float grad_scale, a4r_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K10: item-ID gather  out[r,:] = table[ids[r],:]  (bf16 rows of D elements).  Replaces the CPU fancy-index
+ * `self.item_content[pad_tokens]` of BuildEvalDataset.__getitem__ (Downstream/Text/data_utils/dataset.py:72).
+ * ------------------------------------------------------------------------------------------------ */
+A4R_API int a4r_gather_rows(const void* table, const int64_t* ids, void* out, int64_t rows, int64_t D,
+                            a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K11 + K12: full-ranking scores fused with the history mask and per-user top-k.
+ * Replaces `scores = torch.matmul(prec_emb, item_embeddings.t())`, `score[history] = -inf`, `score[1:]` and the
+ * argsort of metrics_topK (Downstream/Text/data_utils/metrics.py:105-111,51-59).
+ *
+ * users [U, ld_users] bf16 (d columns), items [I, ld_items] bf16 = one shard of the item table whose row r is item
+ * id id_base + r.  history [U, hist_len] int32 ids to exclude (0 = unused slot; may be NULL); item id 0 is always
+ * excluded.  Writes P = a4r_score_topk_partials(U, I) partial lists, each sorted by (score desc, id asc):
+ * out_scores [P, U, k] f32 (-inf = empty slot), out_ids [P, U, k] int32.  k <= 16.
+ * ------------------------------------------------------------------------------------------------ */
+A4R_API int a4r_score_topk_partials(int64_t U, int64_t I);
+A4R_API int a4r_score_topk(const void* users, int64_t ld_users, const void* items, int64_t ld_items, int64_t U, int64_t I,
+                           int64_t d, int64_t id_base, const int32_t* history, int64_t hist_len, int32_t k,
+                           float* out_scores, int32_t* out_ids, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K13: merge P sorted partial top-k lists per user (item splits of one GPU, or the all-gathered lists of all
+ * item shards) under (score desc, id asc); if target != NULL also HR@k and NDCG@k per user exactly as
+ * metrics_topK (metrics.py:51-59): hit = [target in top-k], ndcg = hit / log2(rank + 1).  P <= 64.
+ * ------------------------------------------------------------------------------------------------ */
+A4R_API int a4r_topk_merge(const float* in_scores, const int32_t* in_ids, int32_t P, int64_t U, int32_t k,
+                           float* out_scores, int32_t* out_ids, const int32_t* target, float* hit, float* ndcg,
+                           a4r_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
