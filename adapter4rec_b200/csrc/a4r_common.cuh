@@ -67,6 +67,53 @@ A4R_DEVICE float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// GELU pieces on ONE MUFU op.  With z = |x|/sqrt(2):  erfc(z) = exp(-z^2) * erfcx(z), and erfcx is smooth, so a
+// degree-8 polynomial Q (weighted minimax fit on [0, 4.25], fitted offline; |erfc error| <= 2.1e-6, i.e. far below
+// bf16 resolution) replaces erff's ~25-instruction branchy path — the GELU epilogues are the instruction-bound part
+// of the FFN GEMMs.  The same exponential e = exp(-x^2/2) serves the density term of GELU'.
+A4R_DEVICE float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+A4R_DEVICE void gelu_parts(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  e = ex2_approx(-1.44269504088896340736f * z * z);
+  const float zc = fminf(z, 4.25f);
+  float q = fmaf(0.00121288927f, zc, -0.013924433f);
+  q = fmaf(q, zc, 0.0703962739f);
+  q = fmaf(q, zc, -0.212979268f);
+  q = fmaf(q, zc, 0.449192171f);
+  q = fmaf(q, zc, -0.735232875f);
+  q = fmaf(q, zc, 0.997116424f);
+  q = fmaf(q, zc, -1.1281912f);
+  q = fmaf(q, zc, 0.999997987f);
+  const float half_erfc = 0.5f * q * e;                 // 0.5 * erfc(|x|/sqrt2) = 1 - Phi(|x|)
+  cdf = 0.5f + copysignf(0.5f - half_erfc, x);          // Phi(x)
+}
+A4R_DEVICE float gelu_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
+A4R_DEVICE float gelu_grad_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
+// 256-bit global access (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread per instruction
+A4R_DEVICE void ld_nc_v8(const void* p, uint32_t (&x)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+               : "l"(p));
+}
+A4R_DEVICE void st_na_v8(void* p, const uint32_t (&x)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(x[0]), "r"(x[1]),
+               "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7])
+               : "memory");
+}
+
 A4R_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

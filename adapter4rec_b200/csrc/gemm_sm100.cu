@@ -50,7 +50,49 @@ struct GemmParams {
   int out_f32;
 };
 
-template <int BN>
+// ---- epilogue helpers ---------------------------------------------------------------------------
+// One 32-column chunk of one output row, as 64 bytes of bf16 = 16 x b32 (or 2 x 256-bit / 4 x 128-bit accesses).
+struct Row64 {
+  uint32_t w[16];
+};
+template <bool V32>
+A4R_DEVICE void load_row64(const __nv_bfloat16* p, Row64& r) {
+  if constexpr (V32) {
+    uint32_t a[8], b[8];
+    ld_nc_v8(p, a);
+    ld_nc_v8(p + 16, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      r.w[i] = a[i];
+      r.w[8 + i] = b[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 v = ld_nc_v4(p + 8 * i);
+      r.w[4 * i] = v.x; r.w[4 * i + 1] = v.y; r.w[4 * i + 2] = v.z; r.w[4 * i + 3] = v.w;
+    }
+  }
+}
+template <bool V32>
+A4R_DEVICE void store_row64(__nv_bfloat16* p, const float (&v)[32]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  if constexpr (V32) {
+    const uint32_t a[8] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]};
+    const uint32_t b[8] = {w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]};
+    st_na_v8(p, a);
+    st_na_v8(p + 16, b);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st_na_v4(p + 8 * i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+  }
+}
+
+// EPI: epilogue mode (compile time).  V32: every epilogue tensor is 32-byte aligned with ld % 16 == 0, so rows are
+// moved with 256-bit accesses; the tail chunk of a ragged N falls back to guarded 128-bit accesses.
+template <int BN, int EPI, bool V32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -163,9 +205,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ============================== epilogue ==============================
+    // The (at most one) streamed input tensor of the mode — residual for LINEAR, aux for DGELU/DRELU — is
+    // prefetched into registers TWO chunks ahead, the first two chunks of a tile before the accumulator barrier,
+    // so that its DRAM latency hides behind the MMA of the tile instead of stalling the 8 epilogue warps.
     const int ew = warp - 4;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int group = ew >> 2;
+    constexpr int CHUNKS = BN / 32 / NUM_EPI_GROUPS > 0 ? BN / 32 / NUM_EPI_GROUPS : 1;
+    constexpr bool kHasIn = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_DGELU) || (EPI == A4R_EPI_DRELU);
+    const __nv_bfloat16* in_ptr = nullptr;
+    int64_t in_ld = 0;
+    if constexpr (EPI == A4R_EPI_LINEAR) {
+      in_ptr = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+      in_ld = p.ldr;
+    } else if constexpr (kHasIn) {
+      in_ptr = reinterpret_cast<const __nv_bfloat16*>(p.aux);
+      in_ld = p.ldaux;
+    }
+    const bool has_in = kHasIn && in_ptr != nullptr;
     int as = 0;
     uint32_t aphase = 0;
     const bool out_f32 = p.out_f32 != 0;
@@ -174,10 +231,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % p.tiles_n) * BN;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
+      const int64_t r64 = row;
+      Row64 pre[2];
+      auto chunk_col = [&](int ci) { return n0 + (group + ci * NUM_EPI_GROUPS) * 32; };
+      auto full_chunk = [&](int ci) { return (BN / 32 > group + ci * NUM_EPI_GROUPS) && chunk_col(ci) + 32 <= p.N; };
+      auto prefetch = [&](int ci) {
+        if (has_in && row_ok && ci < CHUNKS && full_chunk(ci)) load_row64<V32>(in_ptr + r64 * in_ld + chunk_col(ci), pre[ci & 1]);
+      };
+      prefetch(0);
+      prefetch(1);
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = group; c < BN / 32; c += NUM_EPI_GROUPS) {
+#pragma unroll
+      for (int ci = 0; ci < CHUNKS; ++ci) {
+        const int c = group + ci * NUM_EPI_GROUPS;
+        if (c >= BN / 32) break;
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t acc[32];
@@ -185,93 +253,114 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                static_cast<uint32_t>(as * BN + c * 32),
                            acc);
         tmem_ld_wait();
+        const bool full = col0 + 32 <= p.N;
         if (row_ok) {
+          float v[32];
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = col0 + j;
-            if (col < p.N) {
-              float v[8];
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (full || col0 + j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] = fmaf(p.alpha, __uint_as_float(acc[j]), b.x);
+              v[j + 1] = fmaf(p.alpha, __uint_as_float(acc[j + 1]), b.y);
+              v[j + 2] = fmaf(p.alpha, __uint_as_float(acc[j + 2]), b.z);
+              v[j + 3] = fmaf(p.alpha, __uint_as_float(acc[j + 3]), b.w);
+            }
+          } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = p.alpha * __uint_as_float(acc[j + e]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              const int64_t r64 = row;
-              switch (p.epilogue) {
-                case A4R_EPI_LINEAR: {
-                  if (p.residual != nullptr) {
-                    const uint4 r = ld_nc_v4(reinterpret_cast<const __nv_bfloat16*>(p.residual) + r64 * p.ldr + col);
-                    float2 f;
-                    f = unpack_bf16x2(r.x); v[0] += f.x; v[1] += f.y;
-                    f = unpack_bf16x2(r.y); v[2] += f.x; v[3] += f.y;
-                    f = unpack_bf16x2(r.z); v[4] += f.x; v[5] += f.y;
-                    f = unpack_bf16x2(r.w); v[6] += f.x; v[7] += f.y;
-                  }
-                  if (p.residual2 != nullptr) {
-                    const uint4 r = ld_nc_v4(reinterpret_cast<const __nv_bfloat16*>(p.residual2) + r64 * p.ldr2 + col);
-                    float2 f;
-                    f = unpack_bf16x2(r.x); v[0] += f.x; v[1] += f.y;
-                    f = unpack_bf16x2(r.y); v[2] += f.x; v[3] += f.y;
-                    f = unpack_bf16x2(r.z); v[4] += f.x; v[5] += f.y;
-                    f = unpack_bf16x2(r.w); v[6] += f.x; v[7] += f.y;
-                  }
-                } break;
-                case A4R_EPI_GELU: {
-                  if (p.aux != nullptr) {
-                    uint4 o;
-                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                    st_na_v4(reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col, o);
-                  }
+            for (int e = 0; e < 32; ++e) v[e] = p.alpha * __uint_as_float(acc[e]);
+          }
+          // streamed input of this chunk: prefetched registers for full chunks, guarded loads for the ragged tail
+          Row64 in;
+          if (has_in) {
+            if (full) {
+              in = pre[ci & 1];
+            } else {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
-                } break;
-                case A4R_EPI_RELU: {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-                } break;
-                case A4R_EPI_DGELU: {
-                  const uint4 r = ld_nc_v4(reinterpret_cast<const __nv_bfloat16*>(p.aux) + r64 * p.ldaux + col);
-                  float u[8];
-                  float2 f;
-                  f = unpack_bf16x2(r.x); u[0] = f.x; u[1] = f.y;
-                  f = unpack_bf16x2(r.y); u[2] = f.x; u[3] = f.y;
-                  f = unpack_bf16x2(r.z); u[4] = f.x; u[5] = f.y;
-                  f = unpack_bf16x2(r.w); u[6] = f.x; u[7] = f.y;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] *= gelu_erf_grad(u[e]);
-                } break;
-                case A4R_EPI_DRELU: {
-                  const uint4 r = ld_nc_v4(reinterpret_cast<const __nv_bfloat16*>(p.aux) + r64 * p.ldaux + col);
-                  float u[8];
-                  float2 f;
-                  f = unpack_bf16x2(r.x); u[0] = f.x; u[1] = f.y;
-                  f = unpack_bf16x2(r.y); u[2] = f.x; u[3] = f.y;
-                  f = unpack_bf16x2(r.z); u[4] = f.x; u[5] = f.y;
-                  f = unpack_bf16x2(r.w); u[6] = f.x; u[7] = f.y;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = u[e] > 0.0f ? v[e] : 0.0f;
-                } break;
-                default: break;
-              }
-              if (out_f32) {
-                float* cp = reinterpret_cast<float*>(p.C) + r64 * p.ldc + col;
-                st_na_v4(cp, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
-                                        __float_as_uint(v[3])));
-                st_na_v4(cp + 4, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]),
-                                            __float_as_uint(v[7])));
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                st_na_v4(reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col, o);
+              for (int j = 0; j < 4; ++j) {
+                uint4 t = make_uint4(0, 0, 0, 0);
+                if (col0 + 8 * j < p.N) t = ld_nc_v4(in_ptr + r64 * in_ld + col0 + 8 * j);
+                in.w[4 * j] = t.x; in.w[4 * j + 1] = t.y; in.w[4 * j + 2] = t.z; in.w[4 * j + 3] = t.w;
               }
             }
           }
+          if constexpr (EPI == A4R_EPI_LINEAR) {
+            if (has_in) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 f = unpack_bf16x2(in.w[i]);
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+            if (p.residual2 != nullptr) {
+              const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(p.residual2) + r64 * p.ldr2 + col0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (full || col0 + 8 * j < p.N) {
+                  const uint4 t = ld_nc_v4(r2 + 8 * j);
+                  float2 f;
+                  f = unpack_bf16x2(t.x); v[8 * j] += f.x; v[8 * j + 1] += f.y;
+                  f = unpack_bf16x2(t.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+                  f = unpack_bf16x2(t.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+                  f = unpack_bf16x2(t.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+                }
+              }
+            }
+          } else if constexpr (EPI == A4R_EPI_GELU) {
+            if (p.aux != nullptr) {
+              __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0;
+              if (full) {
+                store_row64<V32>(ap, v);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (col0 + 8 * j < p.N)
+                    st_na_v4(ap + 8 * j, make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                    pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = gelu_fast(v[e]);
+          } else if constexpr (EPI == A4R_EPI_RELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+          } else if constexpr (EPI == A4R_EPI_DGELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 u = unpack_bf16x2(in.w[i]);
+              v[2 * i] *= gelu_grad_fast(u.x);
+              v[2 * i + 1] *= gelu_grad_fast(u.y);
+            }
+          } else if constexpr (EPI == A4R_EPI_DRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 u = unpack_bf16x2(in.w[i]);
+              v[2 * i] = u.x > 0.0f ? v[2 * i] : 0.0f;
+              v[2 * i + 1] = u.y > 0.0f ? v[2 * i + 1] : 0.0f;
+            }
+          }
+          if (out_f32) {
+            float* cp = reinterpret_cast<float*>(p.C) + r64 * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (full || col0 + 4 * j < p.N)
+                st_na_v4(cp + 4 * j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+          } else {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col0;
+            if (full) {
+              store_row64<V32>(cp, v);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col0 + 8 * j < p.N)
+                  st_na_v4(cp + 8 * j, make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
+            }
+          }
         }
+        prefetch(ci + 2);
       }
       // all of this warp's TMEM reads for this stage are complete (wait::ld above): release it
       tc_fence_before();
@@ -326,7 +415,7 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
   return A4R_OK;
 }
 
-template <int BN>
+template <int BN, int EPI, bool V32>
 int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
   using C = Cfg<BN>;
   CUtensorMap tmA, tmB, tmA2, tmB2;
@@ -362,12 +451,13 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    A4R_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    A4R_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI, V32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::kSmemBytes));
     attr_set = true;
   }
   const int64_t tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
   const int grid = static_cast<int>(tiles < a4r_num_sms() ? tiles : a4r_num_sms());
-  gemm_tn_kernel<BN><<<grid, NUM_THREADS, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  gemm_tn_kernel<BN, EPI, V32><<<grid, NUM_THREADS, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;
@@ -409,10 +499,22 @@ extern "C" int a4r_gemm_bf16_tn(const a4r_gemm_args* a, a4r_stream_t stream_) {
 
   int bn = a->block_n;
   if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
-  switch (bn) {
-    case 256: return launch_gemm<256>(a, stream);
-    case 128: return launch_gemm<128>(a, stream);
-    case 64: return launch_gemm<64>(a, stream);
-    default: return a4r_set_error(A4R_EINVAL, "gemm: block_n must be 0, 64, 128 or 256 (got %d)", bn);
+  if (bn != 64 && bn != 128 && bn != 256)
+    return a4r_set_error(A4R_EINVAL, "gemm: block_n must be 0, 64, 128 or 256 (got %d)", bn);
+  // 256-bit epilogue accesses need 32-byte aligned rows of every bf16 epilogue tensor
+  auto ok32 = [](const void* ptr, int64_t ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31u) == 0 && ld % 16 == 0); };
+  const bool v32 = !a->out_f32 && ok32(a->C, a->ldc) && ok32(a->aux, a->ldaux) && ok32(a->residual, a->ldr);
+#define A4R_DISPATCH_BN(EPI, V)                                   \
+  (bn == 256 ? launch_gemm<256, EPI, V>(a, stream)                \
+             : (bn == 128 ? launch_gemm<128, EPI, V>(a, stream) : launch_gemm<64, EPI, V>(a, stream)))
+#define A4R_DISPATCH(EPI) (v32 ? A4R_DISPATCH_BN(EPI, true) : A4R_DISPATCH_BN(EPI, false))
+  switch (a->epilogue) {
+    case A4R_EPI_LINEAR: return A4R_DISPATCH(A4R_EPI_LINEAR);
+    case A4R_EPI_GELU: return A4R_DISPATCH(A4R_EPI_GELU);
+    case A4R_EPI_RELU: return A4R_DISPATCH(A4R_EPI_RELU);
+    case A4R_EPI_DGELU: return A4R_DISPATCH(A4R_EPI_DGELU);
+    default: return A4R_DISPATCH(A4R_EPI_DRELU);
   }
+#undef A4R_DISPATCH
+#undef A4R_DISPATCH_BN
 }

@@ -113,36 +113,30 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const __nv_bfloat16
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm backward: dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  optional dgamma/dbeta partials
+// LayerNorm backward: dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  optional dgamma/dbeta partials.
+// Inputs stay packed (bf16) in registers between the statistics pass and the output pass and gamma lives in shared
+// memory, so the frozen-LayerNorm instantiation (WGRAD = false) fits 3 CTAs per SM and keeps enough loads in flight
+// to approach HBM bandwidth.
 // ------------------------------------------------------------------------------------------------
-template <int G, int CPL>
-__global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                            const __nv_bfloat16* __restrict__ z,
-                                                            const float* __restrict__ mean_in,
-                                                            const float* __restrict__ rstd_in,
-                                                            const float* __restrict__ gamma,
-                                                            __nv_bfloat16* __restrict__ dz,
-                                                            float* __restrict__ partial /* [grid,2,H] or NULL */,
-                                                            int64_t M, int H) {
+template <int G, int CPL, bool WGRAD>
+__global__ void __launch_bounds__(ROW_THREADS, WGRAD ? 1 : 3)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+              __nv_bfloat16* __restrict__ dz, float* __restrict__ partial /* [grid,2,H] or NULL */, int64_t M, int H) {
+  __shared__ __align__(16) float sgamma[1024];
+  __shared__ float buf[WGRAD ? 8192 : 1];  // (ROW_THREADS/G) * H <= 8192 floats for every supported (G, H)
   const int nchunks = H >> 3;
   const int sub = threadIdx.x % G;
   const int64_t rows_per_block = ROW_THREADS / G;
   const float invH = 1.0f / static_cast<float>(H);
-  float dg[CPL][8], db[CPL][8];
+  for (int j = threadIdx.x; j < H; j += ROW_THREADS) sgamma[j] = gamma[j];
+  __syncthreads();
+  float dg[WGRAD ? CPL : 1][8], db[WGRAD ? CPL : 1][8];
+  if constexpr (WGRAD) {
 #pragma unroll
-  for (int c = 0; c < CPL; ++c)
+    for (int c = 0; c < CPL; ++c)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dg[c][e] = db[c][e] = 0.0f;
-  float gg[CPL][8];
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    const int ch = sub + c * G;
-    if (ch < nchunks) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
-      gg[c][0] = g0.x; gg[c][1] = g0.y; gg[c][2] = g0.z; gg[c][3] = g0.w;
-      gg[c][4] = g1.x; gg[c][5] = g1.y; gg[c][6] = g1.z; gg[c][7] = g1.w;
-    }
+      for (int e = 0; e < 8; ++e) dg[c][e] = db[c][e] = 0.0f;
   }
   // the loop trip count is uniform across the warp (group shuffles use the full mask): out-of-range row
   // slots recompute row M-1 and skip their stores.
@@ -150,25 +144,38 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const __nv_bfloat16
     const int64_t row_raw = base + threadIdx.x / G;
     const bool valid = row_raw < M;
     const int64_t row = valid ? row_raw : M - 1;
+    uint4 pdy[CPL], pz[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
+      if (ch < nchunks) {
+        pdy[c] = ld_nc_v4(dy + row * H + ch * 8);
+        pz[c] = ld_nc_v4(z + row * H + ch * 8);
+      }
+    }
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[CPL][8], gy[CPL][8];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int ch = sub + c * G;
       if (ch < nchunks) {
         float a[8], b[8];
-        unpack8(ld_nc_v4(dy + row * H + ch * 8), a);
-        unpack8(ld_nc_v4(z + row * H + ch * 8), b);
+        unpack8(pdy[c], a);
+        unpack8(pz[c], b);
+        const float4 g0 = *reinterpret_cast<const float4*>(sgamma + ch * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(sgamma + ch * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          xh[c][e] = (b[e] - mean) * rstd;
-          gy[c][e] = a[e] * gg[c][e];
-          s1 += gy[c][e];
-          s2 += gy[c][e] * xh[c][e];
-          if (valid) {
-            dg[c][e] += a[e] * xh[c][e];
-            db[c][e] += a[e];
+          const float xh = (b[e] - mean) * rstd;
+          const float gy = a[e] * gg[e];
+          s1 += gy;
+          s2 += gy * xh;
+          if constexpr (WGRAD) {
+            if (valid) {
+              dg[c][e] += a[e] * xh;
+              db[c][e] += a[e];
+            }
           }
         }
       }
@@ -179,17 +186,21 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const __nv_bfloat16
     for (int c = 0; c < CPL; ++c) {
       const int ch = sub + c * G;
       if (ch < nchunks) {
-        float o[8];
+        float a[8], b[8], o[8];
+        unpack8(pdy[c], a);
+        unpack8(pz[c], b);
+        const float4 g0 = *reinterpret_cast<const float4*>(sgamma + ch * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(sgamma + ch * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rstd * (gy[c][e] - s1 - xh[c][e] * s2);
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (a[e] * gg[e] - s1 - (b[e] - mean) * rstd * s2);
         if (valid) st_na_v4(dz + row * H + ch * 8, pack8(o));
       }
     }
   }
-  if (partial != nullptr) {
+  if constexpr (WGRAD) {
     // block-level reduction of the per-thread column sums over the ROW_THREADS/G row slots (fixed order =>
     // deterministic), one pass for dgamma and one for dbeta through the same shared buffer.
-    __shared__ float buf[8192];  // (ROW_THREADS/G) * H <= 8192 floats for every supported (G, H)
     const int slot = threadIdx.x / G;
     for (int which = 0; which < 2; ++which) {
       __syncthreads();
@@ -434,11 +445,19 @@ extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mea
   return dispatch_ln(static_cast<int>(H), [&](auto G, auto CPL) -> int {
     const int64_t rows_per_block = ROW_THREADS / G.value;
     int64_t blocks = (M + rows_per_block - 1) / rows_per_block;
-    if (blocks > LN_BWD_MAX_BLOCKS) blocks = LN_BWD_MAX_BLOCKS;
     float* partial = want_wgrad ? static_cast<float*>(workspace) : nullptr;
-    ln_bwd_kernel<G.value, CPL.value><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
-        static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H));
+    if (want_wgrad) {
+      if (blocks > LN_BWD_MAX_BLOCKS) blocks = LN_BWD_MAX_BLOCKS;
+      ln_bwd_kernel<G.value, CPL.value, true><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
+          static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H));
+    } else {
+      const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 12;
+      if (blocks > cap) blocks = cap;
+      ln_bwd_kernel<G.value, CPL.value, false><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
+          static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H));
+    }
     A4R_LAUNCH_OK();
     a4r_count_launch(1);
     if (want_wgrad) {

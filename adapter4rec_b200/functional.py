@@ -218,11 +218,19 @@ class QKVFunction(torch.autograd.Function):
             for j, o, r in slots:
                 a_cat[o:o + r] = params[4 * j + 2].detach().to(BF16)
                 b_ext[j * H:(j + 1) * H, o:o + r] = (params[4 * j + 3].detach() * (1.0 / r)).to(BF16)
-            T = ops.gemm(x, a_cat)
+            # column 63 of T is a constant 1 (zero weight row + bias 1): it contributes nothing to qkv (B_ext[:, 63] = 0)
+            # and turns the bias gradients into one more column of the fused dqkvᵀ·T weight-gradient below
+            t_bias = torch.zeros(LORA_PAD, dtype=torch.float32, device=dev)
+            ctx.ones_col = off < LORA_PAD
+            if ctx.ones_col:
+                t_bias[LORA_PAD - 1] = 1.0
+            T = ops.gemm(x, a_cat, bias=t_bias)
             qkv = ops.gemm(x, w, bias=bias, a2=T, b2=b_ext)
         else:
             qkv = ops.gemm(x, w, bias=bias)
         ctx.cache, ctx.slots, ctx.H, ctx.n = cache, slots, H, n
+        if not slots:
+            ctx.ones_col = False
         ctx.n_params = len(params)
         ctx.param_needs = [p is not None and p.requires_grad for p in params]
         need_x = any(ctx.param_needs[4 * j + 2] for j in range(n)) or any(ctx.param_needs[4 * j] for j in range(n))
@@ -244,18 +252,24 @@ class QKVFunction(torch.autograd.Function):
             dx = ops.gemm(dqkv, cache["wt"], a2=dT, b2=a_cat.t().contiguous()) if ctx.needs_input_grad[0] else None
         else:
             dx = ops.gemm(dqkv, cache["wt"]) if ctx.needs_input_grad[0] else None
+        fused = bool(ctx.slots) and ctx.ones_col
+        if fused:
+            # ONE pass over dqkv gives every lora_B and every bias gradient; ONE pass over x gives every lora_A
+            g1 = ops.wgrad(dqkv, T)            # [n*H, 64] = dqkvᵀ · [T | 1]
+            g2 = ops.wgrad(dT, x)              # [64, K]   = dTᵀ · x
         for j in range(n):
             dq = dqkv[:, j * H:(j + 1) * H]
             if ctx.param_needs[4 * j]:
                 grads[4 * j] = ops.wgrad(dq, x)
             if ctx.param_needs[4 * j + 1]:
-                grads[4 * j + 1] = ops.colsum(dq)
+                grads[4 * j + 1] = g1[j * H:(j + 1) * H, LORA_PAD - 1].contiguous() if fused else ops.colsum(dq)
         for j, o, r in ctx.slots:
             dq = dqkv[:, j * H:(j + 1) * H]
             if ctx.param_needs[4 * j + 3]:   # lora_B [H, r] = (1/r) dqᵀ · T_j
-                grads[4 * j + 3] = _pad_cols_wgrad(dq, T, o, r, 1.0 / r, transpose=False)
+                grads[4 * j + 3] = (g1[j * H:(j + 1) * H, o:o + r] * (1.0 / r)) if fused else \
+                    _pad_cols_wgrad(dq, T, o, r, 1.0 / r, transpose=False)
             if ctx.param_needs[4 * j + 2]:   # lora_A [r, K] = dT_jᵀ · x   (dT already carries the 1/r of B_ext)
-                grads[4 * j + 2] = _pad_cols_wgrad(dT, x, o, r, 1.0, transpose=True)
+                grads[4 * j + 2] = g2[o:o + r].contiguous() if fused else _pad_cols_wgrad(dT, x, o, r, 1.0, transpose=True)
         return (dx, None) + tuple(grads)
 
 
