@@ -208,6 +208,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The (at most one) streamed input tensor of the mode — residual for LINEAR, aux for DGELU/DRELU — is
     // prefetched into registers TWO chunks ahead, the first two chunks of a tile before the accumulator barrier,
     // so that its DRAM latency hides behind the MMA of the tile instead of stalling the 8 epilogue warps.
+    // The chunk loop is deliberately NOT fully unrolled (two chunk bodies per iteration): a fully unrolled GELU
+    // epilogue is > 60 KB of SASS and thrashes the 32 KB instruction cache.
     const int ew = warp - 4;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int group = ew >> 2;
@@ -232,137 +234,141 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const int64_t r64 = row;
-      Row64 pre[2];
       auto chunk_col = [&](int ci) { return n0 + (group + ci * NUM_EPI_GROUPS) * 32; };
-      auto full_chunk = [&](int ci) { return (BN / 32 > group + ci * NUM_EPI_GROUPS) && chunk_col(ci) + 32 <= p.N; };
-      auto prefetch = [&](int ci) {
-        if (has_in && row_ok && ci < CHUNKS && full_chunk(ci)) load_row64<V32>(in_ptr + r64 * in_ld + chunk_col(ci), pre[ci & 1]);
+      auto prefetch = [&](int ci, Row64& dst) {
+        if (has_in && row_ok && ci < CHUNKS && (group + ci * NUM_EPI_GROUPS) < BN / 32 && chunk_col(ci) + 32 <= p.N)
+          load_row64<V32>(in_ptr + r64 * in_ld + chunk_col(ci), dst);
       };
-      prefetch(0);
-      prefetch(1);
-      mbar_wait(&tmem_full_bar[as], aphase);
-      tc_fence_after();
-#pragma unroll
-      for (int ci = 0; ci < CHUNKS; ++ci) {
+      // one 32-column chunk: TMEM -> registers -> fused op -> global
+      auto body = [&](int ci, const Row64& pre) {
         const int c = group + ci * NUM_EPI_GROUPS;
-        if (c >= BN / 32) break;
+        if (c >= BN / 32) return;
         const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
+        if (col0 >= p.N) return;  // warp-uniform
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(as * BN + c * 32),
                            acc);
-        tmem_ld_wait();
         const bool full = col0 + 32 <= p.N;
-        if (row_ok) {
-          float v[32];
-          if (p.bias != nullptr) {
+        // the bias slice of this chunk is fetched WHILE the TMEM load is in flight (both latencies overlap)
+        constexpr bool kBias = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_GELU) || (EPI == A4R_EPI_RELU);
+        float4 bv[kBias ? 8 : 1];
+        const bool has_bias = kBias && p.bias != nullptr;
+        if (has_bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (full || col0 + j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] = fmaf(p.alpha, __uint_as_float(acc[j]), b.x);
-              v[j + 1] = fmaf(p.alpha, __uint_as_float(acc[j + 1]), b.y);
-              v[j + 2] = fmaf(p.alpha, __uint_as_float(acc[j + 2]), b.z);
-              v[j + 3] = fmaf(p.alpha, __uint_as_float(acc[j + 3]), b.w);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = p.alpha * __uint_as_float(acc[e]);
-          }
-          // streamed input of this chunk: prefetched registers for full chunks, guarded loads for the ragged tail
-          Row64 in;
-          if (has_in) {
-            if (full) {
-              in = pre[ci & 1];
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 t = make_uint4(0, 0, 0, 0);
-                if (col0 + 8 * j < p.N) t = ld_nc_v4(in_ptr + r64 * in_ld + col0 + 8 * j);
-                in.w[4 * j] = t.x; in.w[4 * j + 1] = t.y; in.w[4 * j + 2] = t.z; in.w[4 * j + 3] = t.w;
-              }
-            }
-          }
-          if constexpr (EPI == A4R_EPI_LINEAR) {
-            if (has_in) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 f = unpack_bf16x2(in.w[i]);
-                v[2 * i] += f.x;
-                v[2 * i + 1] += f.y;
-              }
-            }
-            if (p.residual2 != nullptr) {
-              const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(p.residual2) + r64 * p.ldr2 + col0;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (full || col0 + 8 * j < p.N) {
-                  const uint4 t = ld_nc_v4(r2 + 8 * j);
-                  float2 f;
-                  f = unpack_bf16x2(t.x); v[8 * j] += f.x; v[8 * j + 1] += f.y;
-                  f = unpack_bf16x2(t.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
-                  f = unpack_bf16x2(t.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
-                  f = unpack_bf16x2(t.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
-                }
-              }
-            }
-          } else if constexpr (EPI == A4R_EPI_GELU) {
-            if (p.aux != nullptr) {
-              __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0;
-              if (full) {
-                store_row64<V32>(ap, v);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (col0 + 8 * j < p.N)
-                    st_na_v4(ap + 8 * j, make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                    pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = gelu_fast(v[e]);
-          } else if constexpr (EPI == A4R_EPI_RELU) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
-          } else if constexpr (EPI == A4R_EPI_DGELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 u = unpack_bf16x2(in.w[i]);
-              v[2 * i] *= gelu_grad_fast(u.x);
-              v[2 * i + 1] *= gelu_grad_fast(u.y);
-            }
-          } else if constexpr (EPI == A4R_EPI_DRELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 u = unpack_bf16x2(in.w[i]);
-              v[2 * i] = u.x > 0.0f ? v[2 * i] : 0.0f;
-              v[2 * i + 1] = u.y > 0.0f ? v[2 * i + 1] : 0.0f;
-            }
-          }
-          if (out_f32) {
-            float* cp = reinterpret_cast<float*>(p.C) + r64 * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (full || col0 + 4 * j < p.N)
-                st_na_v4(cp + 4 * j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                                                __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
-          } else {
-            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col0;
-            if (full) {
-              store_row64<V32>(cp, v);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (col0 + 8 * j < p.N)
-                  st_na_v4(cp + 8 * j, make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7])));
-            }
+          for (int j = 0; j < (kBias ? 8 : 0); ++j) {
+            bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (full || col0 + 4 * j < p.N) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
           }
         }
-        prefetch(ci + 2);
+        tmem_ld_wait();
+        if (!row_ok) return;
+        float2 v[16];
+        const float2 al = splat2(p.alpha);
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < (kBias ? 8 : 0); ++j) {
+            v[2 * j] = __ffma2_rn(al, make_float2(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1])),
+                                  make_float2(bv[j].x, bv[j].y));
+            v[2 * j + 1] = __ffma2_rn(al, make_float2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])),
+                                      make_float2(bv[j].z, bv[j].w));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] = __fmul2_rn(al, make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])));
+        }
+        // streamed input of this chunk: prefetched registers for full chunks, guarded loads for the ragged tail
+        Row64 in = pre;
+        if (has_in && !full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (col0 + 8 * j < p.N) t = ld_nc_v4(in_ptr + r64 * in_ld + col0 + 8 * j);
+            in.w[4 * j] = t.x; in.w[4 * j + 1] = t.y; in.w[4 * j + 2] = t.z; in.w[4 * j + 3] = t.w;
+          }
+        }
+        auto store_bf16 = [&](__nv_bfloat16* dst) {
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[i].x, v[i].y);
+          if (full) {
+            if constexpr (V32) {
+              const uint32_t a8[8] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]};
+              const uint32_t b8[8] = {w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]};
+              st_na_v8(dst, a8);
+              st_na_v8(dst + 16, b8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col0 + 8 * j < p.N) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+          }
+        };
+        if constexpr (EPI == A4R_EPI_LINEAR) {
+          if (has_in) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fadd2_rn(v[i], unpack_bf16x2(in.w[i]));
+          }
+          if (p.residual2 != nullptr) {
+            const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(p.residual2) + r64 * p.ldr2 + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (full || col0 + 8 * j < p.N) {
+                const uint4 t = ld_nc_v4(r2 + 8 * j);
+                v[4 * j] = __fadd2_rn(v[4 * j], unpack_bf16x2(t.x));
+                v[4 * j + 1] = __fadd2_rn(v[4 * j + 1], unpack_bf16x2(t.y));
+                v[4 * j + 2] = __fadd2_rn(v[4 * j + 2], unpack_bf16x2(t.z));
+                v[4 * j + 3] = __fadd2_rn(v[4 * j + 3], unpack_bf16x2(t.w));
+              }
+            }
+          }
+        } else if constexpr (EPI == A4R_EPI_GELU) {
+          if (p.aux != nullptr) store_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu_fast2(v[i]);
+        } else if constexpr (EPI == A4R_EPI_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f));
+        } else if constexpr (EPI == A4R_EPI_DGELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], gelu_grad_fast2(unpack_bf16x2(in.w[i])));
+        } else if constexpr (EPI == A4R_EPI_DRELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 u = unpack_bf16x2(in.w[i]);
+            v[i] = make_float2(u.x > 0.0f ? v[i].x : 0.0f, u.y > 0.0f ? v[i].y : 0.0f);
+          }
+        }
+        if (out_f32) {
+          float* cp = reinterpret_cast<float*>(p.C) + r64 * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (full || col0 + 4 * j < p.N)
+              st_na_v4(cp + 4 * j, make_uint4(__float_as_uint(v[2 * j].x), __float_as_uint(v[2 * j].y),
+                                              __float_as_uint(v[2 * j + 1].x), __float_as_uint(v[2 * j + 1].y)));
+        } else {
+          store_bf16(reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col0);
+        }
+      };
+      Row64 pre0, pre1;
+      prefetch(0, pre0);
+      prefetch(1, pre1);
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cp = 0; cp < CHUNKS; cp += 2) {
+        body(cp, pre0);
+        prefetch(cp + 2, pre0);
+        if (cp + 1 < CHUNKS) {
+          body(cp + 1, pre1);
+          prefetch(cp + 3, pre1);
+        }
       }
-      // all of this warp's TMEM reads for this stage are complete (wait::ld above): release it
+      // all of this warp's TMEM reads for this stage are complete (wait::ld in body): release it
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
@@ -486,7 +492,7 @@ extern "C" int a4r_gemm_bf16_tn(const a4r_gemm_args* a, a4r_stream_t stream_) {
   A4R_CHECK_ARG(a->epilogue >= A4R_EPI_LINEAR && a->epilogue <= A4R_EPI_DRELU, "gemm: unknown epilogue %d",
                 a->epilogue);
   if (a->epilogue == A4R_EPI_DGELU || a->epilogue == A4R_EPI_DRELU)
-    A4R_CHECK_ARG(a->aux != nullptr, "gemm: DGELU/DRELU need aux");
+    A4R_CHECK_ARG(a->aux != nullptr && a->bias == nullptr, "gemm: DGELU/DRELU need aux and take no bias");
   if (a->aux) A4R_CHECK_ARG(a4r_aligned16(a->aux) && a->ldaux % 8 == 0 && a->ldaux >= a->N, "gemm: bad aux/ldaux");
   if (a->residual)
     A4R_CHECK_ARG(a4r_aligned16(a->residual) && a->ldr % 8 == 0 && a->ldr >= a->N, "gemm: bad residual/ldr");

@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--users-per-pass", type=int, default=128, help="activation-memory pass size (exact accumulation)")
     ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
     return ap.parse_args()
 
 
@@ -218,6 +219,66 @@ def run_reference(a):
     }))
 
 
+def bench_eval(dev, world, rank, steps, warmup):
+    """Full-ranking evaluation, BASELINE.json configs[4] ("C5"): 10 M-item bf16 table (d = 768) sharded by item id over
+    the ranks (all 10 M on one GPU at N = 1), blocks of 4,096 users with 20 history ids each, top-10 + HR/NDCG.
+    User vectors are synthetic bf16 (kernel-level benchmark: score GEMM + mask + top-k + merge [+ all-gather]);
+    the d = 64 line runs the COMPLETE evaluator (K10 gather, SASRec user encoder, scores, top-k, metrics) on a
+    1 M-item table with the model's real embedding width."""
+    import torch
+    import torch.distributed as dist
+    from adapter4rec_b200 import ops
+    out = {}
+    I_total, d, U = 10_000_000, 768, 4096
+    per = (I_total + 1 + world - 1) // world
+    lo = rank * per
+    n_local = max(0, min(I_total + 1, lo + per) - lo)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    table = torch.empty((n_local, d), dtype=torch.bfloat16, device=dev)
+    for i in range(0, n_local, 1 << 20):
+        j = min(n_local, i + (1 << 20))
+        table[i:j] = (torch.randn((j - i, d), generator=g, device=dev) * d ** -0.5).to(torch.bfloat16)
+    gu = torch.Generator(device=dev).manual_seed(7)
+    users = [torch.randn((U, d), generator=gu, device=dev).to(torch.bfloat16) for _ in range(2)]
+    hist = torch.randint(1, I_total + 1, (U, 20), generator=gu, device=dev, dtype=torch.int32)
+    tgt = torch.randint(1, I_total + 1, (U,), generator=gu, device=dev, dtype=torch.int32)
+
+    def block(u):
+        sc, ids = ops.score_topk(u, table, id_base=lo, history=hist, k=10)
+        if world > 1:
+            lsc, lid, _, _ = ops.topk_merge(sc, ids)
+            gsc = torch.empty((world,) + tuple(lsc.shape), dtype=lsc.dtype, device=dev)
+            gid = torch.empty((world,) + tuple(lid.shape), dtype=lid.dtype, device=dev)
+            dist.all_gather_into_tensor(gsc, lsc)
+            dist.all_gather_into_tensor(gid, lid)
+            sc, ids = gsc, gid
+        return ops.topk_merge(sc.contiguous(), ids.contiguous(), target=tgt)
+
+    for i in range(warmup):
+        block(users[i % 2])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        res = block(users[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / steps
+    flops = 2.0 * U * (I_total + 1) * d
+    out["c5_score_topk"] = {"users_per_s": U / (ms / 1e3), "ms_per_block": ms, "users_per_block": U, "items": I_total,
+                            "d": d, "tflops_per_gpu": flops / world / (ms / 1e3) / 1e12,
+                            "note": "synthetic user vectors; score GEMM + history mask + top-10 + merge%s; table larger "
+                                    "than L2" % (" + all-gather" if world > 1 else "")}
+    del table, users
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -300,6 +361,14 @@ def main():
     e2e_ms = float(t) / a.steps
     h2d = host[0][0].numel() * 8 + host[0][1].numel() * 4
 
+    # ---------------- second half of the metric: full-ranking eval users/s ----------------
+    del trainer, resident
+    model.zero_grad(set_to_none=True)
+    torch.cuda.empty_cache()
+    eval_out = None
+    if not a.no_eval:
+        eval_out = bench_eval(dev, world, rank, max(2, a.steps), 2)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -330,6 +399,10 @@ def main():
                      "kernel": "gemm_tn_kernel (tcgen05+TMA, all %d launches in the timed region; share of step %.1f%%)"
                                % (gemm_calls, 100.0 * gemm_ms / ms), "peak_source": pk_kind + " bf16_tflops_sustained"},
     }
+    if eval_out is not None:
+        pk_b = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+        eval_out["c5_score_topk"]["frac_of_peak"] = eval_out["c5_score_topk"]["tflops_per_gpu"] / pk_b
+        out["eval"] = eval_out
     if not a.no_cpu_baseline:
         import torch as _t
         step = oracle_step_factory({k: v for k, v in model.state_dict().items()}, a.cpu_users)

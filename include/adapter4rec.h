@@ -64,8 +64,8 @@ A4R_API int64_t a4r_launch_count(void);
  *   A4R_EPI_LINEAR : C = v + residual + residual2           (either may be NULL)
  *   A4R_EPI_GELU   : aux = v (if aux != NULL), C = gelu_erf(v)
  *   A4R_EPI_RELU   : C = max(v, 0)
- *   A4R_EPI_DGELU  : C = v * gelu_erf'(aux)                 (aux = saved pre-activation, bf16 [M,N])
- *   A4R_EPI_DRELU  : C = aux > 0 ? v : 0                    (aux = saved ReLU output,   bf16 [M,N])
+ *   A4R_EPI_DGELU  : C = v * gelu_erf'(aux)                 (aux = saved pre-activation, bf16 [M,N]; bias must be NULL)
+ *   A4R_EPI_DRELU  : C = aux > 0 ? v : 0                    (aux = saved ReLU output,   bf16 [M,N]; bias must be NULL)
  * C is bf16 (out_f32 = 0) or f32 (out_f32 = 1).  K % 8 == 0, N % 8 == 0; M, N, K tails are handled.
  * ------------------------------------------------------------------------------------------------ */
 enum {
