@@ -33,13 +33,16 @@ class ItemTable:
     def shard(self):
         return self.table[:self.n_local]
 
+    def local_index(self, ids):
+        """global item ids -> row of self.table: the shard row if this rank owns the id, else the trailing zero row"""
+        local = ids - self.id_base
+        owned = (local >= 0) & (local < self.n_local)
+        return torch.where(owned, local, torch.full_like(local, self.n_local))
+
     def gather(self, ids):
         """Embeddings of arbitrary item ids [.., ..] -> bf16 [.., .., D]; exact under sharding: the owner contributes the
         row, every other rank a zero row, and the sum all-reduce of bf16 values with a single non-zero term is exact."""
-        local = ids - self.id_base
-        owned = (local >= 0) & (local < self.n_local)
-        local = torch.where(owned, local, torch.full_like(local, self.n_local))
-        out = ops.gather_rows(self.table, local)
+        out = ops.gather_rows(self.table, self.local_index(ids))
         if self.world > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM)
         return out

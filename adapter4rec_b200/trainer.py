@@ -90,9 +90,13 @@ class FlatAdamTrainer:
             total = weighted.detach() if total is None else total + weighted.detach()
         return total
 
-    def optimizer_step(self):
+    def reduce_gradients(self):
+        """The ONE collective of a training step: sum all-reduce of the flat gradient buffer (NCCL on GPUs)."""
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        self.reduce_gradients()
         self.step_count += 1
         for _, lr, off, n in self.segments:
             ops.adam_step(self.flat_param[off:off + n], self.flat_grad[off:off + n], self.exp_avg[off:off + n],

@@ -1,0 +1,116 @@
+"""CPU (-m "not gpu"): the N > 1 host logic under a real 2-process gloo group (127.0.0.1): item-id sharding, the
+ownership-masked gather + sum all-reduce (exactness), the all-gather + merge of per-shard top-k lists against the
+unsharded oracle, and the single flat-gradient all-reduce of the trainer."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def _merge_lists(lists, k):
+    """reference merge of sorted (score, id) lists under (score desc, id asc) — what a4r_topk_merge implements"""
+    allc = [c for l in lists for c in l]
+    return sorted(allc, key=lambda c: (-c[0], c[1]))[:k]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import transrec_oracle as O
+        from adapter4rec_b200.data_utils.metrics import ItemTable, shard_range
+        from adapter4rec_b200.trainer import FlatAdamTrainer
+        g = torch.Generator().manual_seed(5)
+        I, d, U, k = 1001, 16, 12, 10
+        items = (torch.randint(-2, 3, (I, d), generator=g).float() * 0.125)      # exact dot products
+        users = (torch.randint(-2, 3, (U, d), generator=g).float() * 0.125)
+        hist = [torch.randint(1, I, (5,), generator=g).tolist() for _ in range(U)]
+        lo, hi = shard_range(I, rank, world)
+        # (1) shards tile [0, I) without overlap
+        bounds = [None] * world
+        dist.all_gather_object(bounds, (lo, hi))
+        assert bounds[0][0] == 0 and bounds[-1][1] == I and all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+        # (2) ownership-masked gather + sum all-reduce reproduces a plain gather exactly (bf16)
+        table = ItemTable(items[lo:hi], lo, I, rank, world)
+        ids = torch.randint(0, I, (U, 7), generator=g)
+        part = table.table[table.local_index(ids)].clone()          # torch gather stands in for a4r_gather_rows on CPU
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        assert torch.equal(part, items.to(torch.bfloat16)[ids])
+        # (3) per-shard top-k, all-gather, merge == unsharded oracle top-k ids
+        scores = users @ items[lo:hi].t()
+        mine = []
+        for u in range(U):
+            cand = []
+            for j in range(hi - lo):
+                gid = lo + j
+                if gid != 0 and gid not in hist[u]:
+                    cand.append((float(scores[u, j]), gid))
+            mine.append(sorted(cand, key=lambda c: (-c[0], c[1]))[:k])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        full_scores = users @ items.t()
+        for u in range(U):
+            merged = [c[1] for c in _merge_lists([gathered[r][u] for r in range(world)], k)]
+            assert merged == O.topk_ids(full_scores[u], hist[u], k)
+        # (4) trainer: one flat all-reduce sums the ranks' gradients; parameter views stay attached to the flat buffer
+        lin = torch.nn.Linear(4, 3)
+        lin.weight.data.fill_(1.0)
+        lin.bias.data.fill_(2.0)
+        model = torch.nn.ModuleDict({"bert_encoder": torch.nn.ModuleDict({"adapter": lin})})
+        tr = FlatAdamTrainer(model, 1e-3, 1e-3, 1e-3, 1e-3)
+        assert tr.world == world and tr.num_trainable == 15
+        assert lin.weight.data_ptr() == tr.flat_param.data_ptr() or lin.bias.data_ptr() == tr.flat_param.data_ptr()
+        tr.zero_grad()
+        lin.weight.grad += float(rank + 1)
+        lin.bias.grad += 10.0 * (rank + 1)
+        tr.reduce_gradients()
+        assert torch.all(lin.weight.grad == 3.0) and torch.all(lin.bias.grad == 30.0)
+        assert float(tr.flat_grad.sum()) == 12 * 3.0 + 3 * 30.0
+        ret[rank] = "ok"
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        ret[rank] = "FAIL: " + traceback.format_exc()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_host_logic():
+    world = 2
+    port = 29600 + (os.getpid() % 200)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
+
+
+def test_parameter_groups_follow_reference_names():
+    """run.py:505-523: 4 groups from ('bert_encoder' in name) x ('adapter' in name or 'lora' in name)."""
+    from adapter4rec_b200.trainer import group_parameters
+    m = torch.nn.ModuleDict({
+        "bert_encoder": torch.nn.ModuleDict({"adapter": torch.nn.Linear(2, 2), "query": torch.nn.Linear(2, 2)}),
+        "user_encoder": torch.nn.ModuleDict({"lora_x": torch.nn.Linear(2, 2), "fc": torch.nn.Linear(2, 2)})})
+    g = group_parameters(m)
+    assert [n for n, _ in g["adapter_bert"]] == ["bert_encoder.adapter.weight", "bert_encoder.adapter.bias"]
+    assert [n for n, _ in g["bert"]] == ["bert_encoder.query.weight", "bert_encoder.query.bias"]
+    assert [n for n, _ in g["adapter_recsys"]] == ["user_encoder.lora_x.weight", "user_encoder.lora_x.bias"]
+    assert [n for n, _ in g["recsys"]] == ["user_encoder.fc.weight", "user_encoder.fc.bias"]
+
+
+def test_eval_arrays_host_restatement():
+    """build_eval_arrays == BuildEvalDataset.__getitem__ (dataset.py:65-78) for every user"""
+    from adapter4rec_b200.data_utils.metrics import build_eval_arrays
+    seqs = {0: [5, 9, 2], 1: [7, 1], 2: [3, 4, 6, 8, 10, 11]}
+    hist = {u: torch.LongTensor(s[:-1]) for u, s in seqs.items()}
+    tok, mask, tgt, h = build_eval_arrays(seqs, hist, 5)
+    assert tok.tolist() == [[0, 0, 0, 5, 9], [0, 0, 0, 0, 7], [3, 4, 6, 8, 10]]
+    assert mask.tolist() == [[0, 0, 0, 1, 1], [0, 0, 0, 0, 1], [1, 1, 1, 1, 1]]
+    assert tgt.tolist() == [2, 1, 11]
+    assert h.tolist() == [[5, 9, 0, 0, 0], [7, 0, 0, 0, 0], [3, 4, 6, 8, 10]]
