@@ -132,8 +132,16 @@ class BertLayer(nn.Module):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config)
 
-    def forward(self, x2d, attention_mask, N, L):
-        y = self.attention(x2d, attention_mask, N, L)
+    def forward(self, x2d, attention_mask, N, L, cls_only=False):
+        """cls_only (last layer when the caller reads hidden[:, 0] only, as Text_Encoder does, encoders.py:55): every
+        op after the attention is row-wise, so only the [CLS] row of each item is pushed through the output
+        projection, the feed-forward and the LayerNorms (1/L of the work); K and V still cover all tokens."""
+        if cls_only:
+            H = x2d.shape[1]
+            ctx = self.attention.self(x2d, attention_mask, N, L)
+            y = self.attention.output(ctx.view(N, L, H)[:, 0], x2d.view(N, L, H)[:, 0])   # strided [N,H] views, no copies
+        else:
+            y = self.attention(x2d, attention_mask, N, L)
         out = self.output
         wi, wf = self.intermediate.dense, getattr(out, "dense", None)
         if type(out) is BertOutput and not (wi.weight.requires_grad or wi.bias.requires_grad or
@@ -186,12 +194,17 @@ class BertModel(nn.Module):
     def set_input_embeddings(self, value):
         self.embeddings.word_embeddings = value
 
-    def forward(self, input_ids=None, attention_mask=None, **unused):
+    supports_cls_only = True
+
+    def forward(self, input_ids=None, attention_mask=None, cls_only=False, **unused):
+        """cls_only=True returns [N, 1, H] (the [CLS] position only), skipping the row-wise tail of the last layer for
+        all other tokens; values at position 0 are identical to the full computation."""
         N, L = input_ids.shape
         x = self.embeddings(input_ids)
-        for layer in self.encoder.layer:
-            x = layer(x, attention_mask, N, L)
-        return (x.view(N, L, -1),)
+        last = len(self.encoder.layer) - 1
+        for i, layer in enumerate(self.encoder.layer):
+            x = layer(x, attention_mask, N, L, cls_only=cls_only and i == last)
+        return (x.view(N, 1 if cls_only else L, -1),)
 
 
 class RobertaModel(BertModel):

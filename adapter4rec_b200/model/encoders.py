@@ -43,7 +43,10 @@ class Text_Encoder(nn.Module):
         num_words = num_words // 2
         text_ids = torch.narrow(text, 1, 0, num_words)
         text_attmask = torch.narrow(text, 1, num_words, num_words)
-        hidden_states = self.bert_model(input_ids=text_ids, attention_mask=text_attmask)[0]
+        if getattr(self.bert_model, "supports_cls_only", False):
+            hidden_states = self.bert_model(input_ids=text_ids, attention_mask=text_attmask, cls_only=True)[0]
+        else:
+            hidden_states = self.bert_model(input_ids=text_ids, attention_mask=text_attmask)[0]
         # CLS rows are read in place by the GEMM's TMA descriptor (row stride = L*H); GELU is its epilogue
         return self.fc(hidden_states[:, 0], act="gelu")
 
