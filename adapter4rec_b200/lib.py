@@ -60,6 +60,8 @@ PROTOTYPES = {
     "a4r_gemm_bf16_tn": (c_int32, [POINTER(GemmArgs), c_void_p]),
     "a4r_attn_small_fwd": (c_int32, [POINTER(AttnArgs), c_void_p]),
     "a4r_attn_small_bwd": (c_int32, [POINTER(AttnArgs), c_void_p]),
+    "a4r_attn_mid_fwd": (c_int32, [POINTER(AttnArgs), c_void_p]),
+    "a4r_attn_mid_bwd": (c_int32, [POINTER(AttnArgs), c_void_p]),
     "a4r_layernorm_fwd": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "a4r_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64]),
@@ -77,6 +79,9 @@ PROTOTYPES = {
     "a4r_bce_loss_bwd": (c_int32, [POINTER(BceArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
     "a4r_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_int64, c_float, c_void_p]),
+    "a4r_patchify": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "a4r_vit_assemble": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                   c_void_p]),
     "a4r_gather_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "a4r_score_topk_partials": (c_int32, [c_int64, c_int64]),
     "a4r_score_topk": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,

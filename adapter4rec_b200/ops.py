@@ -115,12 +115,23 @@ def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg):
     return a
 
 
+def _attn_kernel(L, head_dim, causal, direction):
+    """short-sequence kernel for L <= 32, the CTA-per-(sequence, head) kernel for 32 < L <= 256 (ViT)"""
+    lib = _l.get_lib()
+    if L <= 32:
+        return (lib.a4r_attn_small_fwd if direction == "fwd" else lib.a4r_attn_small_bwd), "a4r_attn_small_" + direction
+    if L <= 256 and head_dim == 64 and not causal:
+        return (lib.a4r_attn_mid_fwd if direction == "fwd" else lib.a4r_attn_mid_bwd), "a4r_attn_mid_" + direction
+    raise RuntimeError("attention: unsupported shape L=%d head_dim=%d causal=%s (no fallback exists)" % (L, head_dim, causal))
+
+
 def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN):
     assert qkv.dtype == BF16 and qkv.shape[0] == N * L
     out = torch.empty((N * L, heads * head_dim), dtype=BF16, device=qkv.device)
     a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg)
     a.out, a.ld_out = _p(out), out.stride(0)
-    _l.check(_l.get_lib().a4r_attn_small_fwd(ctypes.byref(a), _stream()), "a4r_attn_small_fwd")
+    fn, name = _attn_kernel(L, head_dim, causal, "fwd")
+    _l.check(fn(ctypes.byref(a), _stream()), name)
     return out
 
 
@@ -130,7 +141,8 @@ def attn_small_bwd(qkv, dctx, N, L, heads, head_dim, mask=None, causal=False, ma
     a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg)
     assert _rows2d(qkv, "qkv") == dqkv.stride(0), "attention bwd expects a contiguous qkv"
     a.out, a.dout, a.ld_out = _p(dqkv), _p(dctx), _rows2d(dctx, "dctx")
-    _l.check(_l.get_lib().a4r_attn_small_bwd(ctypes.byref(a), _stream()), "a4r_attn_small_bwd")
+    fn, name = _attn_kernel(L, head_dim, causal, "bwd")
+    _l.check(fn(ctypes.byref(a), _stream()), name)
     return dqkv
 
 
@@ -314,3 +326,25 @@ def topk_merge(scores, ids, target=None):
     _l.check(_l.get_lib().a4r_topk_merge(_p(scores), _p(ids), P, U, k, _p(osc), _p(oid), _p(target), _p(hit), _p(ndcg),
                                          _stream()), "a4r_topk_merge")
     return osc, oid, hit, ndcg
+
+
+def patchify(images, patch_size):
+    """[N,C,R,R] f32 -> [N*P, C*ps*ps] bf16 (im2col of the non-overlapping patch convolution)."""
+    assert images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4 and images.shape[2] == images.shape[3]
+    N, C, R, _ = images.shape
+    P = (R // patch_size) ** 2
+    out = torch.empty((N * P, C * patch_size * patch_size), dtype=BF16, device=images.device)
+    _l.check(_l.get_lib().a4r_patchify(_p(images), _p(out), N, C, R, patch_size, _stream()), "a4r_patchify")
+    return out
+
+
+def vit_assemble(patch_emb, cls, pos, prompt, N, P):
+    """[cls + pos[0] | patch_emb + pos[1..P] | prompt] -> [N*(1+P+T), H] bf16."""
+    H = patch_emb.shape[1]
+    T = 0 if prompt is None else prompt.shape[0]
+    for t in (patch_emb, cls, pos) + ((prompt,) if prompt is not None else ()):
+        assert t.dtype == BF16 and t.is_contiguous()
+    out = torch.empty((N * (1 + P + T), H), dtype=BF16, device=patch_emb.device)
+    _l.check(_l.get_lib().a4r_vit_assemble(_p(patch_emb), _p(cls), _p(pos), _p(prompt), _p(out), N, P, T, H, _stream()),
+             "a4r_vit_assemble")
+    return out

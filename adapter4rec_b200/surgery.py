@@ -54,3 +54,40 @@ def unfreeze_layernorm(model, args):
         for name, param in model.named_parameters():
             if "adapter" not in name and ("LayerNorm" in name or "layer_norm" in name):
                 param.requires_grad = True
+
+
+def insert_adapters_cv(model, args):
+    """Image tree: Downstream/CV/run_adapter.py:367-470 (houslby serial, lora with its hard-coded ranks r=12 / r=4 / r=0,
+    prompt which also unfreezes the classifier)."""
+    from .cv.model import SASRecAdaptedSelfOutput as _SAS
+    from .cv.model import SoftPrompt, VITAdaptedOutput, VITAdaptedSelfOutput
+    if 'None' in getattr(args, "adding_adapter_to", "all"):
+        return model
+    net = model.cv_encoder.image_net
+    layers = net.vit.encoder.layer
+    blocks = model.user_encoder.transformer_encoder.transformer_blocks
+    t = args.adapter_type
+    dev = next(model.parameters()).device
+    if "pfeiffer" in t or "kadapter" in t or "compacter" in t:
+        raise NotImplementedError("adapter_type %r is a 'next' row (SURVEY.md §8f-4)" % t)
+    if "lora" in t:                                                    # run_adapter.py:383-395
+        for lm in layers:
+            lm.attention.attention.query = LoRALinear(768, 768, r=12).to(dev)
+            lm.attention.attention.value = LoRALinear(768, 768, r=12).to(dev)
+        for i in range(len(blocks)):
+            blocks[i].multi_head_attention.w_Q = LoRALinear(args.embedding_dim, args.embedding_dim, r=4).to(dev)
+            blocks[i].multi_head_attention.w_V = LoRALinear(args.embedding_dim, args.embedding_dim).to(dev)   # r = 0
+    elif "prompt" in t:                                                # run_adapter.py:413-421
+        net.vit.embeddings = SoftPrompt(net.vit.embeddings, n_tokens=args.n_tokens, embed_dim=768).to(dev)
+        for name, param in model.named_parameters():
+            if "cv_encoder.image_net.classifier" in name:
+                param.requires_grad = True
+    elif "houslby" in t:                                               # run_adapter.py:423-445
+        if "None" in getattr(args, "is_serial", "True"):
+            raise NotImplementedError("parallel Houlsby adapters are a 'next' row (SURVEY.md §8f-4)")
+        for lm in layers:
+            lm.attention.output = VITAdaptedSelfOutput(lm.attention.output, args).to(dev)
+            lm.output = VITAdaptedOutput(lm.output, args).to(dev)
+        for i in range(len(blocks)):
+            blocks[i] = _SAS(blocks[i], args).to(dev)
+    return model

@@ -134,6 +134,12 @@ typedef struct a4r_attn_args {
 A4R_API int a4r_attn_small_fwd(const a4r_attn_args* args, a4r_stream_t stream);
 A4R_API int a4r_attn_small_bwd(const a4r_attn_args* args, a4r_stream_t stream);
 
+/* Same contract for mid-length sequences (L <= 256, head_dim 64, causal = 0): ViT-B/16 attention with L = 197 (+ soft
+ * prompt tokens), transformers' ViTSelfAttention reached from Vit_Encoder.forward (Downstream/CV/model/encoders.py:31-32).
+ * One CTA per (sequence, head) keeps q, k, v (and dctx) in shared memory; flash-style online softmax. */
+A4R_API int a4r_attn_mid_fwd(const a4r_attn_args* args, a4r_stream_t stream);
+A4R_API int a4r_attn_mid_bwd(const a4r_attn_args* args, a4r_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K6: LayerNorm (biased variance, fp32 statistics) with an optional fused residual, forward / backward.
  *
@@ -186,6 +192,18 @@ typedef struct a4r_embed_args {
   float eps;
 } a4r_embed_args;
 A4R_API int a4r_embed_ln_fwd(const a4r_embed_args* args, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K15 support: ViT patch embedding = im2col (this kernel) + a4r_gemm_bf16_tn.  ViTPatchEmbeddings.projection is a
+ * ps x ps convolution with stride ps (transformers, reached from Vit_Encoder.forward,
+ * Downstream/CV/model/encoders.py:31-32): images [N,C,R,R] f32 -> out [N*(R/ps)^2, C*ps*ps] bf16 with column order
+ * (c, py, px) = the flattening of the conv weight [out, C, ps, ps].  ps %% 8 == 0, R %% ps == 0.
+ * a4r_vit_assemble builds the token sequence of ViTEmbeddings.forward / SoftPrompt.forward
+ * (Downstream/CV/model/model.py:523-535): out [N, 1+P+T, H] bf16 = [cls + pos[0] | patch_emb + pos[1..P] | prompt].
+ * ------------------------------------------------------------------------------------------------ */
+A4R_API int a4r_patchify(const float* images, void* out, int64_t N, int64_t C, int64_t R, int64_t ps, a4r_stream_t stream);
+A4R_API int a4r_vit_assemble(const void* patch_emb, const void* cls, const void* pos, const void* prompt, void* out,
+                             int64_t N, int64_t P, int64_t T, int64_t H, a4r_stream_t stream);
 
 /* out = dy * act'(u) elementwise over n bf16 values; kind 0: erf-GELU with u = pre-activation
  * (Text_Encoder.activate, encoders.py:46,57), kind 1: ReLU with u = activation output. */

@@ -254,3 +254,70 @@ def eval_model(seqs, histories, item_emb, sd, rec, topk=10):
     hit = torch.tensor([r[0] for r in res])
     ndcg = torch.tensor([r[1] for r in res])
     return hit, ndcg
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# image tree (Downstream/CV): ViT item encoder with Houlsby / LoRA / soft-prompt variants
+# ------------------------------------------------------------------------------------------------------------------
+VIT_PREFIX = "cv_encoder.image_net.vit."
+CLS_PREFIX = "cv_encoder.image_net.classifier."
+
+
+class VitConfig:
+    def __init__(self, hidden=768, layers=12, heads=12, patch=16, eps=1e-12):
+        self.hidden, self.layers, self.heads, self.patch, self.eps = hidden, layers, heads, patch, eps
+
+
+def vit_embeddings(images, sd, cfg):
+    """ViTEmbeddings.forward (transformers) or SoftPrompt.forward (Downstream/CV/model/model.py:523-535) when
+    `embeddings.Prompt_Tokens` is present: conv patch projection, [cls | patches] + positions, then the prompt tokens
+    appended WITHOUT positions."""
+    e = VIT_PREFIX + "embeddings."
+    w = "wte." if e + "Prompt_Tokens" in sd else ""
+    x = F.conv2d(images, sd[e + w + "patch_embeddings.projection.weight"], sd[e + w + "patch_embeddings.projection.bias"],
+                 stride=cfg.patch).flatten(2).transpose(1, 2)
+    x = torch.cat([sd[e + w + "cls_token"].expand(x.shape[0], -1, -1), x], 1) + sd[e + w + "position_embeddings"]
+    if w:
+        x = torch.cat([x, sd[e + "Prompt_Tokens"].expand(x.shape[0], -1, -1)], 1)
+    return x
+
+
+def vit_layer(x, sd, i, cfg, activation):
+    """transformers' ViTLayer.forward (pre-LN) with the wrappers of Downstream/CV/model/model.py:182-212:
+    VITAdaptedSelfOutput = adapter(dense(ctx)) (no residual), VITAdaptedOutput = adapter(dense(h)) + input."""
+    p = VIT_PREFIX + "encoder.layer.%d." % i
+    N, L, H = x.shape
+    dh = H // cfg.heads
+    xn = layer_norm(x, sd, p + "layernorm_before.", cfg.eps)
+    q = linear_or_lora(xn, sd, p + "attention.attention.query.").view(N, L, cfg.heads, dh).transpose(1, 2)
+    k = linear_or_lora(xn, sd, p + "attention.attention.key.").view(N, L, cfg.heads, dh).transpose(1, 2)
+    v = linear_or_lora(xn, sd, p + "attention.attention.value.").view(N, L, cfg.heads, dh).transpose(1, 2)
+    ctx = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1) @ v).transpose(1, 2).reshape(N, L, H)
+    ao = p + "attention.output."
+    if ao + "self_output.dense.weight" in sd:
+        a = adapter_block(F.linear(ctx, sd[ao + "self_output.dense.weight"], sd[ao + "self_output.dense.bias"]), sd,
+                          ao + "adapter.", activation)
+    else:
+        a = F.linear(ctx, sd[ao + "dense.weight"], sd[ao + "dense.bias"])
+    x1 = a + x
+    f = F.gelu(F.linear(layer_norm(x1, sd, p + "layernorm_after.", cfg.eps), sd[p + "intermediate.dense.weight"],
+                        sd[p + "intermediate.dense.bias"]))
+    o = p + "output."
+    if o + "self_output.dense.weight" in sd:
+        return adapter_block(F.linear(f, sd[o + "self_output.dense.weight"], sd[o + "self_output.dense.bias"]), sd,
+                             o + "adapter.", activation) + x1
+    return F.linear(f, sd[o + "dense.weight"], sd[o + "dense.bias"]) + x1
+
+
+def vit_encoder(images, sd, cfg, rec):
+    """Vit_Encoder.forward (Downstream/CV/model/encoders.py:25-32): GELU(classifier(LN(h)[:, 0]))."""
+    x = vit_embeddings(images, sd, cfg)
+    for i in range(cfg.layers):
+        x = vit_layer(x, sd, i, cfg, rec.adapter_activation)
+    x = layer_norm(x, sd, VIT_PREFIX + "layernorm.", cfg.eps)
+    return F.gelu(F.linear(x[:, 0], sd[CLS_PREFIX + "weight"], sd[CLS_PREFIX + "bias"]))
+
+
+def cv_model_forward(images, log_mask, sd, cfg, rec, cpc=False):
+    """Model.forward / ModelCPC.forward of the image tree (Downstream/CV/model/model.py:54-77)."""
+    return loss_from_embeddings(vit_encoder(images, sd, cfg, rec), log_mask, sd, rec, cpc)

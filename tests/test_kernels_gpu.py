@@ -116,6 +116,9 @@ def _attn_ref(qkv, N, L, heads, dh, mask, causal, mask_neg):
 @pytest.mark.parametrize("N,L,heads,dh,mask_kind,causal", [
     (37, 30, 12, 64, "int64", False), (5, 30, 12, 64, None, False), (64, 20, 2, 32, "f32", True),
     (9, 10, 2, 32, "f32", True), (3, 32, 4, 64, "int64", True), (2, 1, 2, 32, None, False),
+    # mid-length kernel (ViT): L = 197 / 207 (+prompt) / 37 / 256, 64-wide heads, no causal mask
+    (7, 197, 12, 64, None, False), (3, 207, 12, 64, None, False), (5, 37, 12, 64, "int64", False),
+    (2, 256, 2, 64, None, False), (2, 64, 3, 64, "f32", False), (1, 33, 1, 64, None, False),
 ])
 def test_attention_small_fwd_bwd(N, L, heads, dh, mask_kind, causal):
     ops = _ops()
@@ -143,6 +146,15 @@ def test_attention_small_fwd_bwd(N, L, heads, dh, mask_kind, causal):
     dqkv = ops.attn_small_bwd(qkv, dctx, N, L, heads, dh, mask=mask, causal=causal, mask_neg=mask_neg)
     # probabilities and dS are rounded to bf16 before the second contraction: 2^-6 relative + small absolute
     _close(dqkv, qf.grad, 2 ** -5, 6e-2, "attention bwd")
+    # aggregate accuracy per block (dq | dk | dv) and of their column sums (what bias gradients are made of)
+    for j, nm in enumerate(("dq", "dk", "dv")):
+        got, ref_g = dqkv[:, j * H:(j + 1) * H].float(), qf.grad[:, j * H:(j + 1) * H]
+        rel = float((got - ref_g).norm() / (ref_g.norm() + 1e-20))
+        assert rel <= 2e-2, "%s relative L2 error %.4f" % (nm, rel)
+        if nm != "dk":   # the column sum of dk over a sequence is identically 0 (softmax shift invariance)
+            cs, cr = got.sum(0), ref_g.sum(0)
+            relc = float((cs - cr).norm() / (cr.norm() + 1e-20))
+            assert relc <= 5e-2, "%s column-sum relative L2 error %.4f" % (nm, relc)
 
 
 @pytest.mark.parametrize("M,H", [(1000, 768), (515, 64), (33, 256), (7, 128), (4099, 1024), (64, 512)])
