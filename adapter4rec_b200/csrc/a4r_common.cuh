@@ -268,6 +268,21 @@ A4R_DEVICE constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---- counter-based dropout RNG ------------------------------------------------------------------
+// splitmix64 of (seed, counter): 64 random bits = four 16-bit lanes, i.e. one call decides 4 consecutive elements.
+// An element is KEPT iff its 16-bit lane >= thr16 = round(p * 65536); kept values are scaled by 65536 / (65536 - thr16)
+// (the exact reciprocal of the realised keep probability, so the mask is unbiased).  Stateless: the backward pass
+// regenerates the mask from the same (seed, counter) instead of storing it.
+A4R_DEVICE uint64_t rng64(uint64_t seed, uint64_t counter) {
+  uint64_t z = counter * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+A4R_DEVICE bool rng_keep(uint64_t bits, int lane4, uint32_t thr16) {
+  return ((static_cast<uint32_t>(bits >> (16 * lane4))) & 0xFFFFu) >= thr16;
+}
+
 A4R_DEVICE bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -3,9 +3,10 @@
 // One CTA (4 warps) owns one (image, head): Q, K, V (and dO in the backward) of the whole sequence live in swizzled
 // shared memory (<= 32 KB each), so HBM sees q, k, v once and ctx once, exactly like the short-sequence kernel.
 // Forward: each warp takes 16-query tiles and runs a flash-style online softmax over 64-key blocks on mma.sync.
-// Backward (nothing but qkv is saved by the forward):
-//   phase A, per 16-query tile: recompute S, row max / sum -> lse, dP = dO·Vᵀ, delta = rowsum(P ⊙ dP),
-//            dS = P ⊙ (dP − delta) * scale, dQ = dS·K  (written straight to global); lse and delta go to shared memory;
+// The forward also writes the log-sum-exp of every score row (4 B per token and head).  Backward:
+//   prologue: delta_i = <dO_i, O_i> for every query row (O = the forward output), lse and delta to shared memory;
+//   phase A, per 16-query tile: recompute S, P = exp(S − lse), dP = dO·Vᵀ, dS = P ⊙ (dP − delta) * scale, dQ = dS·K
+//            (written straight to global);
 //   phase B, per 16-key tile:   recompute Sᵀ = K·Qᵀ, Pᵀ = exp(Sᵀ*scale − lse), dPᵀ = V·dOᵀ, dSᵀ = Pᵀ ⊙ (dPᵀ − delta) * scale,
 //            dK = dSᵀ·Q, dV = Pᵀ·dO.
 // Attention is ~4 % of a ViT layer's FLOPs; the tensor-pipe budget of the layer is in gemm_sm100.cu.  There is no mask
@@ -17,7 +18,7 @@
 namespace {
 
 constexpr int DH = 64;
-constexpr int WARPS = 4;
+constexpr int WARPS = 8;
 constexpr int LMAX = 256;
 
 A4R_DEVICE uint32_t toff(int row, int chunk) { return static_cast<uint32_t>(row * 128 + (((chunk ^ row) & 7) << 4)); }
@@ -27,6 +28,8 @@ struct MidParams {
   __nv_bfloat16* out;         // fwd: ctx; bwd: dqkv
   const __nv_bfloat16* dout;  // bwd
   const void* mask;
+  float* lse;                 // [N*L, heads] f32: written by fwd, read by bwd
+  const __nv_bfloat16* ctx;   // bwd: the forward output O [N*L, ld_out]
   int64_t ld_qkv, ld_out, mask_ld;
   int N, L, Lp, heads;  // Lp = L rounded up to 64
   int mask_dtype;
@@ -188,6 +191,10 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_fwd_kernel(const MidParam
       const float inv0 = 1.0f / sum[0], inv1 = 1.0f / sum[1];
       __nv_bfloat16* op = p.out + (static_cast<int64_t>(n) * p.L) * p.ld_out + h * DH;
       const int r0 = m0 + g, r1 = m0 + g + 8;
+      if (p.lse != nullptr && t == 0) {
+        if (r0 < p.L) p.lse[(static_cast<int64_t>(n) * p.L + r0) * p.heads + h] = mx[0] + __logf(sum[0]);
+        if (r1 < p.L) p.lse[(static_cast<int64_t>(n) * p.L + r1) * p.heads + h] = mx[1] + __logf(sum[1]);
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int col = nt * 8 + 2 * t;
@@ -224,7 +231,26 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_bwd_kernel(const MidParam
       kvalid[threadIdx.x] = bits;
     }
     __syncthreads();
-    // ---------------- phase A: per query tile -> lse, delta, dQ ----------------
+    // ---------------- prologue: lse (saved by the forward) and delta_i = <dO_i, O_i> into shared memory ----------------
+    for (int r = warp; r < p.Lp; r += WARPS) {
+      float d = 0.0f, l = 0.0f;
+      if (r < p.L) {
+        const int64_t grow = static_cast<int64_t>(n) * p.L + r;
+        const uint32_t o2 = *reinterpret_cast<const uint32_t*>(p.ctx + grow * p.ld_out + h * DH + 2 * lane);
+        const uint32_t d2 = *reinterpret_cast<const uint32_t*>(p.dout + grow * p.ld_out + h * DH + 2 * lane);
+        const float2 of = unpack_bf16x2(o2), df = unpack_bf16x2(d2);
+        d = warp_sum(of.x * df.x + of.y * df.y);
+        l = p.lse[grow * p.heads + h];
+      } else {
+        d = warp_sum(0.0f);
+      }
+      if (lane == 0) {
+        s_delta[r] = d;
+        s_lse[r] = l;
+      }
+    }
+    __syncthreads();
+    // ---------------- phase A: per query tile -> dQ ----------------
     for (int m0 = warp * 16; m0 < Lq; m0 += WARPS * 16) {
       uint32_t qa[4][4], da[4][4];
 #pragma unroll
@@ -232,56 +258,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_bwd_kernel(const MidParam
         lda(qa[ks], sQ, m0, ks * 16, lane);
         lda(da[ks], sdO, m0, ks * 16, lane);
       }
-      // pass 1: row max and sum over all key blocks
-      float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.0f, 0.0f};
-      for (int key0 = 0; key0 < p.Lp; key0 += 64) {
-        float s[8][4];
-        score_block(s, qa, sK, key0, lane);
-        mask_block(s, p, kvalid, key0, lane);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float bm = -INFINITY;
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt) bm = fmaxf(bm, fmaxf(s[nt][hh * 2], s[nt][hh * 2 + 1]));
-          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-          bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-          const float nm = fmaxf(mx[hh], bm);
-          float bs = 0.0f;
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) bs += __expf(s[nt][hh * 2 + e] - nm);
-          bs += __shfl_xor_sync(0xffffffffu, bs, 1);
-          bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-          sum[hh] = sum[hh] * ((mx[hh] == -INFINITY) ? 0.0f : __expf(mx[hh] - nm)) + bs;
-          mx[hh] = nm;
-        }
-      }
-      const float lse[2] = {mx[0] + __logf(sum[0]), mx[1] + __logf(sum[1])};
-      // pass 2: delta = rowsum(P ⊙ dP)
-      float delta[2] = {0.0f, 0.0f};
-      for (int key0 = 0; key0 < p.Lp; key0 += 64) {
-        float s[8][4], dp[8][4];
-        score_block(s, qa, sK, key0, lane);
-        mask_block(s, p, kvalid, key0, lane);
-        score_block(dp, da, sV, key0, lane);  // dP = dO·Vᵀ has the same operand structure
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) delta[e >> 1] += __expf(s[nt][e] - lse[e >> 1]) * dp[nt][e];
-      }
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        delta[hh] += __shfl_xor_sync(0xffffffffu, delta[hh], 1);
-        delta[hh] += __shfl_xor_sync(0xffffffffu, delta[hh], 2);
-      }
-      if (t == 0) {
-        s_lse[m0 + g] = lse[0];
-        s_lse[m0 + g + 8] = lse[1];
-        s_delta[m0 + g] = delta[0];
-        s_delta[m0 + g + 8] = delta[1];
-      }
-      // pass 3: dQ = sum over key blocks of dS_blk · K_blk
+      const float lse[2] = {s_lse[m0 + g], s_lse[m0 + g + 8]};
+      const float delta[2] = {s_delta[m0 + g], s_delta[m0 + g + 8]};
       float acc[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
@@ -291,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_bwd_kernel(const MidParam
         float s[8][4], dp[8][4];
         score_block(s, qa, sK, key0, lane);
         mask_block(s, p, kvalid, key0, lane);
-        score_block(dp, da, sV, key0, lane);
+        score_block(dp, da, sV, key0, lane);  // dP = dO·Vᵀ has the same operand structure
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -319,7 +297,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_bwd_kernel(const MidParam
         if (r1 < p.L) *reinterpret_cast<uint32_t*>(dq + static_cast<int64_t>(r1) * p.ld_qkv + col) = pack_bf16x2(acc[nt][2], acc[nt][3]);
       }
     }
-    __syncthreads();  // lse / delta of every query are in shared memory
+    // (phase B only reads shared tiles and s_lse / s_delta, all written before the barrier above)
     // ---------------- phase B: per key tile -> dK, dV ----------------
     for (int j0 = warp * 16; j0 < Lq; j0 += WARPS * 16) {
       uint32_t ka[4][4], va[4][4];
@@ -398,6 +376,7 @@ int check_mid(const a4r_attn_args* a) {
   A4R_CHECK_ARG(a->L >= 1 && a->L <= LMAX, "attention_mid: L must be in [1,256] (got %lld)", (long long)a->L);
   A4R_CHECK_ARG(a->head_dim == DH, "attention_mid: head_dim must be 64");
   A4R_CHECK_ARG(a->causal == 0, "attention_mid: causal masking is not supported (use the short-sequence kernel)");
+  A4R_CHECK_ARG(a->dropout_p == 0.0f, "attention_mid: probability dropout is not implemented (ViT uses p = 0)");
   A4R_CHECK_ARG(a->heads >= 1 && a->N >= 0, "attention_mid: bad heads/N");
   A4R_CHECK_ARG(a->ld_qkv >= 3 * a->heads * DH && a->ld_qkv % 8 == 0 && a->ld_out >= a->heads * DH && a->ld_out % 8 == 0,
                 "attention_mid: bad leading dimensions");
@@ -413,6 +392,8 @@ MidParams mid_params(const a4r_attn_args* a) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.dout = static_cast<const __nv_bfloat16*>(a->dout);
   p.mask = a->mask;
+  p.lse = a->lse;
+  p.ctx = static_cast<const __nv_bfloat16*>(a->ctx);
   p.ld_qkv = a->ld_qkv;
   p.ld_out = a->ld_out;
   p.mask_ld = a->mask_ld;
@@ -448,6 +429,7 @@ extern "C" int a4r_attn_mid_bwd(const a4r_attn_args* a, a4r_stream_t stream) {
   int rc = check_mid(a);
   if (rc != A4R_OK) return rc;
   A4R_CHECK_ARG(a->dout != nullptr && a4r_aligned16(a->dout), "attention_mid bwd: dout missing or unaligned");
+  A4R_CHECK_ARG(a->lse != nullptr && a->ctx != nullptr, "attention_mid bwd: needs the forward's lse and ctx outputs");
   if (a->N == 0) return A4R_OK;
   const MidParams p = mid_params(a);
   const int smem = 4 * p.Lp * 128;

@@ -31,7 +31,30 @@ struct AttnParams {
   int mask_dtype;  // 0 none, 1 int64, 2 f32
   int causal;
   float scale, mask_neg;
+  uint32_t drop_thr16;  // 0 = no dropout on the attention probabilities
+  float drop_scale;
+  uint64_t drop_seed, drop_offset;
 };
+
+// dropout mask of the probability tile of (sequence n, head h): element (i, j) uses lane (j & 3) of
+// rng64(seed, offset + ((n*heads + h) * 32 + i) * 8 + j / 4).  m[mt][nt][e] follows the accumulator layout.
+A4R_DEVICE void prob_dropout(float (&s)[2][4][4], const AttnParams& p, int n, int h, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const uint64_t base = p.drop_offset + (static_cast<uint64_t>(n) * p.heads + h) * (32 * 8);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = mt * 16 + hh * 8 + g;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int j = nt * 8 + 2 * t;  // j, j+1 share one 4-lane group (j is even, j % 4 in {0, 2})
+        const uint64_t r = rng64(p.drop_seed, base + static_cast<uint64_t>(i) * 8 + (j >> 2));
+        s[mt][nt][hh * 2] = rng_keep(r, j & 3, p.drop_thr16) ? s[mt][nt][hh * 2] * p.drop_scale : 0.0f;
+        s[mt][nt][hh * 2 + 1] = rng_keep(r, (j & 3) + 1, p.drop_thr16) ? s[mt][nt][hh * 2 + 1] * p.drop_scale : 0.0f;
+      }
+    }
+}
 
 // A tile in shared memory: ROWS x COLS bf16, row-major, 16-byte chunks XOR-swizzled by (row & 7) so that
 // ldmatrix (8 rows x 16 B) is bank-conflict free.  COLS is 32 or 64 (4 or 8 chunks per row).
@@ -231,6 +254,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_fwd_kernel(const Attn
     const uint32_t sQ = smem_u32(my), sK = sQ + TB, sV = sK + TB;
     float s[2][4][4];
     scores_softmax<DH>(s, sQ, sK, p, n, lane, km);
+    if (p.drop_thr16 != 0) prob_dropout(s, p, n, h, lane);  // dropout on the probabilities (train mode)
     // O = P·V
     float o[2][DH / 8][4];
 #pragma unroll
@@ -313,6 +337,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_bwd_kernel(const Attn
         mma_bf16_16816(dp[1][np * 2 + 1], a1, b1);
       }
     }
+    // with probability dropout O = (P ⊙ m)·V: dP picks up the mask, dV uses the dropped probabilities
+    float sd[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sd[mt][nt][e] = s[mt][nt][e];
+    if (p.drop_thr16 != 0) {
+      prob_dropout(sd, p, n, h, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dp[mt][nt][e] = (sd[mt][nt][e] != 0.0f) ? dp[mt][nt][e] * p.drop_scale : 0.0f;
+    }
     // dS = P ⊙ (dP − δ) * scale,  δ_i = Σ_j P_ij dP_ij
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -332,7 +373,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_bwd_kernel(const Attn
             dp[mt][nt][hh * 2 + e] = s[mt][nt][hh * 2 + e] * (dp[mt][nt][hh * 2 + e] - d) * p.scale;
       }
     // stage P and dS (bf16, [query][key]) for the transposed products
-    acc_to_tile<32, 4>(tP, s, 1.f, 1.f, 1.f, 1.f, lane);
+    acc_to_tile<32, 4>(tP, sd, 1.f, 1.f, 1.f, 1.f, lane);
     acc_to_tile<32, 4>(tdS, dp, 1.f, 1.f, 1.f, 1.f, lane);
     __syncwarp();
     // dQ = dS·K   (A from registers, B: K stored [key][dim] = [k][n])
@@ -417,6 +458,7 @@ int check_common(const a4r_attn_args* a) {
   A4R_CHECK_ARG(a4r_aligned16(a->qkv) && a4r_aligned16(a->out), "attention: pointers must be 16B aligned");
   A4R_CHECK_ARG(a->mask_dtype >= 0 && a->mask_dtype <= 2, "attention: mask_dtype must be 0,1,2");
   if (a->mask_dtype != 0) A4R_CHECK_ARG(a->mask != nullptr && a->mask_ld >= a->L, "attention: bad mask/mask_ld");
+  A4R_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "attention: dropout_p must be in [0,1)");
   return a4r_device_check();
 }
 
@@ -436,6 +478,10 @@ AttnParams to_params(const a4r_attn_args* a) {
   p.causal = a->causal;
   p.scale = a->scale;
   p.mask_neg = a->mask_neg;
+  p.drop_thr16 = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
+  p.drop_scale = 65536.0f / static_cast<float>(65536u - p.drop_thr16);
+  p.drop_seed = a->dropout_seed;
+  p.drop_offset = a->dropout_offset;
   return p;
 }
 

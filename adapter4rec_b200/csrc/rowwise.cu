@@ -234,14 +234,24 @@ __global__ void ln_reduce_kernel(const float* __restrict__ partial, float* __res
   out[col] = accumulate ? out[col] + acc : acc;
 }
 
-// out[j] = sum_b partial[b, j]  (fixed order => deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks,
-                                       int width, int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= width) return;
+// out[j] = sum_b partial[b, j]  (fixed order => deterministic).  32 x 32 threads: thread (x, y) sums rows y, y+32, ...
+// of column x (32 independent coalesced load streams per column), then the 32 row-slot sums are added in order.
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                               int nblocks, int width, int accumulate) {
+  __shared__ float red[32][33];
+  const int x = threadIdx.x, y = threadIdx.y;
+  const int j = blockIdx.x * 32 + x;
   float acc = 0.0f;
-  for (int b = 0; b < nblocks; ++b) acc += partial[static_cast<int64_t>(b) * width + j];
-  out[j] = accumulate ? out[j] + acc : acc;
+  if (j < width)
+    for (int b = y; b < nblocks; b += 32) acc += partial[static_cast<int64_t>(b) * width + j];
+  red[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && j < width) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) tot += red[r][x];
+    out[j] = accumulate ? out[j] + tot : tot;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,6 +363,30 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
     unpack8(ld_nc_v4(u + i * 8), b);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = kind == 0 ? a[e] * gelu_erf_grad(b[e]) : (b[e] > 0.0f ? a[e] : 0.0f);
+    st_na_v4(out + i * 8, pack8(o));
+  }
+}
+
+// dropout (+ residual): out = x * mask * scale (+ res); element i uses lane (i & 3) of rng64(seed, offset + i / 4)
+__global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                               __nv_bfloat16* __restrict__ out, int64_t nvec, uint32_t thr16, float scale, uint64_t seed,
+                               uint64_t offset) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[8], o[8];
+    unpack8(ld_nc_v4(x + i * 8), a);
+    const uint64_t r0 = rng64(seed, offset + static_cast<uint64_t>(i) * 2), r1 = rng64(seed, offset + static_cast<uint64_t>(i) * 2 + 1);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o[e] = rng_keep(r0, e, thr16) ? a[e] * scale : 0.0f;
+      o[4 + e] = rng_keep(r1, e, thr16) ? a[4 + e] * scale : 0.0f;
+    }
+    if (res != nullptr) {
+      float r[8];
+      unpack8(ld_nc_v4(res + i * 8), r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += r[e];
+    }
     st_na_v4(out + i * 8, pack8(o));
   }
 }
@@ -543,9 +577,32 @@ extern "C" int a4r_colsum(const void* x, int64_t ld, int64_t M, int64_t width, f
   colsum_partial_kernel<<<blocks, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, M,
                                                         static_cast<int>(width), static_cast<float*>(workspace));
   A4R_LAUNCH_OK();
-  reduce_partials_kernel<<<(static_cast<int>(width) + 255) / 256, 256, 0, stream>>>(
+  reduce_partials_kernel<<<(static_cast<int>(width) + 31) / 32, dim3(32, 32), 0, stream>>>(
       static_cast<const float*>(workspace), out, blocks, static_cast<int>(width), accumulate);
   A4R_LAUNCH_OK();
   a4r_count_launch(2);
+  return A4R_OK;
+}
+
+extern "C" int a4r_dropout(const void* x, const void* res, void* out, int64_t n, float p, uint64_t seed, uint64_t offset,
+                           a4r_stream_t stream_) {
+  A4R_CHECK_ARG(x && out, "dropout: NULL pointer");
+  A4R_CHECK_ARG(n >= 0 && n % 8 == 0, "dropout: n must be a multiple of 8");
+  A4R_CHECK_ARG(p >= 0.0f && p < 1.0f, "dropout: p must be in [0, 1)");
+  A4R_CHECK_ARG(a4r_aligned16(x) && a4r_aligned16(res) && a4r_aligned16(out), "dropout: pointers must be 16B aligned");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  if (n == 0) return A4R_OK;
+  const uint32_t thr16 = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+  const float scale = 65536.0f / static_cast<float>(65536u - thr16);
+  const int64_t nvec = n / 8;
+  int64_t blocks = (nvec + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  dropout_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(res), static_cast<__nv_bfloat16*>(out), nvec,
+      thr16, scale, seed, offset);
+  A4R_LAUNCH_OK();
+  a4r_count_launch(1);
   return A4R_OK;
 }

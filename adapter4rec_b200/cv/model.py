@@ -101,8 +101,10 @@ class VITAdaptedOutput(nn.Module):
         self.adapter = AdapterBlock(args, 768, args.cv_adapter_down_size, args.adapter_dropout_rate)
 
     def forward(self, hidden_states, input_tensor):
-        h = self.self_output.dense(to_2d_bf16(hidden_states))
-        return self.adapter(h, extra_residual=to_2d_bf16(input_tensor)).view(input_tensor.shape)
+        return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_from_dense(self, h, input_tensor):
+        return self.adapter(to_2d_bf16(h), extra_residual=to_2d_bf16(input_tensor)).view(input_tensor.shape)
 
 
 class SoftPrompt(nn.Module):

@@ -188,10 +188,16 @@ class ViTLayer(nn.Module):
         x1 = ao.forward_fused(ctx, res) if hasattr(ao, "forward_fused") else (to_2d_bf16(ao(ctx, res)) + res)
         y = self.layernorm_after(x1)
         out = self.output
-        wi, wf = self.intermediate.dense, getattr(out, "dense", None)
-        if type(out) is ViTOutput and not (wi.weight.requires_grad or wi.bias.requires_grad or
-                                           wf.weight.requires_grad or wf.bias.requires_grad):
+        wi = self.intermediate.dense
+        inner = out.self_output if hasattr(out, "self_output") else out
+        wf = getattr(inner, "dense", None)
+        frozen = wf is not None and not (wi.weight.requires_grad or wi.bias.requires_grad or
+                                         wf.weight.requires_grad or wf.bias.requires_grad)
+        if frozen and type(out) is ViTOutput:
             return Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, x1, wi._cache, wf._cache)
+        if frozen and hasattr(out, "forward_from_dense"):
+            h = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, None, wi._cache, wf._cache)
+            return to_2d_bf16(out.forward_from_dense(h, x1))
         return to_2d_bf16(out(self.intermediate(y), x1))
 
 

@@ -152,25 +152,71 @@ def layer_norm(x, weight, bias, eps, res=None):
     return LayerNormFunction.apply(x, weight, bias, eps, res)
 
 
+class DropoutState:
+    """Seed and running counter of the counter-based dropout RNG (a4r_dropout / attention-probability dropout).  Every
+    call site draws a fresh counter range, so masks are independent across sites and steps; the backward of a site reuses
+    the (seed, offset) its forward drew."""
+    seed = 0x5EEDA4D2
+    counter = 0
+
+    @classmethod
+    def manual_seed(cls, seed):
+        cls.seed, cls.counter = int(seed) & 0xFFFFFFFFFFFF, 0
+
+    @classmethod
+    def draw(cls, n_counters):
+        off = cls.counter
+        cls.counter += int(n_counters)
+        return cls.seed, off
+
+
+class DropoutAddFunction(torch.autograd.Function):
+    """out = dropout(x) + res   (nn.Dropout followed by the residual add of the reference's post-LN blocks)."""
+
+    @staticmethod
+    def forward(ctx, x, res, p):
+        ctx.p = p
+        ctx.rng = DropoutState.draw((x.numel() + 3) // 4)
+        ctx.has_res = res is not None
+        return ops.dropout(x.contiguous(), None if res is None else res.contiguous(), p, *ctx.rng)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = ops.dropout(dy, None, ctx.p, *ctx.rng) if ctx.needs_input_grad[0] else None
+        return dx, (dy if ctx.has_res and ctx.needs_input_grad[1] else None), None
+
+
+def dropout_add(x, res, p):
+    """dropout(x) (+ res); identity (+ plain add through the caller's fused path) when p == 0"""
+    return DropoutAddFunction.apply(x, res, float(p))
+
+
 class AttentionFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, mask, N, L, heads, head_dim, causal, mask_neg):
+    def forward(ctx, qkv, mask, N, L, heads, head_dim, causal, mask_neg, dropout_p=0.0):
         ctx.cfg = (N, L, heads, head_dim, causal, mask_neg)
         ctx.mask = mask
-        ctx.save_for_backward(qkv)
-        return ops.attn_small_fwd(qkv, N, L, heads, head_dim, mask=mask, causal=causal, mask_neg=mask_neg)
+        ctx.drop = None
+        if dropout_p > 0.0:
+            ctx.drop = (dropout_p,) + DropoutState.draw(N * heads * 32 * 8)
+        out, lse = ops.attn_small_fwd(qkv, N, L, heads, head_dim, mask=mask, causal=causal, mask_neg=mask_neg, want_lse=True,
+                                      dropout=ctx.drop)
+        # the short-sequence kernel recomputes everything from qkv; the mid-length (ViT) kernel reuses lse and the output
+        ctx.save_for_backward(qkv, lse, out if lse is not None else None)
+        return out
 
     @staticmethod
     def backward(ctx, dctx):
-        (qkv,) = ctx.saved_tensors
+        qkv, lse, out = ctx.saved_tensors
         N, L, heads, head_dim, causal, mask_neg = ctx.cfg
         dqkv = ops.attn_small_bwd(qkv, dctx.contiguous(), N, L, heads, head_dim, mask=ctx.mask, causal=causal,
-                                  mask_neg=mask_neg)
-        return dqkv, None, None, None, None, None, None, None
+                                  mask_neg=mask_neg, lse=lse, ctx=out, dropout=ctx.drop)
+        return dqkv, None, None, None, None, None, None, None, None
 
 
-def attention(qkv, mask, N, L, heads, head_dim, causal=False, mask_neg=ops.F32_MIN):
-    return AttentionFunction.apply(qkv, mask, N, L, heads, head_dim, causal, mask_neg)
+def attention(qkv, mask, N, L, heads, head_dim, causal=False, mask_neg=ops.F32_MIN, dropout_p=0.0):
+    return AttentionFunction.apply(qkv, mask, N, L, heads, head_dim, causal, mask_neg, float(dropout_p))
 
 
 LORA_PAD = 64  # the rank-r intermediates of all LoRA'd projections of one fused QKV share one 64-column k-block

@@ -29,6 +29,8 @@ class AttnArgs(Structure):
         ("ld_qkv", c_int64), ("ld_out", c_int64), ("mask_ld", c_int64),
         ("N", c_int64), ("L", c_int64), ("heads", c_int64), ("head_dim", c_int64),
         ("mask_dtype", c_int32), ("causal", c_int32), ("scale", c_float), ("mask_neg", c_float),
+        ("lse", c_void_p), ("ctx", c_void_p),
+        ("dropout_p", c_float), ("dropout_seed", ctypes.c_uint64), ("dropout_offset", ctypes.c_uint64),
     ]
 
 
@@ -69,6 +71,7 @@ PROTOTYPES = {
                                     c_int32, c_void_p, c_size_t, c_int64, c_int64, c_void_p]),
     "a4r_embed_ln_fwd": (c_int32, [POINTER(EmbedArgs), c_void_p]),
     "a4r_act_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "a4r_dropout": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p]),
     "a4r_colsum_workspace_bytes": (c_size_t, [c_int64]),
     "a4r_colsum": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
     "a4r_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),

@@ -3,8 +3,9 @@
 Downstream/Text/run.py:414-465 and reference checkpoints work unchanged), executing on the sm_100a kernels.
 
 Numerics follow the layer algebra of SURVEY.md Appendix A2: bf16 activations, fp32 accumulation/statistics.
-Dropout: the modules keep a `dropout` attribute for structural compatibility; this path implements the
-deterministic (eval / p = 0) arithmetic the parity tests are defined on."""
+Dropout (train mode): hidden-state dropouts run in a4r_dropout fused with the residual add that follows them, the
+attention-probability dropout inside the attention kernel; both use a counter-based RNG whose masks the backward
+regenerates.  eval() / p = 0 is the deterministic arithmetic the parity tests are defined on."""
 import torch
 import torch.nn as nn
 
@@ -32,6 +33,7 @@ class TextConfigLite:
         self.pad_token_id = src.get("pad_token_id", 0)
         self.model_type = src.get("model_type", "bert")
         self.hidden_dropout_prob = src.get("hidden_dropout_prob", 0.1)
+        self.attention_probs_dropout_prob = src.get("attention_probs_dropout_prob", 0.1)
         self.initializer_range = src.get("initializer_range", 0.02)
 
 
@@ -60,7 +62,10 @@ class BertEmbeddings(nn.Module):
         typ = self._typ_cache.get(self.token_type_embeddings.weight)[0][0]
         tables = (table, self.position_embeddings.table_bf16(), typ)
         g, b = self.LayerNorm.weight.detach().float(), self.LayerNorm.bias.detach().float()
-        return Fn.EmbedLNFunction.apply(input_ids, L, tables, g, b, self.LayerNorm.eps, roberta_pad, prompt)
+        x = Fn.EmbedLNFunction.apply(input_ids, L, tables, g, b, self.LayerNorm.eps, roberta_pad, prompt)
+        if self.training and self.dropout.p > 0:
+            x = Fn.dropout_add(x, None, self.dropout.p)
+        return x
 
 
 class BertSelfAttention(nn.Module):
@@ -72,7 +77,7 @@ class BertSelfAttention(nn.Module):
         self.query = Linear(config.hidden_size, config.hidden_size)
         self.key = Linear(config.hidden_size, config.hidden_size)
         self.value = Linear(config.hidden_size, config.hidden_size)
-        self.dropout = nn.Dropout(0.1)
+        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
         self._qkv_cache = {}
 
     def forward(self, x2d, attention_mask, N, L):
@@ -82,7 +87,7 @@ class BertSelfAttention(nn.Module):
             params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
         qkv = Fn.QKVFunction.apply(x2d, self._qkv_cache, *params)
         return Fn.attention(qkv, attention_mask, N, L, self.num_attention_heads, self.attention_head_size,
-                            causal=False, mask_neg=ops.F32_MIN)
+                            causal=False, mask_neg=ops.F32_MIN, dropout_p=self.dropout.p if self.training else 0.0)
 
 
 class BertSelfOutput(nn.Module):
@@ -96,7 +101,10 @@ class BertSelfOutput(nn.Module):
 
     def forward(self, hidden_states, input_tensor):
         shape = input_tensor.shape
-        z = self.dense(to_2d_bf16(hidden_states), residual=to_2d_bf16(input_tensor))   # residual fused in the epilogue
+        if self.training and self.dropout.p > 0:
+            z = Fn.dropout_add(self.dense(to_2d_bf16(hidden_states)), to_2d_bf16(input_tensor).contiguous(), self.dropout.p)
+        else:
+            z = self.dense(to_2d_bf16(hidden_states), residual=to_2d_bf16(input_tensor))   # residual fused in the epilogue
         return self.LayerNorm(z).view(shape)
 
 
@@ -143,13 +151,23 @@ class BertLayer(nn.Module):
         else:
             y = self.attention(x2d, attention_mask, N, L)
         out = self.output
-        wi, wf = self.intermediate.dense, getattr(out, "dense", None)
-        if type(out) is BertOutput and not (wi.weight.requires_grad or wi.bias.requires_grad or
-                                            wf.weight.requires_grad or wf.bias.requires_grad):
+        wi = self.intermediate.dense
+        inner = out.self_output if hasattr(out, "self_output") else out          # Houlsby wrapper keeps the dense inside
+        wf = getattr(inner, "dense", None)
+        frozen = wf is not None and not (wi.weight.requires_grad or wi.bias.requires_grad or
+                                         wf.weight.requires_grad or wf.bias.requires_grad)
+        if frozen and type(out) is BertOutput:
             # frozen feed-forward: one fused function (GELU' and the residual gradient live in GEMM epilogues)
+            if self.training and out.dropout.p > 0:
+                h = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, None, wi._cache, wf._cache)
+                return out.LayerNorm(Fn.dropout_add(h, y.contiguous(), out.dropout.p))
             z = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, y, wi._cache, wf._cache)
             return out.LayerNorm(z)
-        return out(self.intermediate(y), y)                 # adapter-wrapped or trainable output module
+        if frozen and hasattr(out, "forward_from_dense"):
+            # adapter-wrapped output: the frozen FFN pair stays fused, the wrapper continues from the dense output
+            h = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, None, wi._cache, wf._cache)
+            return to_2d_bf16(out.forward_from_dense(h, y))
+        return out(self.intermediate(y), y)                 # foreign or trainable output module
 
 
 class BertEncoder(nn.Module):

@@ -89,10 +89,16 @@ class BertAdaptedSelfOutput(nn.Module):
         self.adapter = AdapterBlock(args, _word_dim(args), args.bert_adapter_down_size, args.adapter_dropout_rate)
 
     def forward(self, hidden_states, input_tensor):
-        shape = input_tensor.shape
-        h = self.self_output.dense(to_2d_bf16(hidden_states))
+        return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_from_dense(self, h, input_tensor):
+        """everything after self_output.dense (the encoder layer fuses that dense with the GELU GEMM before it)"""
+        h = to_2d_bf16(h)
+        drop = self.self_output.dropout
+        if self.training and drop.p > 0:
+            h = Fn.dropout_add(h, None, drop.p)                   # model.py:294: dropout BEFORE the adapter
         z = self.adapter(h, extra_residual=to_2d_bf16(input_tensor))
-        return self.self_output.LayerNorm(z).view(shape)
+        return self.self_output.LayerNorm(z).view(input_tensor.shape)
 
 
 class SASRecAdaptedSelfOutput(nn.Module):

@@ -23,10 +23,12 @@ class PositionwiseFeedForward(nn.Module):
     def forward(self, x, adapter=None):
         x2 = to_2d_bf16(x)
         h = self.w_1(x2, act="relu")
+        p = self.dropout.p if self.training else 0.0
         if adapter is None:
-            z = self.w_2(h, residual=x2)
+            z = Fn.dropout_add(self.w_2(h), x2.contiguous(), p) if p > 0 else self.w_2(h, residual=x2)
         else:
-            z = adapter(self.w_2(h), extra_residual=x2)
+            o = self.w_2(h)
+            z = adapter(Fn.dropout_add(o, None, p) if p > 0 else o, extra_residual=x2)
         return self.layer_norm(z).view(x.shape)
 
 
@@ -66,11 +68,14 @@ class MultiHeadedAttention(nn.Module):
         for m in (self.w_Q, self.w_K, self.w_V):
             params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
         qkv = Fn.QKVFunction.apply(x2, self._qkv_cache, *params)
-        ctx = Fn.attention(qkv, mask, B, S, self.n_heads, self.d_k, causal=True, mask_neg=SASREC_MASK_NEG)
+        ctx = Fn.attention(qkv, mask, B, S, self.n_heads, self.d_k, causal=True, mask_neg=SASREC_MASK_NEG,
+                           dropout_p=self.self_attention.dropout.p if self.training else 0.0)
+        p = self.dropout.p if self.training else 0.0
         if adapter is None:
-            z = self.fc(ctx, residual=x2)
+            z = Fn.dropout_add(self.fc(ctx), x2.contiguous(), p) if p > 0 else self.fc(ctx, residual=x2)
         else:
-            z = adapter(self.fc(ctx), extra_residual=x2)
+            o = self.fc(ctx)
+            z = adapter(Fn.dropout_add(o, None, p) if p > 0 else o, extra_residual=x2)
         return self.layer_norm(z).view(B, S, D)
 
 
@@ -100,7 +105,10 @@ class TransformerEncoder(nn.Module):
     def forward(self, input_embs, log_mask, att_mask):
         B, S, D = input_embs.shape
         pos = self.position_embedding.table_bf16()[:S].contiguous()
-        output = self.layer_norm(to_2d_bf16(input_embs).contiguous(), res=pos).view(B, S, D)
+        output = self.layer_norm(to_2d_bf16(input_embs).contiguous(), res=pos)
+        if self.training and self.dropout.p > 0:
+            output = Fn.dropout_add(output, None, self.dropout.p)
+        output = output.view(B, S, D)
         for transformer in self.transformer_blocks:
             output = transformer.forward(output, att_mask)
         return output

@@ -101,8 +101,19 @@ def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, au
     return out
 
 
-def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg):
+def dropout(x, res, p, seed, offset):
+    """out = x * mask / (1 - p) (+ res); the mask is a pure function of (seed, offset, element index)."""
+    assert x.dtype == BF16 and x.is_contiguous() and (res is None or (res.dtype == BF16 and res.is_contiguous() and res.shape == x.shape))
+    out = torch.empty_like(x)
+    _l.check(_l.get_lib().a4r_dropout(_p(x), _p(res), _p(out), x.numel(), float(p), int(seed), int(offset), _stream()),
+             "a4r_dropout")
+    return out
+
+
+def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout=None):
     a = _l.AttnArgs()
+    if dropout is not None:
+        a.dropout_p, a.dropout_seed, a.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
     a.qkv, a.ld_qkv = _p(qkv), _rows2d(qkv, "qkv")
     a.N, a.L, a.heads, a.head_dim = N, L, heads, head_dim
     if mask is None:
@@ -125,22 +136,31 @@ def _attn_kernel(L, head_dim, causal, direction):
     raise RuntimeError("attention: unsupported shape L=%d head_dim=%d causal=%s (no fallback exists)" % (L, head_dim, causal))
 
 
-def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN):
+def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN, want_lse=False, dropout=None):
+    """returns ctx, or (ctx, lse) with want_lse (lse is None for the short-sequence kernel, which recomputes it)"""
     assert qkv.dtype == BF16 and qkv.shape[0] == N * L
     out = torch.empty((N * L, heads * head_dim), dtype=BF16, device=qkv.device)
-    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout)
     a.out, a.ld_out = _p(out), out.stride(0)
+    lse = None
+    if want_lse and L > 32:
+        lse = torch.empty((N * L, heads), dtype=torch.float32, device=qkv.device)
+        a.lse = _p(lse)
     fn, name = _attn_kernel(L, head_dim, causal, "fwd")
     _l.check(fn(ctypes.byref(a), _stream()), name)
-    return out
+    return (out, lse) if want_lse else out
 
 
-def attn_small_bwd(qkv, dctx, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN):
+def attn_small_bwd(qkv, dctx, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN, lse=None, ctx=None,
+                   dropout=None):
     assert qkv.dtype == BF16 and dctx.dtype == BF16 and dctx.shape[0] == N * L
     dqkv = torch.empty((N * L, 3 * heads * head_dim), dtype=BF16, device=qkv.device)
-    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout)
     assert _rows2d(qkv, "qkv") == dqkv.stride(0), "attention bwd expects a contiguous qkv"
     a.out, a.dout, a.ld_out = _p(dqkv), _p(dctx), _rows2d(dctx, "dctx")
+    if L > 32:
+        assert lse is not None and ctx is not None and ctx.is_contiguous() and dctx.is_contiguous()
+        a.lse, a.ctx = _p(lse), _p(ctx)
     fn, name = _attn_kernel(L, head_dim, causal, "bwd")
     _l.check(fn(ctypes.byref(a), _stream()), name)
     return dqkv

@@ -387,7 +387,9 @@ def main():
                    "users_per_gpu_per_step": a.users, "sequences_per_gpu_per_step": a.users * 42,
                    "tokens_per_gpu_per_step": tokens, "users_per_pass": a.users_per_pass, "parallelism": "dp%d" % world,
                    "l2": "inputs larger than L2 (>= 1 GB activations per layer per pass); %d rotating batches" % n_pool,
-                   "dropout": "off (deterministic path; see DESIGN.md)"},
+                   "dropout": "on, p=0.1 (BERT hidden + attention-probability, SASRec) as the reference trains: counter-RNG "
+                              "kernels, masks regenerated in the backward",
+                   "last_layer_tail": "[CLS] rows only (identical results: other rows of the last layer never reach the loss)"},
         "model_tflops_per_gpu": algo_flops_step / (ms_per_step / 1e3) / 1e12,
         "loss": loss_val,
         "gpu_launches": int(launches),

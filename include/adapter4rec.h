@@ -129,6 +129,14 @@ typedef struct a4r_attn_args {
   int32_t causal;
   float scale;
   float mask_neg;
+  float* lse;      /* mid-length kernel only: [N*L, heads] f32 log-sum-exp rows, written by fwd, required by bwd */
+  const void* ctx; /* mid-length bwd only: the forward output [N*L, ld_out] */
+  /* dropout on the attention probabilities (BertSelfAttention.dropout, SelfAttention.dropout modules.py:35,41; train
+   * mode only): p = 0 disables it; the backward must be given the same (seed, offset) to regenerate the mask.
+   * Short-sequence kernel only (ViT's dropout probability is 0). */
+  float dropout_p;
+  uint64_t dropout_seed;
+  uint64_t dropout_offset;
 } a4r_attn_args;
 
 A4R_API int a4r_attn_small_fwd(const a4r_attn_args* args, a4r_stream_t stream);
@@ -208,6 +216,13 @@ A4R_API int a4r_vit_assemble(const void* patch_emb, const void* cls, const void*
 /* out = dy * act'(u) elementwise over n bf16 values; kind 0: erf-GELU with u = pre-activation
  * (Text_Encoder.activate, encoders.py:46,57), kind 1: ReLU with u = activation output. */
 A4R_API int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
+
+/* Dropout (+ residual): out = x * mask / (1 - p) (+ res), n bf16 elements (n %% 8 == 0).  Replaces nn.Dropout on the
+ * hidden states (BertSelfOutput.dropout / BertOutput.dropout / BertEmbeddings.dropout, SASRec modules.py:27,72,107)
+ * fused with the residual add that follows it.  Counter-based RNG: element i is decided by (seed, offset + i / 4), so
+ * the backward regenerates the mask by calling the same function on the gradient with the same (seed, offset). */
+A4R_API int a4r_dropout(const void* x, const void* res, void* out, int64_t n, float p, uint64_t seed, uint64_t offset,
+                        a4r_stream_t stream);
 
 /* out[j] (+)= sum_m x[m, j] for a bf16 [M, ld] matrix, j < width: bias gradients of trainable biases
  * (lora.Linear bias, AdapterBlock biases).  Deterministic two-stage reduction through `workspace`. */

@@ -139,11 +139,11 @@ def test_attention_small_fwd_bwd(N, L, heads, dh, mask_kind, causal):
     mask_neg = -1e9 if causal else ops.F32_MIN
     qf = qkv.float().requires_grad_(True)
     ref = _attn_ref(qf, N, L, heads, dh, mask, causal, mask_neg)
-    got = ops.attn_small_fwd(qkv, N, L, heads, dh, mask=mask, causal=causal, mask_neg=mask_neg)
+    got, lse = ops.attn_small_fwd(qkv, N, L, heads, dh, mask=mask, causal=causal, mask_neg=mask_neg, want_lse=True)
     _close(got, ref.detach(), 2 ** -6, 2e-2, "attention fwd")
     dctx = _rand((N * L, H), 1.0, 8)
     ref.backward(dctx.float())
-    dqkv = ops.attn_small_bwd(qkv, dctx, N, L, heads, dh, mask=mask, causal=causal, mask_neg=mask_neg)
+    dqkv = ops.attn_small_bwd(qkv, dctx, N, L, heads, dh, mask=mask, causal=causal, mask_neg=mask_neg, lse=lse, ctx=got)
     # probabilities and dS are rounded to bf16 before the second contraction: 2^-6 relative + small absolute
     _close(dqkv, qf.grad, 2 ** -5, 6e-2, "attention bwd")
     # aggregate accuracy per block (dq | dk | dv) and of their column sums (what bias gradients are made of)

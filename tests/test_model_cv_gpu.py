@@ -60,7 +60,7 @@ def test_cv_train_step_matches_oracle_and_reference(kind):
     assert abs(float(oloss) - float(gold["loss"])) <= 2e-5 * abs(float(gold["loss"]))
     if train:
         oloss.backward()
-    model.train()
+    model.eval()    # parity is defined without dropout
     loss = model(images.cuda(), log_mask.cuda(), 0)
     lv, ov = float(loss.detach()), float(oloss.detach())
     assert abs(lv - ov) <= LOSS_RTOL * abs(ov), "loss %.6f vs oracle %.6f" % (lv, ov)

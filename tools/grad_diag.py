@@ -16,7 +16,7 @@ def oracle_grads(round_w):
     O.cv_model_forward(images, log_mask, osd, cfg, rec).backward()
     return {k: osd[k].grad for k in train}
 og = oracle_grads(False); og16 = oracle_grads(True)
-model.train(); model(images.cuda(), log_mask.cuda(), 0).backward()
+model.eval(); model(images.cuda(), log_mask.cuda(), 0).backward()
 params = dict(model.named_parameters())
 tot = torch.cat([og[k].flatten() for k in train]).norm()
 for k in train:
