@@ -48,6 +48,11 @@ struct GemmParams {
   float alpha;
   int epilogue;
   int out_f32;
+  // dropout on v = alpha*acc + bias (LINEAR mode only), applied BEFORE the residuals: element (row, col) of the logical
+  // [M, N] output uses lane ((row*N + col) & 3) of rng64(seed, offset + (row*N + col) / 4) — the indexing of a4r_dropout
+  uint32_t drop_thr16;
+  float drop_scale;
+  uint64_t drop_seed, drop_offset;
 };
 
 // ---- epilogue helpers ---------------------------------------------------------------------------
@@ -309,6 +314,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         };
         if constexpr (EPI == A4R_EPI_LINEAR) {
+          if (p.drop_thr16 != 0) {
+            const uint64_t ctr = p.drop_offset + ((static_cast<uint64_t>(r64) * static_cast<uint64_t>(p.N) + col0) >> 2);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {   // 4 consecutive columns per counter
+              const uint64_t r = rng64(p.drop_seed, ctr + q);
+              v[2 * q].x = rng_keep(r, 0, p.drop_thr16) ? v[2 * q].x * p.drop_scale : 0.0f;
+              v[2 * q].y = rng_keep(r, 1, p.drop_thr16) ? v[2 * q].y * p.drop_scale : 0.0f;
+              v[2 * q + 1].x = rng_keep(r, 2, p.drop_thr16) ? v[2 * q + 1].x * p.drop_scale : 0.0f;
+              v[2 * q + 1].y = rng_keep(r, 3, p.drop_thr16) ? v[2 * q + 1].y * p.drop_scale : 0.0f;
+            }
+          }
           if (has_in) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __fadd2_rn(v[i], unpack_bf16x2(in.w[i]));
@@ -454,6 +470,10 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
   p.alpha = a->alpha;
   p.epilogue = a->epilogue;
   p.out_f32 = a->out_f32;
+  p.drop_thr16 = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
+  p.drop_scale = 65536.0f / static_cast<float>(65536u - p.drop_thr16);
+  p.drop_seed = a->dropout_seed;
+  p.drop_offset = a->dropout_offset;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -499,6 +519,8 @@ extern "C" int a4r_gemm_bf16_tn(const a4r_gemm_args* a, a4r_stream_t stream_) {
   if (a->residual2)
     A4R_CHECK_ARG(a4r_aligned16(a->residual2) && a->ldr2 % 8 == 0 && a->ldr2 >= a->N, "gemm: bad residual2/ldr2");
   if (a->bias) A4R_CHECK_ARG(a4r_aligned16(a->bias), "gemm: bias must be 16B aligned");
+  A4R_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "gemm: dropout_p must be in [0,1)");
+  A4R_CHECK_ARG(a->dropout_p == 0.0f || a->epilogue == A4R_EPI_LINEAR, "gemm: dropout is a LINEAR-epilogue option");
   int rc = a4r_device_check();
   if (rc != A4R_OK) return rc;
   if (a->M == 0) return A4R_OK;

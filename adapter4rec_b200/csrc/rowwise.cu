@@ -122,7 +122,8 @@ template <int G, int CPL, bool WGRAD>
 __global__ void __launch_bounds__(ROW_THREADS, WGRAD ? 1 : 3)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
-              __nv_bfloat16* __restrict__ dz, float* __restrict__ partial /* [grid,2,H] or NULL */, int64_t M, int H) {
+              __nv_bfloat16* __restrict__ dz, float* __restrict__ partial /* [grid,2,H] or NULL */, int64_t M, int H,
+              __nv_bfloat16* __restrict__ dz_masked, uint32_t thr16, float dscale, uint64_t seed, uint64_t offset) {
   __shared__ __align__(16) float sgamma[1024];
   __shared__ float buf[WGRAD ? 8192 : 1];  // (ROW_THREADS/G) * H <= 8192 floats for every supported (G, H)
   const int nchunks = H >> 3;
@@ -195,6 +196,17 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = rstd * (a[e] * gg[e] - s1 - (b[e] - mean) * rstd * s2);
         if (valid) st_na_v4(dz + row * H + ch * 8, pack8(o));
+        if (dz_masked != nullptr && valid) {
+          // the gradient that flows back through the dropout in front of this LayerNorm's residual add
+          const uint64_t ctr = offset + ((static_cast<uint64_t>(row) * H + ch * 8) >> 2);
+          const uint64_t r0 = rng64(seed, ctr), r1 = rng64(seed, ctr + 1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            o[e] = rng_keep(r0, e, thr16) ? o[e] * dscale : 0.0f;
+            o[4 + e] = rng_keep(r1, e, thr16) ? o[4 + e] * dscale : 0.0f;
+          }
+          st_na_v4(dz_masked + row * H + ch * 8, pack8(o));
+        }
       }
     }
   }
@@ -459,8 +471,12 @@ extern "C" size_t a4r_layernorm_bwd_workspace_bytes(int64_t H) {
 
 extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd,
                                  const float* gamma, void* dz, float* dgamma, float* dbeta, int32_t accumulate,
-                                 void* workspace, size_t workspace_bytes, int64_t M, int64_t H,
+                                 void* workspace, size_t workspace_bytes, int64_t M, int64_t H, void* dz_masked,
+                                 float dropout_p, uint64_t dropout_seed, uint64_t dropout_offset,
                                  a4r_stream_t stream_) {
+  A4R_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f && a4r_aligned16(dz_masked), "layernorm_bwd: bad dropout args");
+  const uint32_t thr16 = static_cast<uint32_t>(dropout_p * 65536.0f + 0.5f);
+  const float dscale = 65536.0f / static_cast<float>(65536u - thr16);
   A4R_CHECK_ARG(dy && z && mean && rstd && gamma && dz, "layernorm_bwd: NULL pointer");
   A4R_CHECK_ARG(H >= 8 && H <= 1024 && H % 8 == 0, "layernorm: H must be a multiple of 8 in [8,1024]");
   A4R_CHECK_ARG(a4r_aligned16(dy) && a4r_aligned16(z) && a4r_aligned16(dz) && a4r_aligned16(gamma),
@@ -484,13 +500,15 @@ extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mea
       if (blocks > LN_BWD_MAX_BLOCKS) blocks = LN_BWD_MAX_BLOCKS;
       ln_bwd_kernel<G.value, CPL.value, true><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
-          static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H));
+          static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H), static_cast<__nv_bfloat16*>(dz_masked), thr16,
+          dscale, dropout_seed, dropout_offset);
     } else {
       const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 12;
       if (blocks > cap) blocks = cap;
       ln_bwd_kernel<G.value, CPL.value, false><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
-          static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H));
+          static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H), static_cast<__nv_bfloat16*>(dz_masked), thr16,
+          dscale, dropout_seed, dropout_offset);
     }
     A4R_LAUNCH_OK();
     a4r_count_launch(1);

@@ -121,6 +121,63 @@ class FFNFunction(torch.autograd.Function):
         return dy, None, None, None, None, dres, None, None
 
 
+class PostLNBlockFunction(torch.autograd.Function):
+    """One frozen post-LN residual block of BERT in a single autograd node:
+
+        out = LayerNorm(dropout(F(x)) + res)       F(x) = x Woᵀ + bo                      (attention.output: BertSelfOutput)
+                                                  F(x) = GELU(x Wiᵀ + bi) Wfᵀ + bf       (intermediate + output: BertOutput)
+
+    Forward: dropout and the residual add live in the epilogue of the last GEMM (counter RNG).  Backward: LayerNorm's
+    backward kernel emits dz AND dz ⊙ mask/(1-p) (the gradient through the dropout) in one pass; GELU′ and the residual
+    gradient live in the epilogues of the data-gradient GEMMs.  Only LayerNorm may be trainable (finetune_layernorm)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps, p, w1, b1, cache1, w2, b2, cache2):
+        ffn = w2 is not None
+        need = any(ctx.needs_input_grad[:4])
+        rng = (float(p),) + DropoutState.draw((x.shape[0] * (w2 if ffn else w1).shape[0] + 3) // 4) if p > 0 else None
+        wa, _ = cache1.get(w1)
+        u = None
+        if ffn:
+            wb, _ = cache2.get(w2)
+            u = torch.empty((x.shape[0], wa.shape[0]), dtype=BF16, device=x.device) if need else None
+            f = ops.gemm(x, wa, bias=b1.detach(), epilogue=ops.EPI_GELU, aux=u)
+            z = ops.gemm(f, wb, bias=b2.detach(), residual=res, dropout=rng)
+        else:
+            z = ops.gemm(x, wa, bias=b1.detach(), residual=res, dropout=rng)
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        out, _, mean, rstd = ops.layernorm_fwd(z, g, b, eps, want_stats=need)
+        ctx.rng, ctx.ffn, ctx.caches = rng, ffn, (cache1, cache2)
+        ctx.res_is_input = res is x
+        if need:
+            ctx.save_for_backward(z, mean, rstd, g, u, w1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, mean, rstd, g, u, w1, w2 = ctx.saved_tensors
+        dout = dout.contiguous()
+        want_ln = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        dg = db = None
+        if want_ln:
+            dg, db = torch.empty_like(g), torch.empty_like(g)
+        r = ops.layernorm_bwd(dout, z, mean, rstd, g, dgamma=dg, dbeta=db, masked=ctx.rng)
+        dz, dzm = r if ctx.rng is not None else (r, r)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            fold = dz if ctx.res_is_input else None      # res is x: the skip gradient rides in the last epilogue
+            if ctx.ffn:
+                _, w2t = ctx.caches[1].get(w2, need_t=True)
+                _, w1t = ctx.caches[0].get(w1, need_t=True)
+                du = ops.gemm(dzm, w2t, epilogue=ops.EPI_DGELU, aux=u)
+                dx = ops.gemm(du, w1t, residual=fold)
+            else:
+                _, w1t = ctx.caches[0].get(w1, need_t=True)
+                dx = ops.gemm(dzm, w1t, residual=fold)
+        dres = dz if (ctx.needs_input_grad[1] and not ctx.res_is_input) else None
+        return dx, dres, dg, db, None, None, None, None, None, None, None, None
+
+
 class LayerNormFunction(torch.autograd.Function):
     """y = LN(x + res[row % res_rows]).  res is a constant (the frozen SASRec position table) or None."""
 

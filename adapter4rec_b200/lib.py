@@ -20,6 +20,7 @@ class GemmArgs(Structure):
         ("residual", c_void_p), ("ldr", c_int64), ("residual2", c_void_p), ("ldr2", c_int64),
         ("bias", c_void_p), ("M", c_int64), ("N", c_int64), ("K", c_int64),
         ("alpha", c_float), ("epilogue", c_int32), ("out_f32", c_int32), ("block_n", c_int32),
+        ("dropout_p", c_float), ("dropout_seed", ctypes.c_uint64), ("dropout_offset", ctypes.c_uint64),
     ]
 
 
@@ -68,7 +69,8 @@ PROTOTYPES = {
                                     c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "a4r_layernorm_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "a4r_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_int32, c_void_p, c_size_t, c_int64, c_int64, c_void_p]),
+                                    c_int32, c_void_p, c_size_t, c_int64, c_int64, c_void_p, c_float, ctypes.c_uint64,
+                                    ctypes.c_uint64, c_void_p]),
     "a4r_embed_ln_fwd": (c_int32, [POINTER(EmbedArgs), c_void_p]),
     "a4r_act_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "a4r_dropout": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p]),

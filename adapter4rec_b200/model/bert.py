@@ -101,10 +101,18 @@ class BertSelfOutput(nn.Module):
 
     def forward(self, hidden_states, input_tensor):
         shape = input_tensor.shape
-        if self.training and self.dropout.p > 0:
-            z = Fn.dropout_add(self.dense(to_2d_bf16(hidden_states)), to_2d_bf16(input_tensor).contiguous(), self.dropout.p)
+        p = self.dropout.p if self.training else 0.0
+        d = self.dense
+        if not (d.weight.requires_grad or d.bias.requires_grad):
+            # frozen dense: dense -> dropout -> + input -> LayerNorm as ONE autograd node (fused epilogues both ways)
+            out = Fn.PostLNBlockFunction.apply(to_2d_bf16(hidden_states), to_2d_bf16(input_tensor), self.LayerNorm.weight,
+                                               self.LayerNorm.bias, self.LayerNorm.eps, p, d.weight, d.bias, d._cache,
+                                               None, None, None)
+            return out.view(shape)
+        if p > 0:
+            z = Fn.dropout_add(d(to_2d_bf16(hidden_states)), to_2d_bf16(input_tensor).contiguous(), p)
         else:
-            z = self.dense(to_2d_bf16(hidden_states), residual=to_2d_bf16(input_tensor))   # residual fused in the epilogue
+            z = d(to_2d_bf16(hidden_states), residual=to_2d_bf16(input_tensor))   # residual fused in the epilogue
         return self.LayerNorm(z).view(shape)
 
 
@@ -157,12 +165,11 @@ class BertLayer(nn.Module):
         frozen = wf is not None and not (wi.weight.requires_grad or wi.bias.requires_grad or
                                          wf.weight.requires_grad or wf.bias.requires_grad)
         if frozen and type(out) is BertOutput:
-            # frozen feed-forward: one fused function (GELU' and the residual gradient live in GEMM epilogues)
-            if self.training and out.dropout.p > 0:
-                h = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, None, wi._cache, wf._cache)
-                return out.LayerNorm(Fn.dropout_add(h, y.contiguous(), out.dropout.p))
-            z = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, y, wi._cache, wf._cache)
-            return out.LayerNorm(z)
+            # frozen feed-forward + dropout + residual + LayerNorm: one autograd node (GELU', dropout and the residual
+            # gradient all live in GEMM / LayerNorm-backward epilogues)
+            p = out.dropout.p if self.training else 0.0
+            return Fn.PostLNBlockFunction.apply(y, y, out.LayerNorm.weight, out.LayerNorm.bias, out.LayerNorm.eps, p,
+                                                wi.weight, wi.bias, wi._cache, wf.weight, wf.bias, wf._cache)
         if frozen and hasattr(out, "forward_from_dense"):
             # adapter-wrapped output: the frozen FFN pair stays fused, the wrapper continues from the dense output
             h = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, None, wi._cache, wf._cache)

@@ -60,7 +60,7 @@ def gemm_profile_stop():
 
 
 def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, aux=None, a2=None, b2=None,
-         alpha=1.0, out=None, out_dtype=BF16, block_n=0):
+         alpha=1.0, out=None, out_dtype=BF16, block_n=0, dropout=None):
     """C[M,N] = epi(alpha * (a @ b.T + a2 @ b2.T) + bias)  — see a4r_gemm_bf16_tn in include/adapter4rec.h."""
     assert a.dtype == BF16 and b.dtype == BF16, "gemm operands must be bf16"
     M, K = a.shape
@@ -88,6 +88,9 @@ def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, au
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
         g.bias = _p(bias)
     g.M, g.N, g.K = M, N, K
+    if dropout is not None:
+        assert out.is_contiguous(), "epilogue dropout indexes the logical [M, N] output"
+        g.dropout_p, g.dropout_seed, g.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
     g.alpha, g.epilogue, g.out_f32, g.block_n = float(alpha), int(epilogue), int(out.dtype == torch.float32), int(block_n)
     assert out.dtype in (BF16, torch.float32)
     if _gemm_profile is not None:
@@ -183,17 +186,21 @@ def layernorm_fwd(x, gamma, beta, eps, res=None, want_z=False, want_stats=True):
     return y, z, mean, rstd
 
 
-def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma=None, dbeta=None, accumulate=False):
+def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma=None, dbeta=None, accumulate=False, masked=None):
+    """returns dz, or (dz, dz * dropout_mask / (1 - p)) when masked = (p, seed, offset)"""
     assert dy.dtype == BF16 and z.dtype == BF16 and dy.is_contiguous() and z.is_contiguous()
     M, H = z.shape
     dz = torch.empty_like(z)
+    dzm = torch.empty_like(z) if masked is not None else None
+    mp, mseed, moff = masked if masked is not None else (0.0, 0, 0)
     ws, wsb = None, 0
     if dgamma is not None:
         wsb = _l.get_lib().a4r_layernorm_bwd_workspace_bytes(H)
         ws = workspace(wsb, z.device)
     _l.check(_l.get_lib().a4r_layernorm_bwd(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(dgamma), _p(dbeta),
-                                            int(accumulate), _p(ws), wsb, M, H, _stream()), "a4r_layernorm_bwd")
-    return dz
+                                            int(accumulate), _p(ws), wsb, M, H, _p(dzm), float(mp), int(mseed), int(moff),
+                                            _stream()), "a4r_layernorm_bwd")
+    return (dz, dzm) if masked is not None else dz
 
 
 def embed_ln_fwd(ids, L, word_emb, pos_emb, type_emb, gamma, beta, eps, pos_offset=0, roberta_pad_id=-1, prompt=None,

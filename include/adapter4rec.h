@@ -100,6 +100,11 @@ typedef struct a4r_gemm_args {
   int32_t epilogue;
   int32_t out_f32;
   int32_t block_n; /* 0 = auto; else 64, 128 or 256 */
+  /* LINEAR epilogue only: dropout on v BEFORE the residuals (the `dense -> dropout -> + input` of BertSelfOutput /
+   * BertOutput); element (row, col) uses the counter indexing of a4r_dropout over the logical [M, N] output */
+  float dropout_p;
+  uint64_t dropout_seed;
+  uint64_t dropout_offset;
 } a4r_gemm_args;
 
 A4R_API int a4r_gemm_bf16_tn(const a4r_gemm_args* args, a4r_stream_t stream);
@@ -159,7 +164,9 @@ A4R_API int a4r_attn_mid_bwd(const a4r_attn_args* args, a4r_stream_t stream);
  *      z_out (optional) receives z rounded to bf16 — the tensor the backward reads; mean/rstd f32 [M] optional.
  * bwd: dz from dy, z, mean, rstd, gamma.  If dgamma/dbeta are non-NULL (finetune_layernorm,
  *      Downstream/Text/run.py:496-501) they receive (accumulate=0) or accumulate (=1) the parameter
- *      gradients via a deterministic two-stage reduction through `workspace`.
+ *      gradients via a deterministic two-stage reduction through `workspace`.  If dz_masked is non-NULL it receives
+ *      dz * mask / (1 - p) with the a4r_dropout mask of (dropout_seed, dropout_offset): the gradient flowing through
+ *      the dropout that precedes this LayerNorm's residual add (saves a separate pass over dz).
  * ------------------------------------------------------------------------------------------------ */
 A4R_API int a4r_layernorm_fwd(const void* x, const void* res, int64_t res_rows, const float* gamma, const float* beta,
                       float eps, void* y, void* z_out, float* mean, float* rstd, int64_t M, int64_t H,
@@ -167,7 +174,8 @@ A4R_API int a4r_layernorm_fwd(const void* x, const void* res, int64_t res_rows, 
 A4R_API size_t a4r_layernorm_bwd_workspace_bytes(int64_t H);
 A4R_API int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
                       void* dz, float* dgamma, float* dbeta, int32_t accumulate, void* workspace,
-                      size_t workspace_bytes, int64_t M, int64_t H, a4r_stream_t stream);
+                      size_t workspace_bytes, int64_t M, int64_t H, void* dz_masked, float dropout_p,
+                      uint64_t dropout_seed, uint64_t dropout_offset, a4r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1: token + position + token-type embedding gather fused with LayerNorm (BertEmbeddings /
