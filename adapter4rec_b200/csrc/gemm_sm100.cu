@@ -22,8 +22,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;               // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;           // fixed for 16-bit inputs
-constexpr int NUM_EPI_GROUPS = 2;    // 2 x 4 epilogue warps; group g owns 32-column chunks c with c % 2 == g
-constexpr int NUM_THREADS = 128 + 128 * NUM_EPI_GROUPS;
+// Epilogue warps come in groups of 4 (one warp per TMEM lane quadrant); group g owns the 32-column chunks c with
+// c % groups == g.  Plain epilogues keep up with the MMAs with 2 groups; the GELU / GELU' epilogues of the 256-wide tile
+// are instruction-latency-bound: GELU gets 3 groups (512 threads, 128 registers), GELU' 4 groups (640 threads, 96 registers);
+// measured on B200 (M = 161,280, N = 3072, K = 768): GELU' 0.94 -> 0.84 ms with 4 groups, GELU 0.81 -> see profiles/.
+template <int BN, int EPI>
+struct EpiGroups {
+  static constexpr int value = BN != 256 ? 2 : (EPI == A4R_EPI_DGELU ? 4 : (EPI == A4R_EPI_GELU ? 3 : 2));
+};
 
 template <int BN>
 struct Cfg {
@@ -98,11 +104,12 @@ A4R_DEVICE void store_row64(__nv_bfloat16* p, const float (&v)[32]) {
 // EPI: epilogue mode (compile time).  V32: every epilogue tensor is 32-byte aligned with ld % 16 == 0, so rows are
 // moved with 256-bit accesses; the tail chunk of a ragged N falls back to guarded 128-bit accesses.
 template <int BN, int EPI, bool V32>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(128 + 128 * EpiGroups<BN, EPI>::value, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const GemmParams p) {
   using C = Cfg<BN>;
+  constexpr int NUM_EPI_GROUPS = EpiGroups<BN, EPI>::value;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -218,7 +225,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 4;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int group = ew >> 2;
-    constexpr int CHUNKS = BN / 32 / NUM_EPI_GROUPS > 0 ? BN / 32 / NUM_EPI_GROUPS : 1;
+    constexpr int CHUNKS = (BN / 32 + NUM_EPI_GROUPS - 1) / NUM_EPI_GROUPS;
     constexpr bool kHasIn = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_DGELU) || (EPI == A4R_EPI_DRELU);
     const __nv_bfloat16* in_ptr = nullptr;
     int64_t in_ld = 0;
@@ -483,7 +490,8 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
   }
   const int64_t tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
   const int grid = static_cast<int>(tiles < a4r_num_sms() ? tiles : a4r_num_sms());
-  gemm_tn_kernel<BN, EPI, V32><<<grid, NUM_THREADS, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  gemm_tn_kernel<BN, EPI, V32><<<grid, 128 + 128 * EpiGroups<BN, EPI>::value, C::kSmemBytes, stream>>>(tmA, tmB, tmA2,
+                                                                                                      tmB2, p);
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;
