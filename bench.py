@@ -279,6 +279,41 @@ def bench_eval(dev, world, rank, steps, warmup):
     return out
 
 
+def bench_eval_full(model, args, dev, world, rank, steps):
+    """The COMPLETE evaluator (eval_arrays: K10 item-ID gather -> SASRec user encoder -> K11/K12 score+mask+top-k ->
+    K13 merge + HR/NDCG [+ all-gather]) at the model's real embedding width (D = 64), 1 M synthetic items sharded by id,
+    blocks of 8,192 users with 20-item histories."""
+    import torch
+    import torch.distributed as dist
+    from adapter4rec_b200.data_utils.metrics import ItemTable, eval_arrays, shard_range
+    I, U, blk = 1_000_000, 8192 * max(2, steps), 8192
+    lo, hi = shard_range(I + 1, rank, world)
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    table = ItemTable((torch.randn((hi - lo, D), generator=g, device=dev) * 0.3).to(torch.bfloat16), lo, I + 1, rank, world)
+    gu = torch.Generator().manual_seed(11)
+    tok = torch.randint(1, I + 1, (U, S), generator=gu)
+    mask = torch.ones((U, S))
+    tgt = torch.randint(1, I + 1, (U,), generator=gu).int()
+    hist = tok.int()
+    tok, mask, tgt, hist = [t.pin_memory() for t in (tok, mask, tgt, hist)]
+    eval_arrays(model, tok[:blk], mask[:blk], tgt[:blk], hist[:blk], table, blk)       # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hit, ndcg, _ = eval_arrays(model, tok, mask, tgt, hist, table, blk)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    return {"users_per_s": U / (ms / 1e3), "users": U, "items": I, "d": D, "ms_total": ms, "hr10": float(hit.mean()),
+            "ndcg10": float(ndcg.mean()),
+            "note": "complete evaluator incl. host->device copy of the per-user arrays; random embeddings => chance-level HR"}
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -368,6 +403,8 @@ def main():
     eval_out = None
     if not a.no_eval:
         eval_out = bench_eval(dev, world, rank, max(2, a.steps), 2)
+        model.eval()
+        eval_out["eval_model_d64"] = bench_eval_full(model, args, dev, world, rank, a.steps)
 
     if rank != 0:
         if world > 1:

@@ -70,3 +70,12 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         lib.get_lib()
+
+
+def test_entry_script_flags_equal_the_reference():
+    """adapter4rec_b200.parameters.parse_args([]) == Downstream/Text/parameters.py parse_args() (names and defaults);
+    tests/golden/text_flags.json was dumped from the reference's own parser in the build container."""
+    import json
+    from adapter4rec_b200.parameters import parse_args
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "text_flags.json")))
+    assert vars(parse_args([])) == ref

@@ -1,0 +1,32 @@
+"""-m gpu: the entry-script mirror (adapter4rec_b200.run.train / run_eval) trains a small Houlsby TransRec on synthetic
+arrays through the same flags as Downstream/Text/run.py and the loss goes down."""
+import logging
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_entry_reduces_loss_and_evaluates():
+    from adapter4rec_b200 import run
+    from adapter4rec_b200.model import TextConfigLite
+    from adapter4rec_b200.parameters import parse_args
+    args = parse_args(["--embedding_dim", "64", "--batch_size", "32", "--epoch", "3", "--adapter_type", "houslby",
+                       "--adding_adapter_to", "all", "--bert_model_load", "bert_tiny", "--word_embedding_dim", "128",
+                       "--bert_adapter_down_size", "16", "--adapter_bert_lr", "5e-3", "--adapter_sasrec_lr", "5e-3",
+                       "--max_seq_len", "10", "--num_words_title", "12", "--drop_rate", "0.0"])
+    run.setup_seed(123456)
+    data = run.synthetic_data(item_num=300, users=96, num_words=12, max_seq_len=10, vocab=500)
+    cfg = TextConfigLite(vocab_size=500, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                         intermediate_size=512, max_position_embeddings=32, hidden_dropout_prob=0.0,
+                         attention_probs_dropout_prob=0.0)
+    log = logging.getLogger("run_test")
+    records = []
+    log.addHandler(type("H", (logging.Handler,), {"emit": lambda self, r: records.append(r.getMessage())})())
+    log.setLevel(logging.INFO)
+    model, trainer, hit10 = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16)
+    losses = [float(m.split(":")[-1]) for m in records if "mean batch loss" in m]
+    assert len(losses) == 3 and losses[-1] < losses[0], losses
+    assert 0.0 <= hit10 <= 1.0 and any("valid_results" in m for m in records)
+    assert trainer.step_count == 9                                        # 96 users / 32 per batch x 3 epochs
