@@ -36,8 +36,9 @@ struct AttnParams {
   uint64_t drop_seed, drop_offset;
 };
 
-// dropout mask of the probability tile of (sequence n, head h): element (i, j) uses lane (j & 3) of
-// rng64(seed, offset + ((n*heads + h) * 32 + i) * 8 + j / 4).  m[mt][nt][e] follows the accumulator layout.
+// dropout mask of the probability tile of (sequence n, head h): element (i, j), with nt = j / 8, t = (j % 8) / 2,
+// e = j % 2, uses lane ((nt & 1) * 2 + e) of rng64(seed, offset + ((n*heads + h) * 32 + i) * 8 + (nt >> 1) * 4 + t),
+// i.e. one 64-bit draw serves the 4 probabilities a thread owns in two adjacent n-tiles (no draw is shared or wasted).
 A4R_DEVICE void prob_dropout(float (&s)[2][4][4], const AttnParams& p, int n, int h, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const uint64_t base = p.drop_offset + (static_cast<uint64_t>(n) * p.heads + h) * (32 * 8);
@@ -47,11 +48,15 @@ A4R_DEVICE void prob_dropout(float (&s)[2][4][4], const AttnParams& p, int n, in
     for (int hh = 0; hh < 2; ++hh) {
       const int i = mt * 16 + hh * 8 + g;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int j = nt * 8 + 2 * t;  // j, j+1 share one 4-lane group (j is even, j % 4 in {0, 2})
-        const uint64_t r = rng64(p.drop_seed, base + static_cast<uint64_t>(i) * 8 + (j >> 2));
-        s[mt][nt][hh * 2] = rng_keep(r, j & 3, p.drop_thr16) ? s[mt][nt][hh * 2] * p.drop_scale : 0.0f;
-        s[mt][nt][hh * 2 + 1] = rng_keep(r, (j & 3) + 1, p.drop_thr16) ? s[mt][nt][hh * 2 + 1] * p.drop_scale : 0.0f;
+      for (int np = 0; np < 2; ++np) {
+        const uint64_t r = rng64(p.drop_seed, base + static_cast<uint64_t>(i) * 8 + np * 4 + t);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float& x = s[mt][np * 2 + q][hh * 2 + e];
+            x = rng_keep(r, q * 2 + e, p.drop_thr16) ? x * p.drop_scale : 0.0f;
+          }
       }
     }
 }
@@ -107,18 +112,23 @@ A4R_DEVICE void load_b_kn(uint32_t (&b)[4], uint32_t base, int n0, int k0, int l
   ldsm_x4_t(b, base + Tile<COLS>::off(row, chunk));
 }
 
-// global [L rows x DH] (row stride ld) -> swizzled smem tile; rows >= L are zero-filled
+// global [L rows x DH] (row stride ld) -> swizzled smem tile with 16-byte cp.async (LDGSTS: no register staging, half the
+// instructions of ld + st); rows >= L are zero-filled (src-size 0).  Completion: cp_async_wait_all() + __syncwarp().
 template <int DH>
 A4R_DEVICE void load_tile(uint8_t* tile, const __nv_bfloat16* g, int64_t ld, int L, int lane) {
   constexpr int CH = DH / 8;
+  const uint32_t base = smem_u32(tile);
 #pragma unroll
   for (int i = lane; i < LP * CH; i += 32) {
     const int row = i / CH, ch = i % CH;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < L) v = ld_nc_v4(g + static_cast<int64_t>(row) * ld + ch * 8);
-    *reinterpret_cast<uint4*>(tile + Tile<DH>::off(row, ch)) = v;
+    const bool ok = row < L;
+    const __nv_bfloat16* src = g + (ok ? static_cast<int64_t>(row) * ld + ch * 8 : 0);
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + Tile<DH>::off(row, ch)), "l"(src), "r"(sz)
+                 : "memory");
   }
 }
+A4R_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int DH>
 A4R_DEVICE void store_tile(const uint8_t* tile, __nv_bfloat16* g, int64_t ld, int L, int lane) {
   constexpr int CH = DH / 8;
@@ -181,6 +191,15 @@ A4R_DEVICE void scores_softmax(float (&s)[2][4][4], uint32_t sQ, uint32_t sK, co
     }
   }
   const int g = lane >> 2, t = lane & 3;
+  // additive term of this thread's 8 columns, computed once per (sequence, head): -inf beyond L, mask_neg for a masked key
+  float colneg[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = nt * 8 + 2 * t + e;
+      colneg[nt][e] = j >= p.L ? -INFINITY : (((keymask_bits >> j) & 1u) ? 0.0f : p.mask_neg);
+    }
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -191,11 +210,9 @@ A4R_DEVICE void scores_softmax(float (&s)[2][4][4], uint32_t sQ, uint32_t sK, co
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int j = nt * 8 + 2 * t + e;
-          float v = s[mt][nt][h * 2 + e] * p.scale;
+          float v = fmaf(s[mt][nt][h * 2 + e], p.scale, colneg[nt][e]);
           // ONE additive term whether the key is masked, in the future, or both (encoders.py:25-28)
-          if (!((keymask_bits >> j) & 1u) || (p.causal && j > i)) v += p.mask_neg;
-          if (j >= p.L) v = -INFINITY;
+          if (p.causal && nt * 8 + 2 * t + e > i && colneg[nt][e] == 0.0f) v += p.mask_neg;
           s[mt][nt][h * 2 + e] = v;
           mx = fmaxf(mx, v);
         }
@@ -235,7 +252,7 @@ A4R_DEVICE void acc_to_a(uint32_t (&a)[4], const float (&c0)[4], const float (&c
 }
 
 template <int DH>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) attn_fwd_kernel(const AttnParams p) {
   extern __shared__ __align__(128) uint8_t smem_attn[];
   constexpr int TB = Tile<DH>::kBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,6 +267,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_fwd_kernel(const Attn
     load_tile<DH>(my + TB, q + Hd, p.ld_qkv, p.L, lane);
     load_tile<DH>(my + 2 * TB, q + 2 * Hd, p.ld_qkv, p.L, lane);
     const uint32_t km = build_keymask(p, n, lane);
+    cp_async_wait_all();
     __syncwarp();
     const uint32_t sQ = smem_u32(my), sK = sQ + TB, sV = sK + TB;
     float s[2][4][4];
@@ -308,6 +326,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_bwd_kernel(const Attn
     load_tile<DH>(tV, q + 2 * Hd, p.ld_qkv, p.L, lane);
     load_tile<DH>(tdO, p.dout + static_cast<int64_t>(n) * p.L * p.ld_out + h * DH, p.ld_out, p.L, lane);
     const uint32_t km = build_keymask(p, n, lane);
+    cp_async_wait_all();
     __syncwarp();
     const uint32_t sQ = smem_u32(tQ), sK = smem_u32(tK), sV = smem_u32(tV), sdO = smem_u32(tdO), sP = smem_u32(tP),
                    sdS = smem_u32(tdS);

@@ -53,8 +53,8 @@ def synthetic_data(item_num=2000, users=256, num_words=30, max_seq_len=20, vocab
     item_content = np.zeros((item_num + 1, 2 * num_words), dtype=np.int64)
     for i in range(1, item_num + 1):
         n = rng.randint(8, num_words + 1)
-        item_content[i, :n] = rng.randint(1000, vocab, n)
-        item_content[i, 0], item_content[i, n - 1] = 101, 102
+        item_content[i, :n] = rng.randint(min(1000, vocab // 2), vocab, n)
+        item_content[i, 0], item_content[i, n - 1] = min(101, vocab - 2), min(102, vocab - 1)
         item_content[i, num_words:num_words + n] = 1
     seqs = {u: (rng.permutation(item_num)[:rng.randint(5, max_seq_len + 4)] + 1).tolist() for u in range(users)}
     d = types.SimpleNamespace(item_content=item_content, item_num=item_num)

@@ -72,12 +72,14 @@ def test_attention_probability_dropout(N, L, heads, dh, causal):
     qkv = torch.randn((N * L, 3 * H), generator=g, device="cuda").to(BF16)
     dctx = torch.randn((N * L, H), generator=g, device="cuda").to(BF16)
     p, seed, off = 0.1, 4242, 1000
-    # mask[n, h, i, j]: lane (j & 3) of rng64(seed, off + ((n*heads + h)*32 + i)*8 + j/4)
+    # mask[n, h, i, j] with nt = j/8, t = (j%8)/2, e = j%2:
+    #   lane ((nt&1)*2 + e) of rng64(seed, off + ((n*heads + h)*32 + i)*8 + (nt>>1)*4 + t)      (attention_small.cu)
     n_i, h_i, i_i, j_i = np.meshgrid(np.arange(N), np.arange(heads), np.arange(L), np.arange(L), indexing="ij")
-    ctr = (off + ((n_i * heads + h_i) * 32 + i_i) * 8 + j_i // 4).astype(np.uint64)
+    nt, tt, ee = j_i // 8, (j_i % 8) // 2, j_i % 2
+    ctr = (off + ((n_i * heads + h_i) * 32 + i_i) * 8 + (nt >> 1) * 4 + tt).astype(np.uint64)
     with np.errstate(over="ignore"):
         bits = rng64(seed, ctr)
-    lane = (bits >> (16 * (j_i & 3)).astype(np.uint64)) & np.uint64(0xFFFF)
+    lane = (bits >> (16 * ((nt & 1) * 2 + ee)).astype(np.uint64)) & np.uint64(0xFFFF)
     thr = int(p * 65536.0 + 0.5)
     mask = torch.from_numpy((lane >= thr).astype(np.float32)).cuda()
     scale = 65536.0 / (65536 - thr)
