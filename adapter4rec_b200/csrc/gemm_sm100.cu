@@ -31,12 +31,15 @@ struct EpiGroups {
   static constexpr int value = BN != 256 ? 2 : (EPI == A4R_EPI_DGELU ? 4 : (EPI == A4R_EPI_GELU ? 3 : 2));
 };
 
-template <int BN>
+// CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 the two SMs of a TPC own one 256 x BN tile, each CTA staging its own
+// 128 rows of A and HALF of the B rows (the pair's MMA reads both halves), which cuts shared-memory and L2->SM operand
+// traffic per CTA by a third — the energy that bounds this kernel under the 1 kW cap.
+template <int BN, int CG = 1>
 struct Cfg {
   static constexpr int kStageBytesA = BM * BK * 2;
-  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytesB = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = CG == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: power of two >= 32
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -103,12 +106,12 @@ A4R_DEVICE void store_row64(__nv_bfloat16* p, const float (&v)[32]) {
 
 // EPI: epilogue mode (compile time).  V32: every epilogue tensor is 32-byte aligned with ld % 16 == 0, so rows are
 // moved with 256-bit accesses; the tail chunk of a ragged N falls back to guarded 128-bit accesses.
-template <int BN, int EPI, bool V32>
+template <int BN, int EPI, bool V32, int CG>
 __global__ void __launch_bounds__(128 + 128 * EpiGroups<BN, EPI>::value, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   constexpr int NUM_EPI_GROUPS = EpiGroups<BN, EPI>::value;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,8 +123,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = p.tiles_m * p.tiles_n;   // tiles of (128*CG) x BN
   const int nk = p.nk1 + p.nk2;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int first_tile = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -133,21 +140,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);   // CG = 2: only the leader's copy is used (its expect_tx covers both CTAs' bytes)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4 * NUM_EPI_GROUPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[s], 4 * NUM_EPI_GROUPS * CG);  // one arrive per epilogue warp of every CTA of the pair
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc2(tmem_slot, C::kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs are initialised past this point
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -156,20 +168,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * BM;
-        const int n0 = (tile % p.tiles_n) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / p.tiles_n) * (BM * CG) + static_cast<int>(cta_rank) * BM;
+        const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(cta_rank) * (BN / CG) * (CG - 1);
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kStageBytesA;
-          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          if (kb < p.nk1) {
-            tma_load_2d(&tmA, sa, &full_bar[stage], kb * BK, m0);
-            tma_load_2d(&tmB, sb, &full_bar[stage], kb * BK, n0);
+          const CUtensorMap* ma = kb < p.nk1 ? &tmA : &tmA2;
+          const CUtensorMap* mb = kb < p.nk1 ? &tmB : &tmB2;
+          const int kc = (kb < p.nk1 ? kb : kb - p.nk1) * BK;
+          if constexpr (CG == 2) {
+            // both CTAs' bytes are credited to the LEADER's full barrier
+            if (leader) mbar_expect_tx(&full_bar[stage], C::kStageBytes * 2);
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2cta(ma, sa, bar, kc, m0);
+            tma_load_2d_2cta(mb, sb, bar, kc, n0);
           } else {
-            tma_load_2d(&tmA2, sa, &full_bar[stage], (kb - p.nk1) * BK, m0);
-            tma_load_2d(&tmB2, sb, &full_bar[stage], (kb - p.nk1) * BK, n0);
+            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            tma_load_2d(ma, sa, &full_bar[stage], kc, m0);
+            tma_load_2d(mb, sb, &full_bar[stage], kc, n0);
           }
           if (++stage == C::kStages) {
             stage = 0;
@@ -179,14 +197,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    // ============================== MMA issuer (leader CTA only when CG = 2) ==============================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
@@ -199,16 +217,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance the start address by k*16 elements (32 B) inside the 128 B swizzle row
-            umma_bf16_ss(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2)
+              umma_bf16_ss_2cta(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of the pair) when these MMAs retire
+          if constexpr (CG == 2) umma_commit_2cta(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if constexpr (CG == 2) umma_commit_2cta(&tmem_full_bar[as], 3); else umma_commit(&tmem_full_bar[as]);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -240,8 +264,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aphase = 0;
     const bool out_f32 = p.out_f32 != 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * BM;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m0 = (tile / p.tiles_n) * (BM * CG) + static_cast<int>(cta_rank) * BM;
       const int n0 = (tile % p.tiles_n) * BN;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
@@ -394,7 +418,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // all of this warp's TMEM reads for this stage are complete (wait::ld in body): release it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // the leader's barrier
+        else mbar_arrive(&tmem_empty_bar[as]);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -403,9 +430,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_dealloc2(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -444,16 +473,16 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
   return A4R_OK;
 }
 
-template <int BN, int EPI, bool V32>
+template <int BN, int EPI, bool V32, int CG>
 int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
   if ((rc = make_tmap(&tmA, a->A, a->M, a->K, a->lda, BM)) != A4R_OK) return rc;
-  if ((rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, BN)) != A4R_OK) return rc;
+  if ((rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, BN / CG)) != A4R_OK) return rc;
   if (a->K2 > 0) {
     if ((rc = make_tmap(&tmA2, a->A2, a->M, a->K2, a->lda2, BM)) != A4R_OK) return rc;
-    if ((rc = make_tmap(&tmB2, a->B2, a->N, a->K2, a->ldb2, BN)) != A4R_OK) return rc;
+    if ((rc = make_tmap(&tmB2, a->B2, a->N, a->K2, a->ldb2, BN / CG)) != A4R_OK) return rc;
   } else {
     tmA2 = tmA;
     tmB2 = tmB;
@@ -472,7 +501,7 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
   p.N = static_cast<int>(a->N);
   p.nk1 = static_cast<int>((a->K + BK - 1) / BK);
   p.nk2 = static_cast<int>((a->K2 + BK - 1) / BK);
-  p.tiles_m = static_cast<int>((a->M + BM - 1) / BM);
+  p.tiles_m = static_cast<int>((a->M + BM * CG - 1) / (BM * CG));
   p.tiles_n = static_cast<int>((a->N + BN - 1) / BN);
   p.alpha = a->alpha;
   p.epilogue = a->epilogue;
@@ -484,14 +513,31 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    A4R_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI, V32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    A4R_CUDA_OK(cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI, V32, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kSmemBytes));
     attr_set = true;
   }
   const int64_t tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
-  const int grid = static_cast<int>(tiles < a4r_num_sms() ? tiles : a4r_num_sms());
-  gemm_tn_kernel<BN, EPI, V32><<<grid, 128 + 128 * EpiGroups<BN, EPI>::value, C::kSmemBytes, stream>>>(tmA, tmB, tmA2,
-                                                                                                      tmB2, p);
+  const int units = a4r_num_sms() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+  const int grid = static_cast<int>(tiles < units ? tiles : units) * CG;
+  const int threads = 128 + 128 * EpiGroups<BN, EPI>::value;
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    A4R_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, EPI, V32, CG>, tmA, tmB, tmA2, tmB2, p));
+  } else {
+    gemm_tn_kernel<BN, EPI, V32, CG><<<grid, threads, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  }
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;
@@ -534,15 +580,21 @@ extern "C" int a4r_gemm_bf16_tn(const a4r_gemm_args* a, a4r_stream_t stream_) {
   if (a->M == 0) return A4R_OK;
 
   int bn = a->block_n;
-  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  // auto: wide outputs run the 256 x 256 CTA-pair tile (cta_group::2: measured +5..15 % over the single-CTA 128 x 256 tile
+  // and above cuBLAS on the K >= 2304 shapes), narrow ones a single-CTA 128 x {128, 64} tile
+  if (bn == 0) bn = a->N > 128 ? (a->M > 128 ? 512 : 256) : (a->N > 64 ? 128 : 64);
+  // block_n = 512 selects the 256-wide tile on a CTA pair (cta_group::2, 256 x 256 per pair)
+  const bool pair = bn == 512;
+  if (pair) bn = 256;
   if (bn != 64 && bn != 128 && bn != 256)
-    return a4r_set_error(A4R_EINVAL, "gemm: block_n must be 0, 64, 128 or 256 (got %d)", bn);
+    return a4r_set_error(A4R_EINVAL, "gemm: block_n must be 0, 64, 128, 256 or 512 (got %d)", a->block_n);
   // 256-bit epilogue accesses need 32-byte aligned rows of every bf16 epilogue tensor
   auto ok32 = [](const void* ptr, int64_t ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31u) == 0 && ld % 16 == 0); };
   const bool v32 = !a->out_f32 && ok32(a->C, a->ldc) && ok32(a->aux, a->ldaux) && ok32(a->residual, a->ldr);
-#define A4R_DISPATCH_BN(EPI, V)                                   \
-  (bn == 256 ? launch_gemm<256, EPI, V>(a, stream)                \
-             : (bn == 128 ? launch_gemm<128, EPI, V>(a, stream) : launch_gemm<64, EPI, V>(a, stream)))
+#define A4R_DISPATCH_BN(EPI, V)                                                                       \
+  (pair ? launch_gemm<256, EPI, V, 2>(a, stream)                                                       \
+        : (bn == 256 ? launch_gemm<256, EPI, V, 1>(a, stream)                                          \
+                     : (bn == 128 ? launch_gemm<128, EPI, V, 1>(a, stream) : launch_gemm<64, EPI, V, 1>(a, stream))))
 #define A4R_DISPATCH(EPI) (v32 ? A4R_DISPATCH_BN(EPI, true) : A4R_DISPATCH_BN(EPI, false))
   switch (a->epilogue) {
     case A4R_EPI_LINEAR: return A4R_DISPATCH(A4R_EPI_LINEAR);

@@ -99,7 +99,7 @@ typedef struct a4r_gemm_args {
   float alpha;
   int32_t epilogue;
   int32_t out_f32;
-  int32_t block_n; /* 0 = auto; else 64, 128 or 256 */
+  int32_t block_n; /* 0 = auto; else 64, 128, 256 (one CTA per tile) or 512 (256 x 256 tile on a CTA pair, cta_group::2) */
   /* LINEAR epilogue only: dropout on v BEFORE the residuals (the `dense -> dropout -> + input` of BertSelfOutput /
    * BertOutput); element (row, col) uses the counter indexing of a4r_dropout over the logical [M, N] output */
   float dropout_p;

@@ -36,6 +36,9 @@ GEMM_SHAPES = [
     (256, 768, 768, 0), (1000, 2304, 768, 0), (300, 3072, 768, 0), (515, 768, 3072, 0),
     (77, 64, 768, 0), (4096, 768, 768, 128), (2048, 256, 64, 64), (130, 72, 40, 0),
     (10240, 64, 256, 0), (148 * 128 * 2 + 5, 768, 768, 0),
+    # block_n = 512: the 256-wide tile on a CTA pair (tcgen05 cta_group::2, 256 x 256 per cluster)
+    (256, 256, 64, 512), (512, 768, 768, 512), (1000, 2304, 768, 512), (300, 3072, 768, 512), (515, 768, 3072, 512),
+    (77, 256, 128, 512), (148 * 256 + 133, 768, 768, 512),
 ]
 
 
@@ -51,25 +54,26 @@ def test_gemm_linear(M, N, K, bn):
     _close(got32, ref, 1e-4, 1e-3, "gemm f32 out")
 
 
-def test_gemm_epilogues():
+@pytest.mark.parametrize("bn", [0, 512])
+def test_gemm_epilogues(bn):
     ops = _ops()
     M, N, K = 700, 768, 256
     a, b = _rand((M, K), 1.0, 1), _rand((N, K), K ** -0.5, 2)
     bias = _rand((N,), 0.5, 3, torch.float32)
     r1, r2 = _rand((M, N), 1.0, 4), _rand((M, N), 1.0, 5)
     v = a.float() @ b.float().t() + bias
-    _close(ops.gemm(a, b, bias=bias, residual=r1, residual2=r2), v + r1.float() + r2.float(), 2 ** -7, 2e-2, "linear+res")
+    _close(ops.gemm(a, b, bias=bias, residual=r1, residual2=r2, block_n=bn), v + r1.float() + r2.float(), 2 ** -7, 2e-2, "linear+res")
     aux = torch.empty((M, N), dtype=BF16, device="cuda")
-    got = ops.gemm(a, b, bias=bias, epilogue=ops.EPI_GELU, aux=aux)
+    got = ops.gemm(a, b, bias=bias, epilogue=ops.EPI_GELU, aux=aux, block_n=bn)
     _close(aux, v, 2 ** -7, 1e-2, "gelu aux (pre-activation)")
     _close(got, torch.nn.functional.gelu(v), 2 ** -7, 1e-2, "gelu")
-    _close(ops.gemm(a, b, bias=bias, epilogue=ops.EPI_RELU), torch.relu(v), 2 ** -7, 1e-2, "relu")
+    _close(ops.gemm(a, b, bias=bias, epilogue=ops.EPI_RELU, block_n=bn), torch.relu(v), 2 ** -7, 1e-2, "relu")
     u = _rand((M, N), 1.5, 6)
     uf = u.float().requires_grad_(True)
     torch.nn.functional.gelu(uf).sum().backward()
-    _close(ops.gemm(a, b, epilogue=ops.EPI_DGELU, aux=u), (v - bias) * uf.grad, 2 ** -6, 2e-2, "dgelu")
-    _close(ops.gemm(a, b, epilogue=ops.EPI_DRELU, aux=u), (v - bias) * (u.float() > 0), 2 ** -7, 1e-2, "drelu")
-    _close(ops.gemm(a, b, alpha=0.125), (v - bias) * 0.125, 2 ** -7, 1e-2, "alpha")
+    _close(ops.gemm(a, b, epilogue=ops.EPI_DGELU, aux=u, block_n=bn), (v - bias) * uf.grad, 2 ** -6, 2e-2, "dgelu")
+    _close(ops.gemm(a, b, epilogue=ops.EPI_DRELU, aux=u, block_n=bn), (v - bias) * (u.float() > 0), 2 ** -7, 1e-2, "drelu")
+    _close(ops.gemm(a, b, alpha=0.125, block_n=bn), (v - bias) * 0.125, 2 ** -7, 1e-2, "alpha")
 
 
 def test_gemm_k_extension_and_strided_a():

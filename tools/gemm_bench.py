@@ -5,6 +5,7 @@ import torch
 from adapter4rec_b200 import ops
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 161280
+BN = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 dev = "cuda"
 def r(*s): return (torch.randn(*s, device=dev) * 0.05).to(torch.bfloat16)
 shapes = [
@@ -25,7 +26,7 @@ shapes = [
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 for name, N, K, o in shapes:
     a, b = r(M, K), r(N, K)
-    kw = {}
+    kw = {"block_n": BN if N >= 256 else 0}
     if o.get("ext"): kw.update(a2=r(M, o["ext"]), b2=r(N, o["ext"]))
     if o.get("bias"): kw["bias"] = torch.randn(N, device=dev)
     if o.get("res"): kw["residual"] = r(M, N)
