@@ -36,14 +36,19 @@ struct MidParams {
   float scale, mask_neg;
 };
 
+// global [L rows x 64] -> swizzled smem tile with 16-byte cp.async (no register staging: all four tiles of a backward
+// item are in flight at once); rows >= L are zero-filled.  Completion: cp_async_wait_all() + __syncthreads().
 A4R_DEVICE void load_rows(uint8_t* tile, const __nv_bfloat16* g, int64_t ld, int L, int Lp) {
+  const uint32_t base = smem_u32(tile);
   for (int i = threadIdx.x; i < Lp * 8; i += WARPS * 32) {
     const int row = i >> 3, ch = i & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < L) v = ld_nc_v4(g + static_cast<int64_t>(row) * ld + ch * 8);
-    *reinterpret_cast<uint4*>(tile + toff(row, ch)) = v;
+    const bool ok = row < L;
+    const __nv_bfloat16* src = g + (ok ? static_cast<int64_t>(row) * ld + ch * 8 : 0);
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + toff(row, ch)), "l"(src), "r"(sz) : "memory");
   }
 }
+A4R_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // A fragment (16 x 16) of a row-major [row][k] tile
 A4R_DEVICE void lda(uint32_t (&a)[4], uint32_t base, int m0, int k0, int lane) {
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_fwd_kernel(const MidParam
       for (int j = 0; j < 32; ++j) bits |= (key_ok(p, n, threadIdx.x * 32 + j) ? 1u : 0u) << j;
       kvalid[threadIdx.x] = bits;
     }
+    cp_async_wait_all();
     __syncthreads();
     for (int m0 = warp * 16; m0 < p.Lp && m0 < ((p.L + 15) & ~15); m0 += WARPS * 16) {
       uint32_t qa[4][4];
@@ -230,24 +236,30 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_bwd_kernel(const MidParam
       for (int j = 0; j < 32; ++j) bits |= (key_ok(p, n, threadIdx.x * 32 + j) ? 1u : 0u) << j;
       kvalid[threadIdx.x] = bits;
     }
+    cp_async_wait_all();
     __syncthreads();
     // ---------------- prologue: lse (saved by the forward) and delta_i = <dO_i, O_i> into shared memory ----------------
-    for (int r = warp; r < p.Lp; r += WARPS) {
-      float d = 0.0f, l = 0.0f;
+    // 8 lanes per row, one 16-byte chunk each: every load of the prologue is independent and issued up front
+    for (int r = threadIdx.x; r < p.Lp; r += WARPS * 32)
+      s_lse[r] = r < p.L ? p.lse[(static_cast<int64_t>(n) * p.L + r) * p.heads + h] : 0.0f;
+    for (int i = threadIdx.x; i < p.Lp * 8; i += WARPS * 32) {   // Lp * 8 is a multiple of 32: whole warps stay together
+      const int r = i >> 3, ch = i & 7;
+      float d = 0.0f;
       if (r < p.L) {
         const int64_t grow = static_cast<int64_t>(n) * p.L + r;
-        const uint32_t o2 = *reinterpret_cast<const uint32_t*>(p.ctx + grow * p.ld_out + h * DH + 2 * lane);
-        const uint32_t d2 = *reinterpret_cast<const uint32_t*>(p.dout + grow * p.ld_out + h * DH + 2 * lane);
-        const float2 of = unpack_bf16x2(o2), df = unpack_bf16x2(d2);
-        d = warp_sum(of.x * df.x + of.y * df.y);
-        l = p.lse[grow * p.heads + h];
-      } else {
-        d = warp_sum(0.0f);
+        const uint4 ov = ld_nc_v4(p.ctx + grow * p.ld_out + h * DH + ch * 8);
+        const uint4 dv4 = *reinterpret_cast<const uint4*>(tdO + toff(r, ch));
+        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = unpack_bf16x2(ow[e]), b = unpack_bf16x2(dw[e]);
+          d += a.x * b.x + a.y * b.y;
+        }
       }
-      if (lane == 0) {
-        s_delta[r] = d;
-        s_lse[r] = l;
-      }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      if (ch == 0) s_delta[r] = d;
     }
     __syncthreads();
     // ---------------- phase A: per query tile -> dQ ----------------

@@ -49,14 +49,24 @@ def gemm_profile_start():
     _gemm_profile = []
 
 
-def gemm_profile_stop():
-    """returns (total algorithmic FLOPs, total device milliseconds, launches) since gemm_profile_start()."""
+def gemm_profile_stop(by_shape=False):
+    """returns (total algorithmic FLOPs, total device milliseconds, launches) since gemm_profile_start(); with by_shape
+    also a dict {(M, N, K+K2, epilogue): [flops, ms, launches]}."""
     global _gemm_profile
     prof, _gemm_profile = _gemm_profile, None
     torch.cuda.synchronize()
-    flops = sum(f for f, _, _ in prof)
-    ms = sum(e0.elapsed_time(e1) for _, e0, e1 in prof)
-    return flops, ms, len(prof)
+    flops = sum(p[0] for p in prof)
+    times = [p[1].elapsed_time(p[2]) for p in prof]
+    ms = sum(times)
+    if not by_shape:
+        return flops, ms, len(prof)
+    groups = {}
+    for p, t in zip(prof, times):
+        g = groups.setdefault(p[3], [0.0, 0.0, 0])
+        g[0] += p[0]
+        g[1] += t
+        g[2] += 1
+    return flops, ms, len(prof), groups
 
 
 def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, aux=None, a2=None, b2=None,
@@ -98,7 +108,8 @@ def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, au
         e0.record()
         _l.check(_l.get_lib().a4r_gemm_bf16_tn(ctypes.byref(g), _stream()), "a4r_gemm_bf16_tn")
         e1.record()
-        _gemm_profile.append((2.0 * M * N * (K + (a2.shape[1] if a2 is not None else 0)), e0, e1))
+        k2 = a2.shape[1] if a2 is not None else 0
+        _gemm_profile.append((2.0 * M * N * (K + k2), e0, e1, (M, N, K + k2, int(epilogue))))
         return out
     _l.check(_l.get_lib().a4r_gemm_bf16_tn(ctypes.byref(g), _stream()), "a4r_gemm_bf16_tn")
     return out

@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--users", type=int, default=512, help="users per GPU per step (C2: 512)")
     ap.add_argument("--users-per-pass", type=int, default=128, help="activation-memory pass size (exact accumulation)")
-    ap.add_argument("--cpu-users", type=int, default=4, help="users in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-users", type=int, default=0,
+                    help="users in the bounded CPU sample (default: 48 for cpu_baseline ~15 s, 16 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     return ap.parse_args()
@@ -198,6 +199,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    a.cpu_users = a.cpu_users or 16
     step = oracle_step_factory(reference_sd(), a.cpu_users)
     for _ in range(min(a.warmup, 1)):
         step()
@@ -212,8 +214,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: SASRec+BERT-base LoRA r=8 train step, S=20, 30 tokens (bounded CPU sample)",
-                   "users_per_step": a.cpu_users},
+        "config": {"workload": "C2: SASRec(D=64,2 blocks)+BERT-base, LoRA r=8 on q/v, S=20, 30 tokens, bf16",
+                   "users_per_gpu_per_step": 512, "sample": "bounded CPU sample of the same workload: %d users per step, fp32"
+                   % a.cpu_users},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -370,7 +373,7 @@ def main():
     ev1.record()
     barrier()
     launches = lib.launch_count() - launches0
-    gemm_flops, gemm_ms, gemm_calls = ops.gemm_profile_stop()
+    gemm_flops, gemm_ms, gemm_calls, gemm_groups = ops.gemm_profile_stop(by_shape=True)
     clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev)
@@ -414,8 +417,20 @@ def main():
     pk, pk_kind = peaks()
     tokens = a.users * 42 * L
     algo_flops_step = 2 * FLOP_FWD_PER_TOKEN * tokens            # forward + data-gradient backward (frozen backbone)
-    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    achieved_all = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    # the dominant kernel = the GEMM shape with the largest share of the timed region
+    dom_shape, dom = max(gemm_groups.items(), key=lambda kv: kv[1][1])
+    achieved = dom[0] / (dom[1] / 1e3) / 1e12
+    epi_names = {0: "linear", 1: "gelu(+pre-activation out)", 2: "relu", 3: "gelu' (dgrad)", 4: "relu' (dgrad)"}
+    # DRAM traffic per launch of that shape from the committed `ncu --set full` capture (profiles/), if it has one
+    traffic = None
+    try:
+        for rec in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_gemm_traffic.json"))):
+            if tuple(rec["shape"]) == tuple(dom_shape):
+                traffic = rec["dram_bytes_per_launch"]
+    except Exception:
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -434,9 +449,14 @@ def main():
         "e2e": {"value": a.users * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
-                     "kernel": "gemm_tn_kernel (tcgen05+TMA, all %d launches in the timed region; share of step %.1f%%)"
-                               % (gemm_calls, 100.0 * gemm_ms / ms), "peak_source": pk_kind + " bf16_tflops_sustained"},
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "kernel": "gemm_tn_kernel (tcgen05 cta_group::2 + TMA), shape M=%d N=%d K=%d epilogue=%s: %d launches, "
+                               "%.1f%% of the timed region; algorithmic FLOPs per launch = 2*M*N*K = %.4g"
+                               % (dom_shape[0], dom_shape[1], dom_shape[2], epi_names.get(dom_shape[3], "?"), dom[2],
+                                  100.0 * dom[1] / ms, dom[0] / dom[2]),
+                     "peak_source": pk_kind + " bf16_tflops_sustained (kernel timed inside a long step)",
+                     "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / peak if peak else None,
+                                           "launches": gemm_calls, "share_of_step": gemm_ms / ms}},
     }
     if eval_out is not None:
         pk_b = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
@@ -444,6 +464,7 @@ def main():
         out["eval"] = eval_out
     if not a.no_cpu_baseline:
         import torch as _t
+        a.cpu_users = a.cpu_users or 48
         step = oracle_step_factory({k: v for k, v in model.state_dict().items()}, a.cpu_users)
         t0 = time.time()
         step()
