@@ -434,3 +434,26 @@ class BceLossFunction(torch.autograd.Function):
 
 def bce_loss(prec, emb, log_mask, cpc=False):
     return BceLossFunction.apply(prec, emb, log_mask, cpc)
+
+
+class InbatchCeFunction(torch.autograd.Function):
+    """K9-S: in-batch softmax + duplicate-item mask + CE (a4r_inbatch_ce_*); nothing but the row log-sum-exps is saved."""
+
+    @staticmethod
+    def forward(ctx, prec, emb, item_ids, log_mask, cand_bias):
+        loss, count, lse = ops.inbatch_ce_fwd(prec, emb, item_ids, log_mask, cand_bias)
+        ctx.aux = (item_ids, log_mask, cand_bias)
+        ctx.save_for_backward(prec, emb, lse, count)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        prec, emb, lse, count = ctx.saved_tensors
+        item_ids, log_mask, cand_bias = ctx.aux
+        go = grad_out.reshape(1).float().contiguous()
+        d_prec, d_emb = ops.inbatch_ce_bwd(prec, emb, item_ids, log_mask, lse, count, cand_bias=cand_bias, grad_out=go)
+        return d_prec, d_emb, None, None, None
+
+
+def inbatch_softmax_loss(prec, emb, item_ids, log_mask, cand_bias=None):
+    return InbatchCeFunction.apply(prec, emb, item_ids, log_mask, cand_bias)

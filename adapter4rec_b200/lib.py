@@ -53,6 +53,14 @@ class BceArgs(Structure):
     ]
 
 
+class InbatchCeArgs(Structure):
+    _fields_ = [
+        ("prec", c_void_p), ("cand", c_void_p), ("ld_cand", c_int64), ("item_ids", c_void_p), ("log_mask", c_void_p),
+        ("cand_bias", c_void_p), ("lse", c_void_p), ("loss", c_void_p), ("count", c_void_p),
+        ("B", c_int64), ("S", c_int64), ("D", c_int64), ("masked_logit", c_float),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/adapter4rec.h declares must appear here
 # (tests/test_abi.py checks header <-> table <-> .so agreement).
 PROTOTYPES = {
@@ -82,6 +90,9 @@ PROTOTYPES = {
     "a4r_bce_workspace_bytes": (c_size_t, []),
     "a4r_bce_loss_fwd": (c_int32, [POINTER(BceArgs), c_void_p, c_size_t, c_void_p]),
     "a4r_bce_loss_bwd": (c_int32, [POINTER(BceArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "a4r_inbatch_ce_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "a4r_inbatch_ce_fwd": (c_int32, [POINTER(InbatchCeArgs), c_void_p, c_size_t, c_void_p]),
+    "a4r_inbatch_ce_bwd": (c_int32, [POINTER(InbatchCeArgs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "a4r_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_int64, c_float, c_void_p]),
     "a4r_patchify": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),

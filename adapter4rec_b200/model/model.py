@@ -53,8 +53,13 @@ class _ModelBase(nn.Module):
         self.criterion = nn.BCEWithLogitsLoss()   # structural parity only; the fused kernel computes the loss
         self._checked = None
 
-    def forward(self, sample_items, log_mask, local_rank=None):
-        """sample_items int64 [B*(S+1)*2, 2L] (ids | mask rows), log_mask f32 [B,S] -> scalar loss."""
+    def forward(self, sample_items, log_mask, local_rank=None, sample_items_id=None, cand_bias=None):
+        """sample_items int64 [B*(S+1)*2, 2L] (ids | mask rows), log_mask f32 [B,S] -> scalar loss.
+
+        Extension beyond the reference signature (model.py:48): with `args.loss_type == "inbatch_softmax"` (an attribute,
+        not a command-line flag — the flag set stays the reference's) the BCE head is replaced by the in-batch softmax
+        head with duplicate-item masking (K9-S); it needs `sample_items_id` int64 [B, S+1] (the item id of every history
+        slot, 0 = padding) and optionally `cand_bias` f32 [B*(S+1)] (log-popularity debias)."""
         if self.training:
             sig = tuple(p.requires_grad for p in self.parameters())
             if sig != self._checked:
@@ -66,6 +71,11 @@ class _ModelBase(nn.Module):
         input_logs_embs = input_embs[:, :-1, 0, :].contiguous()                # history items 0..S-1 as user-encoder input
         log_mask = log_mask.to(device=input_embs_all.device, dtype=torch.float32).contiguous()
         prec_vec = self.user_encoder(input_logs_embs, log_mask, local_rank)
+        if getattr(self.args, "loss_type", "bce") == "inbatch_softmax":
+            if self.cpc or sample_items_id is None:
+                raise ValueError("loss_type='inbatch_softmax' needs sample_items_id [B, S+1] and is not defined for ModelCPC")
+            ids = sample_items_id.to(device=input_embs_all.device, dtype=torch.int64).view(-1, self.max_seq_len).contiguous()
+            return Fn.inbatch_softmax_loss(prec_vec.contiguous(), input_embs.contiguous(), ids, log_mask, cand_bias)
         return Fn.bce_loss(prec_vec.contiguous(), input_embs.contiguous(), None if self.cpc else log_mask, cpc=self.cpc)
 
 

@@ -314,6 +314,52 @@ def bce_loss_bwd(prec, emb, log_mask, pos, neg, count, grad_out=None, cpc=False)
     return d_prec, d_emb
 
 
+MASKED_LOGIT = -1e4  # the constant the in-batch softmax head writes over excluded candidates
+
+
+def _inbatch_args(prec, emb, item_ids, log_mask, cand_bias, lse, loss, count):
+    B, S, D = prec.shape
+    assert prec.dtype == BF16 and emb.dtype == BF16 and prec.is_contiguous() and emb.is_contiguous()
+    assert emb.numel() == B * (S + 1) * 2 * D, "emb must be Model.forward's encoder output [B, S+1, 2, D]"
+    assert item_ids.dtype == torch.int64 and item_ids.is_contiguous() and tuple(item_ids.shape) == (B, S + 1)
+    assert log_mask.dtype == torch.float32 and log_mask.is_contiguous() and tuple(log_mask.shape) == (B, S)
+    if cand_bias is not None:
+        assert cand_bias.dtype == torch.float32 and cand_bias.is_contiguous() and cand_bias.numel() == B * (S + 1)
+    a = _l.InbatchCeArgs()
+    a.prec, a.cand, a.ld_cand = _p(prec), _p(emb), 2 * D     # candidate c = history slot (b, j) = emb[b, j, 0, :]
+    a.item_ids, a.log_mask, a.cand_bias = _p(item_ids), _p(log_mask), _p(cand_bias)
+    a.lse, a.loss, a.count = _p(lse), _p(loss), _p(count)
+    a.B, a.S, a.D, a.masked_logit = B, S, D, MASKED_LOGIT
+    return a
+
+
+def inbatch_ce_fwd(prec, emb, item_ids, log_mask, cand_bias=None):
+    """returns (loss [1] f32, count [1] f32, lse [B*S] f32) — see a4r_inbatch_ce_fwd in include/adapter4rec.h."""
+    B, S, _ = prec.shape
+    dev = prec.device
+    lse = torch.empty(B * S, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.float32, device=dev)
+    a = _inbatch_args(prec, emb, item_ids, log_mask, cand_bias, lse, loss, count)
+    wsb = _l.get_lib().a4r_inbatch_ce_workspace_bytes(B, S)
+    ws = workspace(wsb, dev)
+    _l.check(_l.get_lib().a4r_inbatch_ce_fwd(ctypes.byref(a), _p(ws), wsb, _stream()), "a4r_inbatch_ce_fwd")
+    return loss, count, lse
+
+
+def inbatch_ce_bwd(prec, emb, item_ids, log_mask, lse, count, cand_bias=None, grad_out=None):
+    """returns (d_prec [B,S,D], d_emb [B,S+1,2,D]); the sampled-negative half of d_emb is zero (this head ignores it)."""
+    d_prec = torch.empty_like(prec)
+    d_emb = torch.zeros_like(emb)
+    loss = torch.empty(1, dtype=torch.float32, device=prec.device)
+    a = _inbatch_args(prec, emb, item_ids, log_mask, cand_bias, lse, loss, count)
+    if grad_out is not None:
+        assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
+    _l.check(_l.get_lib().a4r_inbatch_ce_bwd(ctypes.byref(a), _p(grad_out), _p(d_prec), _p(d_emb), 2 * prec.shape[2],
+                                             _stream()), "a4r_inbatch_ce_bwd")
+    return d_prec, d_emb
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     for t in (p, g, m, v):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()

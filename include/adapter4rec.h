@@ -276,6 +276,41 @@ A4R_API int a4r_bce_loss_fwd(const a4r_bce_args* args, void* workspace, size_t w
 A4R_API int a4r_bce_loss_bwd(const a4r_bce_args* args, const float* grad_out, void* d_prec, void* d_emb,
                      a4r_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K9-S: in-batch softmax loss with duplicate-item masking, forward / backward (north-star head).
+ * The reference itself trains with BCE (a4r_bce_loss_*; Downstream/Text/model/model.py:62-68) and has no softmax head,
+ * so this entry point has no reference symbol to replace: its semantics are the in-batch debiased cross-entropy of the
+ * same group's IDvs.MoRec trainer, restated by oracle/transrec_oracle.py:inbatch_softmax_loss ("parity unpinned").
+ *
+ * prec [B,S,D] bf16 (user-encoder output); candidates = the B*(S+1) history items of the batch, candidate
+ * c = b*(S+1)+j read at cand + c*ld_cand (ld_cand = 2*D reads emb[:, :, 0, :] of Model.forward's encoder output in
+ * place); item_ids [B,S+1] int64 (0 = padding); log_mask [B,S] f32; cand_bias [B*(S+1)] f32 or NULL (log-popularity).
+ *   logit[(b,s), c] = <prec[b,s], cand[c]> - cand_bias[c]
+ *   logit := masked_logit  if candidate slot (b',j) is padding (j < S and log_mask[b',j] == 0)
+ *                          or item_ids[c] occurs in item_ids[b, :] and c != target(b,s) = b*(S+1)+s+1
+ *   loss = mean over {(b,s): log_mask[b,s] != 0} of  logsumexp_c logit - logit[target]
+ * fwd writes lse [B*S] f32 (kept for the backward), loss [1], count [1].  bwd (grad_out: device f32 scalar or NULL = 1)
+ * writes d_prec [B,S,D] bf16 and d_cand (row c at d_cand + c*ld_dcand, D columns) bf16; the [B*S, B*(S+1)] logit matrix
+ * is never materialised and there are no atomics (deterministic).  D = 64 or 128.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct a4r_inbatch_ce_args {
+  const void* prec;
+  const void* cand;
+  int64_t ld_cand;
+  const int64_t* item_ids;
+  const float* log_mask;
+  const float* cand_bias;
+  float* lse;
+  float* loss;
+  float* count;
+  int64_t B, S, D;
+  float masked_logit; /* -1e4 in the MoRec statement */
+} a4r_inbatch_ce_args;
+A4R_API size_t a4r_inbatch_ce_workspace_bytes(int64_t B, int64_t S);
+A4R_API int a4r_inbatch_ce_fwd(const a4r_inbatch_ce_args* args, void* workspace, size_t workspace_bytes, a4r_stream_t stream);
+A4R_API int a4r_inbatch_ce_bwd(const a4r_inbatch_ce_args* args, const float* grad_out, void* d_prec, void* d_cand,
+                               int64_t ld_dcand, a4r_stream_t stream);
+
 /* K14: torch.optim.Adam semantics (Downstream/Text/run.py:524-529) over one flat f32 segment.
  * step is 1-based; the gradient is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
 A4R_API int a4r_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -192,6 +192,52 @@ def loss_from_embeddings(embs_all, log_mask, sd, rec, cpc=False):
     return bce_with_logits_mean(ps[idx], True) + bce_with_logits_mean(ns[idx], False)
 
 
+def inbatch_softmax_loss(prec, cand, item_ids, log_mask, cand_bias=None, masked_logit=-1e4):
+    """In-batch softmax loss with duplicate-item masking (BASELINE.json north_star).
+
+    PARITY UNPINNED: /root/reference has no such head (it trains with BCE, Downstream/Text/model/model.py:62-68), so
+    there is no reference output to pin this function to.  It restates, loop for loop, the in-batch debiased
+    cross-entropy of the same group's IDvs.MoRec trainer (not under /root/reference, no pinned version): logits of
+    every position against all B*(S+1) history items of the batch, minus the log-popularity of the candidate; padding
+    candidate slots and every candidate whose item id occurs in the user's own sequence — except the positive itself —
+    are overwritten with -1e4; CrossEntropyLoss(mean) over the valid positions.
+
+    prec [B,S,D], cand [B,S+1,D] (the encoded history items), item_ids [B,S+1] int64, log_mask [B,S]."""
+    B, S, D = prec.shape
+    S1 = S + 1
+    score_embs = cand.reshape(B * S1, D)
+    ce_label = torch.tensor([i * S + i + j for i in range(B) for j in range(1, S1)], dtype=torch.long)
+    logits = torch.matmul(prec.reshape(B * S, D), score_embs.t())                     # [B*S, B*(S+1)]
+    if cand_bias is not None:
+        logits = logits - cand_bias.reshape(1, -1)
+    col_pad = torch.cat((log_mask, torch.ones(B, 1)), dim=1).view(-1) == 0
+    fill = torch.full_like(logits, masked_logit)
+    logits = torch.where(col_pad.unsqueeze(0), fill, logits)
+    logits = logits.view(B, S, -1)
+    flat_ids = item_ids.reshape(-1)
+    out = []
+    for i in range(B):
+        reject = item_ids[i]                                                          # the user's own S+1 items
+        mask_row = (flat_ids.unsqueeze(0) == reject.unsqueeze(1)).any(dim=0)          # [B*(S+1)]
+        mask_mat = mask_row.unsqueeze(0).repeat(S, 1)
+        for j in range(S):
+            mask_mat[j][i * S1 + j + 1] = False                                       # keep the positive
+        out.append(torch.where(mask_mat, torch.full_like(logits[i], masked_logit), logits[i]))
+    logits = torch.stack(out).view(B * S, -1)
+    idx = torch.where(log_mask.reshape(-1) != 0)
+    return F.cross_entropy(logits[idx], ce_label[idx])
+
+
+def loss_from_embeddings_inbatch(embs_all, item_ids, log_mask, sd, rec, cand_bias=None):
+    """Model.forward with the in-batch softmax head instead of BCE: same encoder outputs, same user encoder
+    (model.py:53-60); the sampled negatives embs[:, :, 1] are not used by this head."""
+    S1 = rec.max_seq_len + 1
+    e = embs_all.view(-1, S1, 2, rec.embedding_dim)
+    pos = e[:, :, 0]
+    prec = user_encoder(pos[:, :-1], log_mask, sd, rec)
+    return inbatch_softmax_loss(prec, pos, item_ids, log_mask, cand_bias)
+
+
 def model_forward(sample_items, log_mask, sd, cfg, rec, cpc=False):
     """Model.forward / ModelCPC.forward: sample_items [B*(S+1)*2, 2L] int64, log_mask [B,S] -> scalar loss."""
     return loss_from_embeddings(bert_encoder(sample_items, sd, cfg, rec), log_mask, sd, rec, cpc)
