@@ -38,6 +38,10 @@ int a4r_set_error(int code, const char* fmt, ...);
 int a4r_num_sms();  // cached per process (current device)
 void a4r_count_launch(int n);
 
+// TMA descriptor of a bf16 row-major [rows, cols] matrix (leading dimension ld, elements): box = 64 columns x box_rows,
+// SWIZZLE_128B, out-of-bounds elements read as zero.  Defined in api.cu.
+int a4r_make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
 static inline bool a4r_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------------------------

@@ -457,3 +457,58 @@ class InbatchCeFunction(torch.autograd.Function):
 
 def inbatch_softmax_loss(prec, emb, item_ids, log_mask, cand_bias=None):
     return InbatchCeFunction.apply(prec, emb, item_ids, log_mask, cand_bias)
+
+
+class HoulsbyBlockFunction(torch.autograd.Function):
+    """K5 as one autograd node: out = tail(h + W_u act(W_d h + b_d) + b_u [+ inp]) with tail = LayerNorm (gamma given),
+    or nothing.  Forward = the fused a4r_adapter_ln_fwd kernel; backward = LayerNorm backward, two skinny data-gradient
+    GEMMs (act' and the skip gradient in their epilogues) and the rank-r weight / bias gradients — no torch arithmetic."""
+
+    @staticmethod
+    def forward(ctx, h, inp, w_down, b_down, w_up, b_up, gamma, beta, eps, act, cache_d, cache_u):
+        wd, _ = cache_d.get(w_down)
+        wu, _ = cache_u.get(w_up)
+        tail = 0 if gamma is not None else (1 if inp is not None else 2)
+        need = any(ctx.needs_input_grad[:8])
+        g = b = None
+        if tail == 0:
+            g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        out, z, mean, rstd, s, u = ops.adapter_ln_fwd(h, inp, wd, b_down.detach().float().contiguous(), wu,
+                                                      b_up.detach().float().contiguous(), g, b, eps, act=act, tail=tail,
+                                                      save=need)
+        ctx.act, ctx.tail, ctx.caches, ctx.has_inp = act, tail, (cache_d, cache_u), inp is not None
+        if need:
+            ctx.save_for_backward(h, z, mean, rstd, g, s, u, w_down, w_up)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, z, mean, rstd, g, s, u, w_down, w_up = ctx.saved_tensors
+        dout = dout.contiguous()
+        dg = db = None
+        if ctx.tail == 0:
+            if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
+                dg, db = torch.empty_like(g), torch.empty_like(g)
+            dz = ops.layernorm_bwd(dout, z, mean, rstd, g, dgamma=dg, dbeta=db)
+        else:
+            dz = dout
+        _, wut = ctx.caches[1].get(w_up, need_t=True)      # [r, H]
+        _, wdt = ctx.caches[0].get(w_down, need_t=True)    # [H, r]
+        if ctx.act == "gelu":
+            ds = ops.gemm(dz, wut, epilogue=ops.EPI_DGELU, aux=u)
+        else:
+            ds = ops.gemm(dz, wut, epilogue=ops.EPI_DRELU, aux=s)
+        dh = ops.gemm(ds, wdt, residual=dz) if ctx.needs_input_grad[0] else None
+        dwd = ops.wgrad(ds, h) if ctx.needs_input_grad[2] else None
+        dbd = ops.colsum(ds) if ctx.needs_input_grad[3] else None
+        dwu = ops.wgrad(dz, s) if ctx.needs_input_grad[4] else None
+        dbu = ops.colsum(dz) if ctx.needs_input_grad[5] else None
+        dinp = dz if (ctx.has_inp and ctx.needs_input_grad[1]) else None
+        return dh, dinp, dwd, dbd, dwu, dbu, dg, db, None, None, None, None
+
+
+def houlsby_block(h, inp, adapter_down, adapter_up, act, ln=None):
+    """adapter_down / adapter_up: the AdapterBlock's Linear modules (weight, bias, _cache); ln: a LayerNorm module or None."""
+    return HoulsbyBlockFunction.apply(h, inp, adapter_down.weight, adapter_down.bias, adapter_up.weight, adapter_up.bias,
+                                      None if ln is None else ln.weight, None if ln is None else ln.bias,
+                                      0.0 if ln is None else ln.eps, act, adapter_down._cache, adapter_up._cache)

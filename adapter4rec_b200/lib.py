@@ -53,6 +53,16 @@ class BceArgs(Structure):
     ]
 
 
+class AdapterArgs(Structure):
+    _fields_ = [
+        ("h", c_void_p), ("ldh", c_int64), ("input", c_void_p), ("ldi", c_int64),
+        ("w_down", c_void_p), ("b_down", c_void_p), ("w_up", c_void_p), ("b_up", c_void_p),
+        ("gamma", c_void_p), ("beta", c_void_p), ("out", c_void_p), ("z_out", c_void_p),
+        ("mean", c_void_p), ("rstd", c_void_p), ("s_out", c_void_p), ("u_out", c_void_p),
+        ("M", c_int64), ("H", c_int64), ("r", c_int64), ("act", c_int32), ("tail", c_int32), ("eps", c_float),
+    ]
+
+
 class InbatchCeArgs(Structure):
     _fields_ = [
         ("prec", c_void_p), ("cand", c_void_p), ("ld_cand", c_int64), ("item_ids", c_void_p), ("log_mask", c_void_p),
@@ -79,6 +89,8 @@ PROTOTYPES = {
     "a4r_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int32, c_void_p, c_size_t, c_int64, c_int64, c_void_p, c_float, ctypes.c_uint64,
                                     ctypes.c_uint64, c_void_p]),
+    "a4r_adapter_ln_supported": (c_int32, [c_int64, c_int64]),
+    "a4r_adapter_ln_fwd": (c_int32, [POINTER(AdapterArgs), c_void_p]),
     "a4r_embed_ln_fwd": (c_int32, [POINTER(EmbedArgs), c_void_p]),
     "a4r_act_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "a4r_dropout": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p]),

@@ -107,7 +107,10 @@ class BertAdaptedSelfOutput(nn.Module):
         drop = self.self_output.dropout
         if self.training and drop.p > 0:
             h = Fn.dropout_add(h, None, drop.p)                   # model.py:294: dropout BEFORE the adapter
-        z = self.adapter(h, extra_residual=to_2d_bf16(input_tensor))
+        inp = to_2d_bf16(input_tensor)
+        if self.adapter.fused_ok(h) and inp.is_contiguous():
+            return self.adapter.fused(h, inp, ln=self.self_output.LayerNorm).view(input_tensor.shape)
+        z = self.adapter(h, extra_residual=inp)
         return self.self_output.LayerNorm(z).view(input_tensor.shape)
 
 

@@ -4,6 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fn
+from .. import ops
 from .layers import BF16, Embedding, LayerNorm, Linear, to_2d_bf16
 
 SASREC_MASK_NEG = -1e9   # encoders.py:28
@@ -134,6 +135,17 @@ class AdapterBlock(nn.Module):
         """Returns fc_up(act(fc_down(x))) + x (+ extra_residual: the enclosing block's skip connection, fused into
         the same GEMM epilogue)."""
         x2 = to_2d_bf16(input_embs)
+        if self.fused_ok(x2):
+            return self.fused(x2, extra_residual).view(input_embs.shape)
         s = self.fc_down(x2, act=self.act)
         out = self.fc_up(s, residual=x2, residual2=extra_residual)
         return out.view(input_embs.shape)
+
+    def fused_ok(self, x2):
+        """the one-pass K5 kernel covers H % 64 == 0, H <= 768, r % 8 == 0, r <= 64 (BERT / ViT adapters); other shapes
+        (the D = 64 SASRec adapters sit inside a 64-wide block that is launch-bound anyway) compose GEMM kernels"""
+        return x2.is_contiguous() and ops.adapter_ln_supported(self.fc_down.in_features, self.fc_down.out_features)
+
+    def fused(self, x2, extra_residual=None, ln=None):
+        """tail(x + fc_up(act(fc_down(x))) [+ extra_residual]) in one kernel; tail = ln (a LayerNorm module) or identity"""
+        return Fn.houlsby_block(x2, extra_residual, self.fc_down, self.fc_up, self.act, ln=ln)

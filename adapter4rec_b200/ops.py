@@ -314,6 +314,45 @@ def bce_loss_bwd(prec, emb, log_mask, pos, neg, count, grad_out=None, cpc=False)
     return d_prec, d_emb
 
 
+def adapter_ln_supported(H, r):
+    return bool(_l.get_lib().a4r_adapter_ln_supported(int(H), int(r)))
+
+
+def adapter_ln_fwd(h, inp, w_down, b_down, w_up, b_up, gamma=None, beta=None, eps=0.0, act="relu", tail=0, save=False):
+    """K5 in one kernel: out = tail(h + W_u act(W_d h + b_d) + b_u [+ inp]); tail 0 = LayerNorm, 1 = +inp, 2 = nothing.
+    returns (out, z, mean, rstd, s, u): with save=True the tensors the backward reads (z/mean/rstd for tail 0, s always,
+    u = pre-activation for GELU), else None."""
+    assert h.dtype == BF16 and h.dim() == 2 and w_down.dtype == BF16 and w_up.dtype == BF16
+    assert w_down.is_contiguous() and w_up.is_contiguous()
+    M, H = h.shape
+    r = w_down.shape[0]
+    assert tuple(w_down.shape) == (r, H) and tuple(w_up.shape) == (H, r)
+    for t in (b_down, b_up) + ((gamma, beta) if tail == 0 else ()):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    dev = h.device
+    out = torch.empty((M, H), dtype=BF16, device=dev)
+    z = mean = rstd = s = u = None
+    if save:
+        s = torch.empty((M, r), dtype=BF16, device=dev)
+        if act == "gelu":
+            u = torch.empty((M, r), dtype=BF16, device=dev)
+        if tail == 0:
+            z = torch.empty((M, H), dtype=BF16, device=dev)
+            mean = torch.empty(M, dtype=torch.float32, device=dev)
+            rstd = torch.empty(M, dtype=torch.float32, device=dev)
+    a = _l.AdapterArgs()
+    a.h, a.ldh = _p(h), _rows2d(h, "h")
+    if inp is not None:
+        assert inp.dtype == BF16 and tuple(inp.shape) == (M, H)
+        a.input, a.ldi = _p(inp), _rows2d(inp, "input")
+    a.w_down, a.b_down, a.w_up, a.b_up = _p(w_down), _p(b_down), _p(w_up), _p(b_up)
+    a.gamma, a.beta, a.out, a.z_out, a.mean, a.rstd, a.s_out, a.u_out = (_p(gamma), _p(beta), _p(out), _p(z), _p(mean),
+                                                                         _p(rstd), _p(s), _p(u))
+    a.M, a.H, a.r, a.act, a.tail, a.eps = M, H, r, {"relu": 0, "gelu": 1}[act], int(tail), float(eps)
+    _l.check(_l.get_lib().a4r_adapter_ln_fwd(ctypes.byref(a), _stream()), "a4r_adapter_ln_fwd")
+    return out, z, mean, rstd, s, u
+
+
 MASKED_LOGIT = -1e4  # the constant the in-batch softmax head writes over excluded candidates
 
 

@@ -178,6 +178,47 @@ A4R_API int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, 
                       uint64_t dropout_seed, uint64_t dropout_offset, a4r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K5: the Houlsby adapter block fused into one pass (tcgen05 down/up projections + residuals + LayerNorm).
+ * Replaces everything after `self_output.dense` / `dropout` in BertAdaptedSelfOutput.forward
+ * (Downstream/Text/model/model.py:292-297): AdapterBlock.forward (modules.py:131-134) + the residual add + LayerNorm;
+ * and, with tail 1 / 2, VITAdaptedOutput.forward / VITAdaptedSelfOutput.forward (Downstream/CV/model/model.py:182-212).
+ *
+ *   s = act(h·W_dᵀ + b_d)          act 0 = ReLU, 1 = erf-GELU (args.adapter_activation, modules.py:122-125)
+ *   z = s·W_uᵀ + b_u + h (+ input)
+ *   tail 0: out = LayerNorm(z; gamma, beta, eps)     tail 1: out = z (input added)     tail 2: out = z (no input)
+ *
+ * h [M,H] bf16 (ldh), input [M,H] bf16 (ldi), w_down [r,H] bf16, w_up [H,r] bf16 (both contiguous, nn.Linear layout),
+ * biases / gamma / beta f32, out [M,H] bf16 contiguous.  Optional outputs for the backward: z_out [M,H] bf16 (pre-LN sum,
+ * tail 0), mean / rstd [M] f32 (tail 0), s_out [M,r] bf16 (activation output), u_out [M,r] bf16 (pre-activation; GELU).
+ * Shapes: H %% 64 == 0, H <= 768, r %% 8 == 0, r <= 64 (a4r_adapter_ln_supported); other shapes compose
+ * a4r_gemm_bf16_tn + a4r_layernorm_fwd.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct a4r_adapter_args {
+  const void* h;
+  int64_t ldh;
+  const void* input;
+  int64_t ldi;
+  const void* w_down;
+  const float* b_down;
+  const void* w_up;
+  const float* b_up;
+  const float* gamma;
+  const float* beta;
+  void* out;
+  void* z_out;
+  float* mean;
+  float* rstd;
+  void* s_out;
+  void* u_out;
+  int64_t M, H, r;
+  int32_t act;
+  int32_t tail;
+  float eps;
+} a4r_adapter_args;
+A4R_API int a4r_adapter_ln_supported(int64_t H, int64_t r);
+A4R_API int a4r_adapter_ln_fwd(const a4r_adapter_args* args, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K1: token + position + token-type embedding gather fused with LayerNorm (BertEmbeddings /
  * RobertaEmbeddings, reached from Downstream/Text/model/encoders.py:53), with the soft-prompt
  * substitution of SoftEmbedding.forward (Downstream/Text/model/model.py:620-630).

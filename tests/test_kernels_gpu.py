@@ -280,3 +280,41 @@ def test_adam_matches_torch():
         opt.step()
         ops.adam_step(p, g * 4, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.0, step, grad_scale=0.25)
     _close(p, ref.detach(), 1e-6, 1e-6, "adam")
+
+
+@pytest.mark.parametrize("M,H,r,act,tail", [
+    (128, 768, 64, "relu", 0), (1000, 768, 64, "gelu", 0), (148 * 128 + 77, 768, 64, "relu", 0),
+    (300, 128, 16, "relu", 0), (300, 128, 16, "gelu", 0), (515, 256, 8, "relu", 0), (70, 64, 16, "relu", 0),
+    (1000, 768, 64, "relu", 1), (1000, 768, 64, "gelu", 2), (333, 384, 48, "relu", 0),
+])
+def test_adapter_ln_fused(M, H, r, act, tail):
+    """K5: the fused Houlsby block against the fp32 statement of model.py:292-297 / modules.py:131-134 on bf16-exact
+    inputs.  s and z are rounded to bf16 inside the kernel exactly where the composed GEMM -> GEMM -> LayerNorm path
+    rounds them, so the reference rounds there too; what is left is fp32 summation order and the final bf16 rounding."""
+    ops = _ops()
+    h = _rand((M, H), 1.0, 1)
+    inp = _rand((M, H), 1.0, 2)
+    wd, wu = _rand((r, H), 0.05, 3), _rand((H, r), 0.05, 4)
+    bd, bu = _rand((r,), 0.1, 5, torch.float32), _rand((H,), 0.1, 6, torch.float32)
+    g, b = 1 + _rand((H,), 0.1, 7, torch.float32), _rand((H,), 0.1, 8, torch.float32)
+    eps = 1e-12
+    out, z, mean, rstd, s, u = ops.adapter_ln_fwd(h, None if tail == 2 else inp, wd, bd, wu, bu, g, b, eps, act=act, tail=tail,
+                                                  save=True)
+    pre = h.float() @ wd.float().t() + bd
+    s_ref = (torch.nn.functional.gelu(pre) if act == "gelu" else torch.relu(pre)).to(BF16)
+    z_ref = s_ref.float() @ wu.float().t() + bu + h.float() + (0 if tail == 2 else inp.float())
+    _close(s, s_ref, 2 ** -7, 1e-3, "s")
+    if act == "gelu":
+        _close(u, pre, 2 ** -7, 1e-3, "u")
+    if tail != 0:
+        _close(out, z_ref, 2 ** -7, 2e-2, "out (no LayerNorm)")
+        return
+    _close(z, z_ref, 2 ** -7, 2e-2, "z")
+    zf = z.float()                                   # LayerNorm of the tensor the kernel itself rounded
+    mu, var = zf.mean(-1), zf.var(-1, unbiased=False)
+    _close(mean, mu, 1e-4, 1e-4, "mean")
+    _close(rstd, (var + eps).rsqrt(), 1e-4, 1e-4, "rstd")
+    ref = (zf - mu[:, None]) * (var[:, None] + eps).rsqrt() * g + b
+    _close(out, ref, 2 ** -7, 1e-2, "out")
+    out2 = ops.adapter_ln_fwd(h, inp, wd, bd, wu, bu, g, b, eps, act=act, tail=0, save=False)[0]
+    assert torch.equal(out, out2), "the inference variant (z staged in `out`) must give identical results"
