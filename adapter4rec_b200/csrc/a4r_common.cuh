@@ -303,6 +303,13 @@ A4R_DEVICE uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
 A4R_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive WITHOUT cluster-scope release.  The .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. it
+// waits until every global store of the warp is visible device-wide — the epilogue warps would drain their output
+// stores before they may hand the TMEM stage back.  Handing a TMEM stage back orders only tcgen05 accesses, which
+// tcgen05.fence::before_thread_sync / after_thread_sync around the arrive / wait already do.
+A4R_DEVICE void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 A4R_DEVICE void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
                : "memory");

@@ -419,7 +419,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // the leader's barrier
+        if constexpr (CG == 2) mbar_arrive_remote(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));  // the leader's barrier
         else mbar_arrive(&tmem_empty_bar[as]);
       }
       if (++as == 2) {

@@ -10,19 +10,22 @@
 // Total order everywhere: (score desc, item id asc).  Item id 0 (the padding item) and the user's history ids are
 // excluded, as `score[history] = -inf; score = score[1:]` does in the reference.
 //
-// score_topk mapping: M = users (TMEM lanes: one epilogue thread owns one user), N = items.  A CTA owns one block of
-// 128 users and one contiguous slice of the item shard; it streams item tiles of 256 rows through the same
-// TMA -> smem -> tcgen05.mma -> TMEM pipeline as gemm_sm100.cu while its epilogue threads keep a sorted top-k list
-// in registers.  Work per launch = (U/128) x splits CTAs; each (split, epilogue group) emits one partial list.
+// score_topk mapping: M = users (TMEM lanes: one epilogue thread owns one user), N = items.  A CTA PAIR (cta_group::2, the
+// two SMs of a TPC) owns one block of 256 users and one contiguous slice of the item shard; it streams item tiles of 256
+// rows through the same TMA -> smem -> tcgen05.mma -> TMEM pipeline as gemm_sm100.cu — each CTA stages its own 128 users
+// and HALF of the item rows of a tile, the pair's MMA reads both halves, which cuts shared-memory and L2->SM operand
+// traffic per CTA by a third against the single-CTA 128 x 256 tile — while its epilogue threads keep a sorted top-k
+// list in registers.  Work per launch = ceil(U/256) x splits pairs; each (split, epilogue group) emits one partial list.
 #include "a4r_common.cuh"
 
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int CG = 2;                // CTAs per MMA
+constexpr int STAGES = 6;
 constexpr int EPI_GROUPS = 2;
 constexpr int THREADS = 128 + 128 * EPI_GROUPS;
-constexpr int STAGE_A = BM * BK * 2, STAGE_B = BN * BK * 2, STAGE_BYTES = STAGE_A + STAGE_B;
+constexpr int STAGE_A = BM * BK * 2, STAGE_B = (BN / CG) * BK * 2, STAGE_BYTES = STAGE_A + STAGE_B;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int TMEM_COLS = 2 * BN;
 constexpr int KMAX = 16;  // top-k capacity of the register list
@@ -34,7 +37,7 @@ struct TopkParams {
   int64_t id_base;         // item id of row 0 of this shard
   int U, I, hist_len, k;
   int nk;                  // k-blocks (d / 64, rounded up)
-  int m_blocks, splits, tiles_per_split;
+  int m_blocks, splits, tiles_per_split;   // m_blocks = blocks of 256 users (one per CTA pair)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -48,13 +51,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.x % p.m_blocks;
-  const int split = blockIdx.x / p.m_blocks;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = static_cast<int>(blockIdx.x >> 1);
+  const int m_blk = pair % p.m_blocks;
+  const int split = pair / p.m_blocks;
   const int total_tiles = (p.I + BN - 1) / BN;
   const int t_begin = split * p.tiles_per_split;
   int t_end = t_begin + p.tiles_per_split;
   if (t_end > total_tiles) t_end = total_tiles;
-  const int m0 = m_blk * BM;
+  const int m0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmU);
@@ -67,16 +73,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4 * EPI_GROUPS);
+      mbar_init(&tmem_empty_bar[s], 4 * EPI_GROUPS * CG);   // one arrive per epilogue warp of both CTAs (leader's copy)
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc2(tmem_slot, TMEM_COLS);
+    tmem_relinquish2();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // barriers of BOTH CTAs are initialised past this point
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -88,9 +94,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         for (int kb = 0; kb < p.nk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(&tmU, sa, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(&tmE, sa + STAGE_A, &full_bar[stage], kb * BK, t * BN);
+          // both CTAs' bytes are credited to the LEADER's full barrier
+          if (leader) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_2cta(&tmU, sa, bar, kb * BK, m0);
+          tma_load_2d_2cta(&tmE, sa + STAGE_A, bar, kb * BK, t * BN + static_cast<int>(cta_rank) * (BN / CG));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -99,8 +107,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -114,15 +122,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
           const uint64_t adesc = umma_desc_k_sw128(sa), bdesc = umma_desc_k_sw128(sa + STAGE_A);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_ss(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            umma_bf16_ss_2cta(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty_bar[stage], 3);   // frees the slot in both CTAs of the pair
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[as]);
+        umma_commit_2cta(&tmem_full_bar[as], 3);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -155,14 +163,21 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + c * 32), acc);
         tmem_ld_wait();
-        // cheap pre-filter: does any of the 32 scores beat the current threshold?
-        float mx = -INFINITY;
+        // cheap pre-filter: which of the 32 scores beat the current threshold?  (registers only: the common case ends here)
+        uint32_t cand = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(acc[j]));
-        if (mx > thr && user_ok) {
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(acc[j]);
+        for (int j = 0; j < 32; ++j) cand |= (__uint_as_float(acc[j]) > thr ? 1u : 0u) << j;
+        if (!user_ok) cand = 0;
+        if (__any_sync(0xffffffffu, cand != 0)) {
+          // rare path: only now do the scores go to (thread-local) memory for dynamic indexing; each lane then visits
+          // only its own candidates, in ascending column order
+          float sc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(acc[j]);
+          while (cand != 0) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float s = sc[j];
             if (!(s > thr)) continue;  // ids arrive in ascending order: an equal score never displaces an entry
             const int col = col0 + j;
             if (col >= p.I) break;
@@ -196,7 +211,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));   // the leader's barrier
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -216,9 +231,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 2) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
 // K13: one thread per user merges P partial lists under (score desc, id asc); optional HR/NDCG against `target`.
@@ -299,9 +314,9 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
 }
 
 void plan(int64_t U, int64_t I, int* m_blocks, int* splits, int* tiles_per_split) {
-  *m_blocks = static_cast<int>((U + BM - 1) / BM);
+  *m_blocks = static_cast<int>((U + BM * CG - 1) / (BM * CG));
   const int tiles = static_cast<int>((I + BN - 1) / BN);
-  int s = a4r_num_sms() / *m_blocks;
+  int s = (a4r_num_sms() / CG) / *m_blocks;   // CTA pairs resident at once
   if (s < 1) s = 1;
   if (s > 16) s = 16;  // the merge kernel handles at most 64 partial lists (splits x 2 groups x shards)
   if (s > tiles) s = tiles;
@@ -331,7 +346,7 @@ extern "C" int a4r_score_topk(const void* users, int64_t ld_users, const void* i
   if (rc != A4R_OK) return rc;
   CUtensorMap tmU, tmE;
   if ((rc = make_tmap(&tmU, users, U, d, ld_users, BM)) != A4R_OK) return rc;
-  if ((rc = make_tmap(&tmE, items, I, d, ld_items, BN)) != A4R_OK) return rc;
+  if ((rc = make_tmap(&tmE, items, I, d, ld_items, BN / CG)) != A4R_OK) return rc;
   TopkParams p;
   p.history = history;
   p.out_scores = out_scores;
@@ -348,7 +363,19 @@ extern "C" int a4r_score_topk(const void* users, int64_t ld_users, const void* i
     A4R_CUDA_OK(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  score_topk_kernel<<<p.m_blocks * p.splits, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream_)>>>(tmU, tmE, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.m_blocks * p.splits * CG);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = static_cast<cudaStream_t>(stream_);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  A4R_CUDA_OK(cudaLaunchKernelEx(&cfg, score_topk_kernel, tmU, tmE, p));
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;

@@ -224,7 +224,7 @@ def run_reference(a):
 
 def bench_eval(dev, world, rank, steps, warmup):
     """Full-ranking evaluation, BASELINE.json configs[4] ("C5"): 10 M-item bf16 table (d = 768) sharded by item id over
-    the ranks (all 10 M on one GPU at N = 1), blocks of 4,096 users with 20 history ids each, top-10 + HR/NDCG.
+    the ranks (all 10 M on one GPU at N = 1), blocks of 9,472 users with 20 history ids each, top-10 + HR/NDCG.
     User vectors are synthetic bf16 (kernel-level benchmark: score GEMM + mask + top-k + merge [+ all-gather]);
     the d = 64 line runs the COMPLETE evaluator (K10 gather, SASRec user encoder, scores, top-k, metrics) on a
     1 M-item table with the model's real embedding width."""
@@ -232,7 +232,8 @@ def bench_eval(dev, world, rank, steps, warmup):
     import torch.distributed as dist
     from adapter4rec_b200 import ops
     out = {}
-    I_total, d, U = 10_000_000, 768, 4096
+    # 9,472 users = 37 blocks of 256 (one per CTA pair) x 2 item splits = 74 pairs = all 148 SMs of a B200
+    I_total, d, U = 10_000_000, 768, 9472
     per = (I_total + 1 + world - 1) // world
     lo = rank * per
     n_local = max(0, min(I_total + 1, lo + per) - lo)

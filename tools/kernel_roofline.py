@@ -204,12 +204,12 @@ if want("eval"):
 
 # ------------------------------------------------------------------ K11/K12 score GEMM + top-k  (C5)
 if want("score"):
-    I, d, U = 2_000_000, 768, 4096
+    I, d, U = 2_000_000, 768, 9472
     table = r16(I, d, scale=d ** -0.5)
     users = [r16(U, d, scale=1.0) for _ in range(2)]
     hist = torch.randint(1, I, (U, 20), device=dev, dtype=torch.int32)
     us = timeit(lambda i: ops.score_topk(users[i], table, id_base=0, history=hist, k=10), 2)
-    report("score_topk U=4096 x I=2M x d=768 (+history mask + top-10)", us, flops=2.0 * U * I * d, bound="tensor")
+    report("score_topk U=9472 x I=2M x d=768 (+history mask + top-10)", us, flops=2.0 * U * I * d, bound="tensor")
     del table
     I, d, U = 4_000_000, 64, 8192
     table = r16(I, d, scale=0.3)
