@@ -364,8 +364,34 @@ __global__ void __launch_bounds__(ROW_THREADS) embed_ln_kernel(const a4r_embed_a
 }
 
 // ------------------------------------------------------------------------------------------------
-// elementwise activation gradient: out = dy * act'(u)   (u = saved pre-activation for GELU, output for ReLU)
+// elementwise activation gradient: out = dy * act'(u)   (u = saved pre-activation for GELU / tanh-GELU, output for
+// ReLU / LeakyReLU), and the stand-alone forward for the activations that have no GEMM-epilogue mode
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float t = tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float t = tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+}
+__device__ __forceinline__ float act_grad(int kind, float dy, float u) {
+  switch (kind) {
+    case 0: return dy * gelu_erf_grad(u);
+    case 1: return u > 0.0f ? dy : 0.0f;
+    case 2: return u > 0.0f ? dy : 0.01f * dy;          // nn.LeakyReLU() default slope; sign(out) == sign(in)
+    default: return dy * gelu_tanh_grad(u);
+  }
+}
+__device__ __forceinline__ float act_value(int kind, float u) {
+  switch (kind) {
+    case 0: return gelu_erf(u);
+    case 1: return fmaxf(u, 0.0f);
+    case 2: return u > 0.0f ? u : 0.01f * u;
+    default: return gelu_tanh(u);
+  }
+}
+
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ u,
                                __nv_bfloat16* __restrict__ out, int64_t nvec, int kind) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
@@ -374,7 +400,18 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
     unpack8(ld_nc_v4(dy + i * 8), a);
     unpack8(ld_nc_v4(u + i * 8), b);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = kind == 0 ? a[e] * gelu_erf_grad(b[e]) : (b[e] > 0.0f ? a[e] : 0.0f);
+    for (int e = 0; e < 8; ++e) o[e] = act_grad(kind, a[e], b[e]);
+    st_na_v4(out + i * 8, pack8(o));
+  }
+}
+
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ out, int64_t nvec, int kind) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float b[8], o[8];
+    unpack8(ld_nc_v4(u + i * 8), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = act_value(kind, b[e]);
     st_na_v4(out + i * 8, pack8(o));
   }
 }
@@ -556,7 +593,7 @@ extern "C" int a4r_embed_ln_fwd(const a4r_embed_args* a, a4r_stream_t stream_) {
 extern "C" int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream_) {
   A4R_CHECK_ARG(dy && u && out, "act_bwd: NULL pointer");
   A4R_CHECK_ARG(n >= 0 && n % 8 == 0, "act_bwd: n must be a multiple of 8");
-  A4R_CHECK_ARG(kind == 0 || kind == 1, "act_bwd: kind must be 0 (gelu) or 1 (relu)");
+  A4R_CHECK_ARG(kind >= 0 && kind <= 3, "act_bwd: kind must be 0 (gelu) 1 (relu) 2 (leaky_relu) 3 (gelu_new)");
   A4R_CHECK_ARG(a4r_aligned16(dy) && a4r_aligned16(u) && a4r_aligned16(out), "act_bwd: pointers must be 16B aligned");
   int rc = a4r_device_check();
   if (rc != A4R_OK) return rc;
@@ -568,6 +605,25 @@ extern "C" int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, 
   act_bwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
       nvec, kind);
+  A4R_LAUNCH_OK();
+  a4r_count_launch(1);
+  return A4R_OK;
+}
+
+extern "C" int a4r_act_fwd(const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream_) {
+  A4R_CHECK_ARG(u && out, "act_fwd: NULL pointer");
+  A4R_CHECK_ARG(n >= 0 && n % 8 == 0, "act_fwd: n must be a multiple of 8");
+  A4R_CHECK_ARG(kind >= 0 && kind <= 3, "act_fwd: kind must be 0 (gelu) 1 (relu) 2 (leaky_relu) 3 (gelu_new)");
+  A4R_CHECK_ARG(a4r_aligned16(u) && a4r_aligned16(out), "act_fwd: pointers must be 16B aligned");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  if (n == 0) return A4R_OK;
+  const int64_t nvec = n / 8;
+  int64_t blocks = (nvec + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  act_fwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out), nvec, kind);
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;

@@ -48,6 +48,15 @@ class ItemTable:
         return out
 
 
+def core_model(model):
+    """The object that owns `bert_encoder` / `user_encoder`: strips DDP's `.module` and CompacterModel's `.model`
+    (metrics.py:72-73,101-102 reach through `model.module.model` when 'compacter' is in args.adapter_type)."""
+    m = model.module if hasattr(model, "module") else model
+    if not hasattr(m, "user_encoder") and hasattr(m, "model"):
+        m = m.model
+    return m
+
+
 def _dist_info():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -68,7 +77,7 @@ def print_metrics(x, Log_file, v_or_t):
 def get_item_embeddings(model, item_content, test_batch_size, args, use_modal, local_rank):
     """metrics.py:62-79.  item_content [I+1, 2L] (numpy int or torch int64; row 0 = padding item).  Each rank encodes
     ITS shard of item ids with the item encoder under no_grad and keeps it on the device (an ItemTable)."""
-    module = model.module if hasattr(model, "module") else model
+    module = core_model(model)
     module.eval()
     rank, world = _dist_info()
     rows = torch.as_tensor(np.asarray(item_content) if not torch.is_tensor(item_content) else item_content).long()
@@ -110,7 +119,7 @@ def build_eval_arrays(eval_seq, user_history, max_seq_len):
 def eval_arrays(model, tok, mask, tgt, hist, item_table, user_block, topk=10):
     """Core evaluator on pre-built arrays (torch tensors, host or device): returns per-user (hit, ndcg) on the device
     plus the merged top-k ids."""
-    module = model.module if hasattr(model, "module") else model
+    module = core_model(model)
     module.eval()
     dev = item_table.table.device
     rank, world = item_table.rank, item_table.world
@@ -148,7 +157,7 @@ def eval_model(model, user_history, eval_seq, item_embeddings, test_batch_size, 
     if not isinstance(item_embeddings, ItemTable):
         rank, world = _dist_info()
         assert world == 1, "pass the ItemTable returned by get_item_embeddings when running distributed"
-        dev = next((model.module if hasattr(model, "module") else model).parameters()).device
+        dev = next(core_model(model).parameters()).device
         item_embeddings = ItemTable(item_embeddings.to(dev), 0, item_embeddings.shape[0])
     tok, mask, tgt, hist = build_eval_arrays(eval_seq, user_history, args.max_seq_len)
     hit, ndcg, _ = eval_arrays(model, torch.from_numpy(tok), torch.from_numpy(mask), torch.from_numpy(tgt),

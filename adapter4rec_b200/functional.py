@@ -44,22 +44,27 @@ def _as2d(x):
 
 
 class LinearFunction(torch.autograd.Function):
-    """y = act(x Wᵀ + b) + residual + residual2, act in {none, gelu, relu}."""
+    """y = act(x Wᵀ + b) + residual + residual2, act in {none, gelu, relu} fused in the GEMM epilogue;
+    {leaky_relu, gelu_new} (bottleneck-only activations of the Pfeiffer / Compacter adapters) run as a stand-alone
+    elementwise pass over the r-wide output."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, residual2, cache, act):
         w, _ = cache.get(weight)
-        epi = {None: ops.EPI_LINEAR, "gelu": ops.EPI_GELU, "relu": ops.EPI_RELU}[act]
+        standalone = act in ("leaky_relu", "gelu_new")
+        epi = {None: ops.EPI_LINEAR, "gelu": ops.EPI_GELU, "relu": ops.EPI_RELU}[None if standalone else act]
         b = None if bias is None else bias.detach().float().contiguous()
         need_grad = any(ctx.needs_input_grad[:5])
         aux = None
         if act == "gelu" and need_grad:
             aux = torch.empty((x.shape[0], w.shape[0]), dtype=BF16, device=x.device)
         y = ops.gemm(x, w, bias=b, epilogue=epi, residual=residual, residual2=residual2, aux=aux)
+        if standalone:
+            aux, y = y, ops.act_fwd(y, act)
         ctx.cache, ctx.act = cache, act
         ctx.has_bias, ctx.has_r1, ctx.has_r2 = bias is not None, residual is not None, residual2 is not None
         save_x = x if ctx.needs_input_grad[1] else None
-        act_saved = aux if act == "gelu" else (y if act == "relu" else None)
+        act_saved = aux if act in ("gelu", "gelu_new") else (y if act in ("relu", "leaky_relu") else None)
         ctx.save_for_backward(save_x, act_saved, weight)
         return y
 
@@ -247,6 +252,22 @@ class DropoutAddFunction(torch.autograd.Function):
 def dropout_add(x, res, p):
     """dropout(x) (+ res); identity (+ plain add through the caller's fused path) when p == 0"""
     return DropoutAddFunction.apply(x, res, float(p))
+
+
+class AddFunction(torch.autograd.Function):
+    """out = x + res in bf16 (the p = 0 case of a4r_dropout: every element kept, scale 1)."""
+
+    @staticmethod
+    def forward(ctx, x, res):
+        return ops.dropout(x.contiguous(), res.contiguous(), 0.0, 0, 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return (dy if ctx.needs_input_grad[0] else None), (dy if ctx.needs_input_grad[1] else None)
+
+
+def add(x, res):
+    return AddFunction.apply(x, res)
 
 
 class AttentionFunction(torch.autograd.Function):

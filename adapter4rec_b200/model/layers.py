@@ -70,6 +70,47 @@ class LoRALinear(Linear):
         return y.view(*shape[:-1], self.out_features)
 
 
+class PHMLinear(nn.Module):
+    """Parameterised hypercomplex multiplication layer as HyperComplexAdapterBlock configures it
+    (Downstream/Text/model/layers.py:25-166 with shared_phm_rule=True, factorized_phm=True, phm_rank=1, bias=True,
+    w_init="glorot-uniform"; modules.py:218-245): y = x·H + b with H = Σ_i phm_rule[i] ⊗ (W_left[i]·W_right[i])
+    ([in, out], rebuilt every forward, kronecker.py:23-34).  Parameter names: W_left [n, in/n, 1], W_right
+    [n, 1, out/n], b [out]; `phm_rule` [n, n, n] is the single tensor shared by every PHMLinear of the model, assigned by
+    CompacterModel through set_phm_rule (run.py:70-81) — being an nn.Parameter it is registered here too, so the
+    reference's state_dict repeats it under every layer.
+
+    H has in·out <= 768·64 elements, i.e. it is parameter-space work independent of the batch: it is synthesised with
+    torch tensor ops on the device (autograd carries dH back to W_left / W_right / phm_rule); every per-token
+    operation — the projection, bias, activation, the data gradient and dH = xᵀ·dy — runs in the sm_100a kernels."""
+
+    def __init__(self, in_features, out_features, phm_dim, bias=True, phm_rank=1, **unused):
+        super().__init__()
+        assert in_features % phm_dim == 0, "Argument `in_features`=%d is not divisble be `phm_dim`%d" % (in_features, phm_dim)
+        assert out_features % phm_dim == 0, "Argument `out_features`=%d is not divisble be `phm_dim`%d" % (out_features, phm_dim)
+        self.in_features, self.out_features, self.phm_dim, self.phm_rank = in_features, out_features, phm_dim, phm_rank
+        self.W_left = nn.Parameter(torch.empty(phm_dim, in_features // phm_dim, phm_rank))
+        self.W_right = nn.Parameter(torch.empty(phm_dim, phm_rank, out_features // phm_dim))
+        self.b = nn.Parameter(torch.zeros(out_features)) if bias else None
+        for i in range(phm_dim):                                   # glorot_uniform, inits.py:10-11
+            nn.init.xavier_uniform_(self.W_left.data[i], gain=math.sqrt(2))
+            nn.init.xavier_uniform_(self.W_right.data[i], gain=math.sqrt(2))
+
+    def set_phm_rule(self, phm_rule=None, phm_rule_left=None, phm_rule_right=None):
+        self.phm_rule = phm_rule
+
+    def weight(self):
+        """H transposed to the [out, in] layout of nn.Linear.weight (fp32, differentiable)."""
+        n = self.phm_dim
+        W = torch.bmm(self.W_left, self.W_right)                                        # [n, in/n, out/n]
+        H = torch.einsum('bac,bkp->akcp', self.phm_rule, W).reshape(self.in_features, self.out_features)
+        return H.t().contiguous()
+
+    def forward(self, x, act=None, residual=None):
+        shape = x.shape
+        y = Fn.linear(to_2d_bf16(x), self.weight(), self.b, Fn.WeightCache(), act=act, residual=residual)
+        return y.view(*shape[:-1], self.out_features)
+
+
 class LayerNorm(nn.Module):
     def __init__(self, normalized_shape, eps=1e-5):
         super().__init__()

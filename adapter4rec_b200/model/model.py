@@ -7,7 +7,9 @@ import torch.nn as nn
 from .. import functional as Fn
 from .encoders import Bert_Encoder, User_Encoder
 from .layers import BF16, Embedding, to_2d_bf16
-from .modules import AdapterBlock
+from .layers import LayerNorm
+from .layers import PHMLinear
+from .modules import AdapterBlock, AdapterPfeifferBlock, HyperComplexAdapterBlock
 
 
 def _word_dim(args):
@@ -114,6 +116,51 @@ class BertAdaptedSelfOutput(nn.Module):
         return self.self_output.LayerNorm(z).view(input_tensor.shape)
 
 
+class BertAdaptedParallelSelfOutput(nn.Module):
+    """model.py:246-270 (Houlsby parallel, is_serial = 'None', run.py:466-479): the adapter reads the block INPUT;
+    LayerNorm(adapter(input) + dropout(dense(h)) + input) where adapter(x) = fc_up(act(fc_down(x))) + x, i.e. the
+    input enters the sum twice, as in the reference."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = AdapterBlock(args, _word_dim(args), args.bert_adapter_down_size, args.adapter_dropout_rate)
+
+    def forward(self, hidden_states, input_tensor):
+        return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_from_dense(self, h, input_tensor):
+        inp = to_2d_bf16(input_tensor).contiguous()
+        a = to_2d_bf16(self.adapter(inp, extra_residual=inp))             # up(act(down(inp))) + inp + inp
+        h = to_2d_bf16(h)
+        drop = self.self_output.dropout
+        z = Fn.dropout_add(h, a, drop.p) if (self.training and drop.p > 0) else Fn.add(h, a)
+        return self.self_output.LayerNorm(z).view(input_tensor.shape)
+
+
+class BertPfeifferAdaptedSelfOutput(nn.Module):
+    """model.py:300-329 (wraps layer.output only, run.py:403-406): h = dropout(dense(x)); t = LayerNorm(h + input);
+    LN(adapter(t) + h + input) with a residual-free bottleneck (AdapterPfeifferBlock) and a NEW LayerNorm `LN`
+    (eps 1e-6)."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = AdapterPfeifferBlock(args, _word_dim(args), args.bert_adapter_down_size, args.adapter_dropout_rate)
+        self.LN = LayerNorm(_word_dim(args), eps=1e-06)
+
+    def forward(self, hidden_states, input_tensor):
+        return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_from_dense(self, h, input_tensor):
+        inp = to_2d_bf16(input_tensor).contiguous()
+        h = to_2d_bf16(h)
+        drop = self.self_output.dropout
+        hi = Fn.dropout_add(h, inp, drop.p) if (self.training and drop.p > 0) else Fn.add(h, inp)   # h + input
+        t = self.self_output.LayerNorm(hi)
+        return self.LN(self.adapter(t, extra_residual=hi)).view(input_tensor.shape)
+
+
 class SASRecAdaptedSelfOutput(nn.Module):
     """model.py:332-376: the SASRec block with adapter1 after fc and adapter2 after the feed-forward, both before the
     LayerNorms."""
@@ -128,6 +175,115 @@ class SASRecAdaptedSelfOutput(nn.Module):
         tb = self.transformer_block
         h = tb.multi_head_attention(block_input, block_input, block_input, mask, adapter=self.adapter1)
         return tb.feed_forward(h, adapter=self.adapter2)
+
+
+class SASRecPfeifferVer2AdaptedSelfOutput(nn.Module):
+    """model.py:379-423 (adapter_type 'pfeiffer_ver2', run.py:389-399): only adapter1 (after the attention's fc); the
+    feed-forward half is the plain block."""
+
+    def __init__(self, transformer_block, args):
+        super().__init__()
+        self.transformer_block = transformer_block
+        self.adapter1 = AdapterBlock(args, args.embedding_dim, args.adapter_down_size, args.adapter_dropout_rate)
+
+    def forward(self, block_input, mask):
+        tb = self.transformer_block
+        h = tb.multi_head_attention(block_input, block_input, block_input, mask, adapter=self.adapter1)
+        return tb.feed_forward(h)
+
+
+class SASRecPfeifferAdaptedSelfOutput(nn.Module):
+    """model.py:426-471: plain attention half; feed-forward half h = dropout(ffn(y)), t = layer_norm(y + h),
+    LN(adapter(t) + h + y) with AdapterPfeifferBlock and a new LayerNorm `LN` (eps 1e-6)."""
+
+    def __init__(self, transformer_block, args):
+        super().__init__()
+        self.transformer_block = transformer_block
+        self.adapter = AdapterPfeifferBlock(args, args.embedding_dim, args.adapter_down_size, args.adapter_dropout_rate)
+        self.LN = LayerNorm(args.embedding_dim, eps=1e-06)
+
+    def forward(self, block_input, mask):
+        tb = self.transformer_block
+        y = tb.multi_head_attention(block_input, block_input, block_input, mask)
+        ff = tb.feed_forward
+        hy = ff.presum(to_2d_bf16(y))                                   # y + dropout(ffn(y))
+        t = ff.layer_norm(hy)
+        return self.LN(self.adapter(t, extra_residual=hy)).view(block_input.shape)
+
+
+class SASRecParallelAdaptedSelfOutput(nn.Module):
+    """model.py:474-520: both adapters read the sub-block INPUT: layer_norm(adapter1(x) + x + dropout(fc(attn(x)))),
+    then layer_norm(adapter2(y) + y + dropout(ffn(y))); adapter(x) already contains + x."""
+
+    def __init__(self, transformer_block, args):
+        super().__init__()
+        self.transformer_block = transformer_block
+        self.adapter1 = AdapterBlock(args, args.embedding_dim, args.adapter_down_size, args.adapter_dropout_rate)
+        self.adapter2 = AdapterBlock(args, args.embedding_dim, args.adapter_down_size, args.adapter_dropout_rate)
+
+    def forward(self, block_input, mask):
+        tb = self.transformer_block
+        B, S, D = block_input.shape
+        x2 = to_2d_bf16(block_input).contiguous()
+        a1 = to_2d_bf16(self.adapter1(x2, extra_residual=x2))           # up(act(down(x))) + x + x
+        mha, ff = tb.multi_head_attention, tb.feed_forward
+        y = mha.layer_norm(mha.presum(x2, mask, B, S, extra=a1))
+        a2 = to_2d_bf16(self.adapter2(y, extra_residual=y))
+        return ff.layer_norm(ff.presum(y, extra=a2)).view(B, S, D)
+
+
+class BertCompacterAdaptedSelfOutput(nn.Module):
+    """model.py:696-720: LayerNorm(adapter(dropout(dense(x))) + input) with the residual-free HyperComplexAdapterBlock
+    (the dense output reaches the LayerNorm only THROUGH the adapter, as in the reference)."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = HyperComplexAdapterBlock(args, _word_dim(args), args.bert_adapter_down_size)
+
+    def forward(self, hidden_states, input_tensor):
+        return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_from_dense(self, h, input_tensor):
+        h = to_2d_bf16(h)
+        drop = self.self_output.dropout
+        if self.training and drop.p > 0:
+            h = Fn.dropout_add(h, None, drop.p)
+        z = self.adapter(h, extra_residual=to_2d_bf16(input_tensor).contiguous())
+        return self.self_output.LayerNorm(z).view(input_tensor.shape)
+
+
+class SASRecCompacterAdaptedSelfOutput(nn.Module):
+    """model.py:650-693: the serial-Houlsby placement with HyperComplexAdapterBlocks (no inner residual)."""
+
+    def __init__(self, transformer_block, args):
+        super().__init__()
+        self.transformer_block = transformer_block
+        self.adapter1 = HyperComplexAdapterBlock(args, args.embedding_dim, args.adapter_down_size)
+        self.adapter2 = HyperComplexAdapterBlock(args, args.embedding_dim, args.adapter_down_size)
+
+    def forward(self, block_input, mask):
+        tb = self.transformer_block
+        h = tb.multi_head_attention(block_input, block_input, block_input, mask, adapter=self.adapter1)
+        return tb.feed_forward(h, adapter=self.adapter2)
+
+
+class CompacterModel(nn.Module):
+    """Downstream/Text/run.py:70-81 (the reference defines it in the entry script): owns the shared phm_rule
+    [n, n, n] ~ N(0, phm_init_range²), hands it to every PHMLinear, and forwards to the wrapped model (reached as
+    `.model` by data_utils/metrics.py:72-73,101-102)."""
+
+    def __init__(self, args, model):
+        super().__init__()
+        phm_dim = args.hypercomplex_division
+        self.model = model
+        self.phm_rule = nn.Parameter(torch.empty(phm_dim, phm_dim, phm_dim).normal_(mean=0, std=args.phm_init_range))
+        for name, sub_module in model.named_modules():
+            if isinstance(sub_module, PHMLinear):
+                sub_module.set_phm_rule(phm_rule=self.phm_rule)
+
+    def forward(self, sample_items, log_mask, local_rank=None):
+        return self.model(sample_items, log_mask, local_rank)
 
 
 class SoftEmbedding(nn.Module):

@@ -5,7 +5,7 @@ import torch.nn as nn
 
 from .. import functional as Fn
 from .. import ops
-from .layers import BF16, Embedding, LayerNorm, Linear, to_2d_bf16
+from .layers import BF16, Embedding, LayerNorm, Linear, PHMLinear, to_2d_bf16
 
 SASREC_MASK_NEG = -1e9   # encoders.py:28
 
@@ -21,16 +21,24 @@ class PositionwiseFeedForward(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.activate = nn.ReLU()
 
-    def forward(self, x, adapter=None):
-        x2 = to_2d_bf16(x)
+    def presum(self, x2, adapter=None, extra=None):
+        """x2 + dropout(w_2(relu(w_1 x2))) (+ extra) — the argument of the block's LayerNorm.  `adapter` (serial
+        Houlsby) is applied to the dropped-out FFN output before the skip connection; `extra` (parallel Houlsby) is a
+        second summand that already contains what the caller wants added."""
         h = self.w_1(x2, act="relu")
         p = self.dropout.p if self.training else 0.0
+        res = x2.contiguous() if extra is None else extra
         if adapter is None:
-            z = Fn.dropout_add(self.w_2(h), x2.contiguous(), p) if p > 0 else self.w_2(h, residual=x2)
-        else:
-            o = self.w_2(h)
-            z = adapter(Fn.dropout_add(o, None, p) if p > 0 else o, extra_residual=x2)
-        return self.layer_norm(z).view(x.shape)
+            if p > 0:
+                z = Fn.dropout_add(self.w_2(h), res, p)
+                return z
+            return self.w_2(h, residual=res)
+        assert extra is None
+        o = self.w_2(h)
+        return adapter(Fn.dropout_add(o, None, p) if p > 0 else o, extra_residual=x2)
+
+    def forward(self, x, adapter=None):
+        return self.layer_norm(self.presum(to_2d_bf16(x), adapter)).view(x.shape)
 
 
 class SelfAttention(nn.Module):
@@ -59,24 +67,31 @@ class MultiHeadedAttention(nn.Module):
         self.layer_norm = LayerNorm(d_model, eps=1e-6)
         self._qkv_cache = {}
 
+    def presum(self, x2, mask, B, S, adapter=None, extra=None):
+        """x2 + dropout(fc(attention(x2))) (+ extra) — the argument of the block's LayerNorm (see
+        PositionwiseFeedForward.presum for `adapter` / `extra`)."""
+        params = []
+        for m in (self.w_Q, self.w_K, self.w_V):
+            params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
+        qkv = Fn.QKVFunction.apply(x2, self._qkv_cache, *params)
+        ctx = Fn.attention(qkv, mask, B, S, self.n_heads, self.d_k, causal=self.causal, mask_neg=SASREC_MASK_NEG,
+                           dropout_p=self.self_attention.dropout.p if self.training else 0.0)
+        p = self.dropout.p if self.training else 0.0
+        res = x2.contiguous() if extra is None else extra
+        if adapter is None:
+            return Fn.dropout_add(self.fc(ctx), res, p) if p > 0 else self.fc(ctx, residual=res)
+        assert extra is None
+        o = self.fc(ctx)
+        return adapter(Fn.dropout_add(o, None, p) if p > 0 else o, extra_residual=x2)
+
+    causal = True    # User_Encoder's mask (encoders.py:24-28); KAdapterBlock runs the same block with an all-ones mask
+
     def forward(self, query, key, value, mask, adapter=None):
         """query is key is value = block input [B,S,D]; mask = the [B,S] float log_mask (non-zero = valid key); the
         causal structure of User_Encoder.forward's additive mask is applied inside the kernel."""
         assert query is key and key is value, "SASRec self-attention only"
         B, S, D = query.shape
-        x2 = to_2d_bf16(query)
-        params = []
-        for m in (self.w_Q, self.w_K, self.w_V):
-            params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
-        qkv = Fn.QKVFunction.apply(x2, self._qkv_cache, *params)
-        ctx = Fn.attention(qkv, mask, B, S, self.n_heads, self.d_k, causal=True, mask_neg=SASREC_MASK_NEG,
-                           dropout_p=self.self_attention.dropout.p if self.training else 0.0)
-        p = self.dropout.p if self.training else 0.0
-        if adapter is None:
-            z = Fn.dropout_add(self.fc(ctx), x2.contiguous(), p) if p > 0 else self.fc(ctx, residual=x2)
-        else:
-            o = self.fc(ctx)
-            z = adapter(Fn.dropout_add(o, None, p) if p > 0 else o, extra_residual=x2)
+        z = self.presum(to_2d_bf16(query), mask, B, S, adapter)
         return self.layer_norm(z).view(B, S, D)
 
 
@@ -149,3 +164,49 @@ class AdapterBlock(nn.Module):
     def fused(self, x2, extra_residual=None, ln=None):
         """tail(x + fc_up(act(fc_down(x))) [+ extra_residual]) in one kernel; tail = ln (a LayerNorm module) or identity"""
         return Fn.houlsby_block(x2, extra_residual, self.fc_down, self.fc_up, self.act, ln=ln)
+
+
+class AdapterPfeifferBlock(nn.Module):
+    """modules.py:137-158: fc_up(act(fc_down(x))) WITHOUT the inner residual; default nn.Linear initialisation (the
+    N(0, 0.01²) lines are commented out in the reference); act from args.adapter_activation in {"GELU", "leaky_relu",
+    "relu"} — any other value (including the flag's default "RELU") leaves `activate` undefined in the reference and
+    its forward raises AttributeError; the same happens here, at construction time, with a message."""
+
+    def __init__(self, args, input_size, down_size, dropout=0.1):
+        super().__init__()
+        self.fc_down = Linear(input_size, down_size)
+        kinds = {"GELU": ("gelu", nn.GELU), "leaky_relu": ("leaky_relu", nn.LeakyReLU), "relu": ("relu", nn.ReLU)}
+        if args.adapter_activation not in kinds:
+            raise AttributeError("'AdapterPfeifferBlock' object has no attribute 'activate' (adapter_activation=%r; the "
+                                 "reference defines it only for GELU / leaky_relu / relu, modules.py:144-149)"
+                                 % args.adapter_activation)
+        self.act, cls = kinds[args.adapter_activation]
+        self.activate = cls()
+        self.fc_up = Linear(down_size, input_size)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, input_embs, extra_residual=None):
+        """fc_up(act(fc_down(x))) (+ extra_residual, fused into the up-projection's epilogue)"""
+        x2 = to_2d_bf16(input_embs)
+        s = self.fc_down(x2, act=self.act)
+        return self.fc_up(s, residual=extra_residual).view(input_embs.shape)
+
+
+class HyperComplexAdapterBlock(nn.Module):
+    """modules.py:209-250 (Compacter): up_sampler(gelu_new(down_sampler(x))) — two PHMLinear layers sharing the
+    model-wide phm_rule, tanh-GELU in between, NO inner residual."""
+
+    def __init__(self, args, input_size, down_size):
+        super().__init__()
+        self.args = args
+        self.input_dim, self.down_sample_size = input_size, down_size
+        self.down_sampler = PHMLinear(in_features=input_size, out_features=down_size, bias=True,
+                                      phm_dim=args.hypercomplex_division, phm_rank=1)
+        self.up_sampler = PHMLinear(in_features=down_size, out_features=input_size, bias=True,
+                                    phm_dim=args.hypercomplex_division, phm_rank=1)
+
+    def forward(self, x, extra_residual=None):
+        """up(gelu_new(down(x))) (+ extra_residual: the enclosing block's skip connection, fused in the epilogue)"""
+        x2 = to_2d_bf16(x)
+        z = self.down_sampler(x2, act="gelu_new")
+        return self.up_sampler(z, residual=extra_residual).view(x.shape)

@@ -234,12 +234,22 @@ def embed_ln_fwd(ids, L, word_emb, pos_emb, type_emb, gamma, beta, eps, pos_offs
     return out, z, mean, rstd
 
 
+ACT_KINDS = {"gelu": 0, "relu": 1, "leaky_relu": 2, "gelu_new": 3}
+
+
 def act_bwd(dy, u, kind):
-    """dy * act'(u): kind 'gelu' (u = pre-activation) or 'relu' (u = activation output)."""
+    """dy * act'(u): 'gelu' / 'gelu_new' (u = pre-activation) or 'relu' / 'leaky_relu' (u = activation output)."""
     assert dy.dtype == BF16 and u.dtype == BF16 and dy.is_contiguous() and u.is_contiguous() and dy.shape == u.shape
     out = torch.empty_like(dy)
-    _l.check(_l.get_lib().a4r_act_bwd(_p(dy), _p(u), _p(out), dy.numel(), {"gelu": 0, "relu": 1}[kind], _stream()),
-             "a4r_act_bwd")
+    _l.check(_l.get_lib().a4r_act_bwd(_p(dy), _p(u), _p(out), dy.numel(), ACT_KINDS[kind], _stream()), "a4r_act_bwd")
+    return out
+
+
+def act_fwd(u, kind):
+    """act(u) stand-alone (activations that have no GEMM-epilogue mode: leaky_relu, gelu_new)."""
+    assert u.dtype == BF16 and u.is_contiguous()
+    out = torch.empty_like(u)
+    _l.check(_l.get_lib().a4r_act_fwd(_p(u), _p(out), u.numel(), ACT_KINDS[kind], _stream()), "a4r_act_fwd")
     return out
 
 

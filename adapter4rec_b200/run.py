@@ -78,7 +78,7 @@ def build_model(args, item_num, local_rank, bert_config=None, bert_state_dict=No
         surgery.freeze_all(model)
     elif 'all' not in args.fine_tune_to:
         raise AssertionError("fine_tune_to should be defined properly")
-    surgery.insert_adapters(model, args)
+    model = surgery.insert_adapters(model, args)
     surgery.unfreeze_layernorm(model, args)
     return model
 

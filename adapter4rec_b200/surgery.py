@@ -1,7 +1,10 @@
 """Adapter insertion, mirroring the in-place module surgery of Downstream/Text/run.py:367-479 (which lives inside
 train() in the reference and is therefore restated here as a function with the same flag semantics)."""
 from .model.layers import LoRALinear
-from .model.model import BertAdaptedSelfOutput, SASRecAdaptedSelfOutput, SoftEmbedding
+from .model.model import (BertAdaptedParallelSelfOutput, BertAdaptedSelfOutput, BertCompacterAdaptedSelfOutput,
+                          BertPfeifferAdaptedSelfOutput, CompacterModel, SASRecCompacterAdaptedSelfOutput,
+                          SASRecAdaptedSelfOutput, SASRecParallelAdaptedSelfOutput, SASRecPfeifferAdaptedSelfOutput,
+                          SASRecPfeifferVer2AdaptedSelfOutput, SoftEmbedding)
 
 
 def freeze_all(model):
@@ -20,10 +23,20 @@ def insert_adapters(model, args, log=None):
     blocks = model.user_encoder.transformer_encoder.transformer_blocks
     t = args.adapter_type
     dev = next(model.parameters()).device
-    if "pfeiffer" in t or "kadapter" in t or "compacter" in t:
-        raise NotImplementedError("adapter_type %r is a 'next' row (SURVEY.md §8f-4); implemented: houslby (serial), "
-                                  "lora, prompt" % t)
-    if "lora" in t:                                                    # run.py:414-428
+    if "kadapter" in t and "pfeiffer" not in t:
+        raise NotImplementedError("adapter_type %r is a 'next' row (SURVEY.md §8f-4); implemented: houslby (serial and "
+                                  "parallel), pfeiffer, pfeiffer_ver2, compacter, lora, prompt" % t)
+    if "pfeiffer_ver2" in t:                                           # run.py:389-399
+        for lm in layers:
+            lm.attention.output = BertAdaptedSelfOutput(lm.attention.output, args).to(dev)
+        for i in range(len(blocks)):
+            blocks[i] = SASRecPfeifferVer2AdaptedSelfOutput(blocks[i], args).to(dev)
+    elif "pfeiffer" in t:                                              # run.py:400-409
+        for lm in layers:
+            lm.output = BertPfeifferAdaptedSelfOutput(lm.output, args).to(dev)
+        for i in range(len(blocks)):
+            blocks[i] = SASRecPfeifferAdaptedSelfOutput(blocks[i], args).to(dev)
+    elif "lora" in t:                                                  # run.py:414-428
         for lm in layers:
             lm.attention.self.query = LoRALinear(args.word_embedding_dim, args.word_embedding_dim,
                                                  r=args.bert_adapter_down_size).to(dev)
@@ -37,14 +50,22 @@ def insert_adapters(model, args, log=None):
     elif "prompt" in t:                                                # run.py:429-434
         s_wte = SoftEmbedding(bert.get_input_embeddings(), n_tokens=args.n_tokens, initialize_from_vocab=True)
         bert.set_input_embeddings(s_wte.to(dev))
-    elif "houslby" in t:                                               # run.py:452-465
-        if "None" in getattr(args, "is_serial", "True"):
-            raise NotImplementedError("parallel Houlsby adapters are a 'next' row (SURVEY.md §8f-4)")
+    elif "compacter" in t:                                             # run.py:435-450: returns the WRAPPED model
         for lm in layers:
-            lm.attention.output = BertAdaptedSelfOutput(lm.attention.output, args).to(dev)
-            lm.output = BertAdaptedSelfOutput(lm.output, args).to(dev)
+            lm.attention.output = BertCompacterAdaptedSelfOutput(lm.attention.output, args).to(dev)
+            lm.output = BertCompacterAdaptedSelfOutput(lm.output, args).to(dev)
         for i in range(len(blocks)):
-            blocks[i] = SASRecAdaptedSelfOutput(blocks[i], args).to(dev)
+            blocks[i] = SASRecCompacterAdaptedSelfOutput(blocks[i], args).to(dev)
+        model = CompacterModel(args, model).to(dev)
+    elif "houslby" in t:                                               # run.py:452-465
+        serial = "None" not in getattr(args, "is_serial", "True")       # run.py:454 vs :466
+        bert_cls = BertAdaptedSelfOutput if serial else BertAdaptedParallelSelfOutput
+        rec_cls = SASRecAdaptedSelfOutput if serial else SASRecParallelAdaptedSelfOutput
+        for lm in layers:
+            lm.attention.output = bert_cls(lm.attention.output, args).to(dev)
+            lm.output = bert_cls(lm.output, args).to(dev)
+        for i in range(len(blocks)):
+            blocks[i] = rec_cls(blocks[i], args).to(dev)
     return model
 
 

@@ -263,8 +263,13 @@ A4R_API int a4r_vit_assemble(const void* patch_emb, const void* cls, const void*
                              int64_t N, int64_t P, int64_t T, int64_t H, a4r_stream_t stream);
 
 /* out = dy * act'(u) elementwise over n bf16 values; kind 0: erf-GELU with u = pre-activation
- * (Text_Encoder.activate, encoders.py:46,57), kind 1: ReLU with u = activation output. */
+ * (Text_Encoder.activate, encoders.py:46,57), kind 1: ReLU with u = activation output, kind 2: LeakyReLU(0.01) with
+ * u = activation output (AdapterPfeifferBlock, Downstream/Text/model/modules.py:146-147), kind 3: tanh-GELU
+ * ("gelu_new", HyperComplexAdapterBlock, modules.py:217) with u = pre-activation.
+ * a4r_act_fwd: out = act(u) for the same kinds (the activations without a GEMM-epilogue mode run stand-alone on the
+ * r-wide bottleneck). */
 A4R_API int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
+A4R_API int a4r_act_fwd(const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
 
 /* Dropout (+ residual): out = x * mask / (1 - p) (+ res), n bf16 elements (n %% 8 == 0).  Replaces nn.Dropout on the
  * hidden states (BertSelfOutput.dropout / BertOutput.dropout / BertEmbeddings.dropout, SASRec modules.py:27,72,107)

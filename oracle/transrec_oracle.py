@@ -40,9 +40,12 @@ class RecConfig:
     """argparse fields read by the path (Downstream/Text/parameters.py:25-31,55,62,65,76)."""
 
     def __init__(self, max_seq_len=20, embedding_dim=64, heads=2, blocks=2, num_words_title=30,
-                 adapter_activation="RELU", n_tokens=0):
+                 adapter_activation="RELU", n_tokens=0, parallel=False):
         self.max_seq_len, self.embedding_dim, self.heads, self.blocks = max_seq_len, embedding_dim, heads, blocks
         self.num_words_title, self.adapter_activation, self.n_tokens = num_words_title, adapter_activation, n_tokens
+        # is_serial == "None" (parameters.py:66, run.py:454/466): the parallel Houlsby wrappers have the SAME state_dict
+        # keys as the serial ones, so the variant cannot be read off the checkpoint
+        self.parallel = parallel
 
 
 def layer_norm(x, sd, prefix, eps):
@@ -56,6 +59,41 @@ def adapter_block(x, sd, prefix, activation="RELU"):
     h = F.linear(x, sd[prefix + "fc_down.weight"], sd[prefix + "fc_down.bias"])
     h = F.gelu(h) if activation == "GELU" else F.relu(h)
     return F.linear(h, sd[prefix + "fc_up.weight"], sd[prefix + "fc_up.bias"]) + x
+
+
+def adapter_pfeiffer_block(x, sd, prefix, activation):
+    """AdapterPfeifferBlock.forward, Downstream/Text/model/modules.py:155-158: fc_up(act(fc_down(x))), no residual;
+    act in {GELU, leaky_relu (slope 0.01), relu} (modules.py:144-149)."""
+    h = F.linear(x, sd[prefix + "fc_down.weight"], sd[prefix + "fc_down.bias"])
+    h = {"GELU": F.gelu, "leaky_relu": F.leaky_relu, "relu": F.relu}[activation](h)
+    return F.linear(h, sd[prefix + "fc_up.weight"], sd[prefix + "fc_up.bias"])
+
+
+def unwrap_compacter(sd):
+    """CompacterModel (Downstream/Text/run.py:70-81) wraps the model as `.model` and owns the shared `phm_rule`: its
+    state_dict is {"phm_rule", "model.<inner key>"...} (every PHMLinear repeats the shared rule under its own name; only
+    the top-level entry is read here).  Returns the inner-key view; a no-op for every other variant."""
+    if "phm_rule" not in sd:
+        return sd
+    out = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+    out["phm_rule"] = sd["phm_rule"]
+    return out
+
+
+def phm_linear(x, sd, prefix, phm_rule):
+    """PHMLinear.forward with factorized_phm=True, shared_phm_rule=True (Downstream/Text/model/layers.py:153-166,
+    matvec_product :10-22, kronecker.py:23-34): W = bmm(W_left, W_right); H = Σ_b rule[b] ⊗ W[b]; y = x·H + b."""
+    W = torch.bmm(sd[prefix + "W_left"], sd[prefix + "W_right"])
+    A = phm_rule
+    H = torch.einsum('bac,bkp->bakcp', A, W).reshape(A.size(0), A.size(1) * W.size(1), A.size(2) * W.size(2)).sum(0)
+    return torch.matmul(x, H) + sd[prefix + "b"]
+
+
+def hypercomplex_adapter_block(x, sd, prefix):
+    """HyperComplexAdapterBlock.forward, modules.py:247-250: up_sampler(gelu_new(down_sampler(x))), no residual;
+    gelu_new = transformers' tanh approximation."""
+    z = F.gelu(phm_linear(x, sd, prefix + "down_sampler.", sd["phm_rule"]), approximate="tanh")
+    return phm_linear(z, sd, prefix + "up_sampler.", sd["phm_rule"])
 
 
 def lora_linear(x, sd, prefix):
@@ -72,12 +110,29 @@ def linear_or_lora(x, sd, prefix):
     return lora_linear(x, sd, prefix)
 
 
-def self_output(hidden, input_tensor, sd, prefix, eps, activation):
-    """BertSelfOutput / BertOutput (transformers) or, if the Houlsby wrapper keys are present,
-    BertAdaptedSelfOutput.forward, Downstream/Text/model/model.py:292-297:
-    dense -> dropout (eval: identity) -> adapter -> LayerNorm(h + input)."""
+def self_output(hidden, input_tensor, sd, prefix, eps, activation, parallel=False):
+    """BertSelfOutput / BertOutput (transformers) or, by the wrapper keys present, one of
+    * BertAdaptedSelfOutput.forward, Downstream/Text/model/model.py:292-297 (Houlsby serial):
+      dense -> dropout (eval: identity) -> adapter -> LayerNorm(h + input);
+    * BertAdaptedParallelSelfOutput.forward, model.py:265-270 (`parallel`; same keys as the serial wrapper):
+      LayerNorm(adapter(input) + dense(hidden) + input);
+    * BertPfeifferAdaptedSelfOutput.forward, model.py:321-329 (has the extra `LN`): h = dense(hidden);
+      t = LayerNorm(h + input); LN(adapter(t) + h + input), LN eps 1e-6."""
+    if prefix + "adapter.down_sampler.W_left" in sd:
+        # BertCompacterAdaptedSelfOutput.forward, model.py:715-720: LayerNorm(adapter(dense(hidden)) + input)
+        h = F.linear(hidden, sd[prefix + "self_output.dense.weight"], sd[prefix + "self_output.dense.bias"])
+        h = hypercomplex_adapter_block(h, sd, prefix + "adapter.")
+        return layer_norm(h + input_tensor, sd, prefix + "self_output.LayerNorm.", eps)
+    if prefix + "LN.weight" in sd:
+        h = F.linear(hidden, sd[prefix + "self_output.dense.weight"], sd[prefix + "self_output.dense.bias"])
+        t = layer_norm(h + input_tensor, sd, prefix + "self_output.LayerNorm.", eps)
+        a = adapter_pfeiffer_block(t, sd, prefix + "adapter.", activation) + h
+        return layer_norm(a + input_tensor, sd, prefix + "LN.", 1e-6)
     if prefix + "self_output.dense.weight" in sd:
         h = F.linear(hidden, sd[prefix + "self_output.dense.weight"], sd[prefix + "self_output.dense.bias"])
+        if parallel:
+            a = adapter_block(input_tensor, sd, prefix + "adapter.", activation)
+            return layer_norm(a + h + input_tensor, sd, prefix + "self_output.LayerNorm.", eps)
         h = adapter_block(h, sd, prefix + "adapter.", activation)
         return layer_norm(h + input_tensor, sd, prefix + "self_output.LayerNorm.", eps)
     h = F.linear(hidden, sd[prefix + "dense.weight"], sd[prefix + "dense.bias"])
@@ -104,7 +159,7 @@ def bert_embeddings(ids, sd, cfg, n_tokens=0):
     return layer_norm(x, sd, p + "LayerNorm.", cfg.eps)
 
 
-def bert_layer(x, add_mask, sd, i, cfg, activation):
+def bert_layer(x, add_mask, sd, i, cfg, activation, parallel=False):
     """One BertLayer (post-LN).  q/k/v may be loralib Linears (run.py:416-421); attention.output / output may be
     Houlsby-wrapped (run.py:456-460).  Attention: softmax(q kᵀ / sqrt(d) + mask) v with the transformers additive
     mask (1 - m) * finfo(float32).min."""
@@ -116,29 +171,38 @@ def bert_layer(x, add_mask, sd, i, cfg, activation):
     v = linear_or_lora(x, sd, p + "attention.self.value.").view(N, L, cfg.heads, dh).transpose(1, 2)
     s = q @ k.transpose(-1, -2) / math.sqrt(dh) + add_mask
     ctx = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(N, L, H)
-    y = self_output(ctx, x, sd, p + "attention.output.", cfg.eps, activation)
+    y = self_output(ctx, x, sd, p + "attention.output.", cfg.eps, activation, parallel)
     f = F.gelu(F.linear(y, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
-    return self_output(f, y, sd, p + "output.", cfg.eps, activation)
+    return self_output(f, y, sd, p + "output.", cfg.eps, activation, parallel)
 
 
 def bert_encoder(text, sd, cfg, rec):
     """Bert_Encoder.forward + Text_Encoder.forward, Downstream/Text/model/encoders.py:48-57,89-99:
     text [N, 2L] = ids | attention mask; returns GELU(fc(hidden[:, 0])) [N, D]."""
+    sd = unwrap_compacter(sd)
     L = text.shape[1] // 2
     ids, mask = text[:, :L], text[:, L:]
     x = bert_embeddings(ids, sd, cfg, rec.n_tokens)
     add_mask = (1.0 - mask.float()).view(-1, 1, 1, L) * torch.finfo(torch.float32).min
     for i in range(cfg.layers):
-        x = bert_layer(x, add_mask, sd, i, cfg, rec.adapter_activation)
+        x = bert_layer(x, add_mask, sd, i, cfg, rec.adapter_activation, getattr(rec, "parallel", False))
     cls = F.linear(x[:, 0], sd[FC_PREFIX + "weight"], sd[FC_PREFIX + "bias"])
     return F.gelu(cls)
 
 
 def sasrec_block(x, att_mask, sd, p, rec):
-    """TransformerBlock.forward (Downstream/Text/model/modules.py:45-87) or, when the wrapper keys are present,
-    SASRecAdaptedSelfOutput.forward (model.py:341-376): adapter1 after fc, adapter2 after the FFN, both before the
-    LayerNorms.  w_Q / w_V may be loralib Linears with a bias (run.py:425-428)."""
+    """TransformerBlock.forward (Downstream/Text/model/modules.py:45-87) or, by the wrapper keys present, one of
+    * SASRecAdaptedSelfOutput.forward (model.py:341-376): adapter1 after fc, adapter2 after the FFN, both before the
+      LayerNorms; SASRecPfeifferVer2AdaptedSelfOutput (model.py:389-423) is the same without adapter2;
+    * SASRecParallelAdaptedSelfOutput.forward (model.py:484-520, `rec.parallel`): layer_norm(adapter1(x) + x + fc(..)),
+      layer_norm(adapter2(y) + y + ffn(y));
+    * SASRecPfeifferAdaptedSelfOutput.forward (model.py:437-471; has `adapter.` and `LN.`): plain attention half,
+      t = layer_norm(y + ffn(y)); LN(adapter(t) + ffn(y) + y).
+    w_Q / w_V may be loralib Linears with a bias (run.py:425-428)."""
     wrapped = p + "transformer_block.multi_head_attention.w_Q.weight" in sd
+    pfeiffer = p + "LN.weight" in sd
+    parallel = wrapped and getattr(rec, "parallel", False)
+    act = rec.adapter_activation
     tb = p + ("transformer_block." if wrapped else "")
     a = tb + "multi_head_attention."
     B, S, D = x.shape
@@ -149,19 +213,33 @@ def sasrec_block(x, att_mask, sd, p, rec):
     attn = q @ k.transpose(-2, -1) / (dk ** 0.5) + att_mask
     h = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(B, S, D)
     h = F.linear(h, sd[a + "fc.weight"])
-    if wrapped:
-        h = adapter_block(h, sd, p + "adapter1.", rec.adapter_activation)
-    y = layer_norm(x + h, sd, a + "layer_norm.", 1e-6)
+    compacter = p + "adapter1.down_sampler.W_left" in sd      # SASRecCompacterAdaptedSelfOutput, model.py:659-693
+    if compacter:
+        y = layer_norm(x + hypercomplex_adapter_block(h, sd, p + "adapter1."), sd, a + "layer_norm.", 1e-6)
+    elif parallel:
+        y = layer_norm(adapter_block(x, sd, p + "adapter1.", act) + x + h, sd, a + "layer_norm.", 1e-6)
+    else:
+        if p + "adapter1.fc_down.weight" in sd:
+            h = adapter_block(h, sd, p + "adapter1.", act)
+        y = layer_norm(x + h, sd, a + "layer_norm.", 1e-6)
     f = tb + "feed_forward."
     h = F.linear(F.relu(F.linear(y, sd[f + "w_1.weight"], sd[f + "w_1.bias"])), sd[f + "w_2.weight"], sd[f + "w_2.bias"])
-    if wrapped:
-        h = adapter_block(h, sd, p + "adapter2.", rec.adapter_activation)
+    if compacter:
+        return layer_norm(y + hypercomplex_adapter_block(h, sd, p + "adapter2."), sd, f + "layer_norm.", 1e-6)
+    if parallel:
+        return layer_norm(adapter_block(y, sd, p + "adapter2.", act) + y + h, sd, f + "layer_norm.", 1e-6)
+    if pfeiffer:
+        t = layer_norm(y + h, sd, f + "layer_norm.", 1e-6)
+        return layer_norm(adapter_pfeiffer_block(t, sd, p + "adapter.", act) + h + y, sd, p + "LN.", 1e-6)
+    if p + "adapter2.fc_down.weight" in sd:
+        h = adapter_block(h, sd, p + "adapter2.", act)
     return layer_norm(y + h, sd, f + "layer_norm.", 1e-6)
 
 
 def user_encoder(input_embs, log_mask, sd, rec):
     """User_Encoder.forward (encoders.py:24-29) + TransformerEncoder.forward (modules.py:101-113).
     Mask: 0 where (key j <= query i and log_mask[b, j] != 0) else -1e9, shape [B,1,S,S]."""
+    sd = unwrap_compacter(sd)
     B, S, D = input_embs.shape
     valid = (log_mask != 0).view(B, 1, 1, S).expand(-1, -1, S, -1)
     att_mask = torch.where(torch.tril(valid), 0.0, -1e9)

@@ -12,8 +12,18 @@ FC = "bert_encoder.text_encoders.title.fc."
 USER = "user_encoder.transformer_encoder."
 
 
+ZOO_KINDS = ("parallel", "pfeiffer", "pfeiffer_leaky", "pfeiffer_ver2", "compacter")
+ALL_KINDS = ("base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc") + ZOO_KINDS
+
+
+def _houlsby_like(kind):
+    """kinds whose BERT/SASRec wrappers carry an AdapterBlock bottleneck of rank 16"""
+    return kind.startswith("houlsby") or kind in ZOO_KINDS
+
+
 def tiny_case(kind):
-    """kind: 'base' | 'houlsby' | 'lora' | 'prompt_cpc' (RoBERTa + SoftEmbedding + ModelCPC) | 'houlsby_gelu'."""
+    """kind: 'base' | 'houlsby' | 'lora' | 'prompt_cpc' (RoBERTa + SoftEmbedding + ModelCPC) | 'houlsby_gelu' |
+    'parallel' (Houlsby, is_serial=None) | 'pfeiffer' (GELU) | 'pfeiffer_leaky' | 'pfeiffer_ver2'."""
     c = types.SimpleNamespace()
     c.kind = kind
     c.roberta = kind == "prompt_cpc"
@@ -26,13 +36,16 @@ def tiny_case(kind):
     c.S = 5                    # max_seq_len
     c.D = 64                   # embedding_dim
     c.rec_heads, c.blocks = 2, 2
-    c.bert_r = 16 if kind.startswith("houlsby") else 8   # bert_adapter_down_size (LoRA rank for kind == 'lora')
-    c.rec_r = 16 if kind.startswith("houlsby") else 8    # adapter_down_size
+    c.bert_r = 16 if _houlsby_like(kind) else 8   # bert_adapter_down_size (LoRA rank for kind == 'lora')
+    c.rec_r = 16 if _houlsby_like(kind) else 8    # adapter_down_size
     c.n_tokens = 3 if kind == "prompt_cpc" else 0
-    c.activation = "GELU" if kind == "houlsby_gelu" else "RELU"
+    c.activation = {"houlsby_gelu": "GELU", "pfeiffer": "GELU", "pfeiffer_leaky": "leaky_relu"}.get(kind, "RELU")
+    c.parallel = kind == "parallel"
     c.B = 6
     c.item_num = 40
-    c.seed = {"base": 11, "houlsby": 12, "lora": 13, "prompt_cpc": 14, "houlsby_gelu": 15}[kind]
+    c.seed = {"base": 11, "houlsby": 12, "lora": 13, "prompt_cpc": 14, "houlsby_gelu": 15, "parallel": 16,
+              "pfeiffer": 17, "pfeiffer_leaky": 18, "pfeiffer_ver2": 19, "compacter": 20}[kind]
+    c.phm_dim = 4              # hypercomplex_division
     return c
 
 
@@ -45,8 +58,11 @@ def reference_args(c):
         bert_adapter_down_size=c.bert_r, adapter_down_size=c.rec_r, adapter_dropout_rate=0.1,
         adapter_activation=c.activation, num_workers=0, adapter_type={"houlsby": "houslby", "houlsby_gelu": "houslby",
                                                                       "lora": "lora", "prompt_cpc": "prompt",
-                                                                      "base": "None"}[c.kind],
-        n_tokens=c.n_tokens)
+                                                                      "base": "None", "parallel": "houslby",
+                                                                      "pfeiffer": "pfeiffer", "pfeiffer_leaky": "pfeiffer",
+                                                                      "pfeiffer_ver2": "pfeiffer_ver2", "compacter": "compacter"}[c.kind],
+        hypercomplex_division=c.phm_dim, phm_init_range=0.0001,
+        is_serial="None" if c.kind == "parallel" else "True", n_tokens=c.n_tokens)
 
 
 def _n(g, shape, std):
@@ -69,6 +85,18 @@ def _adapter(sd, g, name, dim, r):
     _linear(sd, g, name + "fc_up.", dim, r)
 
 
+def _phm(sd, g, name, in_f, out_f, n, rule):
+    sd[name + "W_left"] = _n(g, (n, in_f // n, 1), 0.3)
+    sd[name + "W_right"] = _n(g, (n, 1, out_f // n), 0.3)
+    sd[name + "b"] = _n(g, (out_f,), 0.05)
+    sd[name + "phm_rule"] = rule            # the ONE shared tensor, repeated under every PHMLinear by the reference
+
+
+def _phm_adapter(sd, g, name, dim, r, n, rule):
+    _phm(sd, g, name + "down_sampler.", dim, r, n, rule)
+    _phm(sd, g, name + "up_sampler.", r, dim, n, rule)
+
+
 def _lora(sd, g, name, dim, r):
     _linear(sd, g, name, dim, dim, bias=True)
     sd[name + "lora_A"] = _n(g, (r, dim), 0.1)
@@ -80,6 +108,7 @@ def build_state_dict(c):
     g = torch.Generator().manual_seed(c.seed)
     sd = {}
     H = c.hidden
+    rule = _n(g, (c.phm_dim,) * 3, 0.5) if c.kind == "compacter" else None
     e = BERT + "embeddings."
     if c.kind == "prompt_cpc":
         sd[e + "word_embeddings.wte.weight"] = _n(g, (c.vocab, H), 0.05)
@@ -97,10 +126,20 @@ def build_state_dict(c):
             else:
                 _linear(sd, g, p + "attention.self.%s." % nm, H, H)
         for out_name, in_f in (("attention.output.", H), ("output.", c.inter)):
-            if c.kind.startswith("houlsby"):
+            # which of the two sub-layer outputs is wrapped: Houlsby serial/parallel both (run.py:456-460,468-474),
+            # pfeiffer_ver2 attention.output only (:391-394), pfeiffer output only (:403-406)
+            wrapped = (c.kind.startswith("houlsby") or c.kind in ("parallel", "compacter")
+                       or (c.kind == "pfeiffer_ver2" and out_name == "attention.output.")
+                       or (c.kind.startswith("pfeiffer") and c.kind != "pfeiffer_ver2" and out_name == "output."))
+            if wrapped:
                 _linear(sd, g, p + out_name + "self_output.dense.", H, in_f)
                 _ln(sd, g, p + out_name + "self_output.LayerNorm.", H)
-                _adapter(sd, g, p + out_name + "adapter.", H, c.bert_r)
+                if c.kind == "compacter":
+                    _phm_adapter(sd, g, p + out_name + "adapter.", H, c.bert_r, c.phm_dim, rule)
+                else:
+                    _adapter(sd, g, p + out_name + "adapter.", H, c.bert_r)
+                if c.kind in ("pfeiffer", "pfeiffer_leaky"):
+                    _ln(sd, g, p + out_name + "LN.", H)
             else:
                 _linear(sd, g, p + out_name + "dense.", H, in_f)
                 _ln(sd, g, p + out_name + "LayerNorm.", H)
@@ -113,7 +152,7 @@ def build_state_dict(c):
     _ln(sd, g, USER + "layer_norm.", D)
     for j in range(c.blocks):
         p = USER + "transformer_blocks.%d." % j
-        tb = p + ("transformer_block." if c.kind.startswith("houlsby") else "")
+        tb = p + ("transformer_block." if _houlsby_like(c.kind) else "")
         for nm in ("w_Q", "w_K", "w_V", "fc"):
             if c.kind == "lora" and nm in ("w_Q", "w_V"):
                 _lora(sd, g, tb + "multi_head_attention.%s." % nm, D, c.rec_r)
@@ -123,16 +162,31 @@ def build_state_dict(c):
         _linear(sd, g, tb + "feed_forward.w_1.", 4 * D, D, std=0.1)
         _linear(sd, g, tb + "feed_forward.w_2.", D, 4 * D, std=0.1)
         _ln(sd, g, tb + "feed_forward.layer_norm.", D)
-        if c.kind.startswith("houlsby"):
+        if c.kind.startswith("houlsby") or c.kind == "parallel":
             _adapter(sd, g, p + "adapter1.", D, c.rec_r)
             _adapter(sd, g, p + "adapter2.", D, c.rec_r)
+        elif c.kind == "pfeiffer_ver2":
+            _adapter(sd, g, p + "adapter1.", D, c.rec_r)
+        elif c.kind in ("pfeiffer", "pfeiffer_leaky"):
+            _adapter(sd, g, p + "adapter.", D, c.rec_r)
+            _ln(sd, g, p + "LN.", D)
+        elif c.kind == "compacter":
+            _phm_adapter(sd, g, p + "adapter1.", D, c.rec_r, c.phm_dim, rule)
+            _phm_adapter(sd, g, p + "adapter2.", D, c.rec_r, c.phm_dim, rule)
+    if c.kind == "compacter":       # CompacterModel wraps the model as `.model` and owns the shared rule (run.py:70-81)
+        sd = {"model." + k: v for k, v in sd.items()}
+        sd["phm_rule"] = rule
     return sd
 
 
 def trainable_keys(c, sd):
     """Parameters left trainable by Downstream/Text/run.py:367-479 with fine_tune_to=None."""
-    if c.kind.startswith("houlsby"):
+    if c.kind.startswith("houlsby") or c.kind in ("parallel", "pfeiffer_ver2"):
         return [k for k in sd if "adapter" in k]
+    if c.kind == "compacter":     # named_parameters() lists the shared rule once, under the wrapper's own name
+        return [k for k in sd if "adapter" in k and not k.endswith("phm_rule")] + ["phm_rule"]
+    if c.kind in ("pfeiffer", "pfeiffer_leaky"):      # the new `LN` LayerNorms are created after the freeze
+        return [k for k in sd if "adapter" in k or ".LN." in k]
     if c.kind == "lora":
         return [k for k in sd if "lora_" in k or (k.endswith("bias") and (
             ".query." in k or ".value." in k or ".w_Q." in k or ".w_V." in k))]

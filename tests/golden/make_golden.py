@@ -41,7 +41,9 @@ import torch.distributed as dist  # noqa: E402
 from transformers import BertConfig, BertModel, RobertaConfig, RobertaModel  # noqa: E402
 
 from data_utils.metrics import eval_model, get_item_embeddings, metrics_topK  # noqa: E402
-from model import BertAdaptedSelfOutput, Model, ModelCPC, SASRecAdaptedSelfOutput, SoftEmbedding  # noqa: E402
+from model import (BertAdaptedParallelSelfOutput, BertAdaptedSelfOutput, BertPfeifferAdaptedSelfOutput, Model,  # noqa: E402
+                   ModelCPC, SASRecAdaptedSelfOutput, SASRecParallelAdaptedSelfOutput, SASRecPfeifferAdaptedSelfOutput,
+                   SASRecPfeifferVer2AdaptedSelfOutput, SoftEmbedding)
 
 
 def build_reference_model(c):
@@ -64,6 +66,31 @@ def build_reference_model(c):
             lm.output = BertAdaptedSelfOutput(lm.output, args)
         for i, tb in enumerate(blocks):
             blocks[i] = SASRecAdaptedSelfOutput(tb, args)
+    elif c.kind == "parallel":                                     # run.py:466-479 (is_serial == "None")
+        for lm in layers:
+            lm.attention.output = BertAdaptedParallelSelfOutput(lm.attention.output, args)
+            lm.output = BertAdaptedParallelSelfOutput(lm.output, args)
+        for i, tb in enumerate(blocks):
+            blocks[i] = SASRecParallelAdaptedSelfOutput(tb, args)
+    elif c.kind == "pfeiffer_ver2":                                # run.py:389-399
+        for lm in layers:
+            lm.attention.output = BertAdaptedSelfOutput(lm.attention.output, args)
+        for i, tb in enumerate(blocks):
+            blocks[i] = SASRecPfeifferVer2AdaptedSelfOutput(tb, args)
+    elif c.kind in ("pfeiffer", "pfeiffer_leaky"):                 # run.py:400-409
+        for lm in layers:
+            lm.output = BertPfeifferAdaptedSelfOutput(lm.output, args)
+        for i, tb in enumerate(blocks):
+            blocks[i] = SASRecPfeifferAdaptedSelfOutput(tb, args)
+    elif c.kind == "compacter":                                    # run.py:435-450
+        from model import BertCompacterAdaptedSelfOutput, SASRecCompacterAdaptedSelfOutput
+        from run import CompacterModel                             # the reference's own wrapper class (entry script)
+        for lm in layers:
+            lm.attention.output = BertCompacterAdaptedSelfOutput(lm.attention.output, args)
+            lm.output = BertCompacterAdaptedSelfOutput(lm.output, args)
+        for i, tb in enumerate(blocks):
+            blocks[i] = SASRecCompacterAdaptedSelfOutput(tb, args)
+        model = CompacterModel(args, model)
     elif c.kind == "lora":                                         # run.py:414-428
         import loralib as lora
         for lm in layers:
@@ -84,7 +111,8 @@ def main():
     dist.init_process_group("gloo", rank=0, world_size=1)
     import transformers
     meta = {"torch": torch.__version__, "transformers": transformers.__version__}
-    for kind in ("base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc"):
+    only = sys.argv[1:]                                            # optional: regenerate just the named kinds
+    for kind in (only or cases.ALL_KINDS):
         c = cases.tiny_case(kind)
         model, args = build_reference_model(c)
         sd = cases.build_state_dict(c)
@@ -108,7 +136,8 @@ def main():
             out["grads"] = {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
         out["loss"] = loss.detach().clone()
         with torch.no_grad():
-            out["batch_item_emb"] = model.bert_encoder(sample_items.view(-1, 2 * c.L)).clone()
+            inner = model.model if c.kind == "compacter" else model        # as metrics.py:72-73,101-102 reach in
+            out["batch_item_emb"] = inner.bert_encoder(sample_items.view(-1, 2 * c.L)).clone()
             wrapper = types.SimpleNamespace(module=model, eval=model.eval)
             emb = get_item_embeddings(wrapper, items.numpy(), 16, args, True, "cpu")
             out["item_emb"] = emb.clone()
@@ -124,7 +153,7 @@ def main():
                 toks = seq[:-1]
                 pad = [0] * (S - len(toks)) + toks
                 mask = torch.FloatTensor([0] * (S - len(toks)) + [1] * len(toks))
-                prec = model.user_encoder(emb[pad].unsqueeze(0), mask.unsqueeze(0), "cpu")[:, -1]
+                prec = inner.user_encoder(emb[pad].unsqueeze(0), mask.unsqueeze(0), "cpu")[:, -1]
                 score = torch.matmul(prec, emb.t()).squeeze(0)
                 score[torch.LongTensor(hist[u])] = -float("inf")
                 score = score[1:]

@@ -15,7 +15,7 @@ import cases  # noqa: E402
 import transrec_oracle as O  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-KINDS = ["base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc"]
+KINDS = list(cases.ALL_KINDS)
 
 LOSS_RTOL = 2e-2        # |loss - oracle| <= 2e-2 * |oracle|   (bf16 activations through 2 BERT + 2 SASRec layers)
 EMB_ATOL = 3e-2         # item embeddings are O(0.1-1): absolute 3e-2
@@ -28,7 +28,7 @@ def build_gpu_model(c, sd):
     from adapter4rec_b200 import surgery
     from adapter4rec_b200.model import BertModel, Model, ModelCPC, RobertaModel, TextConfigLite
     args = cases.reference_args(c)
-    args.adding_adapter_to, args.is_serial, args.finetune_layernorm = "all", "True", "None"
+    args.adding_adapter_to, args.finetune_layernorm = "all", "None"
     cfg = TextConfigLite(vocab_size=c.vocab, hidden_size=c.hidden, num_hidden_layers=c.layers,
                          num_attention_heads=c.heads, intermediate_size=c.inter, max_position_embeddings=c.max_pos,
                          layer_norm_eps=c.eps, type_vocab_size=1 if c.roberta else 2, pad_token_id=c.pad)
@@ -36,7 +36,7 @@ def build_gpu_model(c, sd):
     model = (ModelCPC if c.cpc else Model)(args, c.item_num, True, bert).cuda()
     surgery.freeze_all(model)
     if c.kind != "base":
-        surgery.insert_adapters(model, args)
+        model = surgery.insert_adapters(model, args)        # compacter returns the CompacterModel wrapper
     assert set(model.state_dict().keys()) == set(sd.keys()), "state_dict keys must equal the reference's"
     model.load_state_dict(sd)
     got_train = sorted(n for n, p in model.named_parameters() if p.requires_grad)
@@ -47,7 +47,7 @@ def build_gpu_model(c, sd):
 def oracle_setup(c):
     cfg = O.TextConfig(hidden=c.hidden, layers=c.layers, heads=c.heads, eps=c.eps, roberta=c.roberta, pad_token_id=c.pad)
     rec = O.RecConfig(max_seq_len=c.S, embedding_dim=c.D, heads=c.rec_heads, blocks=c.blocks, num_words_title=c.L,
-                      adapter_activation=c.activation, n_tokens=c.n_tokens)
+                      adapter_activation=c.activation, n_tokens=c.n_tokens, parallel=c.parallel)
     return cfg, rec
 
 
@@ -109,7 +109,8 @@ def test_item_encoder_matches_reference(kind):
     model.eval()
     items = cases.build_item_content(c)
     with torch.no_grad():
-        emb = model.bert_encoder(items.cuda()).float().cpu()
+        from adapter4rec_b200.data_utils.metrics import core_model
+        emb = core_model(model).bert_encoder(items.cuda()).float().cpu()
     ref = gold["item_emb"]
     err = (emb[1:] - ref[1:]).abs().max()
     assert float(err) <= EMB_ATOL, "max abs err %.4f" % float(err)
