@@ -272,14 +272,14 @@ def add(x, res):
 
 class AttentionFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, mask, N, L, heads, head_dim, causal, mask_neg, dropout_p=0.0):
-        ctx.cfg = (N, L, heads, head_dim, causal, mask_neg)
+    def forward(ctx, qkv, mask, N, L, heads, head_dim, causal, mask_neg, dropout_p=0.0, scale=None):
+        ctx.cfg = (N, L, heads, head_dim, causal, mask_neg, scale)
         ctx.mask = mask
         ctx.drop = None
         if dropout_p > 0.0:
             ctx.drop = (dropout_p,) + DropoutState.draw(N * heads * 32 * 8)
         out, lse = ops.attn_small_fwd(qkv, N, L, heads, head_dim, mask=mask, causal=causal, mask_neg=mask_neg, want_lse=True,
-                                      dropout=ctx.drop)
+                                      dropout=ctx.drop, scale=scale)
         # the short-sequence kernel recomputes everything from qkv; the mid-length (ViT) kernel reuses lse and the output
         ctx.save_for_backward(qkv, lse, out if lse is not None else None)
         return out
@@ -287,14 +287,16 @@ class AttentionFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dctx):
         qkv, lse, out = ctx.saved_tensors
-        N, L, heads, head_dim, causal, mask_neg = ctx.cfg
+        N, L, heads, head_dim, causal, mask_neg, scale = ctx.cfg
         dqkv = ops.attn_small_bwd(qkv, dctx.contiguous(), N, L, heads, head_dim, mask=ctx.mask, causal=causal,
-                                  mask_neg=mask_neg, lse=lse, ctx=out, dropout=ctx.drop)
-        return dqkv, None, None, None, None, None, None, None, None
+                                  mask_neg=mask_neg, lse=lse, ctx=out, dropout=ctx.drop, scale=scale)
+        return dqkv, None, None, None, None, None, None, None, None, None
 
 
-def attention(qkv, mask, N, L, heads, head_dim, causal=False, mask_neg=ops.F32_MIN, dropout_p=0.0):
-    return AttentionFunction.apply(qkv, mask, N, L, heads, head_dim, causal, mask_neg, float(dropout_p))
+def attention(qkv, mask, N, L, heads, head_dim, causal=False, mask_neg=ops.F32_MIN, dropout_p=0.0, scale=None):
+    """scale: softmax temperature override (default head_dim ** -0.5); used when narrow heads are zero-padded to a
+    kernel-supported width"""
+    return AttentionFunction.apply(qkv, mask, N, L, heads, head_dim, causal, mask_neg, float(dropout_p), scale)
 
 
 LORA_PAD = 64  # the rank-r intermediates of all LoRA'd projections of one fused QKV share one 64-column k-block

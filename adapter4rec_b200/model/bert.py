@@ -221,14 +221,25 @@ class BertModel(nn.Module):
 
     supports_cls_only = True
 
-    def forward(self, input_ids=None, attention_mask=None, cls_only=False, **unused):
+    def forward(self, input_ids=None, attention_mask=None, cls_only=False, output_hidden_states=None, **unused):
         """cls_only=True returns [N, 1, H] (the [CLS] position only), skipping the row-wise tail of the last layer for
-        all other tokens; values at position 0 are identical to the full computation."""
+        all other tokens; values at position 0 are identical to the full computation.
+        output_hidden_states (default: config.output_hidden_states, which the reference sets when loading,
+        run.py:286-297) -> (last_hidden_state, None, (embedding output, layer 1 output, ..., layer n output)) — the
+        transformers tuple layout BertKAdaptedBertModel reads as outputs[2] (the pooler output, outputs[1], is never
+        evaluated: SURVEY.md Appendix B-5)."""
         N, L = input_ids.shape
+        if output_hidden_states is None:
+            output_hidden_states = bool(getattr(self.config, "output_hidden_states", False))
         x = self.embeddings(input_ids)
+        all_hidden = [x.view(N, L, -1)] if output_hidden_states else None
         last = len(self.encoder.layer) - 1
         for i, layer in enumerate(self.encoder.layer):
-            x = layer(x, attention_mask, N, L, cls_only=cls_only and i == last)
+            x = layer(x, attention_mask, N, L, cls_only=cls_only and i == last and not output_hidden_states)
+            if output_hidden_states:
+                all_hidden.append(x.view(N, L, -1))
+        if output_hidden_states:
+            return (x.view(N, L, -1), None, tuple(all_hidden))
         return (x.view(N, 1 if cls_only else L, -1),)
 
 

@@ -9,7 +9,8 @@ from .encoders import Bert_Encoder, User_Encoder
 from .layers import BF16, Embedding, to_2d_bf16
 from .layers import LayerNorm
 from .layers import PHMLinear
-from .modules import AdapterBlock, AdapterPfeifferBlock, HyperComplexAdapterBlock
+from .layers import Linear
+from .modules import AdapterBlock, AdapterPfeifferBlock, HyperComplexAdapterBlock, KAdapterBlock
 
 
 def _word_dim(args):
@@ -284,6 +285,58 @@ class CompacterModel(nn.Module):
 
     def forward(self, sample_items, log_mask, local_rank=None):
         return self.model(sample_items, log_mask, local_rank)
+
+
+class BertKAdaptedBertModel(nn.Module):
+    """model.py:523-561 (K-Adapter; replaces `text_encoders.title.bert_model` itself, run.py:410-411): adapters run
+    OUTSIDE the frozen body on its intermediate hidden states: for k in k_adapter_bert_list (+1, i.e. the OUTPUT of that
+    layer): last = adapter_k(hidden_states[k] + last); result = com_dense([sequence_output | last])."""
+
+    def __init__(self, bert_model, args):
+        super().__init__()
+        word_embedding_dim = _word_dim(args)
+        self.bert_model = bert_model
+        self.k_adapter_num_list = [int(i) + 1 for i in list(args.k_adapter_bert_list.split(","))]
+        self.bert_adapter_list = nn.ModuleList([KAdapterBlock(args, args.num_adapter_heads_bert, word_embedding_dim,
+                                                              args.k_adapter_bert_hidden_dim, args.adapter_dropout_rate)
+                                                for i in self.k_adapter_num_list])
+        self.com_dense = Linear(word_embedding_dim * 2, word_embedding_dim)
+
+    def forward(self, input_ids, attention_mask):
+        outputs = self.bert_model(input_ids, attention_mask, output_hidden_states=True)
+        sequence_output, hidden_states = outputs[0], outputs[2]
+        hidden_states_last = None                                  # the reference starts from zeros: x + 0 == x
+        for index, adapter in enumerate(self.bert_adapter_list):
+            hs = hidden_states[self.k_adapter_num_list[index]]
+            fusion_state = hs if hidden_states_last is None else Fn.add(to_2d_bf16(hs), to_2d_bf16(hidden_states_last)).view(hs.shape)
+            hidden_states_last = adapter(fusion_state)
+        if hidden_states_last is None:
+            hidden_states_last = torch.zeros_like(sequence_output)
+        input_embs_all = self.com_dense(torch.cat([sequence_output, hidden_states_last], dim=2))
+        return input_embs_all, outputs[1], outputs[2]
+
+
+class SASRecKAdaptedTransformerBlocks(nn.Module):
+    """model.py:564-583 (replaces `transformer_encoder.transformer_blocks`, run.py:412-413): before each block,
+    last = adapter_i(output + last); after the blocks, com_dense2([output | last])."""
+
+    def __init__(self, transformer_blocks, args):
+        super().__init__()
+        self.transformer_blocks = transformer_blocks
+        self.len_transformer_blocks = self.transformer_blocks.__len__()
+        self.adapter_list = nn.ModuleList([KAdapterBlock(args, args.num_adapter_heads_sasrec, args.embedding_dim,
+                                                         args.adapter_down_size, args.drop_rate)
+                                           for _ in range(self.len_transformer_blocks)])
+        self.com_dense2 = Linear(args.embedding_dim * 2, args.embedding_dim)
+
+    def forward(self, output, att_mask):
+        hidden_states_last = None
+        for index, transformer in enumerate(self.transformer_blocks):
+            fusion_state = output if hidden_states_last is None else \
+                Fn.add(to_2d_bf16(output), to_2d_bf16(hidden_states_last)).view(output.shape)
+            hidden_states_last = self.adapter_list[index](fusion_state)
+            output = transformer(output, att_mask)
+        return self.com_dense2(torch.cat([output, hidden_states_last], dim=2))
 
 
 class SoftEmbedding(nn.Module):

@@ -74,8 +74,20 @@ class MultiHeadedAttention(nn.Module):
         for m in (self.w_Q, self.w_K, self.w_V):
             params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
         qkv = Fn.QKVFunction.apply(x2, self._qkv_cache, *params)
-        ctx = Fn.attention(qkv, mask, B, S, self.n_heads, self.d_k, causal=self.causal, mask_neg=SASREC_MASK_NEG,
-                           dropout_p=self.self_attention.dropout.p if self.training else 0.0)
+        pd = self.self_attention.dropout.p if self.training else 0.0
+        if self.d_k in (32, 64):
+            ctx = Fn.attention(qkv, mask, B, S, self.n_heads, self.d_k, causal=self.causal, mask_neg=SASREC_MASK_NEG,
+                               dropout_p=pd)
+        else:
+            # narrow heads (K-adapter inside SASRec: d = 16, 2 heads -> d_k = 8): every head is zero-padded to the
+            # 32-wide slot the attention kernel handles (q·k and p·v are unchanged by zero columns) with the softmax
+            # temperature of the TRUE head width; pad / slice are pure data movement
+            assert self.d_k < 32, "head width %d: supported are <= 32 and 64" % self.d_k
+            h3, w = 3 * self.n_heads, 32
+            qp = torch.nn.functional.pad(qkv.view(-1, h3, self.d_k), (0, w - self.d_k)).reshape(-1, h3 * w)
+            cp = Fn.attention(qp, mask, B, S, self.n_heads, w, causal=self.causal, mask_neg=SASREC_MASK_NEG,
+                              dropout_p=pd, scale=self.d_k ** -0.5)
+            ctx = cp.view(-1, self.n_heads, w)[:, :, :self.d_k].reshape(-1, self.n_heads * self.d_k)
         p = self.dropout.p if self.training else 0.0
         res = x2.contiguous() if extra is None else extra
         if adapter is None:
@@ -125,6 +137,8 @@ class TransformerEncoder(nn.Module):
         if self.training and self.dropout.p > 0:
             output = Fn.dropout_add(output, None, self.dropout.p)
         output = output.view(B, S, D)
+        if "SASRecKAdaptedTransformerBlocks" in str(type(self.transformer_blocks)):      # modules.py:108-109
+            return self.transformer_blocks(output, att_mask)
         for transformer in self.transformer_blocks:
             output = transformer.forward(output, att_mask)
         return output
@@ -210,3 +224,36 @@ class HyperComplexAdapterBlock(nn.Module):
         x2 = to_2d_bf16(x)
         z = self.down_sampler(x2, act="gelu_new")
         return self.up_sampler(z, residual=extra_residual).view(x.shape)
+
+
+class KAdapterBlock(nn.Module):
+    """modules.py:161-206: down_project -> two TransformerBlocks of width down_size over the whole sequence with an
+    all-ones mask (additive 0: NOT causal, padding positions attend and are attended) -> up_project, + the input.
+    Projections ~ N(0, 2e-4²), zero biases."""
+
+    def __init__(self, args, num_head, input_size, down_size, dropout=0.1):
+        super().__init__()
+        self.args = args
+        self.down_project = Linear(input_size, down_size)
+        self.up_project = Linear(down_size, input_size)
+        self.init_weights()
+        self.transformer_blocks = nn.ModuleList(
+            [TransformerBlock(d_model=down_size, n_heads=num_head, d_inner=down_size * 4, dropout=dropout)
+             for _ in range(2)])
+        for blk in self.transformer_blocks:
+            blk.multi_head_attention.causal = False
+
+    def forward(self, hidden_states):
+        """hidden_states [N, L, H] -> [N, L, H]"""
+        N, L, H = hidden_states.shape
+        x2 = to_2d_bf16(hidden_states).contiguous()
+        output = self.down_project(x2).view(N, L, -1)
+        for transformer in self.transformer_blocks:
+            output = transformer.forward(output, None)
+        return self.up_project(to_2d_bf16(output), residual=x2).view(N, L, H)
+
+    def init_weights(self):
+        self.down_project.weight.data.normal_(mean=0.0, std=2e-4)
+        self.down_project.bias.data.zero_()
+        self.up_project.weight.data.normal_(mean=0.0, std=2e-4)
+        self.up_project.bias.data.zero_()

@@ -124,7 +124,7 @@ def dropout(x, res, p, seed, offset):
     return out
 
 
-def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout=None):
+def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout=None, scale=None):
     a = _l.AttnArgs()
     if dropout is not None:
         a.dropout_p, a.dropout_seed, a.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
@@ -136,7 +136,7 @@ def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout=None)
         assert mask.dim() == 2 and mask.shape[0] == N and mask.shape[1] >= L and mask.stride(1) == 1
         a.mask, a.mask_ld = _p(mask), mask.stride(0)
         a.mask_dtype = {torch.int64: 1, torch.float32: 2}[mask.dtype]
-    a.causal, a.scale, a.mask_neg = int(causal), float(head_dim) ** -0.5, float(mask_neg)
+    a.causal, a.scale, a.mask_neg = int(causal), (float(head_dim) ** -0.5 if scale is None else float(scale)), float(mask_neg)
     return a
 
 
@@ -150,11 +150,12 @@ def _attn_kernel(L, head_dim, causal, direction):
     raise RuntimeError("attention: unsupported shape L=%d head_dim=%d causal=%s (no fallback exists)" % (L, head_dim, causal))
 
 
-def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN, want_lse=False, dropout=None):
+def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN, want_lse=False, dropout=None,
+                   scale=None):
     """returns ctx, or (ctx, lse) with want_lse (lse is None for the short-sequence kernel, which recomputes it)"""
     assert qkv.dtype == BF16 and qkv.shape[0] == N * L
     out = torch.empty((N * L, heads * head_dim), dtype=BF16, device=qkv.device)
-    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout, scale)
     a.out, a.ld_out = _p(out), out.stride(0)
     lse = None
     if want_lse and L > 32:
@@ -166,10 +167,10 @@ def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg
 
 
 def attn_small_bwd(qkv, dctx, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN, lse=None, ctx=None,
-                   dropout=None):
+                   dropout=None, scale=None):
     assert qkv.dtype == BF16 and dctx.dtype == BF16 and dctx.shape[0] == N * L
     dqkv = torch.empty((N * L, 3 * heads * head_dim), dtype=BF16, device=qkv.device)
-    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout, scale)
     assert _rows2d(qkv, "qkv") == dqkv.stride(0), "attention bwd expects a contiguous qkv"
     a.out, a.dout, a.ld_out = _p(dqkv), _p(dctx), _rows2d(dctx, "dctx")
     if L > 32:

@@ -2,6 +2,7 @@
 train() in the reference and is therefore restated here as a function with the same flag semantics)."""
 from .model.layers import LoRALinear
 from .model.model import (BertAdaptedParallelSelfOutput, BertAdaptedSelfOutput, BertCompacterAdaptedSelfOutput,
+                          BertKAdaptedBertModel, SASRecKAdaptedTransformerBlocks,
                           BertPfeifferAdaptedSelfOutput, CompacterModel, SASRecCompacterAdaptedSelfOutput,
                           SASRecAdaptedSelfOutput, SASRecParallelAdaptedSelfOutput, SASRecPfeifferAdaptedSelfOutput,
                           SASRecPfeifferVer2AdaptedSelfOutput, SoftEmbedding)
@@ -23,9 +24,6 @@ def insert_adapters(model, args, log=None):
     blocks = model.user_encoder.transformer_encoder.transformer_blocks
     t = args.adapter_type
     dev = next(model.parameters()).device
-    if "kadapter" in t and "pfeiffer" not in t:
-        raise NotImplementedError("adapter_type %r is a 'next' row (SURVEY.md §8f-4); implemented: houslby (serial and "
-                                  "parallel), pfeiffer, pfeiffer_ver2, compacter, lora, prompt" % t)
     if "pfeiffer_ver2" in t:                                           # run.py:389-399
         for lm in layers:
             lm.attention.output = BertAdaptedSelfOutput(lm.attention.output, args).to(dev)
@@ -36,6 +34,11 @@ def insert_adapters(model, args, log=None):
             lm.output = BertPfeifferAdaptedSelfOutput(lm.output, args).to(dev)
         for i in range(len(blocks)):
             blocks[i] = SASRecPfeifferAdaptedSelfOutput(blocks[i], args).to(dev)
+    elif 'kadapter' in t:                                              # run.py:409-413
+        title = model.bert_encoder.text_encoders.title
+        title.bert_model = BertKAdaptedBertModel(title.bert_model, args).to(dev)
+        te = model.user_encoder.transformer_encoder
+        te.transformer_blocks = SASRecKAdaptedTransformerBlocks(te.transformer_blocks, args).to(dev)
     elif "lora" in t:                                                  # run.py:414-428
         for lm in layers:
             lm.attention.self.query = LoRALinear(args.word_embedding_dim, args.word_embedding_dim,

@@ -40,12 +40,16 @@ class RecConfig:
     """argparse fields read by the path (Downstream/Text/parameters.py:25-31,55,62,65,76)."""
 
     def __init__(self, max_seq_len=20, embedding_dim=64, heads=2, blocks=2, num_words_title=30,
-                 adapter_activation="RELU", n_tokens=0, parallel=False):
+                 adapter_activation="RELU", n_tokens=0, parallel=False, k_adapter_bert_list="0,11",
+                 num_adapter_heads_bert=12, num_adapter_heads_sasrec=2):
         self.max_seq_len, self.embedding_dim, self.heads, self.blocks = max_seq_len, embedding_dim, heads, blocks
         self.num_words_title, self.adapter_activation, self.n_tokens = num_words_title, adapter_activation, n_tokens
         # is_serial == "None" (parameters.py:66, run.py:454/466): the parallel Houlsby wrappers have the SAME state_dict
         # keys as the serial ones, so the variant cannot be read off the checkpoint
         self.parallel = parallel
+        # K-Adapter (parameters.py:68-71): which BERT layers feed adapters, and the adapters' own head counts
+        self.k_adapter_bert_list = k_adapter_bert_list
+        self.num_adapter_heads_bert, self.num_adapter_heads_sasrec = num_adapter_heads_bert, num_adapter_heads_sasrec
 
 
 def layer_norm(x, sd, prefix, eps):
@@ -176,16 +180,49 @@ def bert_layer(x, add_mask, sd, i, cfg, activation, parallel=False):
     return self_output(f, y, sd, p + "output.", cfg.eps, activation, parallel)
 
 
+class _Heads:
+    """the two fields sasrec_block reads, for the TransformerBlocks inside a KAdapterBlock"""
+
+    def __init__(self, heads):
+        self.heads, self.adapter_activation, self.parallel = heads, "RELU", False
+
+
+def kadapter_block(x, sd, prefix, heads):
+    """KAdapterBlock.forward, Downstream/Text/model/modules.py:176-200: down_project -> 2 TransformerBlocks with the
+    additive mask (1 - ones) * -10000 = 0 (no causal structure, no padding mask) -> up_project; + input."""
+    h = F.linear(x, sd[prefix + "down_project.weight"], sd[prefix + "down_project.bias"])
+    for j in range(2):
+        h = sasrec_block(h, 0.0, sd, prefix + "transformer_blocks.%d." % j, _Heads(heads))
+    return x + F.linear(h, sd[prefix + "up_project.weight"], sd[prefix + "up_project.bias"])
+
+
 def bert_encoder(text, sd, cfg, rec):
     """Bert_Encoder.forward + Text_Encoder.forward, Downstream/Text/model/encoders.py:48-57,89-99:
-    text [N, 2L] = ids | attention mask; returns GELU(fc(hidden[:, 0])) [N, D]."""
+    text [N, 2L] = ids | attention mask; returns GELU(fc(hidden[:, 0])) [N, D].
+    With the K-Adapter wrapper (BertKAdaptedBertModel.forward, model.py:545-561; keys `bert_model.bert_model.*`,
+    `bert_model.bert_adapter_list.*`, `bert_model.com_dense.*`): hidden_states = (embeddings, layer outputs...);
+    last = adapter_i(hidden_states[k_i + 1] + last); hidden = com_dense([sequence_output | last])."""
     sd = unwrap_compacter(sd)
+    kad = BERT_PREFIX + "com_dense.weight" in sd
+    if kad:
+        inner = BERT_PREFIX + "bert_model."
+        body = {BERT_PREFIX + k[len(inner):]: v for k, v in sd.items() if k.startswith(inner)}
+    else:
+        body = sd
     L = text.shape[1] // 2
     ids, mask = text[:, :L], text[:, L:]
-    x = bert_embeddings(ids, sd, cfg, rec.n_tokens)
+    x = bert_embeddings(ids, body, cfg, rec.n_tokens)
     add_mask = (1.0 - mask.float()).view(-1, 1, 1, L) * torch.finfo(torch.float32).min
+    hidden_states = [x]
     for i in range(cfg.layers):
-        x = bert_layer(x, add_mask, sd, i, cfg, rec.adapter_activation, getattr(rec, "parallel", False))
+        x = bert_layer(x, add_mask, body, i, cfg, rec.adapter_activation, getattr(rec, "parallel", False))
+        hidden_states.append(x)
+    if kad:
+        last = torch.zeros_like(x)
+        for index, k in enumerate(int(i) + 1 for i in rec.k_adapter_bert_list.split(",")):
+            last = kadapter_block(hidden_states[k] + last, sd, BERT_PREFIX + "bert_adapter_list.%d." % index,
+                                  rec.num_adapter_heads_bert)
+        x = F.linear(torch.cat([x, last], dim=2), sd[BERT_PREFIX + "com_dense.weight"], sd[BERT_PREFIX + "com_dense.bias"])
     cls = F.linear(x[:, 0], sd[FC_PREFIX + "weight"], sd[FC_PREFIX + "bias"])
     return F.gelu(cls)
 
@@ -245,6 +282,14 @@ def user_encoder(input_embs, log_mask, sd, rec):
     att_mask = torch.where(torch.tril(valid), 0.0, -1e9)
     x = input_embs + sd[USER_PREFIX + "position_embedding.weight"][:S].unsqueeze(0)
     x = layer_norm(x, sd, USER_PREFIX + "layer_norm.", 1e-6)
+    kp = USER_PREFIX + "transformer_blocks."
+    if kp + "com_dense2.weight" in sd:
+        # SASRecKAdaptedTransformerBlocks.forward, model.py:575-583 (dispatch: modules.py:108-109)
+        last = torch.zeros_like(x)
+        for j in range(rec.blocks):
+            last = kadapter_block(x + last, sd, kp + "adapter_list.%d." % j, rec.num_adapter_heads_sasrec)
+            x = sasrec_block(x, att_mask, sd, kp + "transformer_blocks.%d." % j, rec)
+        return F.linear(torch.cat([x, last], dim=2), sd[kp + "com_dense2.weight"], sd[kp + "com_dense2.bias"])
     for j in range(rec.blocks):
         x = sasrec_block(x, att_mask, sd, USER_PREFIX + "transformer_blocks.%d." % j, rec)
     return x

@@ -12,7 +12,7 @@ FC = "bert_encoder.text_encoders.title.fc."
 USER = "user_encoder.transformer_encoder."
 
 
-ZOO_KINDS = ("parallel", "pfeiffer", "pfeiffer_leaky", "pfeiffer_ver2", "compacter")
+ZOO_KINDS = ("parallel", "pfeiffer", "pfeiffer_leaky", "pfeiffer_ver2", "compacter", "kadapter")
 ALL_KINDS = ("base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc") + ZOO_KINDS
 
 
@@ -44,7 +44,10 @@ def tiny_case(kind):
     c.B = 6
     c.item_num = 40
     c.seed = {"base": 11, "houlsby": 12, "lora": 13, "prompt_cpc": 14, "houlsby_gelu": 15, "parallel": 16,
-              "pfeiffer": 17, "pfeiffer_leaky": 18, "pfeiffer_ver2": 19, "compacter": 20}[kind]
+              "pfeiffer": 17, "pfeiffer_leaky": 18, "pfeiffer_ver2": 19, "compacter": 20, "kadapter": 21}[kind]
+    # K-Adapter (parameters.py:68-71): adapters after BERT layers 0 and 1 of the 2-layer tiny body, width 64 with
+    # 2 heads (head width 32); the SASRec-side adapters keep the reference default width 16 with 2 heads (head width 8)
+    c.k_list, c.k_hidden, c.k_heads_bert, c.k_heads_rec = "0,1", 64, 2, 2
     c.phm_dim = 4              # hypercomplex_division
     return c
 
@@ -60,7 +63,10 @@ def reference_args(c):
                                                                       "lora": "lora", "prompt_cpc": "prompt",
                                                                       "base": "None", "parallel": "houslby",
                                                                       "pfeiffer": "pfeiffer", "pfeiffer_leaky": "pfeiffer",
-                                                                      "pfeiffer_ver2": "pfeiffer_ver2", "compacter": "compacter"}[c.kind],
+                                                                      "pfeiffer_ver2": "pfeiffer_ver2", "compacter": "compacter",
+                                                                      "kadapter": "kadapter"}[c.kind],
+        k_adapter_bert_list=c.k_list, k_adapter_bert_hidden_dim=c.k_hidden, num_adapter_heads_bert=c.k_heads_bert,
+        num_adapter_heads_sasrec=c.k_heads_rec,
         hypercomplex_division=c.phm_dim, phm_init_range=0.0001,
         is_serial="None" if c.kind == "parallel" else "True", n_tokens=c.n_tokens)
 
@@ -95,6 +101,23 @@ def _phm(sd, g, name, in_f, out_f, n, rule):
 def _phm_adapter(sd, g, name, dim, r, n, rule):
     _phm(sd, g, name + "down_sampler.", dim, r, n, rule)
     _phm(sd, g, name + "up_sampler.", r, dim, n, rule)
+
+
+def _tblock(sd, g, tb, D):
+    """a plain TransformerBlock (modules.py:77-87) of width D"""
+    for nm in ("w_Q", "w_K", "w_V", "fc"):
+        _linear(sd, g, tb + "multi_head_attention.%s." % nm, D, D, bias=False, std=0.1)
+    _ln(sd, g, tb + "multi_head_attention.layer_norm.", D)
+    _linear(sd, g, tb + "feed_forward.w_1.", 4 * D, D, std=0.1)
+    _linear(sd, g, tb + "feed_forward.w_2.", D, 4 * D, std=0.1)
+    _ln(sd, g, tb + "feed_forward.layer_norm.", D)
+
+
+def _kadapter(sd, g, name, dim, r):
+    _linear(sd, g, name + "down_project.", r, dim, std=0.1)
+    _linear(sd, g, name + "up_project.", dim, r, std=0.1)
+    for j in range(2):
+        _tblock(sd, g, name + "transformer_blocks.%d." % j, r)
 
 
 def _lora(sd, g, name, dim, r):
@@ -152,7 +175,7 @@ def build_state_dict(c):
     _ln(sd, g, USER + "layer_norm.", D)
     for j in range(c.blocks):
         p = USER + "transformer_blocks.%d." % j
-        tb = p + ("transformer_block." if _houlsby_like(c.kind) else "")
+        tb = p + ("transformer_block." if (_houlsby_like(c.kind) and c.kind != "kadapter") else "")
         for nm in ("w_Q", "w_K", "w_V", "fc"):
             if c.kind == "lora" and nm in ("w_Q", "w_V"):
                 _lora(sd, g, tb + "multi_head_attention.%s." % nm, D, c.rec_r)
@@ -173,6 +196,18 @@ def build_state_dict(c):
         elif c.kind == "compacter":
             _phm_adapter(sd, g, p + "adapter1.", D, c.rec_r, c.phm_dim, rule)
             _phm_adapter(sd, g, p + "adapter2.", D, c.rec_r, c.phm_dim, rule)
+    if c.kind == "kadapter":
+        # BertKAdaptedBertModel replaces title.bert_model (body moves one level down); SASRecKAdaptedTransformerBlocks
+        # replaces transformer_encoder.transformer_blocks (run.py:409-413)
+        inner, blocks = BERT + "bert_model.", USER + "transformer_blocks."
+        sd = {(inner + k[len(BERT):] if k.startswith(BERT) else
+               blocks + "transformer_blocks." + k[len(blocks):] if k.startswith(blocks) else k): v for k, v in sd.items()}
+        for i in range(len(c.k_list.split(","))):
+            _kadapter(sd, g, BERT + "bert_adapter_list.%d." % i, H, c.k_hidden)
+        _linear(sd, g, BERT + "com_dense.", H, 2 * H)
+        for j in range(c.blocks):
+            _kadapter(sd, g, blocks + "adapter_list.%d." % j, D, c.rec_r)
+        _linear(sd, g, blocks + "com_dense2.", D, 2 * D, std=0.1)
     if c.kind == "compacter":       # CompacterModel wraps the model as `.model` and owns the shared rule (run.py:70-81)
         sd = {"model." + k: v for k, v in sd.items()}
         sd["phm_rule"] = rule
@@ -183,6 +218,8 @@ def trainable_keys(c, sd):
     """Parameters left trainable by Downstream/Text/run.py:367-479 with fine_tune_to=None."""
     if c.kind.startswith("houlsby") or c.kind in ("parallel", "pfeiffer_ver2"):
         return [k for k in sd if "adapter" in k]
+    if c.kind == "kadapter":
+        return [k for k in sd if "adapter_list" in k or "com_dense" in k]
     if c.kind == "compacter":     # named_parameters() lists the shared rule once, under the wrapper's own name
         return [k for k in sd if "adapter" in k and not k.endswith("phm_rule")] + ["phm_rule"]
     if c.kind in ("pfeiffer", "pfeiffer_leaky"):      # the new `LN` LayerNorms are created after the freeze

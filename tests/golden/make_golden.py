@@ -51,6 +51,12 @@ def build_reference_model(c):
     kw = dict(vocab_size=c.vocab, hidden_size=c.hidden, num_hidden_layers=c.layers, num_attention_heads=c.heads,
               intermediate_size=c.inter, max_position_embeddings=c.max_pos, layer_norm_eps=c.eps,
               hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    if c.kind == "kadapter":
+        # K-Adapter is the one variant where the all-masked padding item (row 0) reaches valid positions (its SASRec-side
+        # adapters attend over the whole sequence with an all-ones mask), so the additive-mask softmax of the pinned
+        # transformers 4.20.1 must be reproduced: "eager" attention IS that algorithm (scores + finfo.min mask -> uniform
+        # softmax); the default sdpa path of the installed 5.5.0 returns a zero context for such rows instead
+        kw["attn_implementation"] = "eager"
     if c.roberta:
         bert = RobertaModel(RobertaConfig(type_vocab_size=1, pad_token_id=1, **kw))
     else:
@@ -91,6 +97,13 @@ def build_reference_model(c):
         for i, tb in enumerate(blocks):
             blocks[i] = SASRecCompacterAdaptedSelfOutput(tb, args)
         model = CompacterModel(args, model)
+    elif c.kind == "kadapter":                                     # run.py:409-413
+        from model import BertKAdaptedBertModel, SASRecKAdaptedTransformerBlocks
+        bert.config.output_hidden_states = True                    # the reference loads the config with it (run.py:293)
+        title = model.bert_encoder.text_encoders.title
+        title.bert_model = BertKAdaptedBertModel(title.bert_model, args)
+        te = model.user_encoder.transformer_encoder
+        te.transformer_blocks = SASRecKAdaptedTransformerBlocks(te.transformer_blocks, args)
     elif c.kind == "lora":                                         # run.py:414-428
         import loralib as lora
         for lm in layers:

@@ -47,7 +47,9 @@ def build_gpu_model(c, sd):
 def oracle_setup(c):
     cfg = O.TextConfig(hidden=c.hidden, layers=c.layers, heads=c.heads, eps=c.eps, roberta=c.roberta, pad_token_id=c.pad)
     rec = O.RecConfig(max_seq_len=c.S, embedding_dim=c.D, heads=c.rec_heads, blocks=c.blocks, num_words_title=c.L,
-                      adapter_activation=c.activation, n_tokens=c.n_tokens, parallel=c.parallel)
+                      adapter_activation=c.activation, n_tokens=c.n_tokens, parallel=c.parallel,
+                      k_adapter_bert_list=c.k_list, num_adapter_heads_bert=c.k_heads_bert,
+                      num_adapter_heads_sasrec=c.k_heads_rec)
     return cfg, rec
 
 
