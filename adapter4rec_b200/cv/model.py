@@ -5,8 +5,12 @@ import torch.nn as nn
 from .. import functional as Fn
 from ..model.encoders import User_Encoder
 from ..model.layers import BF16, to_2d_bf16
-from ..model.model import SASRecAdaptedSelfOutput, check_trainable_supported  # same class as the text tree (model.py:344-389)
-from ..model.modules import AdapterBlock
+from ..model.model import (CompacterModel, SASRecAdaptedSelfOutput, SASRecCompacterAdaptedSelfOutput,  # noqa: F401
+                           SASRecParallelAdaptedSelfOutput, SASRecPfeifferVer2AdaptedSelfOutput,
+                           check_trainable_supported)   # the SASRec wrappers are the text tree's classes (CV model.py:235-372,465-510)
+from ..model.modules import AdapterBlock, HyperComplexAdapterBlock
+
+SASRecPfeifferV2AdaptedSelfOutput = SASRecPfeifferVer2AdaptedSelfOutput   # the CV tree's spelling (CV model.py:283)
 
 
 class _Act:
@@ -105,6 +109,89 @@ class VITAdaptedOutput(nn.Module):
 
     def forward_from_dense(self, h, input_tensor):
         return self.adapter(to_2d_bf16(h), extra_residual=to_2d_bf16(input_tensor)).view(input_tensor.shape)
+
+
+class VITAdaptedParallelSelfOutput(nn.Module):
+    """Downstream/CV/model/model.py:149-162: adapter(input) + dropout(dense(x)) (the layer adds its skip afterwards).
+    Defined by the reference but not dispatched by run_adapter.py (its use at :240 is commented out)."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = AdapterBlock(args, 768, args.cv_adapter_down_size, args.adapter_dropout_rate)
+
+    def forward_fused(self, hidden_states, residual):
+        inp = to_2d_bf16(residual).contiguous()
+        a = to_2d_bf16(self.adapter(inp, extra_residual=inp))         # adapter(inp) + the layer's skip connection
+        h = self.self_output.dense(to_2d_bf16(hidden_states))
+        p = self.self_output.dropout.p if self.training else 0.0
+        return Fn.dropout_add(h, a, p) if p > 0 else Fn.add(h, a)
+
+    def forward(self, hidden_states, input_tensor):
+        inp = to_2d_bf16(input_tensor).contiguous()
+        a = to_2d_bf16(self.adapter(inp))
+        h = self.self_output.dense(to_2d_bf16(hidden_states))
+        p = self.self_output.dropout.p if self.training else 0.0
+        return (Fn.dropout_add(h, a, p) if p > 0 else Fn.add(h, a)).view(input_tensor.shape)
+
+
+class VITAdaptedParallelOutput(nn.Module):
+    """Downstream/CV/model/model.py:165-179 (is_serial = 'None' wraps layer.output ONLY, run_adapter.py:236-241):
+    dropout(dense(x)) + input + adapter(input), adapter(x) = fc_up(act(fc_down(x))) + x."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = AdapterBlock(args, 768, args.cv_adapter_down_size, args.adapter_dropout_rate)
+
+    def forward(self, hidden_states, input_tensor):
+        return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_from_dense(self, h, input_tensor):
+        inp = to_2d_bf16(input_tensor).contiguous()
+        a = to_2d_bf16(self.adapter(inp, extra_residual=inp))
+        h = to_2d_bf16(h)
+        p = self.self_output.dropout.p if self.training else 0.0
+        return (Fn.dropout_add(h, a, p) if p > 0 else Fn.add(h, a)).view(input_tensor.shape)
+
+
+class VITCompacterAdaptedSelfOutput(nn.Module):
+    """Downstream/CV/model/model.py:432-445: adapter(dropout(dense(x))) with the residual-free HyperComplexAdapterBlock."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = HyperComplexAdapterBlock(args, 768, args.cv_adapter_down_size)
+
+    def _dense(self, hidden_states):
+        h = self.self_output.dense(to_2d_bf16(hidden_states))
+        p = self.self_output.dropout.p if self.training else 0.0
+        return Fn.dropout_add(h, None, p) if p > 0 else h
+
+    def forward(self, hidden_states, input_tensor=None):
+        return self.adapter(self._dense(hidden_states))
+
+    def forward_fused(self, hidden_states, residual):
+        return to_2d_bf16(self.adapter(self._dense(hidden_states), extra_residual=to_2d_bf16(residual).contiguous()))
+
+
+class VITCompacterAdaptedOutput(nn.Module):
+    """Downstream/CV/model/model.py:448-462: adapter(dropout(dense(x))) + input."""
+
+    def __init__(self, self_output, args):
+        super().__init__()
+        self.self_output = self_output
+        self.adapter = HyperComplexAdapterBlock(args, 768, args.cv_adapter_down_size)
+
+    def forward(self, hidden_states, input_tensor):
+        return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_from_dense(self, h, input_tensor):
+        h = to_2d_bf16(h)
+        p = self.self_output.dropout.p if self.training else 0.0
+        if p > 0:
+            h = Fn.dropout_add(h, None, p)
+        return self.adapter(h, extra_residual=to_2d_bf16(input_tensor).contiguous()).view(input_tensor.shape)
 
 
 class SoftPrompt(nn.Module):

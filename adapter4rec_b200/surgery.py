@@ -84,7 +84,8 @@ def insert_adapters_cv(model, args):
     """Image tree: Downstream/CV/run_adapter.py:367-470 (houslby serial, lora with its hard-coded ranks r=12 / r=4 / r=0,
     prompt which also unfreezes the classifier)."""
     from .cv.model import SASRecAdaptedSelfOutput as _SAS
-    from .cv.model import SoftPrompt, VITAdaptedOutput, VITAdaptedSelfOutput
+    from .cv.model import (SoftPrompt, VITAdaptedOutput, VITAdaptedParallelOutput, VITAdaptedSelfOutput,
+                           VITCompacterAdaptedOutput, VITCompacterAdaptedSelfOutput)
     if 'None' in getattr(args, "adding_adapter_to", "all"):
         return model
     net = model.cv_encoder.image_net
@@ -92,26 +93,46 @@ def insert_adapters_cv(model, args):
     blocks = model.user_encoder.transformer_encoder.transformer_blocks
     t = args.adapter_type
     dev = next(model.parameters()).device
-    if "pfeiffer" in t or "kadapter" in t or "compacter" in t:
-        raise NotImplementedError("adapter_type %r is a 'next' row (SURVEY.md §8f-4)" % t)
-    if "lora" in t:                                                    # run_adapter.py:383-395
+    if "pfeiffer_ver2" in t:                                           # run_adapter.py:367-377
+        for lm in layers:
+            lm.attention.output = VITAdaptedSelfOutput(lm.attention.output, args).to(dev)
+        for i in range(len(blocks)):
+            blocks[i] = SASRecPfeifferVer2AdaptedSelfOutput(blocks[i], args).to(dev)
+    elif "kadapter" in t:
+        # run_adapter.py:378-382 replaces vit.encoder by VITKAdaptedCVModel, whose forward calls the transformers ViT
+        # encoder with a signature the installed transformers no longer has (SURVEY.md §8c probe p4: the reference itself
+        # fails here), so there is no reference output to pin this variant to
+        raise NotImplementedError("adapter_type 'kadapter' on the image tree: the reference's own VITKAdaptedCVModel does "
+                                  "not run under the installed transformers; text-tree kadapter is implemented")
+    elif "lora" in t:                                                  # run_adapter.py:383-395
         for lm in layers:
             lm.attention.attention.query = LoRALinear(768, 768, r=12).to(dev)
             lm.attention.attention.value = LoRALinear(768, 768, r=12).to(dev)
         for i in range(len(blocks)):
             blocks[i].multi_head_attention.w_Q = LoRALinear(args.embedding_dim, args.embedding_dim, r=4).to(dev)
             blocks[i].multi_head_attention.w_V = LoRALinear(args.embedding_dim, args.embedding_dim).to(dev)   # r = 0
+    elif "compacter" in t:                                             # run_adapter.py:396-411: returns the WRAPPED model
+        for lm in layers:
+            lm.attention.output = VITCompacterAdaptedSelfOutput(lm.attention.output, args).to(dev)
+            lm.output = VITCompacterAdaptedOutput(lm.output, args).to(dev)
+        for i in range(len(blocks)):
+            blocks[i] = SASRecCompacterAdaptedSelfOutput(blocks[i], args).to(dev)
+        model = CompacterModel(args, model).to(dev)
     elif "prompt" in t:                                                # run_adapter.py:413-421
         net.vit.embeddings = SoftPrompt(net.vit.embeddings, n_tokens=args.n_tokens, embed_dim=768).to(dev)
         for name, param in model.named_parameters():
             if "cv_encoder.image_net.classifier" in name:
                 param.requires_grad = True
     elif "houslby" in t:                                               # run_adapter.py:423-445
-        if "None" in getattr(args, "is_serial", "True"):
-            raise NotImplementedError("parallel Houlsby adapters are a 'next' row (SURVEY.md §8f-4)")
-        for lm in layers:
-            lm.attention.output = VITAdaptedSelfOutput(lm.attention.output, args).to(dev)
-            lm.output = VITAdaptedOutput(lm.output, args).to(dev)
-        for i in range(len(blocks)):
-            blocks[i] = _SAS(blocks[i], args).to(dev)
+        if "None" not in getattr(args, "is_serial", "True"):
+            for lm in layers:
+                lm.attention.output = VITAdaptedSelfOutput(lm.attention.output, args).to(dev)
+                lm.output = VITAdaptedOutput(lm.output, args).to(dev)
+            for i in range(len(blocks)):
+                blocks[i] = _SAS(blocks[i], args).to(dev)
+        else:                                                          # parallel: layer.output only (:236-247)
+            for lm in layers:
+                lm.output = VITAdaptedParallelOutput(lm.output, args).to(dev)
+            for i in range(len(blocks)):
+                blocks[i] = SASRecParallelAdaptedSelfOutput(blocks[i], args).to(dev)
     return model

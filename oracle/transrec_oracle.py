@@ -451,7 +451,7 @@ def vit_embeddings(images, sd, cfg):
     return x
 
 
-def vit_layer(x, sd, i, cfg, activation):
+def vit_layer(x, sd, i, cfg, activation, parallel=False):
     """transformers' ViTLayer.forward (pre-LN) with the wrappers of Downstream/CV/model/model.py:182-212:
     VITAdaptedSelfOutput = adapter(dense(ctx)) (no residual), VITAdaptedOutput = adapter(dense(h)) + input."""
     p = VIT_PREFIX + "encoder.layer.%d." % i
@@ -463,26 +463,33 @@ def vit_layer(x, sd, i, cfg, activation):
     v = linear_or_lora(xn, sd, p + "attention.attention.value.").view(N, L, cfg.heads, dh).transpose(1, 2)
     ctx = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1) @ v).transpose(1, 2).reshape(N, L, H)
     ao = p + "attention.output."
-    if ao + "self_output.dense.weight" in sd:
-        a = adapter_block(F.linear(ctx, sd[ao + "self_output.dense.weight"], sd[ao + "self_output.dense.bias"]), sd,
-                          ao + "adapter.", activation)
-    else:
-        a = F.linear(ctx, sd[ao + "dense.weight"], sd[ao + "dense.bias"])
-    x1 = a + x
+    x1 = _vit_sublayer_output(ctx, x, sd, ao, activation, parallel)
     f = F.gelu(F.linear(layer_norm(x1, sd, p + "layernorm_after.", cfg.eps), sd[p + "intermediate.dense.weight"],
                         sd[p + "intermediate.dense.bias"]))
-    o = p + "output."
-    if o + "self_output.dense.weight" in sd:
-        return adapter_block(F.linear(f, sd[o + "self_output.dense.weight"], sd[o + "self_output.dense.bias"]), sd,
-                             o + "adapter.", activation) + x1
-    return F.linear(f, sd[o + "dense.weight"], sd[o + "dense.bias"]) + x1
+    return _vit_sublayer_output(f, x1, sd, p + "output.", activation, parallel)
+
+
+def _vit_sublayer_output(hidden, skip, sd, o, activation, parallel):
+    """attention.output / output of one ViTLayer INCLUDING the layer's skip connection, by the wrapper keys present
+    (Downstream/CV/model/model.py): plain dense(h) + skip; VITAdaptedSelfOutput / VITAdaptedOutput (:182-212)
+    adapter(dense(h)) + skip; VITAdaptedParallelOutput (:165-179, `parallel`) dense(h) + skip + adapter(skip);
+    VITCompacterAdapted{Self,}Output (:432-462) hypercomplex_adapter(dense(h)) + skip."""
+    if o + "self_output.dense.weight" not in sd:
+        return F.linear(hidden, sd[o + "dense.weight"], sd[o + "dense.bias"]) + skip
+    h = F.linear(hidden, sd[o + "self_output.dense.weight"], sd[o + "self_output.dense.bias"])
+    if o + "adapter.down_sampler.W_left" in sd:
+        return hypercomplex_adapter_block(h, sd, o + "adapter.") + skip
+    if parallel:
+        return h + skip + adapter_block(skip, sd, o + "adapter.", activation)
+    return adapter_block(h, sd, o + "adapter.", activation) + skip
 
 
 def vit_encoder(images, sd, cfg, rec):
     """Vit_Encoder.forward (Downstream/CV/model/encoders.py:25-32): GELU(classifier(LN(h)[:, 0]))."""
+    sd = unwrap_compacter(sd)
     x = vit_embeddings(images, sd, cfg)
     for i in range(cfg.layers):
-        x = vit_layer(x, sd, i, cfg, rec.adapter_activation)
+        x = vit_layer(x, sd, i, cfg, rec.adapter_activation, getattr(rec, "parallel", False))
     x = layer_norm(x, sd, VIT_PREFIX + "layernorm.", cfg.eps)
     return F.gelu(F.linear(x[:, 0], sd[CLS_PREFIX + "weight"], sd[CLS_PREFIX + "bias"]))
 

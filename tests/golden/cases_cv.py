@@ -3,14 +3,19 @@ import types
 
 import torch
 
-from cases import USER, _adapter, _linear, _ln, _lora, _n
+from cases import USER, _adapter, _linear, _ln, _lora, _n, _phm_adapter
 
 VIT = "cv_encoder.image_net.vit."
 CLS = "cv_encoder.image_net.classifier."
 
 
+CV_ZOO_KINDS = ("cv_parallel", "cv_pfeiffer_ver2", "cv_compacter")          # SURVEY.md §8f-4 on the image tree
+CV_ALL_KINDS = ("cv_base", "cv_houlsby", "cv_lora", "cv_prompt") + CV_ZOO_KINDS
+
+
 def tiny_cv_case(kind):
-    """kind: 'cv_base' | 'cv_houlsby' | 'cv_lora' | 'cv_prompt'.  hidden is 768 because the reference's ViT adapter
+    """kind: 'cv_base' | 'cv_houlsby' | 'cv_lora' | 'cv_prompt' | 'cv_parallel' (Houlsby, is_serial=None: layer.output
+    only) | 'cv_pfeiffer_ver2' (attention.output only) | 'cv_compacter'.  hidden is 768 because the reference's ViT adapter
     wrappers hard-code it (Downstream/CV/model/model.py:186,202); depth / MLP width / image size are reduced."""
     c = types.SimpleNamespace()
     c.kind = kind
@@ -21,10 +26,13 @@ def tiny_cv_case(kind):
     c.eps = 1e-12
     c.S, c.D, c.rec_heads, c.blocks = 4, 64, 2, 2
     c.cv_r, c.rec_r = 16, 8
+    c.phm_dim = 4
+    c.parallel = kind == "cv_parallel"
     c.n_tokens = 3 if kind == "cv_prompt" else 0
     c.cpc = False
     c.B = 3
-    c.seed = {"cv_base": 21, "cv_houlsby": 22, "cv_lora": 23, "cv_prompt": 24}[kind]
+    c.seed = {"cv_base": 21, "cv_houlsby": 22, "cv_lora": 23, "cv_prompt": 24, "cv_parallel": 25, "cv_pfeiffer_ver2": 26,
+              "cv_compacter": 27}[kind]
     return c
 
 
@@ -33,14 +41,17 @@ def reference_args(c):
         max_seq_len=c.S, min_seq_len=2, l2_weight=0, embedding_dim=c.D, num_attention_heads=c.rec_heads, drop_rate=0.1,
         transformer_block=c.blocks, CV_model_load="vit-base-patch16-224", cv_adapter_down_size=c.cv_r,
         adapter_down_size=c.rec_r, adapter_dropout_rate=0.1, adapter_activation="RELU", n_tokens=c.n_tokens,
-        adapter_type={"cv_base": "None", "cv_houlsby": "houslby", "cv_lora": "lora", "cv_prompt": "prompt"}[c.kind],
-        adding_adapter_to="all", is_serial="True", finetune_layernorm="None")
+        adapter_type={"cv_base": "None", "cv_houlsby": "houslby", "cv_lora": "lora", "cv_prompt": "prompt",
+                      "cv_parallel": "houslby", "cv_pfeiffer_ver2": "pfeiffer_ver2", "cv_compacter": "compacter"}[c.kind],
+        adding_adapter_to="all", is_serial="None" if c.kind == "cv_parallel" else "True", finetune_layernorm="None",
+        hypercomplex_division=c.phm_dim, phm_init_range=0.0001)
 
 
 def build_state_dict(c):
     g = torch.Generator().manual_seed(c.seed)
     sd = {}
     H, D = c.hidden, c.D
+    rule = _n(g, (c.phm_dim,) * 3, 0.5) if c.kind == "cv_compacter" else None
     e = VIT + "embeddings."
     names = [e]
     if c.kind == "cv_prompt":
@@ -62,9 +73,15 @@ def build_state_dict(c):
             else:
                 _linear(sd, g, p + "attention.attention.%s." % nm, H, H, std=0.03)
         for out_name, in_f in (("attention.output.", H), ("output.", c.inter)):
-            if c.kind == "cv_houlsby":
+            wrapped = (c.kind in ("cv_houlsby", "cv_compacter")
+                       or (c.kind == "cv_parallel" and out_name == "output.")                  # run_adapter.py:240-241
+                       or (c.kind == "cv_pfeiffer_ver2" and out_name == "attention.output."))  # run_adapter.py:369-372
+            if wrapped:
                 _linear(sd, g, p + out_name + "self_output.dense.", H, in_f, std=0.03)
-                _adapter(sd, g, p + out_name + "adapter.", H, c.cv_r)
+                if c.kind == "cv_compacter":
+                    _phm_adapter(sd, g, p + out_name + "adapter.", H, c.cv_r, c.phm_dim, rule)
+                else:
+                    _adapter(sd, g, p + out_name + "adapter.", H, c.cv_r)
             else:
                 _linear(sd, g, p + out_name + "dense.", H, in_f, std=0.03)
             if out_name == "attention.output.":
@@ -77,7 +94,7 @@ def build_state_dict(c):
     _ln(sd, g, USER + "layer_norm.", D)
     for j in range(c.blocks):
         p = USER + "transformer_blocks.%d." % j
-        tb = p + ("transformer_block." if c.kind == "cv_houlsby" else "")
+        tb = p + ("transformer_block." if c.kind in ("cv_houlsby",) + CV_ZOO_KINDS else "")
         for nm in ("w_Q", "w_K", "w_V", "fc"):
             if c.kind == "cv_lora" and nm == "w_Q":
                 _lora(sd, g, tb + "multi_head_attention.w_Q.", D, 4)          # run_adapter.py:392-393: r = 4
@@ -89,15 +106,25 @@ def build_state_dict(c):
         _linear(sd, g, tb + "feed_forward.w_1.", 4 * D, D, std=0.1)
         _linear(sd, g, tb + "feed_forward.w_2.", D, 4 * D, std=0.1)
         _ln(sd, g, tb + "feed_forward.layer_norm.", D)
-        if c.kind == "cv_houlsby":
+        if c.kind in ("cv_houlsby", "cv_parallel"):
             _adapter(sd, g, p + "adapter1.", D, c.rec_r)
             _adapter(sd, g, p + "adapter2.", D, c.rec_r)
+        elif c.kind == "cv_pfeiffer_ver2":
+            _adapter(sd, g, p + "adapter1.", D, c.rec_r)
+        elif c.kind == "cv_compacter":
+            _phm_adapter(sd, g, p + "adapter1.", D, c.rec_r, c.phm_dim, rule)
+            _phm_adapter(sd, g, p + "adapter2.", D, c.rec_r, c.phm_dim, rule)
+    if c.kind == "cv_compacter":      # CompacterModel (run_adapter.py:85-98) wraps the model and owns the shared rule
+        sd = {"model." + k: v for k, v in sd.items()}
+        sd["phm_rule"] = rule
     return sd
 
 
 def trainable_keys(c, sd):
-    if c.kind == "cv_houlsby":
+    if c.kind in ("cv_houlsby", "cv_parallel", "cv_pfeiffer_ver2"):
         return [k for k in sd if "adapter" in k]
+    if c.kind == "cv_compacter":
+        return [k for k in sd if "adapter" in k and not k.endswith("phm_rule")] + ["phm_rule"]
     if c.kind == "cv_lora":
         return [k for k in sd if "lora_" in k or (".query.bias" in k or ".value.bias" in k or ".w_Q.bias" in k)
                 or ".w_V." in k]

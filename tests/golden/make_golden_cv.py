@@ -40,7 +40,29 @@ sys.modules["loralib"] = types.SimpleNamespace(Linear=_LoraLinear)
 
 from transformers import ViTConfig, ViTForImageClassification  # noqa: E402
 
-from model import Model, SASRecAdaptedSelfOutput, SoftPrompt, VITAdaptedOutput, VITAdaptedSelfOutput  # noqa: E402
+from model import (Model, SASRecAdaptedSelfOutput, SASRecCompacterAdaptedSelfOutput, SASRecParallelAdaptedSelfOutput,  # noqa: E402
+                   SASRecPfeifferV2AdaptedSelfOutput, SoftPrompt, VITAdaptedOutput, VITAdaptedParallelOutput,
+                   VITAdaptedSelfOutput, VITCompacterAdaptedOutput, VITCompacterAdaptedSelfOutput)
+from model.layers import PHMLinear  # noqa: E402
+
+
+class _CompacterModel(nn.Module):
+    """Restates CompacterModel of Downstream/CV/run_adapter.py:85-98 (the entry script imports lmdb-backed data_utils at
+    module level and cannot be imported here; the class is 12 lines: a shared phm_rule handed to every PHMLinear and a
+    pass-through forward)."""
+
+    def __init__(self, args, model):
+        super().__init__()
+        phm_dim = args.hypercomplex_division
+        self.model = model
+        self.phm_rule = nn.Parameter(torch.FloatTensor(phm_dim, phm_dim, phm_dim), requires_grad=True)
+        self.phm_rule.data.normal_(mean=0, std=args.phm_init_range)
+        for name, sub_module in model.named_modules():
+            if isinstance(sub_module, PHMLinear):
+                sub_module.set_phm_rule(phm_rule=self.phm_rule)
+
+    def forward(self, sample_items, log_mask, local_rank):
+        return self.model(sample_items, log_mask, local_rank)
 
 
 def build_reference_model(c):
@@ -60,6 +82,23 @@ def build_reference_model(c):
             lm.output = VITAdaptedOutput(lm.output, args)
         for i, tb in enumerate(blocks):
             blocks[i] = SASRecAdaptedSelfOutput(tb, args)
+    elif c.kind == "cv_parallel":                                  # run_adapter.py:236-247 (is_serial == "None")
+        for lm in layers:
+            lm.output = VITAdaptedParallelOutput(lm.output, args)
+        for i, tb in enumerate(blocks):
+            blocks[i] = SASRecParallelAdaptedSelfOutput(tb, args)
+    elif c.kind == "cv_pfeiffer_ver2":                             # run_adapter.py:367-377
+        for lm in layers:
+            lm.attention.output = VITAdaptedSelfOutput(lm.attention.output, args)
+        for i, tb in enumerate(blocks):
+            blocks[i] = SASRecPfeifferV2AdaptedSelfOutput(tb, args)
+    elif c.kind == "cv_compacter":                                 # run_adapter.py:396-411
+        for lm in layers:
+            lm.attention.output = VITCompacterAdaptedSelfOutput(lm.attention.output, args)
+            lm.output = VITCompacterAdaptedOutput(lm.output, args)
+        for i, tb in enumerate(blocks):
+            blocks[i] = SASRecCompacterAdaptedSelfOutput(tb, args)
+        model = _CompacterModel(args, model)
     elif c.kind == "cv_lora":
         import loralib as lora
         for lm in layers:
@@ -80,7 +119,7 @@ def build_reference_model(c):
 def main():
     import transformers
     meta = {"torch": torch.__version__, "transformers": transformers.__version__}
-    for kind in ("cv_base", "cv_houlsby", "cv_lora", "cv_prompt"):
+    for kind in (sys.argv[1:] or cases_cv.CV_ALL_KINDS):
         c = cases_cv.tiny_cv_case(kind)
         model, args = build_reference_model(c)
         sd = cases_cv.build_state_dict(c)
@@ -99,7 +138,7 @@ def main():
             loss.backward()
             out["grads"] = {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}
         with torch.no_grad():
-            out["item_emb"] = model.cv_encoder(images).clone()
+            out["item_emb"] = (model.model if kind == "cv_compacter" else model).cv_encoder(images).clone()
         path = os.path.join(HERE, "transrec_%s.pt" % kind)
         torch.save(out, path)
         print(kind, "tokens", c.P + 1 + c.n_tokens, "loss %.6f" % float(loss), "->", os.path.getsize(path), "bytes")

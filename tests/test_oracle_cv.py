@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
 import cases_cv  # noqa: E402
 import transrec_oracle as O  # noqa: E402
 
-KINDS = ["cv_base", "cv_houlsby", "cv_lora", "cv_prompt"]
+KINDS = list(cases_cv.CV_ALL_KINDS)
 
 
 def load_case(kind):
@@ -20,7 +20,7 @@ def load_case(kind):
     gold = torch.load(os.path.join(HERE, "golden", "transrec_%s.pt" % kind), weights_only=False)
     sd = cases_cv.build_state_dict(c)
     cfg = O.VitConfig(hidden=c.hidden, layers=c.layers, heads=c.heads, patch=c.patch, eps=c.eps)
-    rec = O.RecConfig(max_seq_len=c.S, embedding_dim=c.D, heads=c.rec_heads, blocks=c.blocks)
+    rec = O.RecConfig(max_seq_len=c.S, embedding_dim=c.D, heads=c.rec_heads, blocks=c.blocks, parallel=c.parallel)
     return c, gold, sd, cfg, rec
 
 
@@ -43,4 +43,7 @@ def test_cv_loss_grads_embeddings_match_reference(kind):
         loss.backward()
         assert sorted(gold["grads"].keys()) == train
         for k in train:
-            torch.testing.assert_close(sd[k].grad, gold["grads"][k], rtol=2e-4, atol=2e-6, msg=lambda m: k + ": " + m)
+            # fp32 summation order differs between the reference's einsum/bmm chain and the oracle's: the absolute
+            # floor scales with the tensor's own magnitude (cv_compacter's loss of ~42 gives gradients of O(1))
+            atol = max(2e-6, 1e-5 * float(gold["grads"][k].abs().max()))
+            torch.testing.assert_close(sd[k].grad, gold["grads"][k], rtol=2e-4, atol=atol, msg=lambda m: k + ": " + m)
