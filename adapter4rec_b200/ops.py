@@ -428,6 +428,26 @@ def gather_rows(table, ids):
     return out
 
 
+def sample_train_batch(seqs, item_content, item_num, seed, offset, neg_in=None):
+    """seqs int64 [B, S1] (left-padded ids), item_content int64 [I+1, W] -> (sample_items [B, S1, 2, W] int64,
+    log_mask [B, S1-1] f32, neg ids [B, S1] int64, fail flag [1] int32 — left on the device, no sync here)."""
+    assert seqs.dtype == torch.int64 and seqs.is_contiguous() and seqs.dim() == 2
+    assert item_content.dtype == torch.int64 and item_content.is_contiguous() and item_content.dim() == 2
+    B, S1 = seqs.shape
+    W = item_content.shape[1]
+    dev = seqs.device
+    out = torch.empty((B, S1, 2, W), dtype=torch.int64, device=dev)
+    log_mask = torch.empty((B, S1 - 1), dtype=torch.float32, device=dev)
+    neg = torch.empty((B, S1), dtype=torch.int64, device=dev)
+    fail = torch.zeros(1, dtype=torch.int32, device=dev)
+    if neg_in is not None:
+        assert neg_in.dtype == torch.int64 and neg_in.is_contiguous() and neg_in.shape == seqs.shape
+    _l.check(_l.get_lib().a4r_sample_train_batch(_p(seqs), _p(item_content), _p(neg_in), _p(out), _p(log_mask), _p(neg),
+                                                 _p(fail), B, S1, W, int(item_num), int(seed) & (2 ** 64 - 1),
+                                                 int(offset) & (2 ** 64 - 1), _stream()), "a4r_sample_train_batch")
+    return out, log_mask, neg, fail
+
+
 def score_topk(users, items, id_base=0, history=None, k=10):
     """Partial top-k lists of users @ items.T over one item shard: returns (scores [P,U,k] f32, ids [P,U,k] i32)."""
     assert users.dtype == BF16 and items.dtype == BF16 and users.shape[1] == items.shape[1]

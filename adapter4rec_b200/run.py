@@ -15,6 +15,7 @@ import torch
 import torch.distributed as dist
 
 from . import surgery
+from .data_utils.dataset import BuildTrainDataset
 from .data_utils.metrics import eval_model, get_item_embeddings
 from .model import BertModel, Model, ModelCPC, RobertaModel, TextConfigLite
 from .trainer import FlatAdamTrainer
@@ -92,6 +93,8 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     users = sorted(data.users_train.keys())
+    train_ds = BuildTrainDataset(data.users_train, data.item_content, data.item_num, args.max_seq_len, True,
+                                 device=next(model.parameters()).device, seed=123456 + rank)   # run.py:686 seed; per-rank stream
     max_hit10 = 0.0
     for ep in range(args.epoch):
         model.train()
@@ -99,10 +102,10 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
         mine = users[rank::world]                                   # DistributedSampler's round-robin split
         loss_sum, batches = 0.0, 0
         for b0 in range(0, len(mine), args.batch_size):
-            items, log_mask = build_train_batch(mine[b0:b0 + args.batch_size], data.users_train, data.item_content,
-                                                data.item_num, args.max_seq_len)
-            items = items.view(-1, items.size(-1)).to(local_rank, non_blocking=True)
-            loss = trainer.train_step(items, log_mask.to(local_rank, non_blocking=True))
+            # negatives + token-row gather on the device (only the user indices cross PCIe); the host restatement
+            # build_train_batch above stays as the reference-order implementation for CPU-side tools
+            items, log_mask = train_ds.batch(mine[b0:b0 + args.batch_size])
+            loss = trainer.train_step(items.view(-1, items.size(-1)), log_mask)
             loss_sum, batches = loss_sum + float(loss), batches + 1
             if loss != loss:                                        # NaN guard of run.py:602-604
                 raise FloatingPointError("loss is NaN")

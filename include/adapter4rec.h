@@ -370,6 +370,24 @@ A4R_API int a4r_gather_rows(const void* table, const int64_t* ids, void* out, in
                             a4r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Train-batch assembly on the device.  Replaces BuildTrainDataset.__getitem__
+ * (Downstream/Text/data_utils/dataset.py:24-49) for a whole batch: per user, one uniform negative in [1, item_num]
+ * per real history slot except the last, redrawn while it occurs in the user's own sequence (:36-40), then
+ * out[b, j, 0, :] = item_content[seqs[b, j]], out[b, j, 1, :] = item_content[neg[b, j]] (:46) and
+ * log_mask[b, j] = (seqs[b, j] != 0) for j < S (:31).
+ *   seqs [B, S1] int64 left-padded item ids (0 = padding), S1 = max_seq_len + 1;  item_content [item_num+1, W] int64
+ *   (W = 2L: ids | attention mask; row 0 = the padding item);  out [B, S1, 2, W] int64;  log_mask [B, S1-1] f32;
+ *   neg_out [B, S1] int64 (the negatives used);  fail_flag: one int32 set to 1 if some slot found no admissible
+ *   negative in 64 draws (item_num <= S1; the reference's loop would not terminate);  neg_in: NULL to sample, or
+ *   [B, S1] int64 negatives to use instead (replay / parity against the reference's Python RNG).
+ * Draw a of slot (b, j) is a pure function of (seed, offset + (b*S1 + j)*64 + a): a caller advances offset by
+ * B*S1*64 per batch.  All pointers are device pointers; item_content and out 16-byte aligned, W even.
+ * ------------------------------------------------------------------------------------------------ */
+A4R_API int a4r_sample_train_batch(const int64_t* seqs, const int64_t* item_content, const int64_t* neg_in, int64_t* out,
+                                   float* log_mask, int64_t* neg_out, int32_t* fail_flag, int64_t B, int64_t S1, int64_t W,
+                                   int64_t item_num, uint64_t seed, uint64_t offset, a4r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K11 + K12: full-ranking scores fused with the history mask and per-user top-k.
  * Replaces `scores = torch.matmul(prec_emb, item_embeddings.t())`, `score[history] = -inf`, `score[1:]` and the
  * argsort of metrics_topK (Downstream/Text/data_utils/metrics.py:105-111,51-59).

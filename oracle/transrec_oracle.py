@@ -426,6 +426,28 @@ def eval_model(seqs, histories, item_emb, sd, rec, topk=10):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# train-batch assembly (Downstream/Text/data_utils/dataset.py:24-49)
+# ------------------------------------------------------------------------------------------------------------------
+def train_sample(seq, item_content, item_num, max_seq_len, rng):
+    """BuildTrainDataset.__getitem__, dataset.py:24-49, for ONE user.  `rng` is Python's `random` module (or a
+    random.Random): the rejection loop calls rng.randint(1, item_num) in the reference's order, so under the same seed it
+    draws the reference's negatives.  Returns (sample_items [S+1, 2, 2L] int64, log_mask [S] f32, ids [S+1, 2] int64)."""
+    S1 = max_seq_len + 1
+    seq = list(seq)
+    tokens_len = len(seq) - 1
+    head = S1 - len(seq)
+    log_mask = [0] * head + [1] * tokens_len
+    neg_items = []
+    for _ in range(tokens_len):
+        sam_neg = rng.randint(1, item_num)
+        while sam_neg in seq:
+            sam_neg = rng.randint(1, item_num)
+        neg_items.append(sam_neg)
+    ids = torch.tensor([[0] * head + seq, [0] * head + neg_items + [0]], dtype=torch.long).t().contiguous()
+    return torch.as_tensor(item_content).long()[ids], torch.tensor(log_mask, dtype=torch.float32), ids
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # image tree (Downstream/CV): ViT item encoder with Houlsby / LoRA / soft-prompt variants
 # ------------------------------------------------------------------------------------------------------------------
 VIT_PREFIX = "cv_encoder.image_net.vit."
