@@ -202,6 +202,17 @@ if want("eval"):
     report("topk_merge 16 partial lists x 65,536 users (+HR/NDCG)", us, nbytes=P * U * 80 + U * 92)
     del tab, idx, sc, ii
 
+# ------------------------------------------------------------------ train-batch assembly (negative sampling + row gather)
+if want("batch"):
+    I, B, S1, W = 80_000, 4096, 21, 60
+    content = torch.randint(0, 30522, (I + 1, W), device=dev)
+    seqs = [torch.stack([torch.randperm(I, device=dev)[:S1] + 1 for _ in range(64)]).repeat(B // 64, 1).contiguous()
+            for _ in range(NR)]
+    us = timeit(lambda i: ops.sample_train_batch(seqs[i], content, I, 7, i << 40), NR)
+    report("sample_train_batch B=4096 users (S=20, L=30): sampler + 2(S+1) int64 rows/user", us,
+           nbytes=B * S1 * (2 * W * 8 * 2 + 8 + 8 + 4), note="reads are random 480 B rows of a 38 MB table (L2-resident)")
+    del content, seqs
+
 # ------------------------------------------------------------------ K11/K12 score GEMM + top-k  (C5)
 if want("score"):
     I, d, U = 2_000_000, 768, 9472
