@@ -100,6 +100,9 @@ PROTOTYPES = {
     "a4r_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "a4r_wgrad_bf16": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                  c_float, c_int32, c_void_p, c_size_t, c_void_p]),
+    "a4r_wgrad_tc_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
+    "a4r_wgrad_tc_bf16": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                    c_float, c_int32, c_void_p, c_size_t, c_void_p]),
     "a4r_bce_workspace_bytes": (c_size_t, []),
     "a4r_bce_loss_fwd": (c_int32, [POINTER(BceArgs), c_void_p, c_size_t, c_void_p]),
     "a4r_bce_loss_bwd": (c_int32, [POINTER(BceArgs), c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -268,8 +268,10 @@ def colsum(x, width=None, out=None, accumulate=False):
     return out
 
 
-def wgrad(a, b, alpha=1.0, out=None, accumulate=False, n=None, k=None):
-    """dW[N,K] (+)= alpha * a[:, :N].T @ b[:, :K]   (a = dY [M,>=N], b = X [M,>=K]; fp32 result)."""
+def wgrad_mma_sync(a, b, alpha=1.0, out=None, accumulate=False, n=None, k=None):
+    """dW[N,K] (+)= alpha * a[:, :N].T @ b[:, :K]   (a = dY [M,>=N], b = X [M,>=K]; fp32 result) on the round-1
+    mma.sync split-M kernel (a4r_wgrad_bf16).  Kept as an ABI entry point and as the cross-check of the tcgen05 kernel
+    in the tests; the product path (`wgrad` below) is the tcgen05 kernel."""
     assert a.dtype == BF16 and b.dtype == BF16 and a.shape[0] == b.shape[0]
     M = a.shape[0]
     N = a.shape[1] if n is None else n
@@ -283,6 +285,26 @@ def wgrad(a, b, alpha=1.0, out=None, accumulate=False, n=None, k=None):
     _l.check(_l.get_lib().a4r_wgrad_bf16(_p(a), _rows2d(a, "a"), _p(b), _rows2d(b, "b"), _p(out), out.stride(0), M, N, K,
                                          float(alpha), int(accumulate), _p(ws), wsb, _stream()), "a4r_wgrad_bf16")
     return out
+
+
+def wgrad_tc(a, b, alpha=1.0, out=None, accumulate=False, n=None, k=None):
+    """dW[N,K] (+)= alpha * a[:, :N].T @ b[:, :K] on tcgen05 (MN-major operands, split over tokens, fp32 result)."""
+    assert a.dtype == BF16 and b.dtype == BF16 and a.shape[0] == b.shape[0]
+    M = a.shape[0]
+    N = a.shape[1] if n is None else n
+    K = b.shape[1] if k is None else k
+    if out is None:
+        out = torch.empty((N, K), dtype=torch.float32, device=a.device)
+        accumulate = False
+    assert out.dtype == torch.float32 and tuple(out.shape) == (N, K) and out.stride(1) == 1
+    wsb = _l.get_lib().a4r_wgrad_tc_workspace_bytes(M, N, K)
+    ws = workspace(wsb, a.device)
+    _l.check(_l.get_lib().a4r_wgrad_tc_bf16(_p(a), _rows2d(a, "a"), _p(b), _rows2d(b, "b"), _p(out), out.stride(0), M, N, K,
+                                            float(alpha), int(accumulate), _p(ws), wsb, _stream()), "a4r_wgrad_tc_bf16")
+    return out
+
+
+wgrad = wgrad_tc   # every weight gradient of the path: 2-5x faster than the mma.sync kernel at every shape measured
 
 
 def _bce_args(prec, emb, log_mask, pos, neg, loss, count, cpc):

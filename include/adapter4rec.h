@@ -296,6 +296,16 @@ A4R_API int a4r_wgrad_bf16(const void* A, int64_t lda, const void* B, int64_t ld
                    int64_t N, int64_t K, float alpha, int32_t accumulate, void* workspace, size_t workspace_bytes,
                    a4r_stream_t stream);
 
+/* The same contraction on tcgen05 (MN-major operand descriptors: the activations are read in place, no transposes),
+ * split over the token axis with a fixed-order reduction: dW[N,K] (+)= alpha * A[M,N]^T . B[M,K], any N, K multiple of 8.
+ * Serves full fine-tuning — every nn.Linear weight of the encoder when fine_tune_to = all
+ * (Pretraining/Text/run.py:241-253, Downstream/Text/run.py:372-376) — and the skinny LoRA / adapter gradients.
+ * dW 16-byte aligned, ldw % 4 == 0. */
+A4R_API size_t a4r_wgrad_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+A4R_API int a4r_wgrad_tc_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* dW, int64_t ldw, int64_t M,
+                              int64_t N, int64_t K, float alpha, int32_t accumulate, void* workspace,
+                              size_t workspace_bytes, a4r_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K9: fused masked dot + BCE-with-logits + mean, forward / backward.
  * Replaces Model.forward's loss (Downstream/Text/model/model.py:53-68) and, with cpc = 1,

@@ -229,14 +229,14 @@ def test_act_bwd_colsum_wgrad():
     for (M, N, K) in [(5000, 768, 8), (3001, 8, 768), (4096, 768, 64), (777, 64, 768), (10240, 64, 16), (100, 16, 64)]:
         a, b = _rand((M, N), 1, 4), _rand((M, K), 1, 5)
         ref = a.float().t() @ b.float()
-        got = ops.wgrad(a, b, alpha=0.5)
+        got = ops.wgrad_mma_sync(a, b, alpha=0.5)
         _close(got, 0.5 * ref, 1e-3, 2e-3 * math.sqrt(M), "wgrad %dx%dx%d" % (M, N, K))
-        got2 = ops.wgrad(a, b, alpha=0.5, out=got.clone(), accumulate=True)
+        got2 = ops.wgrad_mma_sync(a, b, alpha=0.5, out=got.clone(), accumulate=True)
         _close(got2, ref, 1e-3, 4e-3 * math.sqrt(M), "wgrad accumulate")
     # operands that are column slices of wider buffers (T = x·Aᵀ padded to 64 columns)
     t = _rand((3000, 64), 1, 6)
     dq = _rand((3000, 2304), 1, 7)
-    _close(ops.wgrad(dq[:, :768], t, k=8), dq[:, :768].float().t() @ t[:, :8].float(), 1e-3, 0.2, "wgrad sliced")
+    _close(ops.wgrad_mma_sync(dq[:, :768], t, k=8), dq[:, :768].float().t() @ t[:, :8].float(), 1e-3, 0.2, "wgrad sliced")
 
 
 @pytest.mark.parametrize("B,S,D,cpc", [(64, 20, 64, False), (7, 10, 256, False), (33, 20, 768, False), (16, 20, 64, True)])
@@ -318,3 +318,28 @@ def test_adapter_ln_fused(M, H, r, act, tail):
     _close(out, ref, 2 ** -7, 1e-2, "out")
     out2 = ops.adapter_ln_fwd(h, inp, wd, bd, wu, bu, g, b, eps, act=act, tail=0, save=False)[0]
     assert torch.equal(out, out2), "the inference variant (z staged in `out`) must give identical results"
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 768, 8), (3001, 8, 768), (4096, 768, 64), (777, 64, 768), (10240, 64, 16),
+                                   (100, 16, 64), (6400, 768, 768), (4100, 3072, 768), (2050, 768, 3072), (64, 128, 256),
+                                   (63, 136, 264), (0, 64, 64), (20000, 2304, 64)])
+def test_wgrad_tc(M, N, K):
+    """tcgen05 weight gradient (MN-major operands, split over tokens): dW = alpha * A^T B against fp32 torch on the same
+    bf16-rounded operands; tolerance = fp32 accumulation-order noise, sqrt(M)-scaled like the mma.sync kernel's test."""
+    ops = _ops()
+    a, b = _rand((M, N), 1, 4), _rand((M, K), 1, 5)
+    ref = a.float().t() @ b.float()
+    got = ops.wgrad_tc(a, b, alpha=0.5)
+    _close(got, 0.5 * ref, 1e-3, 2e-3 * math.sqrt(max(M, 1)), "wgrad_tc %dx%dx%d" % (M, N, K))
+    got2 = ops.wgrad_tc(a, b, alpha=0.5, out=got.clone(), accumulate=True)
+    _close(got2, ref, 1e-3, 4e-3 * math.sqrt(max(M, 1)), "wgrad_tc accumulate")
+    assert torch.equal(ops.wgrad_tc(a, b, alpha=0.5), got), "fixed-order reduction must be deterministic"
+
+
+def test_wgrad_tc_strided_operands():
+    ops = _ops()
+    t = _rand((3000, 64), 1, 6)
+    dq = _rand((3000, 2304), 1, 7)
+    _close(ops.wgrad_tc(dq[:, :768], t, k=8), dq[:, :768].float().t() @ t[:, :8].float(), 1e-3, 0.2, "wgrad_tc sliced")
+    _close(ops.wgrad_tc(dq[:, 768:1536], dq[:, 1536:], n=768, k=768), dq[:, 768:1536].float().t() @ dq[:, 1536:].float(),
+           1e-3, 0.3, "wgrad_tc two column slices")
