@@ -416,6 +416,29 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat1
   }
 }
 
+// embedding-table gradient: dst[idx[r], :] += src[r, :] (fp32 accumulation of bf16 rows); rows with idx < 0 or
+// idx == skip_idx (nn.Embedding's padding_idx: its row never receives a gradient) are skipped.  One warp per source row,
+// 128-bit loads, red.global.add.v4.f32 (sm_90+): 2 vector atomics per 8 elements.  The accumulation ORDER across rows
+// that hit the same table row is unspecified, as it is in torch's own embedding backward on CUDA.
+__global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld, const int64_t* __restrict__ idx,
+                                        float* __restrict__ dst, int64_t R, int H, int64_t V, int64_t skip_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < R; r += nwarps) {
+    const int64_t t = idx[r];
+    if (t < 0 || t >= V || t == skip_idx) continue;
+    float* row = dst + t * H;
+    for (int c = lane; c < H / 8; c += 32) {
+      float v[8];
+      unpack8(ld_nc_v4(src + r * ld + c * 8), v);
+      float* o = row + c * 8;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+    }
+  }
+}
+
 // dropout (+ residual): out = x * mask * scale (+ res); element i uses lane (i & 3) of rng64(seed, offset + i / 4)
 __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                __nv_bfloat16* __restrict__ out, int64_t nvec, uint32_t thr16, float scale, uint64_t seed,
@@ -676,6 +699,24 @@ extern "C" int a4r_dropout(const void* x, const void* res, void* out, int64_t n,
   dropout_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(res), static_cast<__nv_bfloat16*>(out), nvec,
       thr16, scale, seed, offset);
+  A4R_LAUNCH_OK();
+  a4r_count_launch(1);
+  return A4R_OK;
+}
+
+extern "C" int a4r_scatter_add_rows(const void* src, int64_t ld, const int64_t* idx, float* dst, int64_t R, int64_t H,
+                                    int64_t V, int64_t skip_idx, a4r_stream_t stream_) {
+  A4R_CHECK_ARG(R >= 0 && H >= 8 && H % 8 == 0 && V > 0 && ld >= H && ld % 8 == 0, "scatter_add_rows: bad sizes");
+  if (R == 0) return A4R_OK;
+  A4R_CHECK_ARG(src && idx && dst, "scatter_add_rows: NULL pointer");
+  A4R_CHECK_ARG(a4r_aligned16(src) && a4r_aligned16(dst), "scatter_add_rows: src and dst must be 16B aligned");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  int64_t blocks = (R + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  scatter_add_rows_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(src), ld, idx, dst, R, static_cast<int>(H), V, skip_idx);
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;

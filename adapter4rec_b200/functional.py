@@ -184,17 +184,21 @@ class PostLNBlockFunction(torch.autograd.Function):
 
 
 class LayerNormFunction(torch.autograd.Function):
-    """y = LN(x + res[row % res_rows]).  res is a constant (the frozen SASRec position table) or None."""
+    """y = LN(x + res[row % res_rows]).  res is the bf16 copy of a broadcast table (the SASRec position table) or None;
+    `res_param` is its fp32 master when that table is trainable (full fine-tuning): its gradient is the column sum of dz
+    over the broadcast axis."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, res):
-        need = any(ctx.needs_input_grad[:3])
+    def forward(ctx, x, weight, bias, eps, res, res_param=None):
+        need = any(ctx.needs_input_grad[:3]) or (res_param is not None and res_param.requires_grad)
         g, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
         if res is not None:
             y, z, mean, rstd = ops.layernorm_fwd(x, g, b, eps, res=res, want_z=need, want_stats=need)
         else:
             y, _, mean, rstd = ops.layernorm_fwd(x, g, b, eps, want_stats=need)
             z = x
+        ctx.res_rows = 0 if res is None else res.numel() // res.shape[-1]
+        ctx.res_shape = None if res_param is None else tuple(res_param.shape)
         if need:
             ctx.save_for_backward(z, mean, rstd, g)
         return y
@@ -203,15 +207,20 @@ class LayerNormFunction(torch.autograd.Function):
     def backward(ctx, dy):
         z, mean, rstd, g = ctx.saved_tensors
         dy = dy.contiguous()
+        dg = db = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dg, db = torch.empty_like(g), torch.empty_like(g)
-            dz = ops.layernorm_bwd(dy, z, mean, rstd, g, dgamma=dg, dbeta=db)
-            return dz, dg, db, None, None
-        return ops.layernorm_bwd(dy, z, mean, rstd, g), None, None, None, None
+        dz = ops.layernorm_bwd(dy, z, mean, rstd, g, dgamma=dg, dbeta=db)
+        dres = None
+        if ctx.res_shape is not None and ctx.needs_input_grad[5]:
+            rows, H = ctx.res_rows, dz.shape[1]
+            dres = torch.zeros(ctx.res_shape, dtype=torch.float32, device=dz.device)
+            dres[:rows] = ops.colsum(dz.view(-1, rows * H)).view(rows, H)
+        return dz, dg, db, None, None, dres
 
 
-def layer_norm(x, weight, bias, eps, res=None):
-    return LayerNormFunction.apply(x, weight, bias, eps, res)
+def layer_norm(x, weight, bias, eps, res=None, res_param=None):
+    return LayerNormFunction.apply(x, weight, bias, eps, res, res_param)
 
 
 class DropoutState:
@@ -412,30 +421,68 @@ def _pad_cols_wgrad(a, b, off, r, alpha, transpose):
 
 
 class EmbedLNFunction(torch.autograd.Function):
-    """K1 with the soft-prompt substitution; only the prompt rows are trainable (everything else is a frozen table)."""
+    """K1 with the soft-prompt substitution.  Adapter tuning trains at most the prompt rows; under full fine-tuning
+    (fine_tune_to = all, Pretraining/*) the word / position / token-type tables and the embedding LayerNorm are trainable
+    too: `params` = (word_weight, pos_weight, type_weight, ln_weight, ln_bias) are the fp32 masters, passed so autograd can
+    hand their gradients back (None entries = frozen)."""
 
     @staticmethod
-    def forward(ctx, ids, L, tables, gamma, beta, eps, roberta_pad_id, prompt):
+    def forward(ctx, ids, L, tables, gamma, beta, eps, roberta_pad_id, prompt, word_pad_idx, *params):
         word, pos, typ = tables
-        need = prompt is not None and prompt.requires_grad
+        need_prompt = prompt is not None and prompt.requires_grad
+        need_tab = [p is not None and p.requires_grad for p in params] + [False] * (5 - len(params))
+        need = need_prompt or any(need_tab)
         p16 = None if prompt is None else prompt.detach().to(BF16).contiguous()
         out, z, mean, rstd = ops.embed_ln_fwd(ids, L, word, pos, typ, gamma, beta, eps, roberta_pad_id=roberta_pad_id,
                                               prompt=p16, want_z=need)
-        ctx.L = L
+        ctx.L, ctx.need_prompt, ctx.need_tab, ctx.roberta_pad_id, ctx.word_pad_idx = L, need_prompt, need_tab, roberta_pad_id, word_pad_idx
+        ctx.n_prompt = 0 if prompt is None else prompt.shape[0]
+        ctx.shapes = [None if p is None else tuple(p.shape) for p in params]
         if need:
-            ctx.save_for_backward(z, mean, rstd, gamma)
-            ctx.n_prompt = prompt.shape[0]
+            ctx.save_for_backward(z, mean, rstd, gamma, ids)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        z, mean, rstd, gamma = ctx.saved_tensors
-        dz = ops.layernorm_bwd(dout.contiguous(), z, mean, rstd, gamma)
+        z, mean, rstd, gamma, ids = ctx.saved_tensors
+        need_word, need_pos, need_typ, need_g, need_b = ctx.need_tab
+        dg = db = None
+        if need_g or need_b:
+            dg, db = torch.empty_like(gamma), torch.empty_like(gamma)
+        dz = ops.layernorm_bwd(dout.contiguous(), z, mean, rstd, gamma, dgamma=dg, dbeta=db)
         H = dz.shape[1]
         L, n = ctx.L, ctx.n_prompt
-        # d prompt[t] = sum over items of dz[item, t]: view [N, L*H] and column-sum the first n*H columns
-        dp = ops.colsum(dz.view(-1, L * H), width=n * H).view(n, H)
-        return None, None, None, None, None, None, None, dp
+        dp = None
+        if ctx.need_prompt:
+            # d prompt[t] = sum over items of dz[item, t]: view [N, L*H] and column-sum the first n*H columns
+            dp = ops.colsum(dz.view(-1, L * H), width=n * H).view(n, H)
+        grads = [None] * len(ctx.shapes)
+        tok = ids[:, :L]
+        if need_word:
+            idx = tok.clone()
+            if n > 0:
+                idx[:, :n] = -1                                    # positions replaced by the soft prompt read no table row
+            grads[0] = ops.scatter_add_rows(dz, idx, ctx.shapes[0][0], skip_idx=ctx.word_pad_idx)
+        if need_pos:
+            P = ctx.shapes[1][0]
+            if ctx.roberta_pad_id >= 0:
+                # RobertaEmbeddings: position ids from the token ids (cumsum over non-pad tokens), padding_idx = pad id
+                m = (tok != ctx.roberta_pad_id).long()
+                pos_ids = torch.cumsum(m, 1) * m + ctx.roberta_pad_id
+                grads[1] = ops.scatter_add_rows(dz, pos_ids, P, skip_idx=ctx.roberta_pad_id)
+            else:
+                g = torch.zeros((P, H), dtype=torch.float32, device=dz.device)
+                g[:L] = ops.colsum(dz.view(-1, L * H)).view(L, H)   # position l of every item reads row l
+                grads[1] = g
+        if need_typ:
+            g = torch.zeros(ctx.shapes[2], dtype=torch.float32, device=dz.device)
+            g[0] = ops.colsum(dz)                                   # token_type_ids are all zero on this path
+            grads[2] = g
+        if need_g:
+            grads[3] = dg
+        if need_b and len(grads) > 4:
+            grads[4] = db
+        return (None, None, None, None, None, None, None, dp, None) + tuple(grads)
 
 
 class BceLossFunction(torch.autograd.Function):

@@ -62,7 +62,14 @@ class BertEmbeddings(nn.Module):
         typ = self._typ_cache.get(self.token_type_embeddings.weight)[0][0]
         tables = (table, self.position_embeddings.table_bf16(), typ)
         g, b = self.LayerNorm.weight.detach().float(), self.LayerNorm.bias.detach().float()
-        x = Fn.EmbedLNFunction.apply(input_ids, L, tables, g, b, self.LayerNorm.eps, roberta_pad, prompt)
+        # fp32 masters of whatever is trainable here (full fine-tuning); the word table's padding_idx row never gets a
+        # gradient (transformers builds it with nn.Embedding(..., padding_idx=pad_token_id))
+        wmaster = we.wte.weight if hasattr(we, "learned_embedding") else we.weight
+        masters = [wmaster, self.position_embeddings.weight, self.token_type_embeddings.weight, self.LayerNorm.weight,
+                   self.LayerNorm.bias]
+        masters = [m if m.requires_grad else None for m in masters]
+        x = Fn.EmbedLNFunction.apply(input_ids, L, tables, g, b, self.LayerNorm.eps, roberta_pad, prompt,
+                                     int(self.config.pad_token_id), *masters)
         if self.training and self.dropout.p > 0:
             x = Fn.dropout_add(x, None, self.dropout.p)
         return x

@@ -119,9 +119,9 @@ class LayerNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(n))
         self.bias = nn.Parameter(torch.zeros(n))
 
-    def forward(self, x, res=None):
+    def forward(self, x, res=None, res_param=None):
         shape = x.shape
-        return Fn.layer_norm(to_2d_bf16(x), self.weight, self.bias, self.eps, res=res).view(shape)
+        return Fn.layer_norm(to_2d_bf16(x), self.weight, self.bias, self.eps, res=res, res_param=res_param).view(shape)
 
 
 class Embedding(nn.Module):

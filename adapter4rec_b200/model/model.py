@@ -22,19 +22,19 @@ def _word_dim(args):
     raise AssertionError("The pretrained model name should be defined correctly. such as bert-base-uncased so on")
 
 
-_UNSUPPORTED_TRAINABLE = ("word_embeddings.weight", "word_embeddings.wte.weight", "position_embeddings.weight",
-                          "token_type_embeddings.weight", "position_embedding.weight", "pooler.")
-
-
 def check_trainable_supported(module):
-    """Fail loudly instead of silently leaving a gradient at zero: the path differentiates adapters, LoRA factors,
-    biases, LayerNorms, prompt embeddings and any Linear weight, but not embedding tables (full fine-tuning of the
-    backbone embeddings is outside the adapter-tuning hot path)."""
-    bad = [n for n, p in module.named_parameters() if p.requires_grad and any(k in n for k in _UNSUPPORTED_TRAINABLE)]
+    """Fail loudly instead of silently leaving a gradient at zero.  The sm_100a path differentiates adapters, LoRA factors,
+    biases, LayerNorms, prompt embeddings, every Linear weight and — for full fine-tuning of the TEXT tower — the BERT /
+    RoBERTa / SASRec embedding tables.  The BERT pooler is kept for state_dict compatibility but never evaluated (the
+    reference computes and discards it; Pretraining/Text/run.py:48-64 freezes it): left trainable
+    it simply receives no gradient, as in the reference.  Not implemented: the ViT patch / cls / position embeddings of
+    the image tower (full fine-tuning of ViT below layer 0)."""
+    bad = [n for n, p in module.named_parameters()
+           if p.requires_grad and "vit.embeddings" in n and not n.endswith("Prompt_Tokens")]
     if bad:
         raise NotImplementedError(
-            "adapter4rec_b200: gradients for these parameters are not implemented on the sm_100a path (freeze them as "
-            "Downstream/Text/run.py:369-371 does with fine_tune_to=None): %s" % bad[:6])
+            "adapter4rec_b200: gradients for these parameters are not implemented on the sm_100a path (freeze them, as "
+            "Downstream/CV/run_adapter.py does with freeze_paras_before / fine_tune_to=None): %s" % bad[:6])
 
 
 class _ModelBase(nn.Module):

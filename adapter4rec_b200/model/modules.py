@@ -133,7 +133,8 @@ class TransformerEncoder(nn.Module):
     def forward(self, input_embs, log_mask, att_mask):
         B, S, D = input_embs.shape
         pos = self.position_embedding.table_bf16()[:S].contiguous()
-        output = self.layer_norm(to_2d_bf16(input_embs).contiguous(), res=pos)
+        pe = self.position_embedding.weight
+        output = self.layer_norm(to_2d_bf16(input_embs).contiguous(), res=pos, res_param=pe if pe.requires_grad else None)
         if self.training and self.dropout.p > 0:
             output = Fn.dropout_add(output, None, self.dropout.p)
         output = output.view(B, S, D)

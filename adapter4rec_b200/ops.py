@@ -235,6 +235,17 @@ def embed_ln_fwd(ids, L, word_emb, pos_emb, type_emb, gamma, beta, eps, pos_offs
     return out, z, mean, rstd
 
 
+def scatter_add_rows(src, idx, num_rows, skip_idx=-1):
+    """f32 [num_rows, H] with out[idx[r]] += src[r] (bf16 src [R, H], int64 idx [R]); idx < 0 / == skip_idx skipped."""
+    assert src.dtype == BF16 and src.dim() == 2 and src.stride(1) == 1 and idx.dtype == torch.int64
+    idx = idx.contiguous().view(-1)
+    assert idx.numel() == src.shape[0]
+    out = torch.zeros((num_rows, src.shape[1]), dtype=torch.float32, device=src.device)
+    _l.check(_l.get_lib().a4r_scatter_add_rows(_p(src), src.stride(0), _p(idx), _p(out), src.shape[0], src.shape[1],
+                                               int(num_rows), int(skip_idx), _stream()), "a4r_scatter_add_rows")
+    return out
+
+
 ACT_KINDS = {"gelu": 0, "relu": 1, "leaky_relu": 2, "gelu_new": 3}
 
 

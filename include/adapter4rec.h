@@ -262,6 +262,13 @@ A4R_API int a4r_patchify(const float* images, void* out, int64_t N, int64_t C, i
 A4R_API int a4r_vit_assemble(const void* patch_emb, const void* cls, const void* pos, const void* prompt, void* out,
                              int64_t N, int64_t P, int64_t T, int64_t H, a4r_stream_t stream);
 
+/* Embedding-table gradient (full fine-tuning): dst[idx[r], :] += src[r, :] for r < R, skipping idx < 0,
+ * idx >= V and idx == skip_idx (nn.Embedding's padding_idx — BertEmbeddings.word_embeddings / RobertaEmbeddings'
+ * word and position tables, reached from Text_Encoder.forward, Downstream/Text/model/encoders.py:53).  src bf16 [R, ld],
+ * dst f32 [V, H] (the caller zeroes it), H %% 8 == 0.  fp32 vector atomics: summation order unspecified. */
+A4R_API int a4r_scatter_add_rows(const void* src, int64_t ld, const int64_t* idx, float* dst, int64_t R, int64_t H,
+                                 int64_t V, int64_t skip_idx, a4r_stream_t stream);
+
 /* out = dy * act'(u) elementwise over n bf16 values; kind 0: erf-GELU with u = pre-activation
  * (Text_Encoder.activate, encoders.py:46,57), kind 1: ReLU with u = activation output, kind 2: LeakyReLU(0.01) with
  * u = activation output (AdapterPfeifferBlock, Downstream/Text/model/modules.py:146-147), kind 3: tanh-GELU

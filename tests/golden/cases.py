@@ -13,7 +13,7 @@ USER = "user_encoder.transformer_encoder."
 
 
 ZOO_KINDS = ("parallel", "pfeiffer", "pfeiffer_leaky", "pfeiffer_ver2", "compacter", "kadapter")
-ALL_KINDS = ("base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc") + ZOO_KINDS
+ALL_KINDS = ("base", "houlsby", "houlsby_gelu", "lora", "prompt_cpc") + ZOO_KINDS + ("full_ft", "full_ft_roberta")
 
 
 def _houlsby_like(kind):
@@ -26,7 +26,7 @@ def tiny_case(kind):
     'parallel' (Houlsby, is_serial=None) | 'pfeiffer' (GELU) | 'pfeiffer_leaky' | 'pfeiffer_ver2'."""
     c = types.SimpleNamespace()
     c.kind = kind
-    c.roberta = kind == "prompt_cpc"
+    c.roberta = kind in ("prompt_cpc", "full_ft_roberta")
     c.cpc = kind == "prompt_cpc"
     c.hidden, c.layers, c.heads, c.inter = 128, 2, 2, 512
     c.vocab, c.max_pos = 200, 40
@@ -44,7 +44,7 @@ def tiny_case(kind):
     c.B = 6
     c.item_num = 40
     c.seed = {"base": 11, "houlsby": 12, "lora": 13, "prompt_cpc": 14, "houlsby_gelu": 15, "parallel": 16,
-              "pfeiffer": 17, "pfeiffer_leaky": 18, "pfeiffer_ver2": 19, "compacter": 20, "kadapter": 21}[kind]
+              "pfeiffer": 17, "pfeiffer_leaky": 18, "pfeiffer_ver2": 19, "compacter": 20, "kadapter": 21, "full_ft": 22, "full_ft_roberta": 23}[kind]
     # K-Adapter (parameters.py:68-71): adapters after BERT layers 0 and 1 of the 2-layer tiny body, width 64 with
     # 2 heads (head width 32); the SASRec-side adapters keep the reference default width 16 with 2 heads (head width 8)
     c.k_list, c.k_hidden, c.k_heads_bert, c.k_heads_rec = "0,1", 64, 2, 2
@@ -64,7 +64,8 @@ def reference_args(c):
                                                                       "base": "None", "parallel": "houslby",
                                                                       "pfeiffer": "pfeiffer", "pfeiffer_leaky": "pfeiffer",
                                                                       "pfeiffer_ver2": "pfeiffer_ver2", "compacter": "compacter",
-                                                                      "kadapter": "kadapter"}[c.kind],
+                                                                      "kadapter": "kadapter", "full_ft": "None",
+                                                                      "full_ft_roberta": "None"}[c.kind],
         k_adapter_bert_list=c.k_list, k_adapter_bert_hidden_dim=c.k_hidden, num_adapter_heads_bert=c.k_heads_bert,
         num_adapter_heads_sasrec=c.k_heads_rec,
         hypercomplex_division=c.phm_dim, phm_init_range=0.0001,
@@ -218,6 +219,9 @@ def trainable_keys(c, sd):
     """Parameters left trainable by Downstream/Text/run.py:367-479 with fine_tune_to=None."""
     if c.kind.startswith("houlsby") or c.kind in ("parallel", "pfeiffer_ver2"):
         return [k for k in sd if "adapter" in k]
+    if c.kind.startswith("full_ft"):
+        # fine_tune_to = all with the pooler frozen, as the source-domain stage trains (Pretraining/Text/run.py:48-64)
+        return [k for k in sd if "pooler" not in k]
     if c.kind == "kadapter":
         return [k for k in sd if "adapter_list" in k or "com_dense" in k]
     if c.kind == "compacter":     # named_parameters() lists the shared rule once, under the wrapper's own name

@@ -62,8 +62,9 @@ def build_reference_model(c):
     else:
         bert = BertModel(BertConfig(**kw))
     model = (ModelCPC if c.cpc else Model)(args, c.item_num, True, bert)
-    for p in model.parameters():                                   # run.py:369-371 (fine_tune_to=None)
-        p.requires_grad = False
+    full_ft = c.kind.startswith("full_ft")                         # fine_tune_to = all: nothing frozen but the pooler
+    for n, p in model.named_parameters():                          # run.py:369-371 (fine_tune_to=None)
+        p.requires_grad = full_ft and "pooler" not in n
     layers = model.bert_encoder.text_encoders.title.bert_model.encoder.layer
     blocks = model.user_encoder.transformer_encoder.transformer_blocks
     if c.kind.startswith("houlsby"):                               # run.py:456-465

@@ -35,7 +35,10 @@ def build_gpu_model(c, sd):
     bert = (RobertaModel if c.roberta else BertModel)(cfg)
     model = (ModelCPC if c.cpc else Model)(args, c.item_num, True, bert).cuda()
     surgery.freeze_all(model)
-    if c.kind != "base":
+    if c.kind.startswith("full_ft"):                        # fine_tune_to = all, pooler frozen (Pretraining/Text/run.py:48-64)
+        for n, p in model.named_parameters():
+            p.requires_grad = "pooler" not in n
+    elif c.kind != "base":
         model = surgery.insert_adapters(model, args)        # compacter returns the CompacterModel wrapper
     assert set(model.state_dict().keys()) == set(sd.keys()), "state_dict keys must equal the reference's"
     model.load_state_dict(sd)
@@ -94,7 +97,9 @@ def test_train_step_matches_oracle_and_reference(kind):
             negligible = float((g - og).norm()) <= 5e-3 * total_norm
             assert (rel <= GRAD_REL_L2 and cos >= 0.99) or negligible, "%s: rel L2 %.4f cos %.5f" % (k, rel, cos)
             ref_g = gold["grads"][k]
-            assert float((og - ref_g).norm() / (ref_g.norm() + 1e-12)) < 1e-3
+            # (the key-projection biases have an analytically ZERO gradient — softmax is invariant to a per-query
+            # constant — so both sides hold rounding noise of ~1e-9 there: absolute floor relative to the whole gradient)
+            assert float((og - ref_g).norm()) < 1e-3 * float(ref_g.norm()) + 1e-6 * total_norm
         allg = torch.cat([params[k].grad.float().cpu().flatten() for k in train])
         allo = torch.cat([osd[k].grad.flatten() for k in train])
         assert float((allg - allo).norm() / allo.norm()) <= GRAD_ALL_REL_L2
