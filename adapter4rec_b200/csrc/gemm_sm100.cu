@@ -28,7 +28,7 @@ constexpr int UMMA_K = 16;           // fixed for 16-bit inputs
 // measured on B200 (M = 161,280, N = 3072, K = 768): GELU' 0.94 -> 0.84 ms with 4 groups, GELU 0.81 -> see profiles/.
 template <int BN, int EPI>
 struct EpiGroups {
-  static constexpr int value = BN != 256 ? 2 : (EPI == A4R_EPI_DGELU ? 4 : ((EPI == A4R_EPI_GELU || EPI == A4R_EPI_GELU_G) ? 3 : 2));
+  static constexpr int value = BN != 256 ? 2 : (EPI == A4R_EPI_DGELU ? 4 : (EPI == A4R_EPI_GELU ? 3 : 2));
 };
 
 // CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 the two SMs of a TPC own one 256 x BN tile, each CTA staging its own
@@ -250,7 +250,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int group = ew >> 2;
     constexpr int CHUNKS = (BN / 32 + NUM_EPI_GROUPS - 1) / NUM_EPI_GROUPS;
-    constexpr bool kHasIn = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_DGELU) || (EPI == A4R_EPI_DRELU) || (EPI == A4R_EPI_DMUL);
+    constexpr bool kHasIn = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_DGELU) || (EPI == A4R_EPI_DRELU);
     const __nv_bfloat16* in_ptr = nullptr;
     int64_t in_ld = 0;
     if constexpr (EPI == A4R_EPI_LINEAR) {
@@ -287,7 +287,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                            acc);
         const bool full = col0 + 32 <= p.N;
         // the bias slice of this chunk is fetched WHILE the TMEM load is in flight (both latencies overlap)
-        constexpr bool kBias = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_GELU) || (EPI == A4R_EPI_RELU) || (EPI == A4R_EPI_GELU_G);
+        constexpr bool kBias = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_GELU) || (EPI == A4R_EPI_RELU);
         float4 bv[kBias ? 8 : 1];
         const bool has_bias = kBias && p.bias != nullptr;
         if (has_bias) {
@@ -324,7 +324,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             in.w[4 * j] = t.x; in.w[4 * j + 1] = t.y; in.w[4 * j + 2] = t.z; in.w[4 * j + 3] = t.w;
           }
         }
-        auto store_packed = [&](__nv_bfloat16* dst, const uint32_t (&w)[16]) {
+        auto store_bf16 = [&](__nv_bfloat16* dst) {
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[i].x, v[i].y);
           if (full) {
             if constexpr (V32) {
               const uint32_t a8[8] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]};
@@ -340,12 +343,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 4; ++j)
               if (col0 + 8 * j < p.N) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
           }
-        };
-        auto store_bf16 = [&](__nv_bfloat16* dst) {
-          uint32_t w[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[i].x, v[i].y);
-          store_packed(dst, w);
         };
         if constexpr (EPI == A4R_EPI_LINEAR) {
           if (p.drop_thr16 != 0) {
@@ -380,23 +377,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.aux != nullptr) store_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = gelu_fast2(v[i]);
-        } else if constexpr (EPI == A4R_EPI_GELU_G) {
-          // forward of a block whose backward is known to follow: Phi(x) and exp(-x^2/2) are shared by gelu(x) = x*Phi
-          // and gelu'(x) = Phi + x*pdf, so the DERIVATIVE is written as aux (2 more FMAs per pair) and the backward GEMM's
-          // epilogue is a plain multiply (A4R_EPI_DMUL) instead of a second evaluation of the polynomial
-          uint32_t wg[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float2 cdf, e;
-            gelu_parts2(v[i], cdf, e);
-            const float2 g = __ffma2_rn(__fmul2_rn(v[i], splat2(0.39894228040143267794f)), e, cdf);
-            wg[i] = pack_bf16x2(g.x, g.y);
-            v[i] = __fmul2_rn(v[i], cdf);
-          }
-          store_packed(reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0, wg);
-        } else if constexpr (EPI == A4R_EPI_DMUL) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], unpack_bf16x2(in.w[i]));
         } else if constexpr (EPI == A4R_EPI_RELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float2(fmaxf(v[i].x, 0.0f), fmaxf(v[i].y, 0.0f));
@@ -583,11 +563,10 @@ extern "C" int a4r_gemm_bf16_tn(const a4r_gemm_args* a, a4r_stream_t stream_) {
     A4R_CHECK_ARG(a->A2 && a->B2 && a4r_aligned16(a->A2) && a4r_aligned16(a->B2), "gemm: A2/B2 missing or unaligned");
     A4R_CHECK_ARG(a->lda2 % 8 == 0 && a->ldb2 % 8 == 0 && a->lda2 >= a->K2 && a->ldb2 >= a->K2, "gemm: bad lda2/ldb2");
   }
-  A4R_CHECK_ARG(a->epilogue >= A4R_EPI_LINEAR && a->epilogue <= A4R_EPI_DMUL, "gemm: unknown epilogue %d",
+  A4R_CHECK_ARG(a->epilogue >= A4R_EPI_LINEAR && a->epilogue <= A4R_EPI_DRELU, "gemm: unknown epilogue %d",
                 a->epilogue);
-  if (a->epilogue == A4R_EPI_DGELU || a->epilogue == A4R_EPI_DRELU || a->epilogue == A4R_EPI_DMUL)
-    A4R_CHECK_ARG(a->aux != nullptr && a->bias == nullptr, "gemm: DGELU/DRELU/DMUL need aux and take no bias");
-  if (a->epilogue == A4R_EPI_GELU_G) A4R_CHECK_ARG(a->aux != nullptr, "gemm: GELU_G writes gelu'(v) to aux, which is NULL");
+  if (a->epilogue == A4R_EPI_DGELU || a->epilogue == A4R_EPI_DRELU)
+    A4R_CHECK_ARG(a->aux != nullptr && a->bias == nullptr, "gemm: DGELU/DRELU need aux and take no bias");
   if (a->aux) A4R_CHECK_ARG(a4r_aligned16(a->aux) && a->ldaux % 8 == 0 && a->ldaux >= a->N, "gemm: bad aux/ldaux");
   if (a->residual)
     A4R_CHECK_ARG(a4r_aligned16(a->residual) && a->ldr % 8 == 0 && a->ldr >= a->N, "gemm: bad residual/ldr");
@@ -622,8 +601,6 @@ extern "C" int a4r_gemm_bf16_tn(const a4r_gemm_args* a, a4r_stream_t stream_) {
     case A4R_EPI_GELU: return A4R_DISPATCH(A4R_EPI_GELU);
     case A4R_EPI_RELU: return A4R_DISPATCH(A4R_EPI_RELU);
     case A4R_EPI_DGELU: return A4R_DISPATCH(A4R_EPI_DGELU);
-    case A4R_EPI_GELU_G: return A4R_DISPATCH(A4R_EPI_GELU_G);
-    case A4R_EPI_DMUL: return A4R_DISPATCH(A4R_EPI_DMUL);
     default: return A4R_DISPATCH(A4R_EPI_DRELU);
   }
 #undef A4R_DISPATCH

@@ -102,10 +102,8 @@ class FFNFunction(torch.autograd.Function):
         w1, _ = cache_i.get(wi)
         w2, _ = cache_f.get(wf)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[5]
-        # with a backward to follow, the epilogue writes GELU'(pre-activation) next to GELU(.) (shared Phi / exp), so the
-        # backward GEMM's epilogue is a multiply instead of a second GELU' evaluation
         u = torch.empty((y.shape[0], w1.shape[0]), dtype=BF16, device=y.device) if need else None
-        f = ops.gemm(y, w1, bias=bi.detach(), epilogue=ops.EPI_GELU_G if need else ops.EPI_GELU, aux=u)
+        f = ops.gemm(y, w1, bias=bi.detach(), epilogue=ops.EPI_GELU, aux=u)
         h = ops.gemm(f, w2, bias=bf.detach(), residual=residual)
         ctx.caches = (cache_i, cache_f)
         ctx.has_res = residual is not None
@@ -119,7 +117,7 @@ class FFNFunction(torch.autograd.Function):
         dh = dh.contiguous()
         _, w2t = ctx.caches[1].get(wf, need_t=True)
         _, w1t = ctx.caches[0].get(wi, need_t=True)
-        du = ops.gemm(dh, w2t, epilogue=ops.EPI_DMUL, aux=u)
+        du = ops.gemm(dh, w2t, epilogue=ops.EPI_DGELU, aux=u)
         # when the residual IS the input (post-LN BERT: h = FFN(y) + y) its gradient is folded into the epilogue of the
         # last data-gradient GEMM and nothing is returned for the residual slot (autograd would add them otherwise).
         fold = ctx.has_res and ctx.res_is_input
@@ -147,8 +145,8 @@ class PostLNBlockFunction(torch.autograd.Function):
         u = None
         if ffn:
             wb, _ = cache2.get(w2)
-            u = torch.empty((x.shape[0], wa.shape[0]), dtype=BF16, device=x.device) if need else None   # holds GELU'
-            f = ops.gemm(x, wa, bias=b1.detach(), epilogue=ops.EPI_GELU_G if need else ops.EPI_GELU, aux=u)
+            u = torch.empty((x.shape[0], wa.shape[0]), dtype=BF16, device=x.device) if need else None
+            f = ops.gemm(x, wa, bias=b1.detach(), epilogue=ops.EPI_GELU, aux=u)
             z = ops.gemm(f, wb, bias=b2.detach(), residual=res, dropout=rng)
         else:
             z = ops.gemm(x, wa, bias=b1.detach(), residual=res, dropout=rng)
@@ -176,7 +174,7 @@ class PostLNBlockFunction(torch.autograd.Function):
             if ctx.ffn:
                 _, w2t = ctx.caches[1].get(w2, need_t=True)
                 _, w1t = ctx.caches[0].get(w1, need_t=True)
-                du = ops.gemm(dzm, w2t, epilogue=ops.EPI_DMUL, aux=u)
+                du = ops.gemm(dzm, w2t, epilogue=ops.EPI_DGELU, aux=u)
                 dx = ops.gemm(du, w1t, residual=fold)
             else:
                 _, w1t = ctx.caches[0].get(w1, need_t=True)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libadapter4rec_sm100.so")
 
 A4R_OK, A4R_EINVAL, A4R_ECUDA, A4R_EARCH, A4R_EWORKSPACE = 0, -1, -2, -3, -4
-EPI_LINEAR, EPI_GELU, EPI_RELU, EPI_DGELU, EPI_DRELU, EPI_GELU_G, EPI_DMUL = 0, 1, 2, 3, 4, 5, 6
+EPI_LINEAR, EPI_GELU, EPI_RELU, EPI_DGELU, EPI_DRELU = 0, 1, 2, 3, 4
 
 
 class GemmArgs(Structure):

@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import lib as _l
-from .lib import EPI_DGELU, EPI_DMUL, EPI_DRELU, EPI_GELU, EPI_GELU_G, EPI_LINEAR, EPI_RELU  # noqa: F401
+from .lib import EPI_DGELU, EPI_DRELU, EPI_GELU, EPI_LINEAR, EPI_RELU  # noqa: F401
 
 BF16 = torch.bfloat16
 F32_MIN = -3.4028234663852886e38  # torch.finfo(torch.float32).min: the transformers additive attention mask value

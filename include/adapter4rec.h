@@ -66,9 +66,6 @@ A4R_API int64_t a4r_launch_count(void);
  *   A4R_EPI_RELU   : C = max(v, 0)
  *   A4R_EPI_DGELU  : C = v * gelu_erf'(aux)                 (aux = saved pre-activation, bf16 [M,N]; bias must be NULL)
  *   A4R_EPI_DRELU  : C = aux > 0 ? v : 0                    (aux = saved ReLU output,   bf16 [M,N]; bias must be NULL)
- *   A4R_EPI_GELU_G : aux = gelu_erf'(v), C = gelu_erf(v)     (forward of a block whose backward follows: the derivative
- *                                                            shares Phi(v) and exp(-v^2/2) with the value)
- *   A4R_EPI_DMUL   : C = v * aux                            (backward partner of GELU_G; bias must be NULL)
  * C is bf16 (out_f32 = 0) or f32 (out_f32 = 1).  K % 8 == 0, N % 8 == 0; M, N, K tails are handled.
  * ------------------------------------------------------------------------------------------------ */
 enum {
@@ -76,9 +73,7 @@ enum {
   A4R_EPI_GELU = 1,
   A4R_EPI_RELU = 2,
   A4R_EPI_DGELU = 3,
-  A4R_EPI_DRELU = 4,
-  A4R_EPI_GELU_G = 5,
-  A4R_EPI_DMUL = 6
+  A4R_EPI_DRELU = 4
 };
 
 typedef struct a4r_gemm_args {
