@@ -251,6 +251,10 @@ if want("gemm"):
     report("gemm FFN2 + residual  N=768 K=3072", us, flops=2.0 * M * 4 * H * H, bound="tensor")
     us = timeit(lambda i: ops.gemm(x[i], w1, epilogue=ops.EPI_DGELU, aux=u), 2)
     report("gemm dFFN2 + GELU' epilogue  N=3072 K=768", us, flops=2.0 * M * 4 * H * H, bound="tensor")
+    us = timeit(lambda i: ops.gemm(x[i], w1, bias=b1, epilogue=ops.EPI_GELU), 2)
+    report("gemm FFN1 + GELU, inference (one output)  N=3072 K=768", us, flops=2.0 * M * 4 * H * H, bound="tensor")
+    us = timeit(lambda i: ops.gemm(x[i], w1, bias=b1), 2)
+    report("gemm N=3072 K=768 plain linear + bias (one output)", us, flops=2.0 * M * 4 * H * H, bound="tensor")
     wt = r16(H, 3 * H)
     us = timeit(lambda i: ops.gemm(dq, wt), 1)
     report("gemm dQKV (dx = dqkv.W)  N=768 K=2304", us, flops=2.0 * M * H * 3 * H, bound="tensor")
