@@ -29,6 +29,9 @@ struct AttnParams {
   int64_t ld_qkv, ld_out, mask_ld;
   int N, L, heads;
   int mask_dtype;  // 0 none, 1 int64, 2 f32
+  // packed (variable-length) mode: sequence n owns token rows [cu_seqlens[n], cu_seqlens[n+1]) of qkv / out / dout,
+  // at most 32 of them; the key mask, if any, is then indexed by TOKEN ROW instead of [n, j].  NULL = fixed length L.
+  const int32_t* cu_seqlens;
   int causal;
   float scale, mask_neg;
   uint32_t drop_thr16;  // 0 = no dropout on the attention probabilities
@@ -156,9 +159,24 @@ A4R_DEVICE void acc_to_tile(uint8_t* tile, const float (&acc)[2][NT][4], float s
   }
 }
 
-A4R_DEVICE bool key_valid(const AttnParams& p, int n, int j) {
-  if (p.mask_dtype == 1) return reinterpret_cast<const int64_t*>(p.mask)[static_cast<int64_t>(n) * p.mask_ld + j] != 0;
-  if (p.mask_dtype == 2) return reinterpret_cast<const float*>(p.mask)[static_cast<int64_t>(n) * p.mask_ld + j] != 0.0f;
+// where sequence n lives: first token row, its length, and the index of its first mask element
+struct SeqSpan {
+  int64_t row0, mask0;
+  int L;
+};
+A4R_DEVICE SeqSpan seq_span(const AttnParams& p, int n) {
+  SeqSpan s;
+  if (p.cu_seqlens != nullptr) {
+    const int a = __ldg(p.cu_seqlens + n), b = __ldg(p.cu_seqlens + n + 1);
+    s.row0 = a, s.mask0 = a, s.L = b - a;
+  } else {
+    s.row0 = static_cast<int64_t>(n) * p.L, s.mask0 = static_cast<int64_t>(n) * p.mask_ld, s.L = p.L;
+  }
+  return s;
+}
+A4R_DEVICE bool key_valid(const AttnParams& p, const SeqSpan& sq, int j) {
+  if (p.mask_dtype == 1) return reinterpret_cast<const int64_t*>(p.mask)[sq.mask0 + j] != 0;
+  if (p.mask_dtype == 2) return reinterpret_cast<const float*>(p.mask)[sq.mask0 + j] != 0.0f;
   return true;
 }
 
@@ -166,7 +184,7 @@ A4R_DEVICE bool key_valid(const AttnParams& p, int n, int j) {
 // (columns >= L are exactly 0).  Thread (g = lane/4, t = lane%4) owns rows {g, g+8, 16+g, 24+g} and, in
 // n-tile nt, columns nt*8 + 2t, +1.
 template <int DH>
-A4R_DEVICE void scores_softmax(float (&s)[2][4][4], uint32_t sQ, uint32_t sK, const AttnParams& p, int n, int lane,
+A4R_DEVICE void scores_softmax(float (&s)[2][4][4], uint32_t sQ, uint32_t sK, const AttnParams& p, int L, int lane,
                                uint32_t keymask_bits) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -198,7 +216,7 @@ A4R_DEVICE void scores_softmax(float (&s)[2][4][4], uint32_t sQ, uint32_t sK, co
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int j = nt * 8 + 2 * t + e;
-      colneg[nt][e] = j >= p.L ? -INFINITY : (((keymask_bits >> j) & 1u) ? 0.0f : p.mask_neg);
+      colneg[nt][e] = j >= L ? -INFINITY : (((keymask_bits >> j) & 1u) ? 0.0f : p.mask_neg);
     }
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
@@ -238,8 +256,8 @@ A4R_DEVICE void scores_softmax(float (&s)[2][4][4], uint32_t sQ, uint32_t sK, co
   }
 }
 
-A4R_DEVICE uint32_t build_keymask(const AttnParams& p, int n, int lane) {
-  const bool ok = lane < p.L ? key_valid(p, n, lane) : false;
+A4R_DEVICE uint32_t build_keymask(const AttnParams& p, const SeqSpan& sq, int lane) {
+  const bool ok = lane < sq.L ? key_valid(p, sq, lane) : false;
   return __ballot_sync(0xffffffffu, ok);
 }
 
@@ -262,16 +280,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) attn_fwd_kernel(const A
        w += static_cast<int64_t>(gridDim.x) * WARPS_PER_CTA) {
     const int n = static_cast<int>(w / p.heads), h = static_cast<int>(w % p.heads);
     const int64_t Hd = static_cast<int64_t>(p.heads) * DH;
-    const __nv_bfloat16* q = p.qkv + static_cast<int64_t>(n) * p.L * p.ld_qkv + h * DH;
-    load_tile<DH>(my, q, p.ld_qkv, p.L, lane);
-    load_tile<DH>(my + TB, q + Hd, p.ld_qkv, p.L, lane);
-    load_tile<DH>(my + 2 * TB, q + 2 * Hd, p.ld_qkv, p.L, lane);
-    const uint32_t km = build_keymask(p, n, lane);
+    const SeqSpan sq = seq_span(p, n);
+    const __nv_bfloat16* q = p.qkv + sq.row0 * p.ld_qkv + h * DH;
+    load_tile<DH>(my, q, p.ld_qkv, sq.L, lane);
+    load_tile<DH>(my + TB, q + Hd, p.ld_qkv, sq.L, lane);
+    load_tile<DH>(my + 2 * TB, q + 2 * Hd, p.ld_qkv, sq.L, lane);
+    const uint32_t km = build_keymask(p, sq, lane);
     cp_async_wait_all();
     __syncwarp();
     const uint32_t sQ = smem_u32(my), sK = sQ + TB, sV = sK + TB;
     float s[2][4][4];
-    scores_softmax<DH>(s, sQ, sK, p, n, lane, km);
+    scores_softmax<DH>(s, sQ, sK, p, sq.L, lane, km);
     if (p.drop_thr16 != 0) prob_dropout(s, p, n, h, lane);  // dropout on the probabilities (train mode)
     // O = P·V
     float o[2][DH / 8][4];
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) attn_fwd_kernel(const A
     __syncwarp();
     acc_to_tile<DH, DH / 8>(my, o, 1.f, 1.f, 1.f, 1.f, lane);  // reuse the Q tile as the staging buffer
     __syncwarp();
-    store_tile<DH>(my, p.out + static_cast<int64_t>(n) * p.L * p.ld_out + h * DH, p.ld_out, p.L, lane);
+    store_tile<DH>(my, p.out + sq.row0 * p.ld_out + h * DH, p.ld_out, sq.L, lane);
     __syncwarp();
   }
 }
@@ -319,19 +338,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_bwd_kernel(const Attn
        w += static_cast<int64_t>(gridDim.x) * WARPS_PER_CTA) {
     const int n = static_cast<int>(w / p.heads), h = static_cast<int>(w % p.heads);
     const int64_t Hd = static_cast<int64_t>(p.heads) * DH;
-    const __nv_bfloat16* q = p.qkv + static_cast<int64_t>(n) * p.L * p.ld_qkv + h * DH;
+    const SeqSpan sq = seq_span(p, n);
+    const __nv_bfloat16* q = p.qkv + sq.row0 * p.ld_qkv + h * DH;
     uint8_t *tQ = my, *tK = my + TB, *tV = my + 2 * TB, *tdO = my + 3 * TB, *tP = my + 4 * TB, *tdS = tP + PB;
-    load_tile<DH>(tQ, q, p.ld_qkv, p.L, lane);
-    load_tile<DH>(tK, q + Hd, p.ld_qkv, p.L, lane);
-    load_tile<DH>(tV, q + 2 * Hd, p.ld_qkv, p.L, lane);
-    load_tile<DH>(tdO, p.dout + static_cast<int64_t>(n) * p.L * p.ld_out + h * DH, p.ld_out, p.L, lane);
-    const uint32_t km = build_keymask(p, n, lane);
+    load_tile<DH>(tQ, q, p.ld_qkv, sq.L, lane);
+    load_tile<DH>(tK, q + Hd, p.ld_qkv, sq.L, lane);
+    load_tile<DH>(tV, q + 2 * Hd, p.ld_qkv, sq.L, lane);
+    load_tile<DH>(tdO, p.dout + sq.row0 * p.ld_out + h * DH, p.ld_out, sq.L, lane);
+    const uint32_t km = build_keymask(p, sq, lane);
     cp_async_wait_all();
     __syncwarp();
     const uint32_t sQ = smem_u32(tQ), sK = smem_u32(tK), sV = smem_u32(tV), sdO = smem_u32(tdO), sP = smem_u32(tP),
                    sdS = smem_u32(tdS);
     float s[2][4][4];
-    scores_softmax<DH>(s, sQ, sK, p, n, lane, km);
+    scores_softmax<DH>(s, sQ, sK, p, sq.L, lane, km);
     // dP = dO·Vᵀ   (B operand: V stored [key][dim] = [n][k])
     float dp[2][4][4];
 #pragma unroll
@@ -458,10 +478,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) attn_bwd_kernel(const Attn
     acc_to_tile<DH, DH / 8>(tK, dk, 1.f, 1.f, 1.f, 1.f, lane);
     acc_to_tile<DH, DH / 8>(tV, dv, 1.f, 1.f, 1.f, 1.f, lane);
     __syncwarp();
-    __nv_bfloat16* dq = p.out + static_cast<int64_t>(n) * p.L * p.ld_qkv + h * DH;
-    store_tile<DH>(tQ, dq, p.ld_qkv, p.L, lane);
-    store_tile<DH>(tK, dq + Hd, p.ld_qkv, p.L, lane);
-    store_tile<DH>(tV, dq + 2 * Hd, p.ld_qkv, p.L, lane);
+    __nv_bfloat16* dq = p.out + sq.row0 * p.ld_qkv + h * DH;
+    store_tile<DH>(tQ, dq, p.ld_qkv, sq.L, lane);
+    store_tile<DH>(tK, dq + Hd, p.ld_qkv, sq.L, lane);
+    store_tile<DH>(tV, dq + 2 * Hd, p.ld_qkv, sq.L, lane);
     __syncwarp();
   }
 }
@@ -476,7 +496,8 @@ int check_common(const a4r_attn_args* a) {
   A4R_CHECK_ARG(a->ld_out >= a->heads * a->head_dim && a->ld_out % 8 == 0, "attention: bad ld_out");
   A4R_CHECK_ARG(a4r_aligned16(a->qkv) && a4r_aligned16(a->out), "attention: pointers must be 16B aligned");
   A4R_CHECK_ARG(a->mask_dtype >= 0 && a->mask_dtype <= 2, "attention: mask_dtype must be 0,1,2");
-  if (a->mask_dtype != 0) A4R_CHECK_ARG(a->mask != nullptr && a->mask_ld >= a->L, "attention: bad mask/mask_ld");
+  if (a->mask_dtype != 0)
+    A4R_CHECK_ARG(a->mask != nullptr && (a->cu_seqlens != nullptr || a->mask_ld >= a->L), "attention: bad mask/mask_ld");
   A4R_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "attention: dropout_p must be in [0,1)");
   return a4r_device_check();
 }
@@ -492,6 +513,7 @@ AttnParams to_params(const a4r_attn_args* a) {
   p.mask_ld = a->mask_ld;
   p.N = static_cast<int>(a->N);
   p.L = static_cast<int>(a->L);
+  p.cu_seqlens = a->cu_seqlens;
   p.heads = static_cast<int>(a->heads);
   p.mask_dtype = a->mask_dtype;
   p.causal = a->causal;

@@ -281,14 +281,15 @@ def add(x, res):
 
 class AttentionFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, mask, N, L, heads, head_dim, causal, mask_neg, dropout_p=0.0, scale=None):
+    def forward(ctx, qkv, mask, N, L, heads, head_dim, causal, mask_neg, dropout_p=0.0, scale=None, cu_seqlens=None):
         ctx.cfg = (N, L, heads, head_dim, causal, mask_neg, scale)
+        ctx.cu = cu_seqlens
         ctx.mask = mask
         ctx.drop = None
         if dropout_p > 0.0:
             ctx.drop = (dropout_p,) + DropoutState.draw(N * heads * 32 * 8)
         out, lse = ops.attn_small_fwd(qkv, N, L, heads, head_dim, mask=mask, causal=causal, mask_neg=mask_neg, want_lse=True,
-                                      dropout=ctx.drop, scale=scale)
+                                      dropout=ctx.drop, scale=scale, cu_seqlens=cu_seqlens)
         # the short-sequence kernel recomputes everything from qkv; the mid-length (ViT) kernel reuses lse and the output
         ctx.save_for_backward(qkv, lse, out if lse is not None else None)
         return out
@@ -298,14 +299,37 @@ class AttentionFunction(torch.autograd.Function):
         qkv, lse, out = ctx.saved_tensors
         N, L, heads, head_dim, causal, mask_neg, scale = ctx.cfg
         dqkv = ops.attn_small_bwd(qkv, dctx.contiguous(), N, L, heads, head_dim, mask=ctx.mask, causal=causal,
-                                  mask_neg=mask_neg, lse=lse, ctx=out, dropout=ctx.drop, scale=scale)
-        return dqkv, None, None, None, None, None, None, None, None, None
+                                  mask_neg=mask_neg, lse=lse, ctx=out, dropout=ctx.drop, scale=scale, cu_seqlens=ctx.cu)
+        return dqkv, None, None, None, None, None, None, None, None, None, None
 
 
-def attention(qkv, mask, N, L, heads, head_dim, causal=False, mask_neg=ops.F32_MIN, dropout_p=0.0, scale=None):
+def attention(qkv, mask, N, L, heads, head_dim, causal=False, mask_neg=ops.F32_MIN, dropout_p=0.0, scale=None,
+              cu_seqlens=None):
     """scale: softmax temperature override (default head_dim ** -0.5); used when narrow heads are zero-padded to a
-    kernel-supported width"""
-    return AttentionFunction.apply(qkv, mask, N, L, heads, head_dim, causal, mask_neg, float(dropout_p), scale)
+    kernel-supported width.  cu_seqlens: packed variable-length token layout (short-sequence kernel)."""
+    return AttentionFunction.apply(qkv, mask, N, L, heads, head_dim, causal, mask_neg, float(dropout_p), scale, cu_seqlens)
+
+
+class GatherRowsFunction(torch.autograd.Function):
+    """out[i] = x[idx[i]] for UNIQUE row indices (the [CLS] rows of a packed token matrix, or the valid tokens of a padded
+    one).  Backward = the inverse placement into zeros: pure data movement."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.rows = x.shape[0]
+        ctx.save_for_backward(idx)
+        return ops.gather_rows(x.contiguous(), idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        dx = torch.zeros((ctx.rows, dy.shape[1]), dtype=dy.dtype, device=dy.device)
+        dx.index_copy_(0, idx, dy.contiguous())
+        return dx, None
+
+
+def gather_rows(x, idx):
+    return GatherRowsFunction.apply(x, idx)
 
 
 LORA_PAD = 64  # the rank-r intermediates of all LoRA'd projections of one fused QKV share one 64-column k-block

@@ -32,6 +32,7 @@ class AttnArgs(Structure):
         ("mask_dtype", c_int32), ("causal", c_int32), ("scale", c_float), ("mask_neg", c_float),
         ("lse", c_void_p), ("ctx", c_void_p),
         ("dropout_p", c_float), ("dropout_seed", ctypes.c_uint64), ("dropout_offset", ctypes.c_uint64),
+        ("cu_seqlens", c_void_p),
     ]
 
 

@@ -87,12 +87,17 @@ class BertSelfAttention(nn.Module):
         self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
         self._qkv_cache = {}
 
-    def forward(self, x2d, attention_mask, N, L):
-        """x2d bf16 [N*L, H]; attention_mask int64/f32 [N, L] (non-zero = attend) or None -> context [N*L, H]."""
+    def forward(self, x2d, attention_mask, N, L, packed=None):
+        """x2d bf16 [N*L, H]; attention_mask int64/f32 [N, L] (non-zero = attend) or None -> context [N*L, H].
+        packed = PackedTokens: x2d holds only the kept tokens [T, H]; the mask is per token row."""
         params = []
         for m in (self.query, self.key, self.value):     # any of them may have been replaced by a loralib Linear
             params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
         qkv = Fn.QKVFunction.apply(x2d, self._qkv_cache, *params)
+        if packed is not None:
+            return Fn.attention(qkv, packed.token_mask, N, L, self.num_attention_heads, self.attention_head_size,
+                                causal=False, mask_neg=ops.F32_MIN, dropout_p=self.dropout.p if self.training else 0.0,
+                                cu_seqlens=packed.cu_seqlens)
         return Fn.attention(qkv, attention_mask, N, L, self.num_attention_heads, self.attention_head_size,
                             causal=False, mask_neg=ops.F32_MIN, dropout_p=self.dropout.p if self.training else 0.0)
 
@@ -134,8 +139,8 @@ class BertAttention(nn.Module):
         self.self = BertSelfAttention(config)
         self.output = BertSelfOutput(config)
 
-    def forward(self, x2d, attention_mask, N, L):
-        ctx = self.self(x2d, attention_mask, N, L)
+    def forward(self, x2d, attention_mask, N, L, packed=None):
+        ctx = self.self(x2d, attention_mask, N, L, packed)
         return self.output(ctx, x2d)
 
 
@@ -155,16 +160,19 @@ class BertLayer(nn.Module):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config)
 
-    def forward(self, x2d, attention_mask, N, L, cls_only=False):
+    def forward(self, x2d, attention_mask, N, L, cls_only=False, packed=None):
         """cls_only (last layer when the caller reads hidden[:, 0] only, as Text_Encoder does, encoders.py:55): every
         op after the attention is row-wise, so only the [CLS] row of each item is pushed through the output
         projection, the feed-forward and the LayerNorms (1/L of the work); K and V still cover all tokens."""
         if cls_only:
             H = x2d.shape[1]
-            ctx = self.attention.self(x2d, attention_mask, N, L)
-            y = self.attention.output(ctx.view(N, L, H)[:, 0], x2d.view(N, L, H)[:, 0])   # strided [N,H] views, no copies
+            ctx = self.attention.self(x2d, attention_mask, N, L, packed)
+            if packed is not None:   # the [CLS] token is the first row of every packed sequence
+                y = self.attention.output(Fn.gather_rows(ctx, packed.cls_rows), Fn.gather_rows(x2d, packed.cls_rows))
+            else:
+                y = self.attention.output(ctx.view(N, L, H)[:, 0], x2d.view(N, L, H)[:, 0])   # strided [N,H] views, no copies
         else:
-            y = self.attention(x2d, attention_mask, N, L)
+            y = self.attention(x2d, attention_mask, N, L, packed)
         out = self.output
         wi = self.intermediate.dense
         inner = out.self_output if hasattr(out, "self_output") else out          # Houlsby wrapper keeps the dense inside
@@ -182,6 +190,30 @@ class BertLayer(nn.Module):
             h = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, None, wi._cache, wf._cache)
             return to_2d_bf16(out.forward_from_dense(h, y))
         return out(self.intermediate(y), y)                 # foreign or trainable output module
+
+
+class PackedTokens:
+    """Variable-length ("unpadded") token layout of one forward pass: only the tokens the attention mask keeps exist, the
+    sequences lie back to back.  Exact for what Text_Encoder consumes (hidden[:, 0], encoders.py:53-55): a padded token is
+    never a key (additive finfo.min mask) and every other op of the layer is row-wise, so it cannot influence a kept
+    token.  An item whose mask is ALL zero (the padding item, row 0 of item_content) keeps its L tokens and its zero
+    mask: with every key masked the additive mask yields the uniform softmax of the reference.
+
+    token_rows: int64 [T] rows of the padded [N*L] layout that are kept; cu_seqlens: int32 [N+1]; token_mask: f32 [T];
+    cls_rows: int64 [N] first packed row of every sequence."""
+
+    def __init__(self, attention_mask):
+        m = attention_mask != 0
+        keep = m | (~m.any(dim=1, keepdim=True))
+        flat = keep.reshape(-1)
+        self.token_rows = flat.nonzero().squeeze(1)                      # (one host sync: T is data dependent)
+        lens = keep.sum(dim=1)
+        cu = torch.zeros(m.shape[0] + 1, dtype=torch.int32, device=m.device)
+        cu[1:] = torch.cumsum(lens, 0)
+        self.cu_seqlens = cu
+        self.cls_rows = cu[:-1].long()
+        self.token_mask = m.reshape(-1)[self.token_rows].float().contiguous()
+        self.num_tokens = int(self.token_rows.numel())
 
 
 class BertEncoder(nn.Module):
@@ -241,8 +273,16 @@ class BertModel(nn.Module):
         x = self.embeddings(input_ids)
         all_hidden = [x.view(N, L, -1)] if output_hidden_states else None
         last = len(self.encoder.layer) - 1
+        # `unpad` (opt-in attribute): run the layers on the kept tokens only.  Needs the [CLS]-only consumer (nothing else
+        # reads per-token outputs), the short-sequence attention kernel, and embeddings that are not being trained (their
+        # gradient would have to be scattered back to the padded layout; adapter tuning never needs it)
+        packed = None
+        if (getattr(self, "unpad", False) and cls_only and not output_hidden_states and attention_mask is not None
+                and L <= 32 and not x.requires_grad):
+            packed = PackedTokens(attention_mask)
+            x = Fn.gather_rows(x, packed.token_rows)
         for i, layer in enumerate(self.encoder.layer):
-            x = layer(x, attention_mask, N, L, cls_only=cls_only and i == last and not output_hidden_states)
+            x = layer(x, attention_mask, N, L, cls_only=cls_only and i == last and not output_hidden_states, packed=packed)
             if output_hidden_states:
                 all_hidden.append(x.view(N, L, -1))
         if output_hidden_states:

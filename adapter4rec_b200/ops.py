@@ -124,15 +124,23 @@ def dropout(x, res, p, seed, offset):
     return out
 
 
-def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout=None, scale=None):
+def _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout=None, scale=None, cu_seqlens=None):
     a = _l.AttnArgs()
+    if cu_seqlens is not None:
+        # packed layout: rows [cu[n], cu[n+1]) belong to sequence n; the mask (if any) is per token row
+        assert cu_seqlens.dtype == torch.int32 and cu_seqlens.is_contiguous() and cu_seqlens.numel() == N + 1 and L <= 32
+        a.cu_seqlens = _p(cu_seqlens)
+        if mask is not None:
+            assert mask.dim() == 1 and mask.numel() == qkv.shape[0] and mask.is_contiguous()
+            a.mask, a.mask_ld = _p(mask), 0
+            a.mask_dtype = {torch.int64: 1, torch.float32: 2}[mask.dtype]
     if dropout is not None:
         a.dropout_p, a.dropout_seed, a.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
     a.qkv, a.ld_qkv = _p(qkv), _rows2d(qkv, "qkv")
     a.N, a.L, a.heads, a.head_dim = N, L, heads, head_dim
     if mask is None:
         a.mask_dtype = 0
-    else:
+    elif cu_seqlens is None:
         assert mask.dim() == 2 and mask.shape[0] == N and mask.shape[1] >= L and mask.stride(1) == 1
         a.mask, a.mask_ld = _p(mask), mask.stride(0)
         a.mask_dtype = {torch.int64: 1, torch.float32: 2}[mask.dtype]
@@ -151,11 +159,12 @@ def _attn_kernel(L, head_dim, causal, direction):
 
 
 def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN, want_lse=False, dropout=None,
-                   scale=None):
-    """returns ctx, or (ctx, lse) with want_lse (lse is None for the short-sequence kernel, which recomputes it)"""
-    assert qkv.dtype == BF16 and qkv.shape[0] == N * L
-    out = torch.empty((N * L, heads * head_dim), dtype=BF16, device=qkv.device)
-    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout, scale)
+                   scale=None, cu_seqlens=None):
+    """returns ctx, or (ctx, lse) with want_lse (lse is None for the short-sequence kernel, which recomputes it).
+    cu_seqlens (int32 [N+1]): packed variable-length layout, L = the longest sequence (<= 32)."""
+    assert qkv.dtype == BF16 and (cu_seqlens is not None or qkv.shape[0] == N * L)
+    out = torch.empty((qkv.shape[0], heads * head_dim), dtype=BF16, device=qkv.device)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout, scale, cu_seqlens)
     a.out, a.ld_out = _p(out), out.stride(0)
     lse = None
     if want_lse and L > 32:
@@ -167,10 +176,11 @@ def attn_small_fwd(qkv, N, L, heads, head_dim, mask=None, causal=False, mask_neg
 
 
 def attn_small_bwd(qkv, dctx, N, L, heads, head_dim, mask=None, causal=False, mask_neg=F32_MIN, lse=None, ctx=None,
-                   dropout=None, scale=None):
-    assert qkv.dtype == BF16 and dctx.dtype == BF16 and dctx.shape[0] == N * L
-    dqkv = torch.empty((N * L, 3 * heads * head_dim), dtype=BF16, device=qkv.device)
-    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout, scale)
+                   dropout=None, scale=None, cu_seqlens=None):
+    assert qkv.dtype == BF16 and dctx.dtype == BF16 and dctx.shape[0] == qkv.shape[0]
+    assert cu_seqlens is not None or qkv.shape[0] == N * L
+    dqkv = torch.empty((qkv.shape[0], 3 * heads * head_dim), dtype=BF16, device=qkv.device)
+    a = _attn_args(qkv, N, L, heads, head_dim, mask, causal, mask_neg, dropout, scale, cu_seqlens)
     assert _rows2d(qkv, "qkv") == dqkv.stride(0), "attention bwd expects a contiguous qkv"
     a.out, a.dout, a.ld_out = _p(dqkv), _p(dctx), _rows2d(dctx, "dctx")
     if L > 32:

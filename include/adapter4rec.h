@@ -142,6 +142,11 @@ typedef struct a4r_attn_args {
   float dropout_p;
   uint64_t dropout_seed;
   uint64_t dropout_offset;
+  /* short-sequence kernel only — packed (variable-length) token layout: sequence n owns token rows
+   * [cu_seqlens[n], cu_seqlens[n+1]) (int32 [N+1], device), each at most 32 long (L = that maximum); the mask, if given, is
+   * indexed by token row.  Padded tokens — which HF BERT computes and then ignores (they are masked as keys and only
+   * position 0 is read, encoders.py:53-55) — simply do not exist in this layout.  NULL = fixed length L per sequence. */
+  const int32_t* cu_seqlens;
 } a4r_attn_args;
 
 A4R_API int a4r_attn_small_fwd(const a4r_attn_args* args, a4r_stream_t stream);

@@ -122,3 +122,32 @@ def test_item_encoder_matches_reference(kind):
     err = (emb[1:] - ref[1:]).abs().max()
     assert float(err) <= EMB_ATOL, "max abs err %.4f" % float(err)
     assert torch.isfinite(emb).all()   # incl. the all-masked padding item (row 0)
+
+
+@pytest.mark.parametrize("kind", ["lora", "houlsby", "pfeiffer_ver2", "compacter"])
+def test_unpadded_token_layout_gives_the_same_step(kind):
+    """bert_model.unpad = True runs the encoder on the kept tokens only (PackedTokens).  Every kept token's arithmetic is
+    the same instruction sequence on the same inputs, so embeddings and loss must agree to the last bf16 bit; gradients are
+    sums over tokens whose split order changes with the token count (fp32 reassociation only: 1e-3)."""
+    from adapter4rec_b200.data_utils.metrics import core_model
+    c = cases.tiny_case(kind)
+    sd = cases.build_state_dict(c)
+    items = cases.build_item_content(c)
+    sample_items, log_mask, _ = cases.build_batch(c, items)
+    rows = sample_items.view(-1, 2 * c.L).cuda()
+    out = {}
+    for unpad in (False, True):
+        model, _ = build_gpu_model(c, sd)
+        model.eval()
+        core_model(model).bert_encoder.text_encoders.title.bert_model.unpad = unpad
+        with torch.no_grad():
+            emb = core_model(model).bert_encoder(items.cuda()).float().cpu()
+        loss = model(rows, log_mask.cuda(), 0)
+        loss.backward()
+        grads = {n: p.grad.float().cpu() for n, p in model.named_parameters() if p.requires_grad}
+        out[unpad] = (emb, float(loss.detach()), grads)
+    assert torch.equal(out[True][0], out[False][0]), "item embeddings must be bit-identical"
+    assert out[True][1] == out[False][1], "loss must be bit-identical"
+    tot = float(torch.cat([g.flatten() for g in out[False][2].values()]).norm())
+    for n, g in out[False][2].items():
+        assert float((out[True][2][n] - g).norm()) <= 1e-3 * float(g.norm()) + 1e-5 * tot, n
