@@ -211,7 +211,7 @@ def run_reference(a):
     dt = (time.time() - t0) / steps
     v = a.cpu_users / dt
     sample = "%d users (= %d sequences x %d tokens) per step, fp32, torch CPU" % (a.cpu_users, a.cpu_users * 42, L)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": min(a.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -319,8 +319,29 @@ def bench_eval_full(model, args, dev, world, rank, steps):
             "note": "complete evaluator incl. host->device copy of the per-user arrays; random embeddings => chance-level HR"}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout when
+    NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the duration of the run and the
+    JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def main():
     a = parse()
+    _claim_stdout()
     if a.impl == "reference":
         return run_reference(a)
     import torch
@@ -507,7 +528,7 @@ def main():
         out["cpu_baseline"] = {"value": a.cpu_users / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
                                "sample": "1 step over %d users (= %d sequences x %d tokens), fp32 oracle port, %.1f s"
                                          % (a.cpu_users, a.cpu_users * 42, L, dt)}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
