@@ -220,7 +220,7 @@ def run_reference(a):
                    % a.cpu_users},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def bench_eval(dev, world, rank, steps, warmup):
