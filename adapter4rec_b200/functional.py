@@ -345,6 +345,13 @@ class QKVFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cache, *params):
+        """params may end with the marker string "skip": the function then ALSO returns x (as a second output).  A caller
+        that feeds this second output to the block's skip connection gets the skip gradient delivered to THIS node, where
+        it rides in the epilogue of the data-gradient GEMM instead of costing a separate elementwise add per layer."""
+        ctx.with_skip = len(params) > 0 and isinstance(params[-1], str) and params[-1] == "skip"
+        if ctx.with_skip:
+            params = params[:-1]
+        ctx.set_materialize_grads(False)
         assert len(params) % 4 == 0
         n = len(params) // 4
         H = params[0].shape[0]
@@ -357,10 +364,19 @@ class QKVFunction(torch.autograd.Function):
             cache["w"] = torch.cat([params[i].detach().to(BF16) for i in range(0, 4 * n, 4)], 0).contiguous()
             cache["wt"] = None
         w = cache["w"]
-        bias = torch.zeros(n * H, dtype=torch.float32, device=dev)
-        for j in range(n):
-            if params[4 * j + 1] is not None:
-                bias[j * H:(j + 1) * H] = params[4 * j + 1].detach()
+        # the fused bias and the LoRA operand matrices depend on TRAINABLE tensors: rebuilt once per optimizer step (or
+        # whenever a parameter object / version changes), not once per forward
+        small = [params[4 * j + i] for j in range(n) for i in (1, 2, 3)]
+        skey = (PARAM_EPOCH[0],) + tuple(None if p is None else (p.data_ptr(), p._version) for p in small)
+        reuse = cache.get("small_key") == skey
+        if reuse:
+            bias = cache["bias"]
+        else:
+            bias = torch.zeros(n * H, dtype=torch.float32, device=dev)
+            for j in range(n):
+                if params[4 * j + 1] is not None:
+                    bias[j * H:(j + 1) * H] = params[4 * j + 1].detach()
+            cache["small_key"], cache["bias"] = skey, bias
         # LoRA bookkeeping: slot j occupies columns [off_j, off_j + r_j) of the 64-wide T
         slots, off = [], 0
         for j in range(n):
@@ -372,17 +388,22 @@ class QKVFunction(torch.autograd.Function):
         assert off <= LORA_PAD, "sum of LoRA ranks of one fused projection must be <= 64"
         T = a_cat = b_ext = None
         if slots:
-            a_cat = torch.zeros((LORA_PAD, K), dtype=BF16, device=dev)
-            b_ext = torch.zeros((n * H, LORA_PAD), dtype=BF16, device=dev)
-            for j, o, r in slots:
-                a_cat[o:o + r] = params[4 * j + 2].detach().to(BF16)
-                b_ext[j * H:(j + 1) * H, o:o + r] = (params[4 * j + 3].detach() * (1.0 / r)).to(BF16)
-            # column 63 of T is a constant 1 (zero weight row + bias 1): it contributes nothing to qkv (B_ext[:, 63] = 0)
-            # and turns the bias gradients into one more column of the fused dqkvᵀ·T weight-gradient below
-            t_bias = torch.zeros(LORA_PAD, dtype=torch.float32, device=dev)
             ctx.ones_col = off < LORA_PAD
-            if ctx.ones_col:
-                t_bias[LORA_PAD - 1] = 1.0
+            if reuse and "a_cat" in cache:
+                a_cat, b_ext, t_bias = cache["a_cat"], cache["b_ext"], cache["t_bias"]
+            else:
+                a_cat = torch.zeros((LORA_PAD, K), dtype=BF16, device=dev)
+                b_ext = torch.zeros((n * H, LORA_PAD), dtype=BF16, device=dev)
+                for j, o, r in slots:
+                    a_cat[o:o + r] = params[4 * j + 2].detach().to(BF16)
+                    b_ext[j * H:(j + 1) * H, o:o + r] = (params[4 * j + 3].detach() * (1.0 / r)).to(BF16)
+                # column 63 of T is a constant 1 (zero weight row + bias 1): it contributes nothing to qkv (B_ext[:, 63] = 0)
+                # and turns the bias gradients into one more column of the fused dqkvᵀ·T weight-gradient below
+                t_bias = torch.zeros(LORA_PAD, dtype=torch.float32, device=dev)
+                if ctx.ones_col:
+                    t_bias[LORA_PAD - 1] = 1.0
+                cache["a_cat"], cache["b_ext"], cache["t_bias"] = a_cat, b_ext, t_bias
+                cache["a_cat_t"] = cache["b_ext_t"] = None
             T = ops.gemm(x, a_cat, bias=t_bias)
             qkv = ops.gemm(x, w, bias=bias, a2=T, b2=b_ext)
         else:
@@ -394,23 +415,36 @@ class QKVFunction(torch.autograd.Function):
         ctx.param_needs = [p is not None and p.requires_grad for p in params]
         need_x = any(ctx.param_needs[4 * j + 2] for j in range(n)) or any(ctx.param_needs[4 * j] for j in range(n))
         ctx.save_for_backward(x if need_x else None, T, a_cat, b_ext)
+        if ctx.with_skip:
+            return qkv, x          # autograd treats a returned input as x.view_as(x)
         return qkv
 
     @staticmethod
-    def backward(ctx, dqkv):
+    def backward(ctx, dqkv, dskip=None):
         x, T, a_cat, b_ext = ctx.saved_tensors
-        dqkv = dqkv.contiguous()
         H, cache, n = ctx.H, ctx.cache, ctx.n
+        tail = (None,) if ctx.with_skip else ()
+        if dqkv is None:                                  # only the skip output was used downstream
+            return (dskip, None) + (None,) * ctx.n_params + tail
+        dqkv = dqkv.contiguous()
+        if dskip is not None:
+            dskip = dskip.contiguous()
         if cache.get("wt") is None:
             cache["wt"] = cache["w"].t().contiguous()
         grads = [None] * ctx.n_params
         dT = None
         if ctx.slots:
-            # dT = dqkv·B_ext  [M,64];  dx = [dqkv | dT]·[W_catᵀ | A_catᵀ]ᵀ
-            dT = ops.gemm(dqkv, b_ext.t().contiguous())
-            dx = ops.gemm(dqkv, cache["wt"], a2=dT, b2=a_cat.t().contiguous()) if ctx.needs_input_grad[0] else None
+            # dT = dqkv·B_ext  [M,64];  dx = [dqkv | dT]·[W_catᵀ | A_catᵀ]ᵀ (+ the skip gradient in the epilogue)
+            if cache.get("b_ext") is b_ext and cache.get("b_ext_t") is not None:
+                b_ext_t, a_cat_t = cache["b_ext_t"], cache["a_cat_t"]
+            else:
+                b_ext_t, a_cat_t = b_ext.t().contiguous(), a_cat.t().contiguous()
+                if cache.get("b_ext") is b_ext:
+                    cache["b_ext_t"], cache["a_cat_t"] = b_ext_t, a_cat_t
+            dT = ops.gemm(dqkv, b_ext_t)
+            dx = ops.gemm(dqkv, cache["wt"], a2=dT, b2=a_cat_t, residual=dskip) if ctx.needs_input_grad[0] else None
         else:
-            dx = ops.gemm(dqkv, cache["wt"]) if ctx.needs_input_grad[0] else None
+            dx = ops.gemm(dqkv, cache["wt"], residual=dskip) if ctx.needs_input_grad[0] else None
         fused = bool(ctx.slots) and ctx.ones_col
         if fused:
             # ONE pass over dqkv gives every lora_B and every bias gradient; ONE pass over x gives every lora_A
@@ -429,7 +463,7 @@ class QKVFunction(torch.autograd.Function):
                     _pad_cols_wgrad(dq, T, o, r, 1.0 / r, transpose=False)
             if ctx.param_needs[4 * j + 2]:   # lora_A [r, K] = dT_jᵀ · x   (dT already carries the 1/r of B_ext)
                 grads[4 * j + 2] = g2[o:o + r].contiguous() if fused else _pad_cols_wgrad(dT, x, o, r, 1.0, transpose=True)
-        return (dx, None) + tuple(grads)
+        return (dx, None) + tuple(grads) + tail
 
 
 def _pad_cols_wgrad(a, b, off, r, alpha, transpose):

@@ -87,19 +87,27 @@ class BertSelfAttention(nn.Module):
         self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
         self._qkv_cache = {}
 
-    def forward(self, x2d, attention_mask, N, L, packed=None):
+    def forward(self, x2d, attention_mask, N, L, packed=None, want_skip=False):
         """x2d bf16 [N*L, H]; attention_mask int64/f32 [N, L] (non-zero = attend) or None -> context [N*L, H].
-        packed = PackedTokens: x2d holds only the kept tokens [T, H]; the mask is per token row."""
+        packed = PackedTokens: x2d holds only the kept tokens [T, H]; the mask is per token row.
+        want_skip: also return x2d as an output of the projection's autograd node — the caller uses THAT tensor as the
+        sub-layer's skip input, so the skip gradient is added inside the data-gradient GEMM's epilogue."""
         params = []
         for m in (self.query, self.key, self.value):     # any of them may have been replaced by a loralib Linear
             params += [m.weight, m.bias, getattr(m, "lora_A", None), getattr(m, "lora_B", None)]
-        qkv = Fn.QKVFunction.apply(x2d, self._qkv_cache, *params)
+        skip = x2d
+        if want_skip and x2d.requires_grad:
+            qkv, skip = Fn.QKVFunction.apply(x2d, self._qkv_cache, *params, "skip")
+        else:
+            qkv = Fn.QKVFunction.apply(x2d, self._qkv_cache, *params)
         if packed is not None:
-            return Fn.attention(qkv, packed.token_mask, N, L, self.num_attention_heads, self.attention_head_size,
-                                causal=False, mask_neg=ops.F32_MIN, dropout_p=self.dropout.p if self.training else 0.0,
-                                cu_seqlens=packed.cu_seqlens)
-        return Fn.attention(qkv, attention_mask, N, L, self.num_attention_heads, self.attention_head_size,
-                            causal=False, mask_neg=ops.F32_MIN, dropout_p=self.dropout.p if self.training else 0.0)
+            ctx = Fn.attention(qkv, packed.token_mask, N, L, self.num_attention_heads, self.attention_head_size,
+                               causal=False, mask_neg=ops.F32_MIN, dropout_p=self.dropout.p if self.training else 0.0,
+                               cu_seqlens=packed.cu_seqlens)
+        else:
+            ctx = Fn.attention(qkv, attention_mask, N, L, self.num_attention_heads, self.attention_head_size,
+                               causal=False, mask_neg=ops.F32_MIN, dropout_p=self.dropout.p if self.training else 0.0)
+        return (ctx, skip) if want_skip else ctx
 
 
 class BertSelfOutput(nn.Module):
@@ -140,8 +148,8 @@ class BertAttention(nn.Module):
         self.output = BertSelfOutput(config)
 
     def forward(self, x2d, attention_mask, N, L, packed=None):
-        ctx = self.self(x2d, attention_mask, N, L, packed)
-        return self.output(ctx, x2d)
+        ctx, skip = self.self(x2d, attention_mask, N, L, packed, want_skip=True)
+        return self.output(ctx, skip)
 
 
 class BertIntermediate(nn.Module):
@@ -166,11 +174,11 @@ class BertLayer(nn.Module):
         projection, the feed-forward and the LayerNorms (1/L of the work); K and V still cover all tokens."""
         if cls_only:
             H = x2d.shape[1]
-            ctx = self.attention.self(x2d, attention_mask, N, L, packed)
+            ctx, skip = self.attention.self(x2d, attention_mask, N, L, packed, want_skip=True)
             if packed is not None:   # the [CLS] token is the first row of every packed sequence
-                y = self.attention.output(Fn.gather_rows(ctx, packed.cls_rows), Fn.gather_rows(x2d, packed.cls_rows))
+                y = self.attention.output(Fn.gather_rows(ctx, packed.cls_rows), Fn.gather_rows(skip, packed.cls_rows))
             else:
-                y = self.attention.output(ctx.view(N, L, H)[:, 0], x2d.view(N, L, H)[:, 0])   # strided [N,H] views, no copies
+                y = self.attention.output(ctx.view(N, L, H)[:, 0], skip.view(N, L, H)[:, 0])   # strided [N,H] views, no copies
         else:
             y = self.attention(x2d, attention_mask, N, L, packed)
         out = self.output
