@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--users", type=int, default=512, help="users per GPU per step (C2: 512)")
-    ap.add_argument("--users-per-pass", type=int, default=128, help="activation-memory pass size (exact accumulation)")
+    ap.add_argument("--users-per-pass", type=int, default=256, help="activation-memory pass size (exact accumulation)")
     ap.add_argument("--cpu-users", type=int, default=0,
                     help="users in the bounded CPU sample (default: 48 for cpu_baseline ~15 s, 16 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

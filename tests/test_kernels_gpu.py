@@ -343,3 +343,41 @@ def test_wgrad_tc_strided_operands():
     _close(ops.wgrad_tc(dq[:, :768], t, k=8), dq[:, :768].float().t() @ t[:, :8].float(), 1e-3, 0.2, "wgrad_tc sliced")
     _close(ops.wgrad_tc(dq[:, 768:1536], dq[:, 1536:], n=768, k=768), dq[:, 768:1536].float().t() @ dq[:, 1536:].float(),
            1e-3, 0.3, "wgrad_tc two column slices")
+
+
+def test_scatter_add_rows_matches_embedding_backward():
+    """dst[idx[r]] += src[r] with nn.Embedding's padding_idx semantics (the row never receives a gradient), negative and
+    out-of-range indices skipped; fp32 accumulation of bf16 rows against torch.index_add_ on the same values."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    R, H, V, pad = 20000, 768, 300, 1
+    src = _rand((R, H), 1.0, 8)
+    idx = torch.randint(-1, V + 2, (R,), generator=g).cuda()          # includes -1 and V, V+1 (skipped)
+    got = ops.scatter_add_rows(src, idx, V, skip_idx=pad)
+    ok = (idx >= 0) & (idx < V) & (idx != pad)
+    ref = torch.zeros((V, H), dtype=torch.float32, device="cuda").index_add_(0, idx[ok], src.float()[ok])
+    _close(got, ref, 1e-5, 1e-3, "scatter_add_rows")
+    assert float(got[pad].abs().max()) == 0.0
+    # a strided source (column slice) and an empty call
+    wide = _rand((64, 2 * H), 1.0, 9)
+    i2 = torch.arange(64).cuda() % 7
+    _close(ops.scatter_add_rows(wide[:, H:], i2, 7), torch.zeros((7, H), device="cuda").index_add_(0, i2, wide[:, H:].float()),
+           1e-5, 1e-3, "scatter_add_rows strided")
+    assert ops.scatter_add_rows(src[:0], idx[:0], V).abs().sum() == 0
+
+
+@pytest.mark.parametrize("kind,fn", [("leaky_relu", torch.nn.functional.leaky_relu),
+                                     ("gelu_new", lambda x: torch.nn.functional.gelu(x, approximate="tanh")),
+                                     ("gelu", torch.nn.functional.gelu), ("relu", torch.relu)])
+def test_act_fwd_bwd_kinds(kind, fn):
+    """stand-alone activations of the Pfeiffer (LeakyReLU 0.01) and Compacter (tanh-GELU) bottlenecks"""
+    ops = _ops()
+    u = _rand((1000, 64), 1.5, 11)
+    dy = _rand((1000, 64), 1.0, 12)
+    uf = u.float().requires_grad_(True)
+    y = fn(uf)
+    y.sum().backward()
+    out = ops.act_fwd(u, kind)
+    _close(out, y.detach(), 2 ** -7, 1e-2, "act_fwd " + kind)
+    saved = out if kind in ("relu", "leaky_relu") else u       # what the backward is given (output vs pre-activation)
+    _close(ops.act_bwd(dy, saved, kind), dy.float() * uf.grad, 2 ** -6, 1e-2, "act_bwd " + kind)
