@@ -49,7 +49,27 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const __nv_bfloat16
   const float invH = 1.0f / static_cast<float>(H);
   // the loop trip count is uniform across the warp (group shuffles use the full mask): out-of-range row
   // slots recompute row M-1 and skip their stores.
-  for (int64_t base = blockIdx.x * rows_per_block; base < M; base += gridDim.x * rows_per_block) {
+  // gamma / beta live in shared memory (one fill per block) instead of 4 L1 loads per chunk and row
+  __shared__ __align__(16) float s_gamma[1024], s_beta[1024];
+  for (int i = threadIdx.x; i < H; i += ROW_THREADS) {
+    s_gamma[i] = gamma[i];
+    s_beta[i] = beta[i];
+  }
+  __syncthreads();
+  // The NEXT row's x chunks are fetched (still packed: CPL x 16 bytes) before the current row is reduced, so every warp
+  // keeps two rows of loads in flight: the kernel is latency-bound otherwise (ncu: long_scoreboard 10.8 per issue).
+  const int64_t row_step = gridDim.x * rows_per_block;
+  uint4 nxt[CPL];
+  {
+    const int64_t r0 = blockIdx.x * rows_per_block + threadIdx.x / G;
+    const int64_t rr = r0 < M ? r0 : M - 1;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
+      if (ch < nchunks) nxt[c] = ld_nc_v4(x + rr * H + ch * 8);
+    }
+  }
+  for (int64_t base = blockIdx.x * rows_per_block; base < M; base += row_step) {
     const int64_t row_raw = base + threadIdx.x / G;
     const bool valid = row_raw < M;
     const int64_t row = valid ? row_raw : M - 1;
@@ -58,8 +78,21 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const __nv_bfloat16
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int ch = sub + c * G;
+      if (ch < nchunks) unpack8(nxt[c], v[c]);
+    }
+    if (base + row_step < M) {   // uniform across the block
+      const int64_t rn_raw = row_raw + row_step;
+      const int64_t rn = rn_raw < M ? rn_raw : M - 1;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const int ch = sub + c * G;
+        if (ch < nchunks) nxt[c] = ld_nc_v4(x + rn * H + ch * 8);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ch = sub + c * G;
       if (ch < nchunks) {
-        unpack8(ld_nc_v4(x + row * H + ch * 8), v[c]);
         if (res != nullptr) {
           float r[8];
           unpack8(ld_nc_v4(res + (row % res_rows) * H + ch * 8), r);
@@ -93,10 +126,10 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const __nv_bfloat16
     for (int c = 0; c < CPL; ++c) {
       const int ch = sub + c * G;
       if (ch < nchunks) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + ch * 8 + 4));
+        const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + ch * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(s_gamma + ch * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_beta + ch * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_beta + ch * 8 + 4);
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o[8];
