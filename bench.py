@@ -481,8 +481,10 @@ def main():
     traffic = None
     try:
         for rec in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_gemm_traffic.json"))):
-            if tuple(rec["shape"]) == tuple(dom_shape):
-                traffic = rec["dram_bytes_per_launch"]
+            # the capture was taken at M = 161,280 rows (one 128-user pass); operand A, C and the residual are all linear in
+            # M (the weight operand is L2-resident), so a launch with more rows is scaled by the row ratio
+            if tuple(rec["shape"][1:]) == tuple(dom_shape[1:]):
+                traffic = rec["dram_bytes_per_launch"] * (dom_shape[0] / float(rec["shape"][0]))
     except Exception:
         pass
     out = {
