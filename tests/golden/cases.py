@@ -52,12 +52,28 @@ def tiny_case(kind):
     return c
 
 
+def full_case(kind):
+    """The same generators at the REAL sizes of BASELINE.json's text configurations: BERT-base body (768 / 12 layers /
+    12 heads / 3072, vocabulary 30,522), 30 title tokens, max_seq_len 20, embedding_dim 64, adapter ranks 64 (BERT) and
+    16 (SASRec) as parameters.py:55,62 default them (LoRA: r = 8), 2 users = 84 item sequences = 2,520 tokens."""
+    c = tiny_case(kind)
+    c.hidden, c.layers, c.heads, c.inter = 768, 12, 12, 3072
+    c.vocab, c.max_pos = 30522, 512
+    c.L, c.S, c.D = 30, 20, 64
+    c.bert_r = 8 if kind == "lora" else 64
+    c.rec_r = 8 if kind == "lora" else 16
+    c.B, c.item_num = 2, 60
+    c.seed += 100
+    return c
+
+
 def reference_args(c):
     """The argparse namespace the reference modules read (Downstream/Text/parameters.py)."""
     return types.SimpleNamespace(
         max_seq_len=c.S, min_seq_len=2, l2_weight=0, embedding_dim=c.D, num_attention_heads=c.rec_heads,
         drop_rate=0.1, transformer_block=c.blocks, num_words_title=c.L, num_words_abstract=50, num_words_body=50,
-        news_attributes=["title"], word_embedding_dim=c.hidden, bert_model_load="bert_tiny",
+        news_attributes=["title"], word_embedding_dim=c.hidden,
+        bert_model_load={128: "bert_tiny", 768: "bert_base_uncased"}[c.hidden],
         bert_adapter_down_size=c.bert_r, adapter_down_size=c.rec_r, adapter_dropout_rate=0.1,
         adapter_activation=c.activation, num_workers=0, adapter_type={"houlsby": "houslby", "houlsby_gelu": "houslby",
                                                                       "lora": "lora", "prompt_cpc": "prompt",
