@@ -48,35 +48,49 @@ class ViTPatchEmbeddings(nn.Module):
         self.projection = PatchProjection(config.num_channels, config.hidden_size, config.patch_size)
 
     def forward(self, pixel_values):
-        """[N,C,R,R] f32 -> patch embeddings [N*P, H] bf16: im2col kernel + tcgen05 GEMM (frozen projection)."""
+        """[N,C,R,R] f32 -> patch embeddings [N*P, H] bf16: im2col kernel + tcgen05 GEMM.  With a trainable projection
+        (full fine-tuning: Downstream/CV/run_adapter.py `fine_tune_to=all`, Pretraining/CV) the conv's weight gradient is
+        the weight-gradient GEMM d_embᵀ · patches over the saved im2col rows, its bias gradient a column sum."""
         pr = self.projection
-        if pr.weight.requires_grad or pr.bias.requires_grad:
-            raise NotImplementedError("the ViT patch projection is frozen on this path (adapter tuning)")
-        w2d = pr._cache.get(pr.weight.view(pr.weight.shape[0], -1))[0]
         patches = ops.patchify(pixel_values.float().contiguous(), self.patch_size)
-        return ops.gemm(patches, w2d, bias=pr.bias.detach().float().contiguous())
+        w2d = pr.weight.view(pr.weight.shape[0], -1)
+        if pr.weight.requires_grad or pr.bias.requires_grad:
+            return Fn.linear(patches, w2d, pr.bias, pr._cache)
+        return ops.gemm(patches, pr._cache.get(w2d)[0], bias=pr.bias.detach().float().contiguous())
 
 
 class _AssembleFunction(torch.autograd.Function):
-    """Token assembly; only the appended soft-prompt tokens are trainable."""
+    """Token assembly out[n] = [cls + pos[0] | patch_emb[n] + pos[1:] | prompt].  Adapter tuning trains the appended
+    soft-prompt tokens only; full fine-tuning also needs d_patch_emb (a row slice of d_out), d_pos = the sum of d_out over
+    the images (deterministic two-stage column sum) and d_cls = d_pos[0] (cls and pos[0] feed the same token)."""
 
     @staticmethod
-    def forward(ctx, patch_emb, cls16, pos16, prompt, N, P):
+    def forward(ctx, patch_emb, cls, pos, prompt, N, P, cls16, pos16):
         p16 = None if prompt is None else prompt.detach().reshape(-1, prompt.shape[-1]).to(BF16).contiguous()
-        out = ops.vit_assemble(patch_emb, cls16, pos16, p16, N, P)
+        out = ops.vit_assemble(patch_emb.detach(), cls16, pos16, p16, N, P)
         ctx.dims = (N, P, 0 if p16 is None else p16.shape[0], patch_emb.shape[1])
-        ctx.pshape = None if prompt is None else prompt.shape
+        ctx.shapes = (cls.shape, pos.shape, None if prompt is None else prompt.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         N, P, T, H = ctx.dims
-        dprompt = None
+        cls_shape, pos_shape, prompt_shape = ctx.shapes
+        L = 1 + P + T
+        dout = dout.contiguous()
+        d2 = dout.view(N, L * H)
+        dpe = dcls = dpos = dprompt = None
+        if ctx.needs_input_grad[0]:
+            dpe = dout.view(N, L, H)[:, 1:1 + P].reshape(N * P, H)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dsum = ops.colsum(d2, width=(1 + P) * H)
+            if ctx.needs_input_grad[1]:
+                dcls = dsum[:H].clone().view(cls_shape)
+            if ctx.needs_input_grad[2]:
+                dpos = dsum.view(pos_shape)
         if T > 0 and ctx.needs_input_grad[3]:
-            L = 1 + P + T
-            d2 = dout.contiguous().view(N, L * H)
-            dprompt = ops.colsum(d2[:, (1 + P) * H:], width=T * H).view(ctx.pshape)
-        return None, None, None, dprompt, None, None
+            dprompt = ops.colsum(d2[:, (1 + P) * H:], width=T * H).view(prompt_shape)
+        return dpe, dcls, dpos, dprompt, None, None, None, None
 
 
 class ViTEmbeddings(nn.Module):
@@ -91,12 +105,10 @@ class ViTEmbeddings(nn.Module):
     def tokens(self, pixel_values, prompt=None):
         N = pixel_values.shape[0]
         P = self.patch_embeddings.num_patches
-        if self.cls_token.requires_grad or self.position_embeddings.requires_grad:
-            raise NotImplementedError("cls_token / position_embeddings are frozen on this path (adapter tuning)")
         pe = self.patch_embeddings(pixel_values)
         cls16 = self._cls_cache.get(self.cls_token.view(1, -1))[0].view(-1)
         pos16 = self._pos_cache.get(self.position_embeddings.view(P + 1, -1))[0]
-        x = _AssembleFunction.apply(pe, cls16, pos16, prompt, N, P)
+        x = _AssembleFunction.apply(pe, self.cls_token, self.position_embeddings, prompt, N, P, cls16, pos16)
         T = 0 if prompt is None else prompt.shape[-2]
         return x, 1 + P + T
 

@@ -24,17 +24,13 @@ def _word_dim(args):
 
 def check_trainable_supported(module):
     """Fail loudly instead of silently leaving a gradient at zero.  The sm_100a path differentiates adapters, LoRA factors,
-    biases, LayerNorms, prompt embeddings, every Linear weight and — for full fine-tuning of the TEXT tower — the BERT /
-    RoBERTa / SASRec embedding tables.  The BERT pooler is kept for state_dict compatibility but never evaluated (the
-    reference computes and discards it; Pretraining/Text/run.py:48-64 freezes it): left trainable
-    it simply receives no gradient, as in the reference.  Not implemented: the ViT patch / cls / position embeddings of
-    the image tower (full fine-tuning of ViT below layer 0)."""
-    bad = [n for n, p in module.named_parameters()
-           if p.requires_grad and "vit.embeddings" in n and not n.endswith("Prompt_Tokens")]
-    if bad:
-        raise NotImplementedError(
-            "adapter4rec_b200: gradients for these parameters are not implemented on the sm_100a path (freeze them, as "
-            "Downstream/CV/run_adapter.py does with freeze_paras_before / fine_tune_to=None): %s" % bad[:6])
+    biases, LayerNorms, prompt embeddings, every Linear weight and — for full fine-tuning — the BERT / RoBERTa / SASRec
+    embedding tables and the ViT patch projection / cls token / position embeddings.  The BERT pooler is kept for
+    state_dict compatibility but never evaluated (the reference computes and discards it, SURVEY.md Appendix B-5;
+    Pretraining/Text/run.py:48-64 freezes it): left trainable it simply receives no gradient, as in the reference.
+    Nothing on the modality-encoder path is refused today; the hook stays so that a future parameter kind without a
+    gradient kernel can be rejected here."""
+    return None
 
 
 class _ModelBase(nn.Module):

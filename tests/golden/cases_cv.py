@@ -10,16 +10,20 @@ CLS = "cv_encoder.image_net.classifier."
 
 
 CV_ZOO_KINDS = ("cv_parallel", "cv_pfeiffer_ver2", "cv_compacter")          # SURVEY.md §8f-4 on the image tree
-CV_ALL_KINDS = ("cv_base", "cv_houlsby", "cv_lora", "cv_prompt") + CV_ZOO_KINDS
+CV_ALL_KINDS = ("cv_base", "cv_houlsby", "cv_lora", "cv_prompt") + CV_ZOO_KINDS + ("cv_full_ft",)
 
 
 def tiny_cv_case(kind):
     """kind: 'cv_base' | 'cv_houlsby' | 'cv_lora' | 'cv_prompt' | 'cv_parallel' (Houlsby, is_serial=None: layer.output
-    only) | 'cv_pfeiffer_ver2' (attention.output only) | 'cv_compacter'.  hidden is 768 because the reference's ViT adapter
+    only) | 'cv_pfeiffer_ver2' (attention.output only) | 'cv_compacter' | 'cv_full_ft' (nothing frozen: the source-domain
+    stage Pretraining/CV/run.py and `fine_tune_to=all`, incl. the patch projection, cls token and position embeddings).
+    hidden is 768 because the reference's ViT adapter
     wrappers hard-code it (Downstream/CV/model/model.py:186,202); depth / MLP width / image size are reduced."""
     c = types.SimpleNamespace()
     c.kind = kind
     c.hidden, c.heads, c.layers, c.inter = 768, 12, 2, 256
+    if kind == "cv_full_ft":        # no adapter wrappers => no hard-coded 768; a narrow body keeps the golden at 1.7 MB
+        c.hidden, c.heads = 128, 2
     c.patch = 16
     c.image = 96 if kind in ("cv_lora", "cv_prompt") else 64      # 37 tokens (mid-length kernel) / 17 tokens (short kernel)
     c.P = (c.image // c.patch) ** 2
@@ -32,7 +36,7 @@ def tiny_cv_case(kind):
     c.cpc = False
     c.B = 3
     c.seed = {"cv_base": 21, "cv_houlsby": 22, "cv_lora": 23, "cv_prompt": 24, "cv_parallel": 25, "cv_pfeiffer_ver2": 26,
-              "cv_compacter": 27}[kind]
+              "cv_compacter": 27, "cv_full_ft": 28}[kind]
     return c
 
 
@@ -42,7 +46,8 @@ def reference_args(c):
         transformer_block=c.blocks, CV_model_load="vit-base-patch16-224", cv_adapter_down_size=c.cv_r,
         adapter_down_size=c.rec_r, adapter_dropout_rate=0.1, adapter_activation="RELU", n_tokens=c.n_tokens,
         adapter_type={"cv_base": "None", "cv_houlsby": "houslby", "cv_lora": "lora", "cv_prompt": "prompt",
-                      "cv_parallel": "houslby", "cv_pfeiffer_ver2": "pfeiffer_ver2", "cv_compacter": "compacter"}[c.kind],
+                      "cv_parallel": "houslby", "cv_pfeiffer_ver2": "pfeiffer_ver2", "cv_compacter": "compacter",
+                      "cv_full_ft": "None"}[c.kind],
         adding_adapter_to="all", is_serial="None" if c.kind == "cv_parallel" else "True", finetune_layernorm="None",
         hypercomplex_division=c.phm_dim, phm_init_range=0.0001)
 
@@ -130,6 +135,8 @@ def trainable_keys(c, sd):
                 or ".w_V." in k]
     if c.kind == "cv_prompt":
         return [k for k in sd if k.endswith("Prompt_Tokens") or k.startswith(CLS)]
+    if c.kind == "cv_full_ft":
+        return list(sd)
     return []
 
 

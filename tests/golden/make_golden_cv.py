@@ -107,6 +107,9 @@ def build_reference_model(c):
         for i in range(len(blocks)):
             blocks[i].multi_head_attention.w_Q = lora.Linear(args.embedding_dim, args.embedding_dim, r=4)
             blocks[i].multi_head_attention.w_V = lora.Linear(args.embedding_dim, args.embedding_dim)
+    elif c.kind == "cv_full_ft":                                   # fine_tune_to = all: nothing frozen
+        for p in model.parameters():
+            p.requires_grad = True
     elif c.kind == "cv_prompt":
         s_wte = SoftPrompt(cv_model.vit.embeddings, n_tokens=args.n_tokens, embed_dim=768)
         model.cv_encoder.image_net.vit.embeddings = s_wte

@@ -34,7 +34,10 @@ def build_gpu_cv_model(c, sd):
     net.classifier = Linear(c.hidden, args.embedding_dim)            # run_adapter.py:293-294
     model = Model(args, 100, True, net).cuda()
     surgery.freeze_all(model)
-    if c.kind != "cv_base":
+    if c.kind == "cv_full_ft":                                   # fine_tune_to = all: nothing frozen
+        for p in model.parameters():
+            p.requires_grad = True
+    elif c.kind != "cv_base":
         model = surgery.insert_adapters_cv(model, args)          # compacter returns the CompacterModel wrapper
     assert set(model.state_dict().keys()) == set(sd.keys()), "state_dict keys must equal the reference's"
     model.load_state_dict(sd)
