@@ -322,6 +322,94 @@ def bench_eval_full(model, args, dev, world, rank, steps):
 _REAL_STDOUT = None
 
 
+def _time_steps(trainer, batches, steps, warmup, dev, world):
+    """max-over-ranks device time per step of `trainer.train_step` over rotating resident batches"""
+    import torch
+    import torch.distributed as dist
+    for i in range(warmup):
+        trainer.train_step(*batches[i % len(batches)])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = trainer.train_step(*batches[i % len(batches)])
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t) / steps, float(loss)
+
+
+def bench_c1_houlsby(dev, world, rank, steps, users=256):
+    """BASELINE.json configs[0] ("C1") on the GPU: SASRec + BERT-base with serial Houlsby adapters (r = 64 in BERT, 16 in
+    SASRec: parameters.py:55,62), S=20, 30 tokens — the configuration that runs the fused adapter block (K5) 24 times per
+    forward.  Same synthetic catalogue shapes as the headline; non-headline figure."""
+    import torch
+    from adapter4rec_b200 import surgery
+    from adapter4rec_b200.model import BertModel, Model, TextConfigLite
+    from adapter4rec_b200.trainer import FlatAdamTrainer
+    args = make_args(r=64)
+    args.adapter_type, args.adapter_down_size = "houslby", 16
+    torch.manual_seed(123456)
+    model = Model(args, ITEMS, True, BertModel(TextConfigLite())).to(dev)
+    surgery.freeze_all(model)
+    surgery.insert_adapters(model, args)
+    model.train()
+    trainer = FlatAdamTrainer(model, args.lr, args.fine_tune_lr, args.adapter_bert_lr, args.adapter_sasrec_lr,
+                              users_per_pass=min(users, 128))
+    gen = torch.Generator().manual_seed(4242 + rank)
+    cat = synth_catalogue(gen)
+    batches = [tuple(t.to(dev) for t in synth_batch(cat, users, gen)) for _ in range(2)]
+    ms, loss = _time_steps(trainer, batches, steps, 2, dev, world)
+    tokens = users * 42 * L
+    flops = 2 * 12 * (14155776 + 92160 + 393216) * tokens      # SURVEY.md §8d, C1: forward + data-gradient backward
+    return {"value": users * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "users_per_gpu_per_step": users,
+            "users_per_pass": min(users, 128), "model_tflops_per_gpu": flops / (ms / 1e3) / 1e12,
+            "trainable_params": trainer.num_trainable, "loss": loss,
+            "note": "C1 shapes (Houlsby r=64, S=20, 30 tokens) at %d users per GPU per step, dropout on; NOT the headline value" % users}
+
+
+def bench_c3_vit(dev, world, rank, steps, users=64):
+    """BASELINE.json configs[2] ("C3"): SASRec + ViT-B/16-224 with Houlsby adapters (r = 64), S=10 => 22 images per user,
+    synthetic images in (-1, 1) (the post-Normalize(0.5, 0.5) range), bf16.  Non-headline figure."""
+    import types
+    import torch
+    from adapter4rec_b200 import surgery
+    from adapter4rec_b200.cv import Model as CVModel, ViTConfigLite, ViTForImageClassification
+    from adapter4rec_b200.model.layers import Linear
+    from adapter4rec_b200.trainer import FlatAdamTrainer
+    S3 = 10
+    args = types.SimpleNamespace(max_seq_len=S3, l2_weight=0, embedding_dim=D, num_attention_heads=2, drop_rate=0.1,
+                                 transformer_block=2, CV_model_load="vit-base-patch16-224", cv_adapter_down_size=64,
+                                 adapter_down_size=16, adapter_dropout_rate=0.1, adapter_activation="RELU", n_tokens=10,
+                                 adapter_type="houslby", adding_adapter_to="all", is_serial="True", finetune_layernorm="None")
+    torch.manual_seed(12345)
+    net = ViTForImageClassification(ViTConfigLite())
+    net.classifier = Linear(768, D)
+    model = CVModel(args, 1000, True, net).to(dev)
+    surgery.freeze_all(model)
+    surgery.insert_adapters_cv(model, args)
+    model.train()
+    trainer = FlatAdamTrainer(model, 1e-4, 1e-5, 5e-4, 1e-4, users_per_pass=32)
+    n_img = users * (S3 + 1) * 2
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    batches = [(torch.rand((n_img, 3, 224, 224), generator=g, device=dev) * 2 - 1, torch.ones((users, S3), device=dev))
+               for _ in range(2)]
+    ms, loss = _time_steps(trainer, batches, steps, 2, dev, world)
+    fwd_flops_img = 12 * 197 * (14155776 + 4 * 197 * 768 + 393216) + 196 * 2 * 768 * 768
+    return {"value": users * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "users_per_gpu_per_step": users,
+            "images_per_gpu_per_step": n_img, "users_per_pass": 32,
+            "model_tflops_per_gpu": 2 * fwd_flops_img * n_img / (ms / 1e3) / 1e12,
+            "trainable_params": trainer.num_trainable, "loss": loss,
+            "note": "C3 shapes (ViT-B/16-224 Houlsby r=64, 197 tokens per image, 22 images per user), images resident in HBM; "
+                    "NOT the headline value"}
+
+
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout when
     NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the duration of the run and the
@@ -462,6 +550,13 @@ def main():
         eval_out = bench_eval(dev, world, rank, max(2, a.steps), 2)
         model.eval()
         eval_out["eval_model_d64"] = bench_eval_full(model, args, dev, world, rank, a.steps)
+    # ---------------- the other two training configurations of BASELINE.json (non-headline) ----------------
+    if not a.no_variants:
+        torch.cuda.empty_cache()
+        variants["c1_bert_houlsby"] = bench_c1_houlsby(dev, world, rank, max(2, min(a.steps, 3)))
+        torch.cuda.empty_cache()
+        variants["c3_vit_houlsby"] = bench_c3_vit(dev, world, rank, max(2, min(a.steps, 3)))
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
