@@ -22,6 +22,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;               // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;           // fixed for 16-bit inputs
+// Internal epilogue id (not part of the ABI enum): LINEAR whose dropout mask is applied to v + residual(s) instead of v —
+// a4r_gemm_args.dropout_after_residual.  A separate instantiation, so the hot LINEAR kernel keeps its register budget.
+constexpr int EPI_LINEAR_DROPSUM = 100;
 // Epilogue warps come in groups of 4 (one warp per TMEM lane quadrant); group g owns the 32-column chunks c with
 // c % groups == g.  Plain epilogues keep up with the MMAs with 2 groups; the GELU / GELU' epilogues of the 256-wide tile
 // are instruction-latency-bound: GELU gets 3 groups (512 threads, 128 registers), GELU' 4 groups (640 threads, 96 registers);
@@ -250,10 +253,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int group = ew >> 2;
     constexpr int CHUNKS = (BN / 32 + NUM_EPI_GROUPS - 1) / NUM_EPI_GROUPS;
-    constexpr bool kHasIn = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_DGELU) || (EPI == A4R_EPI_DRELU);
+    constexpr bool kLinear = (EPI == A4R_EPI_LINEAR) || (EPI == EPI_LINEAR_DROPSUM);
+    constexpr bool kHasIn = kLinear || (EPI == A4R_EPI_DGELU) || (EPI == A4R_EPI_DRELU);
     const __nv_bfloat16* in_ptr = nullptr;
     int64_t in_ld = 0;
-    if constexpr (EPI == A4R_EPI_LINEAR) {
+    if constexpr (kLinear) {
       in_ptr = reinterpret_cast<const __nv_bfloat16*>(p.residual);
       in_ld = p.ldr;
     } else if constexpr (kHasIn) {
@@ -287,7 +291,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                            acc);
         const bool full = col0 + 32 <= p.N;
         // the bias slice of this chunk is fetched WHILE the TMEM load is in flight (both latencies overlap)
-        constexpr bool kBias = (EPI == A4R_EPI_LINEAR) || (EPI == A4R_EPI_GELU) || (EPI == A4R_EPI_RELU);
+        constexpr bool kBias = kLinear || (EPI == A4R_EPI_GELU) || (EPI == A4R_EPI_RELU);
         float4 bv[kBias ? 8 : 1];
         const bool has_bias = kBias && p.bias != nullptr;
         if (has_bias) {
@@ -344,9 +348,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (col0 + 8 * j < p.N) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
           }
         };
-        if constexpr (EPI == A4R_EPI_LINEAR) {
-          if (p.drop_thr16 != 0) {
-            const uint64_t ctr = p.drop_offset + ((static_cast<uint64_t>(r64) * static_cast<uint64_t>(p.N) + col0) >> 2);
+        auto drop_v = [&]() {
+          const uint64_t ctr = p.drop_offset + ((static_cast<uint64_t>(r64) * static_cast<uint64_t>(p.N) + col0) >> 2);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {   // 4 consecutive columns per counter
               const uint64_t r = rng64(p.drop_seed, ctr + q);
@@ -355,6 +358,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[2 * q + 1].x = rng_keep(r, 2, p.drop_thr16) ? v[2 * q + 1].x * p.drop_scale : 0.0f;
               v[2 * q + 1].y = rng_keep(r, 3, p.drop_thr16) ? v[2 * q + 1].y * p.drop_scale : 0.0f;
             }
+        };
+        if constexpr (kLinear) {
+          if constexpr (EPI == A4R_EPI_LINEAR) {
+            if (p.drop_thr16 != 0) drop_v();                      // forward: dropout(x Wᵀ + b) + residual
           }
           if (has_in) {
 #pragma unroll
@@ -373,6 +380,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          // gradient through a dropout whose input gradient is the sum formed above: mask the SUM
+          if constexpr (EPI == EPI_LINEAR_DROPSUM) drop_v();
         } else if constexpr (EPI == A4R_EPI_GELU) {
           if (p.aux != nullptr) store_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0);
 #pragma unroll
@@ -596,6 +605,8 @@ extern "C" int a4r_gemm_bf16_tn(const a4r_gemm_args* a, a4r_stream_t stream_) {
         : (bn == 256 ? launch_gemm<256, EPI, V, 1>(a, stream)                                          \
                      : (bn == 128 ? launch_gemm<128, EPI, V, 1>(a, stream) : launch_gemm<64, EPI, V, 1>(a, stream))))
 #define A4R_DISPATCH(EPI) (v32 ? A4R_DISPATCH_BN(EPI, true) : A4R_DISPATCH_BN(EPI, false))
+  if (a->epilogue == A4R_EPI_LINEAR && a->dropout_after_residual != 0 && a->dropout_p > 0.0f)
+    return A4R_DISPATCH(EPI_LINEAR_DROPSUM);
   switch (a->epilogue) {
     case A4R_EPI_LINEAR: return A4R_DISPATCH(A4R_EPI_LINEAR);
     case A4R_EPI_GELU: return A4R_DISPATCH(A4R_EPI_GELU);

@@ -640,3 +640,93 @@ def houlsby_block(h, inp, adapter_down, adapter_up, act, ln=None):
     return HoulsbyBlockFunction.apply(h, inp, adapter_down.weight, adapter_down.bias, adapter_up.weight, adapter_up.bias,
                                       None if ln is None else ln.weight, None if ln is None else ln.bias,
                                       0.0 if ln is None else ln.eps, act, adapter_down._cache, adapter_up._cache)
+
+
+class HoulsbyPostLNBlockFunction(torch.autograd.Function):
+    """One frozen post-LN block of BERT under a serial Houlsby wrapper (BertAdaptedSelfOutput.forward,
+    Downstream/Text/model/model.py:292-297) as a single autograd node:
+
+        h   = dropout(F(x))          F(x) = x Woᵀ + bo  (attention.output)  |  GELU(x Wiᵀ + bi) Wfᵀ + bf  (intermediate + output)
+        out = LayerNorm(h + W_u act(W_d h + b_d) + b_u + inp)
+
+    Forward: the dropout lives in the epilogue of F's last GEMM (counter RNG), everything after it is the fused K5 kernel.
+    Backward: LayerNorm backward -> two skinny data-gradient GEMMs; the second one forms (ds W_d + dz) and masks the SUM
+    with the regenerated dropout mask in its epilogue (`dropout_after_residual`), so no stand-alone dropout pass exists in
+    either direction; GELU' and — when `inp` is the block input x itself (the feed-forward block) — the skip gradient
+    ride in the epilogues of F's data-gradient GEMMs.  Trainable: the adapter and (finetune_layernorm) the LayerNorm."""
+
+    @staticmethod
+    def forward(ctx, x, inp, p, w1, b1, cache1, w2, b2, cache2, w_down, b_down, w_up, b_up, gamma, beta, eps, act,
+                cache_d, cache_u):
+        ffn = w2 is not None
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or any(ctx.needs_input_grad[9:15])
+        wa, _ = cache1.get(w1)
+        n_out = (w2 if ffn else w1).shape[0]
+        rng = (float(p),) + DropoutState.draw((x.shape[0] * n_out + 3) // 4) if p > 0 else None
+        u = None
+        if ffn:
+            wb, _ = cache2.get(w2)
+            u = torch.empty((x.shape[0], wa.shape[0]), dtype=BF16, device=x.device) if need else None
+            f = ops.gemm(x, wa, bias=b1.detach(), epilogue=ops.EPI_GELU, aux=u)
+            h = ops.gemm(f, wb, bias=b2.detach(), dropout=rng)
+        else:
+            h = ops.gemm(x, wa, bias=b1.detach(), dropout=rng)
+        wd, _ = cache_d.get(w_down)
+        wu, _ = cache_u.get(w_up)
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        out, z, mean, rstd, s, u_ad = ops.adapter_ln_fwd(h, inp, wd, b_down.detach().float().contiguous(), wu,
+                                                         b_up.detach().float().contiguous(), g, b, eps, act=act, tail=0,
+                                                         save=need)
+        ctx.rng, ctx.ffn, ctx.act = rng, ffn, act
+        ctx.caches = (cache1, cache2, cache_d, cache_u)
+        ctx.inp_is_x = inp is x
+        if need:
+            ctx.save_for_backward(h, z, mean, rstd, g, s, u_ad, u, w1, w2, w_down, w_up)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, z, mean, rstd, g, s, u_ad, u, w1, w2, w_down, w_up = ctx.saved_tensors
+        cache1, cache2, cache_d, cache_u = ctx.caches
+        dout = dout.contiguous()
+        dg = db = None
+        if ctx.needs_input_grad[13] or ctx.needs_input_grad[14]:
+            dg, db = torch.empty_like(g), torch.empty_like(g)
+        dz = ops.layernorm_bwd(dout, z, mean, rstd, g, dgamma=dg, dbeta=db)
+        _, wut = cache_u.get(w_up, need_t=True)      # [r, H]
+        _, wdt = cache_d.get(w_down, need_t=True)    # [H, r]
+        if ctx.act == "gelu":
+            ds = ops.gemm(dz, wut, epilogue=ops.EPI_DGELU, aux=u_ad)
+        else:
+            ds = ops.gemm(dz, wut, epilogue=ops.EPI_DRELU, aux=s)
+        dwd = ops.wgrad(ds, h) if ctx.needs_input_grad[9] else None
+        dbd = ops.colsum(ds) if ctx.needs_input_grad[10] else None
+        dwu = ops.wgrad(dz, s) if ctx.needs_input_grad[11] else None
+        dbu = ops.colsum(dz) if ctx.needs_input_grad[12] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # gradient at the dense output, through the dropout: (ds W_d + dz) * mask / (1 - p) in ONE epilogue
+            dhm = ops.gemm(ds, wdt, residual=dz, dropout=ctx.rng, dropout_after=True)
+            fold = dz if ctx.inp_is_x else None
+            _, w1t = cache1.get(w1, need_t=True)
+            if ctx.ffn:
+                _, w2t = cache2.get(w2, need_t=True)
+                du = ops.gemm(dhm, w2t, epilogue=ops.EPI_DGELU, aux=u)
+                dx = ops.gemm(du, w1t, residual=fold)
+            else:
+                dx = ops.gemm(dhm, w1t, residual=fold)
+        dinp = dz if (ctx.needs_input_grad[1] and not ctx.inp_is_x) else None
+        return (dx, dinp, None, None, None, None, None, None, None, dwd, dbd, dwu, dbu, dg, db, None, None, None, None)
+
+
+def houlsby_postln_block(x, inp, p, dense, intermediate, adapter, ln):
+    """dense / intermediate: the frozen Linear modules of the block (intermediate None for attention.output);
+    adapter: the AdapterBlock; ln: the block's LayerNorm module."""
+    if intermediate is None:
+        w1, b1, c1, w2, b2, c2 = dense.weight, dense.bias, dense._cache, None, None, None
+    else:
+        w1, b1, c1 = intermediate.weight, intermediate.bias, intermediate._cache
+        w2, b2, c2 = dense.weight, dense.bias, dense._cache
+    return HoulsbyPostLNBlockFunction.apply(x, inp, p, w1, b1, c1, w2, b2, c2, adapter.fc_down.weight, adapter.fc_down.bias,
+                                            adapter.fc_up.weight, adapter.fc_up.bias, ln.weight, ln.bias, ln.eps,
+                                            adapter.act, adapter.fc_down._cache, adapter.fc_up._cache)

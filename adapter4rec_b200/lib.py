@@ -21,6 +21,7 @@ class GemmArgs(Structure):
         ("bias", c_void_p), ("M", c_int64), ("N", c_int64), ("K", c_int64),
         ("alpha", c_float), ("epilogue", c_int32), ("out_f32", c_int32), ("block_n", c_int32),
         ("dropout_p", c_float), ("dropout_seed", ctypes.c_uint64), ("dropout_offset", ctypes.c_uint64),
+        ("dropout_after_residual", c_int32),
     ]
 
 

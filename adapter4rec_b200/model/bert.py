@@ -193,6 +193,11 @@ class BertLayer(nn.Module):
             p = out.dropout.p if self.training else 0.0
             return Fn.PostLNBlockFunction.apply(y, y, out.LayerNorm.weight, out.LayerNorm.bias, out.LayerNorm.eps, p,
                                                 wi.weight, wi.bias, wi._cache, wf.weight, wf.bias, wf._cache)
+        if frozen and hasattr(out, "forward_block"):
+            # serial Houlsby wrapper: FFN pair + dropout + adapter + LayerNorm in one autograd node
+            fused = out.forward_block(y, y, wi)
+            if fused is not None:
+                return to_2d_bf16(fused)
         if frozen and hasattr(out, "forward_from_dense"):
             # adapter-wrapped output: the frozen FFN pair stays fused, the wrapper continues from the dense output
             h = Fn.FFNFunction.apply(y, wi.weight, wi.bias, wf.weight, wf.bias, None, wi._cache, wf._cache)

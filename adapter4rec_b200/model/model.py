@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fn
+from .. import ops
 from .encoders import Bert_Encoder, User_Encoder
 from .layers import BF16, Embedding, to_2d_bf16
 from .layers import LayerNorm
@@ -98,7 +99,26 @@ class BertAdaptedSelfOutput(nn.Module):
         self.adapter = AdapterBlock(args, _word_dim(args), args.bert_adapter_down_size, args.adapter_dropout_rate)
 
     def forward(self, hidden_states, input_tensor):
+        out = self.forward_block(to_2d_bf16(hidden_states), input_tensor, None)
+        if out is not None:
+            return out
         return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
+
+    def forward_block(self, x2, input_tensor, intermediate):
+        """dense (or intermediate -> GELU -> dense when `intermediate` is given) -> dropout -> adapter -> LayerNorm as ONE
+        autograd node (Fn.HoulsbyPostLNBlockFunction) when the block's dense layers are frozen and the adapter has the
+        fused kernel's shape; None otherwise (the caller composes the pieces)."""
+        d = self.self_output.dense
+        inp = x2 if input_tensor is x2 else to_2d_bf16(input_tensor)   # identity matters: inp is x folds the skip gradient
+        mods = (d,) if intermediate is None else (d, intermediate)
+        if any(m.weight.requires_grad or m.bias.requires_grad for m in mods):
+            return None
+        if not (ops.adapter_ln_supported(self.adapter.fc_down.in_features, self.adapter.fc_down.out_features)
+                and inp.is_contiguous() and x2.shape[0] == inp.shape[0]):
+            return None
+        p = self.self_output.dropout.p if self.training else 0.0
+        out = Fn.houlsby_postln_block(x2, inp, p, d, intermediate, self.adapter, self.self_output.LayerNorm)
+        return out.view(input_tensor.shape)
 
     def forward_from_dense(self, h, input_tensor):
         """everything after self_output.dense (the encoder layer fuses that dense with the GELU GEMM before it)"""

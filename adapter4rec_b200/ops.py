@@ -70,8 +70,9 @@ def gemm_profile_stop(by_shape=False):
 
 
 def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, aux=None, a2=None, b2=None,
-         alpha=1.0, out=None, out_dtype=BF16, block_n=0, dropout=None):
-    """C[M,N] = epi(alpha * (a @ b.T + a2 @ b2.T) + bias)  — see a4r_gemm_bf16_tn in include/adapter4rec.h."""
+         alpha=1.0, out=None, out_dtype=BF16, block_n=0, dropout=None, dropout_after=False):
+    """C[M,N] = epi(alpha * (a @ b.T + a2 @ b2.T) + bias)  — see a4r_gemm_bf16_tn in include/adapter4rec.h.
+    dropout = (p, seed, offset): mask on the LINEAR epilogue value before the residuals, or (dropout_after) on the sum."""
     assert a.dtype == BF16 and b.dtype == BF16, "gemm operands must be bf16"
     M, K = a.shape
     N, Kb = b.shape
@@ -101,6 +102,7 @@ def gemm(a, b, bias=None, epilogue=EPI_LINEAR, residual=None, residual2=None, au
     if dropout is not None:
         assert out.is_contiguous(), "epilogue dropout indexes the logical [M, N] output"
         g.dropout_p, g.dropout_seed, g.dropout_offset = float(dropout[0]), int(dropout[1]), int(dropout[2])
+        g.dropout_after_residual = int(bool(dropout_after))
     g.alpha, g.epilogue, g.out_f32, g.block_n = float(alpha), int(epilogue), int(out.dtype == torch.float32), int(block_n)
     assert out.dtype in (BF16, torch.float32)
     if _gemm_profile is not None:

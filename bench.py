@@ -607,7 +607,11 @@ def main():
                                   100.0 * dom[1] / ms, dom[0] / dom[2]),
                      "peak_source": pk_kind + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / peak if peak else None,
-                                           "launches": gemm_calls, "share_of_step": gemm_ms / ms}},
+                                           "launches": gemm_calls, "share_of_step": gemm_ms / ms},
+                     "by_shape": [{"M": k[0], "N": k[1], "K": k[2], "epilogue": epi_names.get(k[3], "?"), "launches": v[2],
+                                   "share_of_step": v[1] / ms, "tflops": v[0] / (v[1] / 1e3) / 1e12,
+                                   "frac": v[0] / (v[1] / 1e3) / 1e12 / peak if peak else None}
+                                  for k, v in sorted(gemm_groups.items(), key=lambda kv: -kv[1][1])[:12]]},
     }
     if eval_out is not None:
         pk_b = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))

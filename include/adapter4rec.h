@@ -105,6 +105,10 @@ typedef struct a4r_gemm_args {
   float dropout_p;
   uint64_t dropout_seed;
   uint64_t dropout_offset;
+  /* 0: the mask is applied to v BEFORE the residuals (forward).  1: to v + residual + residual2 — the gradient through
+   * a dropout whose input gradient is a sum that this GEMM forms in its epilogue (the fused Houlsby block's backward:
+   * d_dense_out = (ds W_d + dz) * mask / (1 - p), Downstream/Text/model/model.py:293-295 read backwards) */
+  int32_t dropout_after_residual;
 } a4r_gemm_args;
 
 A4R_API int a4r_gemm_bf16_tn(const a4r_gemm_args* args, a4r_stream_t stream);

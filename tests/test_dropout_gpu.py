@@ -126,3 +126,67 @@ def test_train_mode_step_is_deterministic_given_the_seed_and_close_to_eval():
     assert torch.isfinite(grads[0]).all() and float(grads[0].norm()) > 0
     Fn.DropoutState.manual_seed(8)
     assert float(model(rows, lm, 0)) != losses[0]                             # another seed, another mask
+
+
+@pytest.mark.parametrize("after", [False, True])
+def test_gemm_epilogue_dropout_before_and_after_the_residual(after):
+    """a4r_gemm_bf16_tn LINEAR epilogue: dropout(acc + bias) + residual (forward of dense -> dropout -> + input) and
+    dropout(acc + residual) (dropout_after_residual: the gradient through a dropout whose input gradient is a sum),
+    against torch with the host-restated mask."""
+    from adapter4rec_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K, p = 1000, 768, 64, 0.1
+    a = (torch.randn((M, K), generator=g, device="cuda") * 0.5).to(BF16)
+    w = (torch.randn((N, K), generator=g, device="cuda") * 0.2).to(BF16)
+    res = torch.randn((M, N), generator=g, device="cuda").to(BF16)
+    seed, off = 0x1234567, 4096
+    out = ops.gemm(a, w, residual=res, dropout=(p, seed, off), dropout_after=after)
+    mask, scale = keep_mask(seed, off, M * N, p)
+    mask = mask.view(M, N).cuda()
+    acc = a.float() @ w.float().t()
+    ref = (acc + res.float()) * mask * scale if after else acc * mask * scale + res.float()
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1e-2 + 8e-3 * ref.abs()).all()), float(err.max())
+    if after:   # dropped elements of the SUM are exactly zero
+        assert bool((out[mask == 0] == 0).all())
+
+
+def test_fused_houlsby_block_matches_the_composed_path_in_train_mode():
+    """HoulsbyPostLNBlockFunction (dense + dropout + adapter + LayerNorm in one node, dropout in GEMM epilogues both ways)
+    against dense -> a4r_dropout -> fused adapter block: both draw the same counters in the same order, so under one
+    seed the masks are identical and the results differ by bf16 rounding only."""
+    import cases
+    from adapter4rec_b200 import functional as Fn
+    from adapter4rec_b200.model import model as M
+    from test_model_gpu import build_gpu_model
+    c = cases.tiny_case("houlsby")
+    sd = cases.build_state_dict(c)
+    model, _ = build_gpu_model(c, sd)
+    items = cases.build_item_content(c)
+    sample_items, log_mask, _ = cases.build_batch(c, items)
+    rows, lm = sample_items.view(-1, 2 * c.L).cuda(), log_mask.cuda()
+    model.train()
+    results = []
+    fused_forward_block = M.BertAdaptedSelfOutput.forward_block
+    calls = [0]
+
+    def counting(self, *a, **k):
+        r = fused_forward_block(self, *a, **k)
+        calls[0] += r is not None
+        return r
+    try:
+        for variant in (counting, lambda self, *a, **k: None):
+            M.BertAdaptedSelfOutput.forward_block = variant
+            Fn.DropoutState.manual_seed(11)
+            model.zero_grad(set_to_none=True)
+            loss = model(rows, lm, 0)
+            loss.backward()
+            results.append((float(loss), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None}))
+    finally:
+        M.BertAdaptedSelfOutput.forward_block = fused_forward_block
+    assert calls[0] >= 2 * c.layers - 1, "the fused node must be the path that runs (%d calls)" % calls[0]
+    (l0, g0), (l1, g1) = results
+    assert abs(l0 - l1) <= 5e-3 * abs(l1), (l0, l1)
+    assert g0.keys() == g1.keys()
+    a0, a1 = torch.cat([g0[k].flatten() for k in g0]), torch.cat([g1[k].flatten() for k in g0])
+    assert float((a0 - a1).norm() / a1.norm()) <= 3e-2

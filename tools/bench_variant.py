@@ -1,0 +1,21 @@
+"""Runs one of bench.py's non-headline training configurations alone (for ncu launch lists / quick A-B timing):
+    python tools/bench_variant.py c1 [--users 128] [--steps 2]
+    python tools/bench_variant.py c3 [--users 32]"""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+
+ap = argparse.ArgumentParser()
+ap.add_argument("which", choices=["c1", "c3"])
+ap.add_argument("--users", type=int, default=0)
+ap.add_argument("--steps", type=int, default=2)
+a = ap.parse_args()
+torch.cuda.set_device(0)
+dev = torch.device("cuda", 0)
+if a.which == "c1":
+    out = bench.bench_c1_houlsby(dev, 1, 0, a.steps, users=a.users or 256)
+else:
+    out = bench.bench_c3_vit(dev, 1, 0, a.steps, users=a.users or 64)
+print(json.dumps(out))
