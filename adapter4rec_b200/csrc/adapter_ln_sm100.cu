@@ -61,6 +61,7 @@ struct AdParams {
   __nv_bfloat16* s_out;
   __nv_bfloat16* u_out;
   int M, H, r, UC, nstage;
+  int lds;      // row stride of s_out (elements); lds >= r + 8: columns [r, r + 8) of s_out receive [1, 0, ..., 0]
   int act, tail;
   float eps;
 };
@@ -364,7 +365,9 @@ adapter_ln_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           for (int i = threadIdx.x - 128; i < BM * 8; i += EPI_THREADS) {
             const int r_ = i >> 3, ch = i & 7;
             if (row0 + r_ < p.M && ch * 8 < p.r)
-              st_na_v4(p.s_out + static_cast<int64_t>(row0 + r_) * p.r + ch * 8, lds_v4(sact + r_ * 128 + ((ch ^ (r_ & 7)) << 4)));
+              st_na_v4(p.s_out + static_cast<int64_t>(row0 + r_) * p.lds + ch * 8, lds_v4(sact + r_ * 128 + ((ch ^ (r_ & 7)) << 4)));
+            if (row0 + r_ < p.M && ch == 0 && p.lds >= p.r + 8)   // the ones column of [s | 1] (bf16 1.0 = 0x3F80)
+              st_na_v4(p.s_out + static_cast<int64_t>(row0 + r_) * p.lds + p.r, make_uint4(0x00003F80u, 0u, 0u, 0u));
           }
         }
         const float4 bu = __ldg(reinterpret_cast<const float4*>(p.b_up + c * CW + 4 * s16));
@@ -477,6 +480,7 @@ extern "C" int a4r_adapter_ln_fwd(const a4r_adapter_args* a, a4r_stream_t stream
   A4R_CHECK_ARG(a4r_adapter_ln_supported(a->H, a->r), "adapter_ln: needs H %% 64 == 0, H <= 768, r %% 8 == 0, r <= 64 (H=%lld r=%lld)",
                 (long long)a->H, (long long)a->r);
   A4R_CHECK_ARG(a->tail >= 0 && a->tail <= 2 && (a->act == 0 || a->act == 1), "adapter_ln: bad tail/act");
+  A4R_CHECK_ARG(a->lds == 0 || (a->lds >= a->r && a->lds % 8 == 0 && a->lds < (1 << 20)), "adapter_ln: bad lds");
   A4R_CHECK_ARG(a->tail != 0 || (a->gamma && a->beta), "adapter_ln: tail 0 (LayerNorm) needs gamma and beta");
   A4R_CHECK_ARG(a->tail == 2 || a->input != nullptr, "adapter_ln: tails 0 and 1 add `input`");
   A4R_CHECK_ARG(a->ldh >= a->H && a->ldh % 8 == 0 && a4r_aligned16(a->h), "adapter_ln: bad h/ldh");
@@ -509,6 +513,7 @@ extern "C" int a4r_adapter_ln_fwd(const a4r_adapter_args* a, a4r_stream_t stream
   p.M = static_cast<int>(a->M);
   p.H = static_cast<int>(a->H);
   p.r = static_cast<int>(a->r);
+  p.lds = a->lds == 0 ? p.r : static_cast<int>(a->lds);
   p.UC = a->H % 192 == 0 ? 192 : (a->H % 128 == 0 ? 128 : 64);
   p.act = a->act;
   p.tail = a->tail;

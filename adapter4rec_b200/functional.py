@@ -629,8 +629,10 @@ class HoulsbyBlockFunction(torch.autograd.Function):
         dh = ops.gemm(ds, wdt, residual=dz) if ctx.needs_input_grad[0] else None
         dwd = ops.wgrad(ds, h) if ctx.needs_input_grad[2] else None
         dbd = ops.colsum(ds) if ctx.needs_input_grad[3] else None
-        dwu = ops.wgrad(dz, s) if ctx.needs_input_grad[4] else None
-        dbu = ops.colsum(dz) if ctx.needs_input_grad[5] else None
+        dwu = dbu = None
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            full = ops.wgrad(dz, ops.s_ext(s))               # dzᵀ · [s | 1]: weight and bias gradient in one pass over dz
+            dwu, dbu = full[:, :s.shape[1]], full[:, s.shape[1]]
         dinp = dz if (ctx.has_inp and ctx.needs_input_grad[1]) else None
         return dh, dinp, dwd, dbd, dwu, dbu, dg, db, None, None, None, None
 
@@ -701,8 +703,10 @@ class HoulsbyPostLNBlockFunction(torch.autograd.Function):
             ds = ops.gemm(dz, wut, epilogue=ops.EPI_DRELU, aux=s)
         dwd = ops.wgrad(ds, h) if ctx.needs_input_grad[9] else None
         dbd = ops.colsum(ds) if ctx.needs_input_grad[10] else None
-        dwu = ops.wgrad(dz, s) if ctx.needs_input_grad[11] else None
-        dbu = ops.colsum(dz) if ctx.needs_input_grad[12] else None
+        dwu = dbu = None
+        if ctx.needs_input_grad[11] or ctx.needs_input_grad[12]:
+            full = ops.wgrad(dz, ops.s_ext(s))               # dzᵀ · [s | 1]: weight and bias gradient in one pass over dz
+            dwu, dbu = full[:, :s.shape[1]], full[:, s.shape[1]]
         dx = None
         if ctx.needs_input_grad[0]:
             # gradient at the dense output, through the dropout: (ds W_d + dz) * mask / (1 - p) in ONE epilogue

@@ -377,7 +377,8 @@ def adapter_ln_supported(H, r):
 def adapter_ln_fwd(h, inp, w_down, b_down, w_up, b_up, gamma=None, beta=None, eps=0.0, act="relu", tail=0, save=False):
     """K5 in one kernel: out = tail(h + W_u act(W_d h + b_d) + b_u [+ inp]); tail 0 = LayerNorm, 1 = +inp, 2 = nothing.
     returns (out, z, mean, rstd, s, u): with save=True the tensors the backward reads (z/mean/rstd for tail 0, s always,
-    u = pre-activation for GELU), else None."""
+    u = pre-activation for GELU), else None.  s is a [M, r] VIEW of a [M, r + 16] buffer (32-byte aligned rows) whose column r holds ones
+    (s_ext(s) returns it): dzᵀ · [s | 1] is d(fc_up.weight) and d(fc_up.bias) in one weight-gradient GEMM."""
     assert h.dtype == BF16 and h.dim() == 2 and w_down.dtype == BF16 and w_up.dtype == BF16
     assert w_down.is_contiguous() and w_up.is_contiguous()
     M, H = h.shape
@@ -389,7 +390,7 @@ def adapter_ln_fwd(h, inp, w_down, b_down, w_up, b_up, gamma=None, beta=None, ep
     out = torch.empty((M, H), dtype=BF16, device=dev)
     z = mean = rstd = s = u = None
     if save:
-        s = torch.empty((M, r), dtype=BF16, device=dev)
+        s = torch.empty((M, r + 16), dtype=BF16, device=dev)[:, :r]
         if act == "gelu":
             u = torch.empty((M, r), dtype=BF16, device=dev)
         if tail == 0:
@@ -405,8 +406,16 @@ def adapter_ln_fwd(h, inp, w_down, b_down, w_up, b_up, gamma=None, beta=None, ep
     a.gamma, a.beta, a.out, a.z_out, a.mean, a.rstd, a.s_out, a.u_out = (_p(gamma), _p(beta), _p(out), _p(z), _p(mean),
                                                                          _p(rstd), _p(s), _p(u))
     a.M, a.H, a.r, a.act, a.tail, a.eps = M, H, r, {"relu": 0, "gelu": 1}[act], int(tail), float(eps)
+    a.lds = 0 if s is None else s.stride(0)
     _l.check(_l.get_lib().a4r_adapter_ln_fwd(ctypes.byref(a), _stream()), "a4r_adapter_ln_fwd")
     return out, z, mean, rstd, s, u
+
+
+def s_ext(s):
+    """[s | 1 0 .. 0]: the [M, r + 8] window of the padded buffer behind the s view that adapter_ln_fwd returned"""
+    M, r = s.shape
+    assert s.stride(0) == r + 16 and s.storage_offset() == 0
+    return s.as_strided((M, r + 8), (r + 16, 1))
 
 
 MASKED_LOGIT = -1e4  # the constant the in-batch softmax head writes over excluded candidates

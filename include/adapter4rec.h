@@ -199,6 +199,8 @@ A4R_API int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, 
  * h [M,H] bf16 (ldh), input [M,H] bf16 (ldi), w_down [r,H] bf16, w_up [H,r] bf16 (both contiguous, nn.Linear layout),
  * biases / gamma / beta f32, out [M,H] bf16 contiguous.  Optional outputs for the backward: z_out [M,H] bf16 (pre-LN sum,
  * tail 0), mean / rstd [M] f32 (tail 0), s_out [M,r] bf16 (activation output), u_out [M,r] bf16 (pre-activation; GELU).
+ * lds (0 = r) is the row stride of s_out in elements; with lds >= r + 8 the kernel also writes [1, 0, ..., 0] into columns
+ * [r, r + 8) of every row, so that ONE weight-gradient GEMM dzᵀ·[s | 1] yields d(fc_up.weight) and d(fc_up.bias) together.
  * Shapes: H %% 64 == 0, H <= 768, r %% 8 == 0, r <= 64 (a4r_adapter_ln_supported); other shapes compose
  * a4r_gemm_bf16_tn + a4r_layernorm_fwd.
  * ------------------------------------------------------------------------------------------------ */
@@ -223,6 +225,7 @@ typedef struct a4r_adapter_args {
   int32_t act;
   int32_t tail;
   float eps;
+  int64_t lds;
 } a4r_adapter_args;
 A4R_API int a4r_adapter_ln_supported(int64_t H, int64_t r);
 A4R_API int a4r_adapter_ln_fwd(const a4r_adapter_args* args, a4r_stream_t stream);
