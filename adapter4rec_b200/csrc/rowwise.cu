@@ -151,12 +151,15 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const __nv_bfloat16
 // memory, so the frozen-LayerNorm instantiation (WGRAD = false) fits 3 CTAs per SM and keeps enough loads in flight
 // to approach HBM bandwidth.
 // ------------------------------------------------------------------------------------------------
-template <int G, int CPL, bool WGRAD>
-__global__ void __launch_bounds__(ROW_THREADS, WGRAD ? 1 : 3)
+// SKIP: dz also receives `dskip` (the gradient that reached the LayerNorm's INPUT over a skip connection that branches
+// off before it — pre-LN blocks: x1 = x + f(LN(x))), so autograd never runs a separate add over [M, H].
+template <int G, int CPL, bool WGRAD, bool SKIP = false>
+__global__ void __launch_bounds__(ROW_THREADS, WGRAD ? 1 : (SKIP ? 2 : 3))
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
               __nv_bfloat16* __restrict__ dz, float* __restrict__ partial /* [grid,2,H] or NULL */, int64_t M, int H,
-              __nv_bfloat16* __restrict__ dz_masked, uint32_t thr16, float dscale, uint64_t seed, uint64_t offset) {
+              __nv_bfloat16* __restrict__ dz_masked, uint32_t thr16, float dscale, uint64_t seed, uint64_t offset,
+              const __nv_bfloat16* __restrict__ dskip = nullptr) {
   __shared__ __align__(16) float sgamma[1024];
   __shared__ float buf[WGRAD ? 8192 : 1];  // (ROW_THREADS/G) * H <= 8192 floats for every supported (G, H)
   const int nchunks = H >> 3;
@@ -178,13 +181,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     const int64_t row_raw = base + threadIdx.x / G;
     const bool valid = row_raw < M;
     const int64_t row = valid ? row_raw : M - 1;
-    uint4 pdy[CPL], pz[CPL];
+    uint4 pdy[CPL], pz[CPL], psk[SKIP ? CPL : 1];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int ch = sub + c * G;
       if (ch < nchunks) {
         pdy[c] = ld_nc_v4(dy + row * H + ch * 8);
         pz[c] = ld_nc_v4(z + row * H + ch * 8);
+        if constexpr (SKIP) psk[c] = ld_nc_v4(dskip + row * H + ch * 8);
       }
     }
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -228,6 +232,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = rstd * (a[e] * gg[e] - s1 - (b[e] - mean) * rstd * s2);
+        if constexpr (SKIP) {
+          float sk[8];
+          unpack8(psk[c], sk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += sk[e];
+        }
         if (valid) st_na_v4(dz + row * H + ch * 8, pack8(o));
         if (dz_masked != nullptr && valid) {
           // the gradient that flows back through the dropout in front of this LayerNorm's residual add
@@ -562,11 +572,13 @@ extern "C" size_t a4r_layernorm_bwd_workspace_bytes(int64_t H) {
   return static_cast<size_t>(LN_BWD_MAX_BLOCKS) * 2 * static_cast<size_t>(H) * sizeof(float);
 }
 
-extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd,
-                                 const float* gamma, void* dz, float* dgamma, float* dbeta, int32_t accumulate,
-                                 void* workspace, size_t workspace_bytes, int64_t M, int64_t H, void* dz_masked,
-                                 float dropout_p, uint64_t dropout_seed, uint64_t dropout_offset,
-                                 a4r_stream_t stream_) {
+static int layernorm_bwd_impl(const void* dy, const void* z, const float* mean, const float* rstd,
+                              const float* gamma, void* dz, float* dgamma, float* dbeta, int32_t accumulate,
+                              void* workspace, size_t workspace_bytes, int64_t M, int64_t H, void* dz_masked,
+                              float dropout_p, uint64_t dropout_seed, uint64_t dropout_offset, const void* dskip,
+                              a4r_stream_t stream_) {
+  A4R_CHECK_ARG(dskip == nullptr || (a4r_aligned16(dskip) && dz_masked == nullptr && dgamma == nullptr && dbeta == nullptr),
+                "layernorm_bwd_add: dskip must be 16B aligned and excludes dz_masked / dgamma / dbeta");
   A4R_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f && a4r_aligned16(dz_masked), "layernorm_bwd: bad dropout args");
   const uint32_t thr16 = static_cast<uint32_t>(dropout_p * 65536.0f + 0.5f);
   const float dscale = 65536.0f / static_cast<float>(65536u - thr16);
@@ -598,6 +610,12 @@ extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mea
     } else {
       const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 12;
       if (blocks > cap) blocks = cap;
+      if (dskip != nullptr)
+        ln_bwd_kernel<G.value, CPL.value, false, true><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
+            static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H), nullptr, thr16, dscale, dropout_seed,
+            dropout_offset, static_cast<const __nv_bfloat16*>(dskip));
+      else
       ln_bwd_kernel<G.value, CPL.value, false><<<static_cast<int>(blocks), ROW_THREADS, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), mean, rstd, gamma,
           static_cast<__nv_bfloat16*>(dz), partial, M, static_cast<int>(H), static_cast<__nv_bfloat16*>(dz_masked), thr16,
@@ -613,6 +631,23 @@ extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mea
     }
     return A4R_OK;
   });
+}
+
+extern "C" int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd,
+                                 const float* gamma, void* dz, float* dgamma, float* dbeta, int32_t accumulate,
+                                 void* workspace, size_t workspace_bytes, int64_t M, int64_t H, void* dz_masked,
+                                 float dropout_p, uint64_t dropout_seed, uint64_t dropout_offset,
+                                 a4r_stream_t stream_) {
+  return layernorm_bwd_impl(dy, z, mean, rstd, gamma, dz, dgamma, dbeta, accumulate, workspace, workspace_bytes, M, H,
+                            dz_masked, dropout_p, dropout_seed, dropout_offset, nullptr, stream_);
+}
+
+extern "C" int a4r_layernorm_bwd_add(const void* dy, const void* z, const float* mean, const float* rstd,
+                                     const float* gamma, const void* dskip, void* dz, int64_t M, int64_t H,
+                                     a4r_stream_t stream_) {
+  A4R_CHECK_ARG(dskip != nullptr, "layernorm_bwd_add: dskip is NULL");
+  return layernorm_bwd_impl(dy, z, mean, rstd, gamma, dz, nullptr, nullptr, 0, nullptr, 0, M, H, nullptr, 0.0f, 0, 0, dskip,
+                            stream_);
 }
 
 extern "C" int a4r_embed_ln_fwd(const a4r_embed_args* a, a4r_stream_t stream_) {

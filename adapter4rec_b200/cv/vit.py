@@ -192,13 +192,13 @@ class ViTLayer(nn.Module):
         """x1 = x + A1(dense(attn(LN(x)))),  x2 = x1 + A2(dense(GELU(dense(LN(x1)))))   (A = identity without adapters).
         cls_only (last layer, classifier reads token 0 only): the row-wise tail runs on the [CLS] rows alone."""
         H = x2d.shape[1]
-        ctx = self.attention.attention(self.layernorm_before(x2d), N, L)
-        res = x2d
+        ln0, res = self.layernorm_before.forward_skip(x2d)      # the skip gradient is added inside LN-backward
+        ctx = self.attention.attention(ln0, N, L)
         if cls_only:
-            ctx, res = ctx.view(N, L, H)[:, 0], x2d.view(N, L, H)[:, 0]
+            ctx, res = ctx.view(N, L, H)[:, 0], res.view(N, L, H)[:, 0]
         ao = self.attention.output
         x1 = ao.forward_fused(ctx, res) if hasattr(ao, "forward_fused") else (to_2d_bf16(ao(ctx, res)) + res)
-        y = self.layernorm_after(x1)
+        y, x1 = self.layernorm_after.forward_skip(x1)
         out = self.output
         wi = self.intermediate.dense
         inner = out.self_output if hasattr(out, "self_output") else out

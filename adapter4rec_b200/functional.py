@@ -223,6 +223,42 @@ def layer_norm(x, weight, bias, eps, res=None, res_param=None):
     return LayerNormFunction.apply(x, weight, bias, eps, res, res_param)
 
 
+class LayerNormSkipFunction(torch.autograd.Function):
+    """(LN(x), x): a pre-LN block x1 = x + f(LN(x)) takes its skip connection from the SECOND output, so the skip gradient
+    is delivered to this node and added inside the LayerNorm-backward kernel (a4r_layernorm_bwd_add) instead of by a
+    separate autograd accumulation pass over [M, H].  Same trick as QKVFunction's "skip" output on the post-LN side."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        need = any(ctx.needs_input_grad[:3])
+        g, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y, _, mean, rstd = ops.layernorm_fwd(x, g, b, eps, want_stats=need)
+        if need:
+            ctx.save_for_backward(x, mean, rstd, g)
+        return y, x          # autograd treats a returned input as x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x, mean, rstd, g = ctx.saved_tensors
+        want_ln = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if dy is None:                                   # only the skip output was used downstream
+            return dskip, None, None, None
+        dy = dy.contiguous()
+        if dskip is not None and not want_ln:
+            return ops.layernorm_bwd_add(dy, x, mean, rstd, g, dskip.contiguous()), None, None, None
+        dg = db = None
+        if want_ln:
+            dg, db = torch.empty_like(g), torch.empty_like(g)
+        dx = ops.layernorm_bwd(dy, x, mean, rstd, g, dgamma=dg, dbeta=db)
+        if dskip is not None:
+            dx = dx + dskip
+        return dx, dg, db, None
+
+
+def layer_norm_skip(x, weight, bias, eps):
+    return LayerNormSkipFunction.apply(x, weight, bias, eps)
+
+
 class DropoutState:
     """Seed and running counter of the counter-based dropout RNG (a4r_dropout / attention-probability dropout).  Every
     call site draws a fresh counter range, so masks are independent across sites and steps; the backward of a site reuses

@@ -92,6 +92,8 @@ PROTOTYPES = {
     "a4r_layernorm_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int32, c_void_p, c_size_t, c_int64, c_int64, c_void_p, c_float, ctypes.c_uint64,
                                     ctypes.c_uint64, c_void_p]),
+    "a4r_layernorm_bwd_add": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                        c_void_p]),
     "a4r_adapter_ln_supported": (c_int32, [c_int64, c_int64]),
     "a4r_adapter_ln_fwd": (c_int32, [POINTER(AdapterArgs), c_void_p]),
     "a4r_embed_ln_fwd": (c_int32, [POINTER(EmbedArgs), c_void_p]),

@@ -123,6 +123,12 @@ class LayerNorm(nn.Module):
         shape = x.shape
         return Fn.layer_norm(to_2d_bf16(x), self.weight, self.bias, self.eps, res=res, res_param=res_param).view(shape)
 
+    def forward_skip(self, x2d):
+        """(LN(x), x') for pre-LN blocks: use x' as the skip input so its gradient is added inside the LN-backward kernel"""
+        if not (x2d.requires_grad and x2d.is_contiguous()):
+            return self.forward(x2d), x2d
+        return Fn.layer_norm_skip(x2d, self.weight, self.bias, self.eps)
+
 
 class Embedding(nn.Module):
     """A frozen lookup table (`weight` [V,H]); gathers happen inside the fused embedding kernel."""

@@ -227,6 +227,17 @@ def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma=None, dbeta=None, accumulate=
     return (dz, dzm) if masked is not None else dz
 
 
+def layernorm_bwd_add(dy, z, mean, rstd, gamma, dskip):
+    """dz = LayerNorm-backward(dy) + dskip in one pass (pre-LN skip connections); frozen LayerNorm only"""
+    assert dy.dtype == BF16 and z.dtype == BF16 and dskip.dtype == BF16
+    assert dy.is_contiguous() and z.is_contiguous() and dskip.is_contiguous() and dskip.shape == z.shape
+    M, H = z.shape
+    dz = torch.empty_like(z)
+    _l.check(_l.get_lib().a4r_layernorm_bwd_add(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dskip), _p(dz), M, H,
+                                                _stream()), "a4r_layernorm_bwd_add")
+    return dz
+
+
 def embed_ln_fwd(ids, L, word_emb, pos_emb, type_emb, gamma, beta, eps, pos_offset=0, roberta_pad_id=-1, prompt=None,
                  want_z=False):
     """ids: int64 [N, >=L] (row stride arbitrary); returns (out [N*L,H], z, mean, rstd)."""

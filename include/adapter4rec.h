@@ -185,6 +185,11 @@ A4R_API int a4r_layernorm_bwd(const void* dy, const void* z, const float* mean, 
                       void* dz, float* dgamma, float* dbeta, int32_t accumulate, void* workspace,
                       size_t workspace_bytes, int64_t M, int64_t H, void* dz_masked, float dropout_p,
                       uint64_t dropout_seed, uint64_t dropout_offset, a4r_stream_t stream);
+/* dz = LayerNorm-backward(dy) + dskip: pre-LN blocks (ViT: x1 = x + f(LN(x)), transformers' ViTLayer reached from
+ * Downstream/CV/model/encoders.py:31-32) deliver the skip-connection gradient to the LayerNorm's input; adding it here
+ * replaces a separate elementwise pass over [M, H].  Frozen LayerNorm only (no dgamma / dbeta). */
+A4R_API int a4r_layernorm_bwd_add(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                          const void* dskip, void* dz, int64_t M, int64_t H, a4r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5: the Houlsby adapter block fused into one pass (tcgen05 down/up projections + residuals + LayerNorm).

@@ -381,3 +381,22 @@ def test_act_fwd_bwd_kinds(kind, fn):
     _close(out, y.detach(), 2 ** -7, 1e-2, "act_fwd " + kind)
     saved = out if kind in ("relu", "leaky_relu") else u       # what the backward is given (output vs pre-activation)
     _close(ops.act_bwd(dy, saved, kind), dy.float() * uf.grad, 2 ** -6, 1e-2, "act_bwd " + kind)
+
+
+def test_layernorm_bwd_add_fuses_the_skip_gradient():
+    """a4r_layernorm_bwd_add == a4r_layernorm_bwd followed by `+ dskip` (fp32 sum, one bf16 rounding)."""
+    from adapter4rec_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for M, H in ((1000, 768), (333, 64), (77, 128)):
+        x = torch.randn((M, H), generator=g, device="cuda").to(torch.bfloat16)
+        dy = torch.randn((M, H), generator=g, device="cuda").to(torch.bfloat16)
+        dskip = torch.randn((M, H), generator=g, device="cuda").to(torch.bfloat16)
+        gamma = torch.rand(H, generator=g, device="cuda") + 0.5
+        beta = torch.zeros(H, device="cuda")
+        _, _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-6, want_stats=True)
+        fused = ops.layernorm_bwd_add(dy, x, mean, rstd, gamma, dskip)
+        xr = x.float().requires_grad_(True)
+        torch.nn.functional.layer_norm(xr, (H,), gamma, beta, 1e-6).backward(dy.float())
+        ref = xr.grad + dskip.float()
+        err = (fused.float() - ref).abs()
+        assert bool((err <= 2e-2 + 8e-3 * ref.abs()).all()), (M, H, float(err.max()))
