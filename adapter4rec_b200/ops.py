@@ -292,6 +292,14 @@ def colsum(x, width=None, out=None, accumulate=False):
     assert x.dtype == BF16 and x.dim() == 2
     M = x.shape[0]
     width = x.shape[1] if width is None else width
+    if out is None and width == x.shape[1] and width <= 128 and x.is_contiguous() and M >= 4096:
+        # narrow matrices (rank-r bottleneck gradients): a row is one or two 128-byte lines, so the row-per-step kernel
+        # idles most of a warp; fold f rows into one (a contiguous reshape) and add the f partial sums afterwards
+        f = 16
+        while f > 1 and M % f:
+            f //= 2
+        if f > 1:
+            return colsum(x.view(M // f, f * width)).view(f, width).sum(0)
     if out is None:
         out = torch.empty(width, dtype=torch.float32, device=x.device)
         accumulate = False

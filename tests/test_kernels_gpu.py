@@ -226,6 +226,9 @@ def test_act_bwd_colsum_wgrad():
     x = _rand((5000, 2304), 1, 3)
     _close(ops.colsum(x), x.float().sum(0), 1e-4, 2e-2, "colsum")
     _close(ops.colsum(x[:, 768:1536]), x[:, 768:1536].float().sum(0), 1e-4, 2e-2, "colsum strided")
+    for M, W in ((40960, 64), (4104, 16), (4097, 64)):      # narrow: rows folded 16 / 8 / 1 at a time
+        xn = _rand((M, W), 1, 6)
+        _close(ops.colsum(xn), xn.float().sum(0), 1e-4, 2e-2, "colsum narrow %dx%d" % (M, W))
     for (M, N, K) in [(5000, 768, 8), (3001, 8, 768), (4096, 768, 64), (777, 64, 768), (10240, 64, 16), (100, 16, 64)]:
         a, b = _rand((M, N), 1, 4), _rand((M, K), 1, 5)
         ref = a.float().t() @ b.float()
