@@ -368,6 +368,51 @@ def gather_rows(x, idx):
     return GatherRowsFunction.apply(x, idx)
 
 
+class ExpandRowsFunction(torch.autograd.Function):
+    """out[i] = x[inverse[i]] where several i may share a row (the item embeddings of a batch in which an item occurs more
+    than once: it is encoded ONCE).  Backward = the sum of the gradient rows of every occurrence, formed deterministically:
+    the gradient rows are brought into group order (stable sort of `inverse`) and each group is summed sequentially
+    (segment reduction over `counts`) — no atomics, no host synchronisation."""
+
+    @staticmethod
+    def forward(ctx, x, inverse, counts):
+        ctx.save_for_backward(inverse, counts)
+        return ops.gather_rows(x.contiguous(), inverse)
+
+    @staticmethod
+    def backward(ctx, dy):
+        inverse, counts = ctx.saved_tensors
+        order = torch.argsort(inverse, stable=True)
+        grouped = dy.contiguous()[order].float()
+        return torch.segment_reduce(grouped, "sum", lengths=counts, axis=0).to(dy.dtype), None, None
+
+
+def expand_rows(x, inverse, counts):
+    return ExpandRowsFunction.apply(x, inverse, counts)
+
+
+_ROW_HASH = {}
+
+
+def unique_rows(rows):
+    """(unique rows [U, W], inverse [N], counts [U]) of an int64 matrix.  torch.unique(dim=0) sorts rows lexicographically
+    (tens of milliseconds for a 10 k x 60 batch); here rows are compared through a 64-bit multiplicative hash (1-D radix
+    sort) and the result is VERIFIED against the rows — on a hash collision the exact routine runs instead."""
+    N, W = rows.shape
+    key = (rows.device, W)
+    if key not in _ROW_HASH:
+        g = torch.Generator().manual_seed(0x5EED)
+        _ROW_HASH[key] = (torch.randint(-2 ** 62, 2 ** 62, (W,), generator=g, dtype=torch.int64) | 1).to(rows.device)
+    h = (rows * _ROW_HASH[key]).sum(1)                      # int64 arithmetic wraps: a hash, not a value
+    uh, inverse, counts = torch.unique(h, return_inverse=True, return_counts=True)
+    first = torch.full((uh.numel(),), N, dtype=torch.int64, device=rows.device)
+    first.scatter_reduce_(0, inverse, torch.arange(N, device=rows.device), reduce="amin")
+    uniq = rows[first]
+    if not bool((uniq[inverse] == rows).all()):             # two different rows with one hash: vanishingly rare
+        uniq, inverse, counts = torch.unique(rows, dim=0, return_inverse=True, return_counts=True)
+    return uniq, inverse, counts
+
+
 LORA_PAD = 64  # the rank-r intermediates of all LoRA'd projections of one fused QKV share one 64-column k-block
 
 

@@ -65,7 +65,16 @@ class _ModelBase(nn.Module):
             if sig != self._checked:
                 check_trainable_supported(self)
                 self._checked = sig
-        input_embs_all = self.bert_encoder(sample_items)                       # [N, D] bf16
+        if getattr(self, "dedup_items", False):
+            # Optional (off by default, not what the reference executes): an item that occurs several times in the batch
+            # — as a positive of several users, as a sampled negative, as the padding row — is encoded ONCE and its
+            # embedding row is shared; the backward sums the gradient rows of its occurrences.  Identical forward values
+            # (every op of the encoder is independent across items); in train mode the occurrences now share one dropout
+            # mask where the reference draws one per occurrence.
+            uniq, inverse, counts = Fn.unique_rows(sample_items)
+            input_embs_all = Fn.expand_rows(self.bert_encoder(uniq), inverse, counts)
+        else:
+            input_embs_all = self.bert_encoder(sample_items)                   # [N, D] bf16
         D = self.args.embedding_dim
         input_embs = input_embs_all.view(-1, self.max_seq_len, 2, D)
         input_logs_embs = input_embs[:, :-1, 0, :].contiguous()                # history items 0..S-1 as user-encoder input

@@ -151,3 +151,27 @@ def test_unpadded_token_layout_gives_the_same_step(kind):
     tot = float(torch.cat([g.flatten() for g in out[False][2].values()]).norm())
     for n, g in out[False][2].items():
         assert float((out[True][2][n] - g).norm()) <= 1e-3 * float(g.norm()) + 1e-5 * tot, n
+
+
+def test_item_dedup_gives_the_same_loss_and_gradients():
+    """Model.dedup_items: every distinct item row of the batch is encoded once (tiny case: 72 slots over 40 items + the
+    padding row).  Forward values are identical (the encoder is independent across items), so the loss is bit-equal in
+    eval mode; gradients differ by the summation order of the occurrences only."""
+    c = cases.tiny_case("lora")
+    sd = cases.build_state_dict(c)
+    model, _ = build_gpu_model(c, sd)
+    items = cases.build_item_content(c)
+    sample_items, log_mask, _ = cases.build_batch(c, items)
+    rows, lm = sample_items.view(-1, 2 * c.L).cuda(), log_mask.cuda()
+    assert torch.unique(rows, dim=0).shape[0] < rows.shape[0], "the case must contain repeated items"
+    model.eval()
+    out = []
+    for flag in (False, True):
+        model.dedup_items = flag
+        model.zero_grad(set_to_none=True)
+        loss = model(rows, lm, 0)
+        loss.backward()
+        out.append((float(loss), torch.cat([p.grad.float().flatten() for p in model.parameters() if p.grad is not None])))
+    model.dedup_items = False
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    assert float((out[0][1] - out[1][1]).norm() / out[0][1].norm()) <= 2e-2

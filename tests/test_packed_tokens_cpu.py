@@ -27,3 +27,16 @@ def test_packed_tokens_accepts_a_strided_mask_view_and_non_prefix_masks():
     assert p.cu_seqlens.tolist() == [0, 3, 4, 9]
     assert p.token_rows.tolist() == [0, 1, 3, 5, 10, 11, 12, 13, 14]
     assert bool((p.token_mask == 1).all())
+
+
+def test_unique_rows_matches_torch_unique():
+    """functional.unique_rows (hash + verification) returns a valid (unique, inverse, counts) triple"""
+    import torch
+    from adapter4rec_b200 import functional as Fn
+    g = torch.Generator().manual_seed(0)
+    rows = torch.randint(0, 4, (500, 6), generator=g)
+    u, inv, cnt = Fn.unique_rows(rows)
+    ref = torch.unique(rows, dim=0)
+    assert u.shape == ref.shape and bool((u[inv] == rows).all()) and int(cnt.sum()) == rows.shape[0]
+    assert torch.equal(torch.unique(u, dim=0), ref)
+    assert torch.equal(cnt, torch.bincount(inv, minlength=u.shape[0]))
