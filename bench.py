@@ -319,6 +319,35 @@ def bench_eval_full(model, args, dev, world, rank, steps):
             "note": "complete evaluator incl. host->device copy of the per-user arrays; random embeddings => chance-level HR"}
 
 
+def bench_item_table(model, args, catalogue, dev, world, rank):
+    """get_item_embeddings (data_utils/metrics.py:62-79): the item encoder over the whole 80,001-row catalogue under
+    no_grad, item ids sharded over the ranks, the table stays on the device (timed separately from the ranking)."""
+    import torch
+    import torch.distributed as dist
+    from adapter4rec_b200.data_utils.metrics import get_item_embeddings
+    out = {}
+    bert = model.bert_encoder.text_encoders.title.bert_model
+    for name, unpad in (("padded", False), ("unpadded_tokens", True)):
+        bert.unpad = unpad
+        get_item_embeddings(model, catalogue[:8192], 4096, args, True, dev)          # warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        table = get_item_embeddings(model, catalogue, 4096, args, True, dev)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = {"items_per_s": catalogue.shape[0] / (float(t) / 1e3), "ms_total": float(t)}
+    bert.unpad = False
+    out["items"] = int(catalogue.shape[0])
+    out["note"] = "BERT-base forward over every catalogue row (30 token slots), host rows copied per 4,096-item block"
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -566,6 +595,7 @@ def main():
         eval_out = bench_eval(dev, world, rank, max(2, a.steps), 2)
         model.eval()
         eval_out["eval_model_d64"] = bench_eval_full(model, args, dev, world, rank, a.steps)
+        eval_out["item_table_build"] = bench_item_table(model, args, cat, dev, world, rank)
     # ---------------- the other two training configurations of BASELINE.json (non-headline) ----------------
     if not a.no_variants:
         torch.cuda.empty_cache()
