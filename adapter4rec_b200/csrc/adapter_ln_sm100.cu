@@ -24,6 +24,8 @@
 // HBM traffic per token (H = 768): read h + input, write out = 4,608 B (+ z = 1,536 B and s = 2r B when the backward
 // needs them) against ~9.5 KB for the composition GEMM -> GEMM(+2 residuals) -> LayerNorm; the contraction FLOPs
 // (2 x 2 x 768 x 64 per token) are ~5 % of what the tensor pipe could do in the time HBM needs, so the bound is HBM.
+#include <stdlib.h>
+
 #include "a4r_common.cuh"
 
 namespace {
@@ -469,6 +471,10 @@ int adapter_stages(int64_t H) {
 
 }  // namespace
 
+// adapter_rows_sm100.cu: the row-per-thread / TMA formulation of the same block
+bool a4r_adapter_rows_supported(int64_t H, int64_t r);
+int a4r_adapter_rows_launch(const a4r_adapter_args* a, cudaStream_t stream);
+
 extern "C" int a4r_adapter_ln_supported(int64_t H, int64_t r) {
   return (H % 64 == 0 && H >= 64 && H <= 768 && r % 8 == 0 && r >= 8 && r <= 64) ? 1 : 0;
 }
@@ -494,6 +500,14 @@ extern "C" int a4r_adapter_ln_fwd(const a4r_adapter_args* a, a4r_stream_t stream
   int rc = a4r_device_check();
   if (rc != A4R_OK) return rc;
   if (a->M == 0) return A4R_OK;
+  {
+    static int impl = -1;
+    if (impl < 0) {
+      const char* e = getenv("A4R_K5_IMPL");
+      impl = e ? atoi(e) : 3;
+    }
+    if (impl == 3 && a4r_adapter_rows_supported(a->H, a->r)) return a4r_adapter_rows_launch(a, static_cast<cudaStream_t>(stream_));
+  }
 
   AdParams p;
   p.h = static_cast<const __nv_bfloat16*>(a->h);
