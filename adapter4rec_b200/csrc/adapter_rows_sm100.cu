@@ -10,7 +10,8 @@
 // layout (one token row per thread) from the accumulator to the result and ALL global traffic is TMA:
 //   warp 0   TMA producer of the down-projection operands (h k-blocks + W_d k-blocks, 2-stage ring), W_u resident;
 //   warp 1   tcgen05 issuer: S1 = h · W_dᵀ, then U = s · W_uᵀ in 32-column chunks, chunk c into TMEM stage c & 1;
-//   warp 3   TMA producer of the RESIDUALS: [128 x 32] boxes of h and input (SWIZZLE_64B) into one stage per chunk parity;
+//   warps 2, 3  TMA producers of the RESIDUALS, one per epilogue group: [128 x 32] boxes of h and input (SWIZZLE_64B) through a
+//            ring of three single boxes per group (each ring has ONE consumer group: no cross-group barrier phases);
 //   warps 4-19 epilogue in two groups of 8 warps (chunk parity): residual rows from shared memory (conflict-free 16-byte
 //            reads), z = U + b_u + h + input in registers, then
 //              tail 1 / 2: bf16 row segment -> SWIZZLE_64B out tile -> TMA store;
@@ -36,6 +37,8 @@ constexpr int S_TILE = BM * RP * 2;           // 16 KB operand tile of the up-pr
 constexpr int IN_HALF = BM * CC * 2;          // 8 KB: one [128 x 32] bf16 box
 constexpr int IN_STAGE = 2 * IN_HALF;         // h box + input box
 constexpr int OUT_STAGE = IN_HALF;
+constexpr int IN_BOXES = 3;                   // residual boxes per group: a ring of single [128 x 32] boxes (h, input, h, ...), so
+                                              // a group's next chunk is in flight while it works on the current one
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GROUP_THREADS = EPI_THREADS / 2;
@@ -91,19 +94,18 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   uint8_t* s_wu = smem;                                          // [H][64] bf16, SW128
   uint8_t* s_ring = s_wu + static_cast<size_t>(p.H) * 128;
   uint8_t* s_act = s_ring + NSTAGE * STAGE_BYTES;                // [128][64] bf16, SW128
-  uint8_t* s_in = s_act + S_TILE;                                // 2 x (h box | input box), SW64
-  uint8_t* s_o = s_in + 2 * IN_STAGE;                            // 2 x out box
-  uint8_t* s_z = s_o + 2 * OUT_STAGE;                            // 2 x z box (tail 0 with store_z)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_z + 2 * OUT_STAGE);
+  uint8_t* s_in = s_act + S_TILE;                                // 2 groups x IN_BOXES residual boxes, SW64
+  uint8_t* s_o = s_in + 2 * IN_BOXES * IN_HALF;                  // 2 x out box (one per group; z_out leaves through it too)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_o + 2 * OUT_STAGE);
   uint64_t* empty_bar = full_bar + NSTAGE;
   uint64_t* wu_bar = empty_bar + NSTAGE;
   uint64_t* s1_full = wu_bar + 1;
   uint64_t* s_ready = s1_full + 1;
   uint64_t* u_full = s_ready + 1;     // [2]
   uint64_t* u_empty = u_full + 2;     // [2]
-  uint64_t* in_full = u_empty + 2;    // [2]
-  uint64_t* in_empty = in_full + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + 2);
+  uint64_t* in_full = u_empty + 2;                // [2][IN_BOXES]
+  uint64_t* in_empty = in_full + 2 * IN_BOXES;    // [2][IN_BOXES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + 2 * IN_BOXES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M + BM - 1) / BM;
@@ -130,8 +132,10 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&u_full[s], 1);
       mbar_init(&u_empty[s], EPI_WARPS / 2);
+    }
+    for (int s = 0; s < 2 * IN_BOXES; ++s) {
       mbar_init(&in_full[s], 1);
-      mbar_init(&in_empty[s], EPI_WARPS / 2);
+      mbar_init(&in_empty[s], EPI_WARPS / 2);   // a box is consumed by ONE group of 8 warps
     }
     mbar_fence_init();
   }
@@ -165,20 +169,24 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         }
       }
     }
-  } else if (warp == 3) {
-    // ============================== TMA producer: residual boxes ==============================
+  } else if (warp == 2 || warp == 3) {
+    // ============================== TMA producers of the residual boxes: warp 2 feeds group 0, warp 3 group 1 ==============
+    // (each ring belongs to ONE group, so a consumer is never more than one phase away from its barrier)
     if (lane == 0) {
-      uint32_t n[2] = {0u, 0u};
-      const uint32_t bytes = p.has_in ? IN_STAGE : IN_HALF;
+      const int g = warp - 2;
+      uint32_t nb = 0;                                  // running box number of this group: ring slot nb % IN_BOXES
+      auto load_box = [&](const CUtensorMap* tm, int c, int tile) {
+        const uint32_t b = nb % IN_BOXES;
+        uint64_t* full = &in_full[g * IN_BOXES + b];
+        mbar_wait(&in_empty[g * IN_BOXES + b], ((nb / IN_BOXES) & 1u) ^ 1u);
+        mbar_expect_tx(full, IN_HALF);
+        tma_load_2d(tm, s_in + (g * IN_BOXES + b) * IN_HALF, full, c * CC, tile * BM);
+        ++nb;
+      };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < nch; ++c) {
-          const int g = c & 1;
-          mbar_wait(&in_empty[g], (n[g] & 1u) ^ 1u);
-          uint8_t* dst = s_in + g * IN_STAGE;
-          mbar_expect_tx(&in_full[g], bytes);
-          tma_load_2d(&tmHr, dst, &in_full[g], c * CC, tile * BM);
-          if (p.has_in) tma_load_2d(&tmIr, dst + IN_HALF, &in_full[g], c * CC, tile * BM);
-          ++n[g];
+        for (int c = g; c < nch; c += 2) {
+          load_box(&tmHr, c, tile);
+          if (p.has_in) load_box(&tmIr, c, tile);
         }
       }
     }
@@ -255,11 +263,11 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     // this thread's two 16-byte chunks inside a [128 x 32] bf16 SWIZZLE_64B box: chunk index ^ ((row >> 1) & 3)
     const uint32_t sw = static_cast<uint32_t>((rl >> 1) & 3);
     const uint32_t toff0 = rl * 64 + (((2u * hf) ^ sw) << 4), toff1 = rl * 64 + (((2u * hf + 1u) ^ sw) << 4);
-    const uint32_t sin_g = smem_u32(s_in) + grp * IN_STAGE;
+    const uint32_t sin0 = smem_u32(s_in) + grp * IN_BOXES * IN_HALF;
+    uint32_t nb = 0;                                     // running residual-box number of this group (as in its producer)
     const uint32_t so_g = smem_u32(s_o) + grp * OUT_STAGE;
-    const uint32_t sz_g = smem_u32(s_z) + grp * OUT_STAGE;
     float* stats = reinterpret_cast<float*>(s_act);      // [128][4][2] after the tile's last up-projection has retired
-    uint32_t n_in = 0, n_u = 0, it = 0;
+    uint32_t n_u = 0, it = 0;
 
     auto emit = [&](uint32_t stage_addr, const CUtensorMap* tm, const uint32_t (&w)[8], int c, int row0) {
       if (elect) bulk_wait_read0();                      // the previous store out of this stage has read its bytes
@@ -334,17 +342,27 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       // ---- pass A: z = U + b_u + h + input for this group's chunks ----
       float sum = 0.0f, sq = 0.0f;
       for (int c = grp; c < nch; c += 2) {
-        mbar_wait(&in_full[grp], n_in & 1u);
-        const uint4 h0 = lds_v4(sin_g + toff0), h1 = lds_v4(sin_g + toff1);
-        uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
-        if (p.has_in) {
-          i0 = lds_v4(sin_g + IN_HALF + toff0);
-          i1 = lds_v4(sin_g + IN_HALF + toff1);
+        uint4 h0, h1, i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
+        {
+          const uint32_t b = nb % IN_BOXES;
+          mbar_wait(&in_full[grp * IN_BOXES + b], (nb / IN_BOXES) & 1u);
+          h0 = lds_v4(sin0 + b * IN_HALF + toff0);
+          h1 = lds_v4(sin0 + b * IN_HALF + toff1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&in_empty[grp * IN_BOXES + b]);
+          __syncwarp();
+          ++nb;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&in_empty[grp]);
-        __syncwarp();
-        ++n_in;
+        if (p.has_in) {
+          const uint32_t b = nb % IN_BOXES;
+          mbar_wait(&in_full[grp * IN_BOXES + b], (nb / IN_BOXES) & 1u);
+          i0 = lds_v4(sin0 + b * IN_HALF + toff0);
+          i1 = lds_v4(sin0 + b * IN_HALF + toff1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&in_empty[grp * IN_BOXES + b]);
+          __syncwarp();
+          ++nb;
+        }
         mbar_wait(&u_full[grp], n_u & 1u);
         tc_fence_after();
         uint32_t acc[16];
@@ -377,7 +395,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         }
         if (p.tail == 0) {
           tmem_st_32x32b_x8(tmem_base + lane_addr + Z_COL + c * (CC / 2) + hf * 8, w);
-          if (p.store_z) emit(sz_g, &tmZ, w, c, row0);
+          if (p.store_z) emit(so_g, &tmZ, w, c, row0);
         } else {
           emit(so_g, &tmOut, w, c, row0);
         }
@@ -505,8 +523,8 @@ int a4r_adapter_rows_launch(const a4r_adapter_args* a, cudaStream_t stream) {
   } else {
     tmZ = tmOut;
   }
-  const size_t smem = static_cast<size_t>(a->H) * 128 + NSTAGE * STAGE_BYTES + S_TILE + 2 * IN_STAGE + 4 * OUT_STAGE +
-                      24 * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = static_cast<size_t>(a->H) * 128 + NSTAGE * STAGE_BYTES + S_TILE + 2 * IN_BOXES * IN_HALF + 2 * OUT_STAGE +
+                      32 * sizeof(uint64_t) + 16 + 1024;
   A4R_CUDA_OK(cudaFuncSetAttribute(adapter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int tiles = (p.M + BM - 1) / BM;
   const int grid = tiles < a4r_num_sms() ? tiles : a4r_num_sms();

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from adapter4rec_b200 import ops
-M, H = 161280, 768
+M, H = int(os.environ.get('K5_M', '161280')), 768
 def r(*s, sc=1.0): return (torch.randn(*s, device="cuda") * sc).to(torch.bfloat16)
 h, inp = [r(M, H) for _ in range(3)], [r(M, H) for _ in range(3)]
 wd, wu = r(64, H, sc=0.05), r(H, 64, sc=0.05)
