@@ -14,7 +14,7 @@
 //            ring of three single boxes per group (each ring has ONE consumer group: no cross-group barrier phases);
 //   warps 4-19 epilogue in two groups of 8 warps (chunk parity): residual rows from shared memory (conflict-free 16-byte
 //            reads), z = U + b_u + h + input in registers, then
-//              tail 1 / 2: bf16 row segment -> SWIZZLE_64B out tile -> TMA store;
+//              tail 1 / 2: bf16 row segment -> the warp's private 1 KB box -> TMA store (no barrier wider than a warp);
 //              tail 0: z is parked as packed bf16 in 384 TMEM columns (tcgen05.st) while the row statistics accumulate,
 //                      [training: also TMA-stored to z_out], and a second pass reads it back (tcgen05.ld), normalises
 //                      and TMA-stores the result.  Nothing is re-read from L2.
@@ -35,13 +35,11 @@ constexpr int STAGE_B = RP * BK * 2;          // 8 KB of W_d
 constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
 constexpr int S_TILE = BM * RP * 2;           // 16 KB operand tile of the up-projection (also: row-statistics exchange)
 constexpr int IN_HALF = BM * CC * 2;          // 8 KB: one [128 x 32] bf16 box
-constexpr int IN_STAGE = 2 * IN_HALF;         // h box + input box
-constexpr int OUT_STAGE = IN_HALF;
+constexpr int OUT_STAGE = IN_HALF;          // 16 per-warp result boxes of 1 KB = two of these
 constexpr int IN_BOXES = 3;                   // residual boxes per group: a ring of single [128 x 32] boxes (h, input, h, ...), so
                                               // a group's next chunk is in flight while it works on the current one
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int GROUP_THREADS = EPI_THREADS / 2;
 constexpr int THREADS = 128 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
 constexpr int U_COL = 0;                      // two 32-column U stages
@@ -95,7 +93,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   uint8_t* s_ring = s_wu + static_cast<size_t>(p.H) * 128;
   uint8_t* s_act = s_ring + NSTAGE * STAGE_BYTES;                // [128][64] bf16, SW128
   uint8_t* s_in = s_act + S_TILE;                                // 2 groups x IN_BOXES residual boxes, SW64
-  uint8_t* s_o = s_in + 2 * IN_BOXES * IN_HALF;                  // 2 x out box (one per group; z_out leaves through it too)
+  uint8_t* s_o = s_in + 2 * IN_BOXES * IN_HALF;                  // 16 x 1 KB: one result box per epilogue warp (out and z_out)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_o + 2 * OUT_STAGE);
   uint64_t* empty_bar = full_bar + NSTAGE;
   uint64_t* wu_bar = empty_bar + NSTAGE;
@@ -257,28 +255,27 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     const int grp = cs >> 1, hf = cs & 1;                // chunk parity this warp serves; 16-column half of the 32-column chunk
     const int rl = quad * 32 + lane;                     // row within the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const int bar_id = 1 + grp;
-    const bool elect = (ew == grp * 8) && lane == 0;     // issues this group's TMA stores
     const uint32_t sact = smem_u32(s_act);
     // this thread's two 16-byte chunks inside a [128 x 32] bf16 SWIZZLE_64B box: chunk index ^ ((row >> 1) & 3)
     const uint32_t sw = static_cast<uint32_t>((rl >> 1) & 3);
     const uint32_t toff0 = rl * 64 + (((2u * hf) ^ sw) << 4), toff1 = rl * 64 + (((2u * hf + 1u) ^ sw) << 4);
     const uint32_t sin0 = smem_u32(s_in) + grp * IN_BOXES * IN_HALF;
     uint32_t nb = 0;                                     // running residual-box number of this group (as in its producer)
-    const uint32_t so_g = smem_u32(s_o) + grp * OUT_STAGE;
+    const uint32_t so_w = smem_u32(s_o) + ew * 1024;     // this warp's private out box
     float* stats = reinterpret_cast<float*>(s_act);      // [128][4][2] after the tile's last up-projection has retired
     uint32_t n_u = 0, it = 0;
 
-    auto emit = [&](uint32_t stage_addr, const CUtensorMap* tm, const uint32_t (&w)[8], int c, int row0) {
-      if (elect) bulk_wait_read0();                      // the previous store out of this stage has read its bytes
-      __syncwarp();                                      // bar.sync / tcgen05.* are .aligned: the warp must be converged
-      named_bar(bar_id, GROUP_THREADS);
-      sts_v4(stage_addr + toff0, w[0], w[1], w[2], w[3]);
-      sts_v4(stage_addr + toff1, w[4], w[5], w[6], w[7]);
+    // Results leave per WARP: its 32 rows x 16 columns form a private 1 KB box (row pitch 32 B, no swizzle) that lane 0 hands to
+    // TMA — no barrier wider than the warp, so the 16 warps drift freely instead of waiting for the slowest of a group.
+    auto emit = [&](const CUtensorMap* tm, const uint32_t (&w)[8], int c, int row0) {
+      if (lane == 0) bulk_wait_read0();                  // this warp's previous store has read its bytes
+      __syncwarp();                                      // (tcgen05.* / bar.sync are .aligned: keep the warp converged)
+      sts_v4(so_w + lane * 32, w[0], w[1], w[2], w[3]);
+      sts_v4(so_w + lane * 32 + 16, w[4], w[5], w[6], w[7]);
       fence_proxy_async_smem();
-      named_bar(bar_id, GROUP_THREADS);
-      if (elect) {
-        tma_store_2d(tm, stage_addr, c * CC, row0);      // rows past M are clipped by the tensor map
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tm, so_w, c * CC + hf * 16, row0 + quad * 32);   // rows past M are clipped by the tensor map
         bulk_commit();
       }
       __syncwarp();
@@ -395,9 +392,9 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         }
         if (p.tail == 0) {
           tmem_st_32x32b_x8(tmem_base + lane_addr + Z_COL + c * (CC / 2) + hf * 8, w);
-          if (p.store_z) emit(so_g, &tmZ, w, c, row0);
+          if (p.store_z) emit(&tmZ, w, c, row0);
         } else {
-          emit(so_g, &tmOut, w, c, row0);
+          emit(&tmOut, w, c, row0);
         }
       }
       if (p.tail == 0) tmem_st_wait();
@@ -440,10 +437,10 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           w[2 * q] = pack_bf16x2(o0.x, o0.y);
           w[2 * q + 1] = pack_bf16x2(o1.x, o1.y);
         }
-        emit(so_g, &tmOut, w, c, row0);
+        emit(&tmOut, w, c, row0);
       }
     }
-    if (elect) bulk_wait0();   // the last stores have left shared memory (and are complete) before the CTA retires
+    if (lane == 0) bulk_wait0();   // the last stores have left shared memory (and are complete) before the CTA retires
   }
 
   tc_fence_before();
@@ -456,8 +453,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// bf16 row-major [rows, cols], leading dimension ld: box = 32 columns x 128 rows, 64-byte swizzle
-int make_tmap_box32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+// bf16 row-major [rows, cols], leading dimension ld: box = 32 columns x 128 rows with the 64-byte swizzle (residual loads), or
+// 16 columns x 32 rows unswizzled (the per-warp result boxes)
+int make_tmap_box32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, bool warp_box = false) {
   static PFN_encodeTiled fn = nullptr;
   if (fn == nullptr) {
     void* ptr = nullptr;
@@ -469,11 +467,11 @@ int make_tmap_box32(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
   if (fn == nullptr) return a4r_set_error(A4R_ECUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(CC), static_cast<cuuint32_t>(BM)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(warp_box ? 16 : CC), static_cast<cuuint32_t>(warp_box ? 32 : BM)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, warp_box ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return a4r_set_error(A4R_ECUDA, "cuTensorMapEncodeTiled (32-column box) failed (%d)", (int)r);
   return A4R_OK;
 }
@@ -517,9 +515,9 @@ int a4r_adapter_rows_launch(const a4r_adapter_args* a, cudaStream_t stream) {
   } else {
     tmIr = tmHr;
   }
-  if ((rc = make_tmap_box32(&tmOut, a->out, a->M, a->H, a->H)) != A4R_OK) return rc;
+  if ((rc = make_tmap_box32(&tmOut, a->out, a->M, a->H, a->H, true)) != A4R_OK) return rc;
   if (p.store_z) {
-    if ((rc = make_tmap_box32(&tmZ, a->z_out, a->M, a->H, a->H)) != A4R_OK) return rc;
+    if ((rc = make_tmap_box32(&tmZ, a->z_out, a->M, a->H, a->H, true)) != A4R_OK) return rc;
   } else {
     tmZ = tmOut;
   }
