@@ -403,3 +403,18 @@ def test_layernorm_bwd_add_fuses_the_skip_gradient():
         ref = xr.grad + dskip.float()
         err = (fused.float() - ref).abs()
         assert bool((err <= 2e-2 + 8e-3 * ref.abs()).all()), (M, H, float(err.max()))
+
+
+@pytest.mark.parametrize("impl", ["2", "3"])
+def test_adapter_block_both_formulations(impl):
+    """K5 has two kernels behind a4r_adapter_ln_fwd: the row-per-thread TMA kernel (default, adapter_rows_sm100.cu) and the
+    staged one (A4R_K5_IMPL=2, adapter_ln_sm100.cu).  tools/k5_check.py runs every tail x activation x save combination at
+    M = 128 / 1,000 / 20,000 (ragged last tile, several tiles per CTA) against torch; the selection is read once per process,
+    hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "k5_check.py")], env=dict(os.environ, A4R_K5_IMPL=impl),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ALL OK"), (r.stdout[-800:], r.stderr[-800:])
