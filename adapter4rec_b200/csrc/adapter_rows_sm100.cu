@@ -286,6 +286,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       const bool row_ok = row0 + rl < p.M;
       // ---- phase 1: s = act(S1 + b_d) -> bf16 operand tile (columns [16 cs, 16 cs + 16)) ----
       mbar_wait(s1_full, it & 1);
+      __syncwarp();            // lanes may leave the spin loop in different iterations; tcgen05.ld is .aligned
       tc_fence_after();
       {
         uint32_t acc[16];
@@ -361,6 +362,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           ++nb;
         }
         mbar_wait(&u_full[grp], n_u & 1u);
+        __syncwarp();
         tc_fence_after();
         uint32_t acc[16];
         tmem_ld_32x32b_x16(tmem_base + lane_addr + U_COL + grp * CC + hf * 16, acc);
