@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--users", type=int, default=512, help="users per GPU per step (C2: 512)")
-    ap.add_argument("--users-per-pass", type=int, default=256, help="activation-memory pass size (exact accumulation)")
+    ap.add_argument("--users-per-pass", type=int, default=512,
+                    help="activation-memory pass size (exact gradient accumulation over passes); 512 = the whole batch in one pass "
+                         "(112 GB peak of the 180 GB), 256 = two passes (60 GB)")
     ap.add_argument("--cpu-users", type=int, default=0,
                     help="users in the bounded CPU sample (default: 48 for cpu_baseline ~15 s, 16 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -512,6 +514,7 @@ def main():
     ev1.record()
     barrier()
     launches = lib.launch_count() - launches0
+    max_mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     gemm_flops, gemm_ms, gemm_calls, gemm_groups = ops.gemm_profile_stop(by_shape=True)
     clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
@@ -641,6 +644,7 @@ def main():
         "model_tflops_per_gpu": algo_flops_step / (ms_per_step / 1e3) / 1e12,
         "loss": loss_val,
         "gpu_launches": int(launches),
+        "max_mem_gb": max_mem_gb,
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "e2e": {"value": a.users * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
