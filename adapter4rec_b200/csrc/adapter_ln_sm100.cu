@@ -500,14 +500,10 @@ extern "C" int a4r_adapter_ln_fwd(const a4r_adapter_args* a, a4r_stream_t stream
   int rc = a4r_device_check();
   if (rc != A4R_OK) return rc;
   if (a->M == 0) return A4R_OK;
-  {
-    static int impl = -1;
-    if (impl < 0) {
-      const char* e = getenv("A4R_K5_IMPL");
-      impl = e ? atoi(e) : 3;
-    }
-    if (impl == 3 && a4r_adapter_rows_supported(a->H, a->r)) return a4r_adapter_rows_launch(a, static_cast<cudaStream_t>(stream_));
-  }
+  A4R_CHECK_ARG(a->impl == 0 || a->impl == 2 || a->impl == 3, "adapter_ln: impl must be 0 (default), 2 (staged) or 3 (rows)");
+  A4R_CHECK_ARG(a->impl != 3 || a4r_adapter_rows_supported(a->H, a->r), "adapter_ln: impl 3 does not support H=%lld r=%lld",
+                (long long)a->H, (long long)a->r);
+  if (a->impl != 2 && a4r_adapter_rows_supported(a->H, a->r)) return a4r_adapter_rows_launch(a, static_cast<cudaStream_t>(stream_));
 
   AdParams p;
   p.h = static_cast<const __nv_bfloat16*>(a->h);

@@ -25,6 +25,13 @@ class ViTConfigLite:
         self.num_channels = src.get("num_channels", 3)
         self.layer_norm_eps = src.get("layer_norm_eps", 1e-12)
         self.hidden_dropout_prob = src.get("hidden_dropout_prob", 0.0)
+        self.attention_probs_dropout_prob = src.get("attention_probs_dropout_prob", 0.0)
+        # ViT-base's defaults (and every checkpoint the reference loads, Downstream/CV/run_adapter.py:283-297) have both
+        # dropouts at 0.0, and the serial wrappers / plain ViT blocks of this package do not apply them: refuse a config
+        # that asks for dropout rather than train silently without it.
+        if self.hidden_dropout_prob != 0.0 or self.attention_probs_dropout_prob != 0.0:
+            raise NotImplementedError("ViT hidden_dropout_prob / attention_probs_dropout_prob must be 0.0 (got %r / %r)"
+                                      % (self.hidden_dropout_prob, self.attention_probs_dropout_prob))
         self.initializer_range = src.get("initializer_range", 0.02)
         self.num_labels = src.get("num_labels", 2)
 

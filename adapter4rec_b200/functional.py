@@ -528,9 +528,12 @@ class QKVFunction(torch.autograd.Function):
             dx = ops.gemm(dqkv, cache["wt"], residual=dskip) if ctx.needs_input_grad[0] else None
         fused = bool(ctx.slots) and ctx.ones_col
         if fused:
-            # ONE pass over dqkv gives every lora_B and every bias gradient; ONE pass over x gives every lora_A
-            g1 = ops.wgrad(dqkv, T)            # [n*H, 64] = dqkvᵀ · [T | 1]
-            g2 = ops.wgrad(dT, x)              # [64, K]   = dTᵀ · x
+            # ONE pass over dqkv gives every lora_B and every bias gradient; ONE pass over x gives every lora_A.  Each pass
+            # runs only if one of its results is wanted (x is saved only when a lora_A or a weight trains).
+            want_g1 = any(ctx.param_needs[4 * j + 1] for j in range(n)) or any(ctx.param_needs[4 * j + 3] for j, _, _ in ctx.slots)
+            want_g2 = any(ctx.param_needs[4 * j + 2] for j, _, _ in ctx.slots)
+            g1 = ops.wgrad(dqkv, T) if want_g1 else None            # [n*H, 64] = dqkvᵀ · [T | 1]
+            g2 = ops.wgrad(dT, x) if want_g2 else None              # [64, K]   = dTᵀ · x
         for j in range(n):
             dq = dqkv[:, j * H:(j + 1) * H]
             if ctx.param_needs[4 * j]:

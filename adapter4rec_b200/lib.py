@@ -62,7 +62,7 @@ class AdapterArgs(Structure):
         ("gamma", c_void_p), ("beta", c_void_p), ("out", c_void_p), ("z_out", c_void_p),
         ("mean", c_void_p), ("rstd", c_void_p), ("s_out", c_void_p), ("u_out", c_void_p),
         ("M", c_int64), ("H", c_int64), ("r", c_int64), ("act", c_int32), ("tail", c_int32), ("eps", c_float),
-        ("lds", c_int64),
+        ("lds", c_int64), ("impl", c_int32),
     ]
 
 

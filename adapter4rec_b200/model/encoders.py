@@ -52,27 +52,34 @@ class Text_Encoder(nn.Module):
 
 
 class Bert_Encoder(nn.Module):
-    """encoders.py:60-99 (only news_attributes = ['title'] is functional in the reference)."""
+    """Item text encoder of the reference (encoders.py:60-99).  An item row is the concatenation of one [ids | mask] block
+    per selected text field, in the fixed field order title, abstract, body; every selected field is encoded by the ONE
+    Text_Encoder registered as `text_encoders.title` (the reference never builds the other two — SURVEY.md Appendix B-9 —
+    and its state_dict keys depend on that) and several fields are averaged.  The hot path has exactly one field."""
+
+    FIELDS = ("title", "abstract", "body")
 
     def __init__(self, args, bert_model):
         super().__init__()
+        if not args.news_attributes:
+            raise AssertionError("news_attributes must name at least one text field")
         self.args = args
-        self.attributes2length = {'title': args.num_words_title * 2, 'abstract': args.num_words_abstract * 2,
-                                  'body': args.num_words_body * 2}
-        for key in list(self.attributes2length.keys()):
-            if key not in args.news_attributes:
-                self.attributes2length[key] = 0
-        self.attributes2start = {
-            key: sum(list(self.attributes2length.values())[:list(self.attributes2length.keys()).index(key)])
-            for key in self.attributes2length.keys()}
-        assert len(args.news_attributes) > 0
-        self.text_encoders = nn.ModuleDict({'title': Text_Encoder(bert_model, args.embedding_dim, args.word_embedding_dim)})
-        self.newsname = [name for name in set(args.news_attributes) & {'title', 'abstract', 'body'}]
+        widths = {"title": args.num_words_title, "abstract": args.num_words_abstract, "body": args.num_words_body}
+        # column span of each field inside an item row; an unselected field occupies no columns
+        self.attributes2length, self.attributes2start, column = {}, {}, 0
+        for field in self.FIELDS:
+            self.attributes2start[field] = column
+            self.attributes2length[field] = 2 * widths[field] if field in args.news_attributes else 0
+            column += self.attributes2length[field]
+        self.newsname = [field for field in self.FIELDS if field in args.news_attributes]
+        self.text_encoders = nn.ModuleDict({"title": Text_Encoder(bert_model, args.embedding_dim, args.word_embedding_dim)})
 
     def forward(self, news):
-        text_vectors = [
-            self.text_encoders['title'](torch.narrow(news, 1, self.attributes2start[name], self.attributes2length[name]))
-            for name in self.newsname]
-        if len(text_vectors) == 1:
-            return text_vectors[0]
-        return torch.mean(torch.stack(text_vectors, dim=1), dim=1)
+        encoder = self.text_encoders["title"]
+        if len(self.newsname) == 1:          # the hot path: the row IS the field, no slicing copy
+            field = self.newsname[0]
+            lo, n = self.attributes2start[field], self.attributes2length[field]
+            return encoder(news if (lo == 0 and n == news.shape[1]) else news[:, lo:lo + n])
+        vectors = [encoder(news[:, self.attributes2start[f]:self.attributes2start[f] + self.attributes2length[f]])
+                   for f in self.newsname]
+        return torch.stack(vectors, dim=1).float().mean(dim=1).to(vectors[0].dtype)

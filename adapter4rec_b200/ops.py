@@ -393,7 +393,8 @@ def adapter_ln_supported(H, r):
     return bool(_l.get_lib().a4r_adapter_ln_supported(int(H), int(r)))
 
 
-def adapter_ln_fwd(h, inp, w_down, b_down, w_up, b_up, gamma=None, beta=None, eps=0.0, act="relu", tail=0, save=False):
+def adapter_ln_fwd(h, inp, w_down, b_down, w_up, b_up, gamma=None, beta=None, eps=0.0, act="relu", tail=0, save=False,
+                   impl=0):
     """K5 in one kernel: out = tail(h + W_u act(W_d h + b_d) + b_u [+ inp]); tail 0 = LayerNorm, 1 = +inp, 2 = nothing.
     returns (out, z, mean, rstd, s, u): with save=True the tensors the backward reads (z/mean/rstd for tail 0, s always,
     u = pre-activation for GELU), else None.  s is a [M, r] VIEW of a [M, r + 16] buffer (32-byte aligned rows) whose column r holds ones
@@ -426,6 +427,7 @@ def adapter_ln_fwd(h, inp, w_down, b_down, w_up, b_up, gamma=None, beta=None, ep
                                                                          _p(rstd), _p(s), _p(u))
     a.M, a.H, a.r, a.act, a.tail, a.eps = M, H, r, {"relu": 0, "gelu": 1}[act], int(tail), float(eps)
     a.lds = 0 if s is None else s.stride(0)
+    a.impl = int(impl)       # 0 = default, 2 = staged kernel, 3 = row-per-thread kernel (include/adapter4rec.h)
     _l.check(_l.get_lib().a4r_adapter_ln_fwd(ctypes.byref(a), _stream()), "a4r_adapter_ln_fwd")
     return out, z, mean, rstd, s, u
 

@@ -7,13 +7,16 @@ The reference's TSV readers / tokeniser (data_utils/preprocess.py) are host-side
 caller hands in the arrays they produce — `item_content` [I+1, 2L] int (ids | mask rows), `users_train` {uid: [item
 ids]}, and the eval dictionaries — via `data`.  `synthetic_data` builds such arrays for smoke runs."""
 import logging
+import os
 import random
+import re
 import types
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import functional as Fn
 from . import surgery
 from .data_utils.dataset import BuildTrainDataset
 from .data_utils.metrics import eval_model, get_item_embeddings
@@ -26,6 +29,7 @@ def setup_seed(seed):      # run.py:673-678
     torch.cuda.manual_seed_all(seed)
     np.random.seed(seed)
     random.seed(seed)
+    Fn.DropoutState.manual_seed(seed)     # the counter-RNG behind every dropout kernel of this package
 
 
 def build_train_batch(users, u2seq, item_content, item_num, max_seq_len):
@@ -67,24 +71,84 @@ def synthetic_data(item_num=2000, users=256, num_words=30, max_seq_len=20, vocab
     return d
 
 
+# run.py:302-317: hidden width and the named_parameters() indices of the pooler, by body size
+_BODY_SIZES = (("tiny", 128, (37, 38)), ("mini", 256, (69, 70)), ("medium", 512, (133, 134)), ("base", 768, (197, 198)),
+               ("large", 1024, (389, 390)))
+
+
+def freeze_bert_prefix(bert_model, args):
+    """run.py:302-320: sets args.word_embedding_dim from the body's name and freezes every BERT parameter whose
+    named_parameters() index is below --freeze_paras_before (default 165: everything up to and including encoder layer 9
+    of a base body), plus the pooler.  Runs BEFORE the Model is built, exactly as the reference does, so with
+    --fine_tune_to all only the tail of the body (and everything outside it) trains."""
+    pooler_para = ()
+    for tag, width, pooler in _BODY_SIZES:
+        if tag in args.bert_model_load:
+            pooler_para, args.word_embedding_dim = pooler, width
+    for index, (_, param) in enumerate(bert_model.named_parameters()):
+        if index < getattr(args, "freeze_paras_before", 0) or index in pooler_para:
+            param.requires_grad = False
+
+
+def _checkpoint_path(directory, name):
+    """data_utils/utils.py get_checkpoint: the file must exist"""
+    path = os.path.join(directory, name)
+    if not os.path.exists(path):
+        raise FileNotFoundError("checkpoint %s not found" % path)
+    return path
+
+
 def build_model(args, item_num, local_rank, bert_config=None, bert_state_dict=None):
-    """run.py:286-503 without the DDP wrap (the trainer owns the gradient all-reduce)."""
+    """run.py:286-503 without the DDP wrap (the trainer owns the gradient all-reduce): body -> prefix/pooler freeze ->
+    Model / ModelCPC -> fine_tune_to freeze -> --pretrained_model_name checkpoint (BEFORE the surgery, run.py:374-381) ->
+    adapter insertion -> LayerNorm unfreeze."""
     cfg = bert_config if bert_config is not None else TextConfigLite()
     roberta = 'roberta' in args.bert_model_load
     bert_model = (RobertaModel if roberta else BertModel)(cfg)
     if bert_state_dict is not None:
         bert_model.load_state_dict(bert_state_dict, strict=False)
+    freeze_bert_prefix(bert_model, args)
+    if args.word_embedding_dim != cfg.hidden_size:
+        raise ValueError("bert_model_load %r implies hidden width %d, the body has %d"
+                         % (args.bert_model_load, args.word_embedding_dim, cfg.hidden_size))
     model = (ModelCPC if "cpc" in args.arch else Model)(args, item_num, True, bert_model).to(local_rank)
     if 'None' in args.fine_tune_to:
         surgery.freeze_all(model)
     elif 'all' not in args.fine_tune_to:
         raise AssertionError("fine_tune_to should be defined properly")
+    if 'None' not in getattr(args, "pretrained_model_name", "None"):
+        ckpt = torch.load(_checkpoint_path(args.pretrained_model_dir, "%s.pt" % args.pretrained_model_name),
+                          map_location="cpu", weights_only=False)
+        model.load_state_dict(ckpt['model_state_dict'])
     model = surgery.insert_adapters(model, args)
     surgery.unfreeze_layernorm(model, args)
     return model
 
 
-def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, users_per_pass=128):
+def rank_shard(users, rank, world):
+    """torch.utils.data.DistributedSampler's split (run.py:347): the list is padded to a multiple of the world size by
+    wrapping around, then dealt round-robin — every rank gets ceil(len / world) users and therefore takes the SAME number
+    of optimizer steps (each step holds one all-reduce, so unequal step counts would hang or mis-pair collectives)."""
+    per = (len(users) + world - 1) // world
+    padded = list(users)
+    while len(padded) < per * world:
+        padded += users[:per * world - len(padded)]
+    return padded[rank:per * world:world]
+
+
+def save_model(now_epoch, model, model_dir, trainer, Log_file):
+    """data_utils/utils.py:109-115: epoch-{n}.pt with the model state dict (reference key names), the optimizer state and
+    the RNG states (torch, CUDA, and this package's dropout counter)."""
+    os.makedirs(model_dir, exist_ok=True)
+    ckpt_path = os.path.join(model_dir, 'epoch-%d.pt' % now_epoch)
+    torch.save({'model_state_dict': model.state_dict(), 'optimizer': trainer.state_dict(),
+                'rng_state': torch.get_rng_state(),
+                'cuda_rng_state': torch.cuda.get_rng_state() if torch.cuda.is_available() else None}, ckpt_path)
+    Log_file.info("Model saved to %s" % ckpt_path)
+    return ckpt_path
+
+
+def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, users_per_pass=128, model_dir=None):
     Log_file = Log_file or logging.getLogger("adapter4rec_b200")
     model = build_model(args, data.item_num, local_rank, bert_config)
     trainer = FlatAdamTrainer(model, args.lr, args.fine_tune_lr, args.adapter_bert_lr, args.adapter_sasrec_lr,
@@ -92,14 +156,26 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
     Log_file.info("##### trainable_num {} #####".format(trainer.num_trainable))
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
+    start_epoch = 0
+    if 'None' not in getattr(args, "load_ckpt_name", "None"):          # run.py:481-493: resume
+        if model_dir is None:
+            raise ValueError("--load_ckpt_name needs the model_dir the checkpoint lives in")
+        ckpt = torch.load(_checkpoint_path(model_dir, args.load_ckpt_name), map_location="cpu", weights_only=False)
+        model.load_state_dict(ckpt['model_state_dict'])
+        trainer.load_state_dict(ckpt['optimizer'])
+        start_epoch = int(re.split(r'[._-]', args.load_ckpt_name)[1])
+        torch.set_rng_state(ckpt['rng_state'])
+        if ckpt.get('cuda_rng_state') is not None and torch.cuda.is_available():
+            torch.cuda.set_rng_state(ckpt['cuda_rng_state'])
     users = sorted(data.users_train.keys())
     train_ds = BuildTrainDataset(data.users_train, data.item_content, data.item_num, args.max_seq_len, True,
                                  device=next(model.parameters()).device, seed=123456 + rank)   # run.py:686 seed; per-rank stream
     max_hit10 = 0.0
     for ep in range(args.epoch):
+        now_epoch = start_epoch + ep + 1
         model.train()
-        random.Random(ep).shuffle(users)
-        mine = users[rank::world]                                   # DistributedSampler's round-robin split
+        random.Random(now_epoch - 1).shuffle(users)                 # sampler.set_epoch(now_epoch), run.py:576
+        mine = rank_shard(users, rank, world)
         loss_sum, batches = 0.0, 0
         for b0 in range(0, len(mine), args.batch_size):
             # negatives + token-row gather on the device (only the user indices cross PCIe); the host restatement
@@ -109,9 +185,12 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
             loss_sum, batches = loss_sum + float(loss), batches + 1
             if loss != loss:                                        # NaN guard of run.py:602-604
                 raise FloatingPointError("loss is NaN")
-        Log_file.info('epoch {} mean batch loss: {:.5f}'.format(ep + 1, loss_sum / max(1, batches)))
+        Log_file.info('epoch {} mean batch loss: {:.5f}'.format(now_epoch, loss_sum / max(1, batches)))
         hit10 = run_eval(model, data, args, Log_file, "valid", local_rank)
-        max_hit10 = max(max_hit10, hit10)
+        if hit10 > max_hit10 or max_hit10 == 0:                     # run.py:620-626: test + checkpoint on improvement
+            max_hit10 = hit10
+            if model_dir is not None and rank == 0:
+                save_model(now_epoch, model, model_dir, trainer, Log_file)
     return model, trainer, max_hit10
 
 

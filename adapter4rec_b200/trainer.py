@@ -111,10 +111,16 @@ class FlatAdamTrainer:
         return loss
 
     def state_dict(self):
+        """optimizer state + the dropout RNG position (the reference checkpoints torch's RNG states for the same purpose:
+        a resumed run draws the masks the uninterrupted run would have drawn)"""
         return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "names": list(self.names)}
+                "names": list(self.names), "dropout_seed": Fn.DropoutState.seed, "dropout_counter": Fn.DropoutState.counter}
 
     def load_state_dict(self, sd):
+        if [tuple(x) for x in sd["names"]] != [tuple(x) for x in self.names]:
+            raise ValueError("optimizer state was saved for a different set of trainable parameters")
         self.step_count = sd["step"]
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        if "dropout_seed" in sd:
+            Fn.DropoutState.seed, Fn.DropoutState.counter = int(sd["dropout_seed"]), int(sd["dropout_counter"])

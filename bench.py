@@ -154,6 +154,18 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs run on rank 0 alone (the other ranks idle), so they
+    take every core this process may run on.  Returns the thread count actually in use."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def oracle_step_factory(model_sd, users, seed=7):
     """One adapter-tuning step of the reference's arithmetic on the CPU (oracle port, fp32, torch CPU threads):
     forward + backward + torch.optim.Adam over `users` users of the same workload."""
@@ -181,6 +193,68 @@ def oracle_step_factory(model_sd, users, seed=7):
     return step
 
 
+def cpu_eval_legs(model_sd, cores):
+    """BASELINE.md §3 items 2-3 on the host cores (oracle port, fp32): the item-table encode over 512 catalogue rows, the
+    reference evaluator's arithmetic (eval_model, metrics.py:82-116) at I = 100,000 / D = 64 / 256 users, and a clearly
+    labelled RESTATEMENT for the C5 shape (chunked matmul + topk, I = 1 M, d = 768, 256 users; the reference evaluator
+    itself cannot run C5: 80 MB of float64 labels per user, dataset.py:73-74)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import transrec_oracle as O
+    cfg = O.TextConfig(hidden=768, layers=12, heads=12, eps=1e-12)
+    rec = O.RecConfig(max_seq_len=S, embedding_dim=D, heads=2, blocks=2, num_words_title=L)
+    sd = {k: v.detach().float().cpu() for k, v in model_sd.items()}
+    out = {}
+    gen = torch.Generator().manual_seed(31)
+    cat = synth_catalogue(gen)[:512]
+    with torch.no_grad():
+        t0 = time.time()
+        O.item_embeddings(cat, sd, cfg, rec, batch=512)
+        dt = time.time() - t0
+    out["item_encode"] = {"value": 512 / dt, "unit": "items/s", "cores": cores, "kind": "port",
+                          "sample": "512 catalogue rows x %d tokens, BERT-base + LoRA forward, fp32, %.1f s" % (L, dt)}
+    I, U = 100_000, 4096
+    emb = torch.randn((I + 1, D), generator=gen) * 0.3
+    seqs = [torch.randint(1, I + 1, (S + 1,), generator=gen).tolist() for _ in range(U)]
+    hist = [q[:-1] for q in seqs]
+    t0 = time.time()
+    hit, _ = O.eval_model(seqs, hist, emb, sd, rec)
+    dt = time.time() - t0
+    out["eval_model_d64"] = {"value": U / dt, "unit": "users/s", "cores": cores, "kind": "port",
+                             "sample": "%d users against %d items, D=%d: SASRec user encoder + score row + history mask + rank "
+                                       "of the target per user (rank = 1 + #{s_j > s_t}; the reference argsorts every row: 58 users/s on "
+                                       "8 cores, BASELINE.md §2), fp32, %.1f s" % (U, I, D, dt)}
+    I5, d5, U5, chunk = 1_000_000, 768, 1024, 65536
+    table = torch.empty((I5 + 1, d5), dtype=torch.bfloat16)
+    for i in range(0, I5 + 1, chunk):
+        j = min(I5 + 1, i + chunk)
+        table[i:j] = (torch.randn((j - i, d5), generator=gen) * d5 ** -0.5).to(torch.bfloat16)
+    users = torch.randn((U5, d5), generator=gen).to(torch.bfloat16).float()
+    h5 = torch.randint(1, I5 + 1, (U5, S), generator=gen)
+    t0 = time.time()
+    best_s = torch.full((U5, 10), -float("inf"))
+    best_i = torch.zeros((U5, 10), dtype=torch.long)
+    for i in range(0, I5 + 1, chunk):
+        j = min(I5 + 1, i + chunk)
+        sc = users @ table[i:j].float().t()
+        inside = (h5 >= i) & (h5 < j)
+        rows = torch.arange(U5).unsqueeze(1).expand_as(h5)[inside]
+        sc[rows, (h5 - i)[inside]] = -float("inf")
+        if i == 0:
+            sc[:, 0] = -float("inf")
+        cs, ci = torch.topk(sc, 10, dim=1)
+        ms, mi = torch.topk(torch.cat([best_s, cs], 1), 10, dim=1)
+        best_i = torch.gather(torch.cat([best_i, ci + i], 1), 1, mi)
+        best_s = ms
+    dt = time.time() - t0
+    out["c5_restatement"] = {"value": U5 / dt, "unit": "users/s", "cores": cores, "kind": "port",
+                             "sample": "RESTATEMENT (chunked torch.matmul + torch.topk, history masked, id 0 dropped): %d users x "
+                                       "%d items x d=%d, bf16 table -> fp32, %.1f s; C5 (10 M items) is 10x the items per user"
+                                       % (U5, I5, d5, dt),
+                             "extrapolated_c5_users_per_s": U5 / dt / 10.0}
+    return out
+
+
 def reference_sd():
     """Random-init C2 model on the CPU, only to obtain a state dict with the reference's key names for the oracle."""
     import torch
@@ -201,6 +275,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = use_all_host_threads()
     a.cpu_users = a.cpu_users or 16
     step = oracle_step_factory(reference_sd(), a.cpu_users)
     for _ in range(min(a.warmup, 1)):
@@ -219,7 +294,7 @@ def run_reference(a):
         "config": {"workload": "C2: SASRec(D=64,2 blocks)+BERT-base, LoRA r=8 on q/v, S=20, 30 tokens, bf16",
                    "users_per_gpu_per_step": 512, "sample": "bounded CPU sample of the same workload: %d users per step, fp32"
                    % a.cpu_users},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -616,18 +691,25 @@ def main():
     algo_flops_step = 2 * FLOP_FWD_PER_TOKEN * tokens            # forward + data-gradient backward (frozen backbone)
     achieved_all = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    # the dominant kernel = the GEMM shape with the largest share of the timed region
-    dom_shape, dom = max(gemm_groups.items(), key=lambda kv: kv[1][1])
-    achieved = dom[0] / (dom[1] / 1e3) / 1e12
+    # the dominant kernel = gemm_tn_kernel over ALL its launches of the timed region (every shape and epilogue: the
+    # kernel with the largest share of the step); the per-shape table sits beside it in `by_shape`
+    achieved = achieved_all
     epi_names = {0: "linear", 1: "gelu(+pre-activation out)", 2: "relu", 3: "gelu' (dgrad)", 4: "relu' (dgrad)"}
-    # DRAM traffic per launch of that shape from the committed `ncu --set full` capture (profiles/), if it has one
+    # DRAM traffic per launch: launch-weighted mean over the shapes of the committed `ncu --set full` captures (profiles/)
     traffic = None
     try:
-        for rec in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_gemm_traffic.json"))):
-            # the capture was taken at M = 161,280 rows (one 128-user pass); operand A, C and the residual are all linear in
-            # M (the weight operand is L2-resident), so a launch with more rows is scaled by the row ratio
-            if tuple(rec["shape"][1:]) == tuple(dom_shape[1:]):
-                traffic = rec["dram_bytes_per_launch"] * (dom_shape[0] / float(rec["shape"][0]))
+        recs = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_gemm_traffic.json")))
+        tot_b, tot_n = 0.0, 0
+        for shape, g in gemm_groups.items():
+            for rec in recs:
+                # captures were taken at a smaller row count; A, C and the streamed epilogue operands are linear in M (the
+                # weight operand is L2-resident), so a launch with more rows is scaled by the row ratio
+                if tuple(rec["shape"][1:]) == tuple(shape[1:4]):
+                    tot_b += rec["dram_bytes_per_launch"] * (shape[0] / float(rec["shape"][0])) * g[2]
+                    tot_n += g[2]
+                    break
+        if tot_n >= 0.9 * gemm_calls:
+            traffic = tot_b / tot_n
     except Exception:
         pass
     out = {
@@ -650,10 +732,10 @@ def main():
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "kernel": "gemm_tn_kernel (tcgen05 cta_group::2 + TMA), shape M=%d N=%d K=%d epilogue=%s: %d launches, "
-                               "%.1f%% of the timed region; algorithmic FLOPs per launch = 2*M*N*K = %.4g"
-                               % (dom_shape[0], dom_shape[1], dom_shape[2], epi_names.get(dom_shape[3], "?"), dom[2],
-                                  100.0 * dom[1] / ms, dom[0] / dom[2]),
+                     "kernel": "gemm_tn_kernel (tcgen05 cta_group::2 + TMA), all %d launches of the timed region (every shape "
+                               "and epilogue): %.1f%% of the step; algorithmic FLOPs = sum of 2*M*N*(K+K2) = %.4g per launch "
+                               "on average; per-shape figures in by_shape"
+                               % (gemm_calls, 100.0 * gemm_ms / ms, gemm_flops / max(1, gemm_calls)),
                      "peak_source": pk_kind + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "all_gemm_launches": {"achieved": achieved_all, "frac": achieved_all / peak if peak else None,
                                            "launches": gemm_calls, "share_of_step": gemm_ms / ms},
@@ -668,16 +750,20 @@ def main():
         out["eval"] = eval_out
     if variants:
         out["variants"] = variants
-    if not a.no_cpu_baseline:
-        import torch as _t
+    if not a.no_cpu_baseline and world == 1:
+        # rank 0 at N = 1 only (the contract): a bounded sample of the same workload on every host core
+        cores = use_all_host_threads()
         a.cpu_users = a.cpu_users or 48
-        step = oracle_step_factory({k: v for k, v in model.state_dict().items()}, a.cpu_users)
+        msd = {k: v for k, v in model.state_dict().items()}
+        step = oracle_step_factory(msd, a.cpu_users)
         t0 = time.time()
         step()
         dt = time.time() - t0
-        out["cpu_baseline"] = {"value": a.cpu_users / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+        out["cpu_baseline"] = {"value": a.cpu_users / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": "1 step over %d users (= %d sequences x %d tokens), fp32 oracle port, %.1f s"
                                          % (a.cpu_users, a.cpu_users * 42, L, dt)}
+        if not a.no_eval:
+            out["cpu_baseline"]["eval_half"] = cpu_eval_legs(msd, cores)
     emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -208,6 +208,9 @@ A4R_API int a4r_layernorm_bwd_add(const void* dy, const void* z, const float* me
  * [r, r + 8) of every row, so that ONE weight-gradient GEMM dzᵀ·[s | 1] yields d(fc_up.weight) and d(fc_up.bias) together.
  * Shapes: H %% 64 == 0, H <= 768, r %% 8 == 0, r <= 64 (a4r_adapter_ln_supported); other shapes compose
  * a4r_gemm_bf16_tn + a4r_layernorm_fwd.
+ * impl selects the kernel formulation explicitly (no environment variables, no process state): 0 = default (the
+ * row-per-thread TMA kernel where the shape allows it, else the staged kernel), 2 = staged kernel, 3 = row-per-thread kernel
+ * (A4R_EINVAL if the shape is outside a4r_adapter_rows_supported).  Both formulations produce the same tensors.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct a4r_adapter_args {
   const void* h;
@@ -231,6 +234,7 @@ typedef struct a4r_adapter_args {
   int32_t tail;
   float eps;
   int64_t lds;
+  int32_t impl;
 } a4r_adapter_args;
 A4R_API int a4r_adapter_ln_supported(int64_t H, int64_t r);
 A4R_API int a4r_adapter_ln_fwd(const a4r_adapter_args* args, a4r_stream_t stream);

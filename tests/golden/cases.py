@@ -59,9 +59,13 @@ def full_case(kind):
     c = tiny_case(kind)
     c.hidden, c.layers, c.heads, c.inter = 768, 12, 12, 3072
     c.vocab, c.max_pos = 30522, 512
+    if c.roberta:              # RoBERTa-base (BASELINE.json configs[3], "C4"): vocabulary 50,265, 514 positions
+        c.vocab, c.max_pos = 50265, 514
     c.L, c.S, c.D = 30, 20, 64
     c.bert_r = 8 if kind == "lora" else 64
     c.rec_r = 8 if kind == "lora" else 16
+    if kind == "prompt_cpc":
+        c.n_tokens = 10        # SoftEmbedding with n_tokens = 10
     c.B, c.item_num = 2, 60
     c.seed += 100
     return c

@@ -40,6 +40,22 @@ def tiny_cv_case(kind):
     return c
 
 
+def full_cv_case(kind):
+    """The same generators at the REAL sizes of BASELINE.json configs[2] ("C3"): ViT-B/16-224 (768 / 12 layers / 12 heads /
+    3072, 196 patches + cls = 197 tokens), adapter rank 64 (Downstream/CV/parameters.py), 2 users with max_seq_len 5 =
+    24 images = 4,728 tokens (the oracle's forward + backward stays under a minute and a few GB)."""
+    c = tiny_cv_case(kind)
+    c.hidden, c.heads, c.layers, c.inter = 768, 12, 12, 3072
+    c.image = 224
+    c.P = (c.image // c.patch) ** 2
+    c.S, c.B = 5, 2
+    c.cv_r, c.rec_r = 64, 16
+    if kind == "cv_prompt":
+        c.n_tokens = 10
+    c.seed += 100
+    return c
+
+
 def reference_args(c):
     return types.SimpleNamespace(
         max_seq_len=c.S, min_seq_len=2, l2_weight=0, embedding_dim=c.D, num_attention_heads=c.rec_heads, drop_rate=0.1,

@@ -114,3 +114,53 @@ def test_eval_arrays_host_restatement():
     assert mask.tolist() == [[0, 0, 0, 1, 1], [0, 0, 0, 0, 1], [1, 1, 1, 1, 1]]
     assert tgt.tolist() == [2, 1, 11]
     assert h.tolist() == [[5, 9, 0, 0, 0], [7, 0, 0, 0, 0], [3, 4, 6, 8, 10]]
+
+
+@pytest.mark.parametrize("n_users,world,batch", [(129, 2, 64), (7, 4, 2), (64, 2, 64), (1, 2, 8), (1000, 8, 32)])
+def test_rank_shard_gives_every_rank_the_same_number_of_steps(n_users, world, batch):
+    """run.rank_shard == DistributedSampler's padded round-robin split (Downstream/Text/run.py:347): with 129 users on 2
+    ranks at batch 64 an unpadded split gives 2 and 1 optimizer steps — one unmatched all-reduce; padded, both take 2."""
+    from adapter4rec_b200.run import rank_shard
+    users = list(range(100, 100 + n_users))
+    shards = [rank_shard(users, r, world) for r in range(world)]
+    per = (n_users + world - 1) // world
+    assert all(len(s) == per for s in shards)
+    steps = {(len(s) + batch - 1) // batch for s in shards}
+    assert len(steps) == 1
+    seen = [u for s in shards for u in s]
+    assert set(seen) == set(users) and len(seen) - n_users < world          # everyone covered, < world repeats
+    # identical to torch's sampler on the same (unshuffled) list
+    from torch.utils.data import DistributedSampler
+    for r in range(world):
+        ref = list(DistributedSampler(users, num_replicas=world, rank=r, shuffle=False))
+        assert [users[i] for i in ref] == shards[r]
+
+
+def test_build_model_applies_the_reference_freeze_and_refuses_missing_checkpoints(tmp_path):
+    """run.py:302-320 (prefix + pooler freeze before the Model is built, word_embedding_dim from the body's name) and
+    :374-381 (--pretrained_model_name is loaded before the surgery; a missing file is an error, not a silent skip)."""
+    from adapter4rec_b200 import run
+    from adapter4rec_b200.model import TextConfigLite
+    from adapter4rec_b200.parameters import parse_args
+    cfg = TextConfigLite(vocab_size=100, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                         intermediate_size=256, max_position_embeddings=32)
+    base = ["--embedding_dim", "64", "--bert_model_load", "bert_tiny", "--word_embedding_dim", "999", "--max_seq_len", "5",
+            "--num_words_title", "8", "--adapter_type", "None", "--adding_adapter_to", "None", "--fine_tune_to", "all"]
+    args = parse_args(base + ["--freeze_paras_before", "21", "--pretrained_model_name", "None"])
+    model = run.build_model(args, 50, "cpu", cfg)
+    assert args.word_embedding_dim == 128
+    bert = model.bert_encoder.text_encoders.title.bert_model
+    flags = [p.requires_grad for _, p in bert.named_parameters()]
+    names = [n for n, _ in bert.named_parameters()]
+    assert not any(flags[:21]) and all(f for i, f in enumerate(flags[21:], 21) if i not in (37, 38))
+    assert names[37].startswith("pooler") and names[38].startswith("pooler") and not flags[37] and not flags[38]
+    assert all(p.requires_grad for p in model.user_encoder.parameters())
+    # checkpoint round trip through --pretrained_model_name
+    torch.save({"model_state_dict": model.state_dict()}, tmp_path / "epoch-3.pt")
+    args2 = parse_args(base + ["--pretrained_model_dir", str(tmp_path), "--pretrained_model_name", "epoch-3"])
+    model2 = run.build_model(args2, 50, "cpu", cfg)
+    for (n, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        assert torch.equal(a, b), n
+    args3 = parse_args(base + ["--pretrained_model_dir", str(tmp_path), "--pretrained_model_name", "epoch-15"])
+    with pytest.raises(FileNotFoundError):
+        run.build_model(args3, 50, "cpu", cfg)

@@ -13,49 +13,30 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(HERE, "golden"))
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
 
-import cases  # noqa: E402
-import transrec_oracle as O  # noqa: E402
-from test_model_gpu import build_gpu_model, oracle_setup  # noqa: E402
+import cases  # noqa: E402,F401
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kind,unpad", [("houlsby", False), ("lora", False), ("lora", True)])
+@pytest.mark.parametrize("kind,unpad", [("houlsby", False), ("lora", False), ("lora", True), ("prompt_cpc", False)])
 def test_full_size_step_matches_oracle(kind, unpad):
-    c = cases.full_case(kind)
-    sd = cases.build_state_dict(c)
-    items = cases.build_item_content(c)
-    sample_items, log_mask, _ = cases.build_batch(c, items)
-    rows = sample_items.view(-1, 2 * c.L)
-    cfg, rec = oracle_setup(c)
-    osd = {k: v.clone() for k, v in sd.items()}
-    train = cases.trainable_keys(c, sd)
-    for k in train:
-        osd[k].requires_grad_(True)
-    oloss = O.model_forward(rows, log_mask, osd, cfg, rec)
-    oloss.backward()
-
-    model, _ = build_gpu_model(c, sd)
-    model.eval()
-    model.bert_encoder.text_encoders.title.bert_model.unpad = unpad
-    loss = model(rows.cuda(), log_mask.cuda(), 0)
-    loss.backward()
-    lv, ov = float(loss.detach()), float(oloss.detach())
-    # 12 post-LN layers in bf16: 3e-2 relative on the loss; all trainable gradients concatenated: 8e-2 relative L2
-    assert abs(lv - ov) <= 3e-2 * abs(ov), "loss %.5f vs oracle %.5f" % (lv, ov)
-    params = dict(model.named_parameters())
-    allg = torch.cat([params[k].grad.float().cpu().flatten() for k in train])
-    allo = torch.cat([osd[k].grad.flatten() for k in train])
-    rel = float((allg - allo).norm() / allo.norm())
-    cos = float((allg * allo).sum() / (allg.norm() * allo.norm()))
-    assert rel <= 8e-2 and cos >= 0.995, "gradient rel L2 %.4f cos %.5f" % (rel, cos)
-    with torch.no_grad():
-        emb = model.bert_encoder(items.cuda()).float().cpu()
-        oemb = O.item_embeddings(items, sd, cfg, rec, batch=16)
-    # embeddings reach |x| ~ 3 with these random weights; bf16 activations through 12 post-LN layers: relative L2 of the
-    # whole matrix <= 2e-2 and no element off by more than 0.12 absolute (measured: 7e-3 and 0.07)
-    d = emb[1:] - oemb[1:]
-    rel_e, max_e = float(d.norm() / oemb[1:].norm()), float(d.abs().max())
+    """BERT-base Houlsby / LoRA (C1, C2) and RoBERTa-base + SoftEmbedding(n_tokens = 10) + ModelCPC (C4,
+    Downstream/Text/model/model.py:113-135,586-630)."""
+    import parity_util as P
+    fig, _ = P.text_case(kind, full=True, unpad=unpad)
     print("full-size %s unpad=%s: loss %.5f vs %.5f, grad rel L2 %.4f cos %.5f, emb rel L2 %.4f max abs %.4f"
-          % (kind, unpad, lv, ov, rel, cos, rel_e, max_e))
-    assert rel_e <= 2e-2 and max_e <= 0.12, (rel_e, max_e)
+          % (kind, unpad, fig["loss"], fig["oracle_loss"], fig["grad_all_rel"], fig["grad_all_cos"], fig["emb_rel_l2"],
+             fig["emb_max_abs"]))
+    P.check_against_table(fig, P.measured(), "text_full/%s%s" % (kind, "/unpad" if unpad else ""), True)
+
+
+@pytest.mark.parametrize("kind", ["cv_houlsby"])
+def test_full_size_vit_step_matches_oracle(kind):
+    """ViT-B/16-224 (12 layers, 197 tokens per image, r = 64 Houlsby wrappers on both sub-layer outputs; C3,
+    Downstream/CV/model/model.py:54-77,182-212, encoders.py:31-32): 2 users = 24 images through the mid-length attention
+    kernel, the fused adapter kernel's ViT tails and the patch-projection GEMM."""
+    import parity_util as P
+    fig, _ = P.cv_case(kind, full=True)
+    print("full-size %s: loss %.5f vs %.5f, grad rel L2 %.4f cos %.5f, emb rel L2 %.4f max abs %.4f"
+          % (kind, fig["loss"], fig["oracle_loss"], fig["grad_all_rel"], fig["grad_all_cos"], fig["emb_rel_l2"], fig["emb_max_abs"]))
+    P.check_against_table(fig, P.measured(), "cv_full/" + kind, True)

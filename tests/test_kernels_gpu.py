@@ -405,16 +405,72 @@ def test_layernorm_bwd_add_fuses_the_skip_gradient():
         assert bool((err <= 2e-2 + 8e-3 * ref.abs()).all()), (M, H, float(err.max()))
 
 
-@pytest.mark.parametrize("impl", ["2", "3"])
-def test_adapter_block_both_formulations(impl):
-    """K5 has two kernels behind a4r_adapter_ln_fwd: the row-per-thread TMA kernel (default, adapter_rows_sm100.cu) and the
-    staged one (A4R_K5_IMPL=2, adapter_ln_sm100.cu).  tools/k5_check.py runs every tail x activation x save combination at
-    M = 128 / 1,000 / 20,000 (ragged last tile, several tiles per CTA) against torch; the selection is read once per process,
-    hence the subprocess."""
+def _run_tool(*argv, timeout=600):
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "k5_check.py")], env=dict(os.environ, A4R_K5_IMPL=impl),
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and r.stdout.strip().endswith("ALL OK"), (r.stdout[-800:], r.stderr[-800:])
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", argv[0])] + list(argv[1:]), capture_output=True, text=True,
+                       timeout=timeout)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ALL OK"), (r.stdout[-1500:], r.stderr[-1500:])
+
+
+@pytest.mark.parametrize("impl", ["2", "3"])
+def test_adapter_block_both_formulations(impl):
+    """K5 has two kernels behind a4r_adapter_ln_fwd, selected by the explicit `impl` field of a4r_adapter_args: the
+    row-per-thread TMA kernel (3, the default; adapter_rows_sm100.cu) and the staged one (2; adapter_ln_sm100.cu).
+    tools/k5_check.py runs every tail x activation x save combination at M = 128 / 1,000 / 20,000 (ragged last tile, several
+    tiles per CTA) against torch."""
+    _run_tool("k5_check.py", impl)
+
+
+def test_adapter_block_at_the_benchmarked_row_counts():
+    """K5 (default formulation) at M = 161,280 (8.5 tiles per persistent CTA: C1 at 128 users per pass) and M = 645,120 (+ a
+    ragged 645,197): the multi-tile ring / phase path the benchmark runs, every row against torch fp32, both ViT tails, both
+    activations, save on and off."""
+    _run_tool("k5_check.py", "3", "--big", timeout=900)
+
+
+@pytest.mark.parametrize("M,N,K,K2,epi", [(645120, 768, 3072, 0, "res"), (645120, 3072, 768, 0, "gelu"),
+                                          (645120, 2304, 768, 64, "linear"), (645120, 768, 768, 0, "res"),
+                                          (645120, 768, 3072, 0, "dgelu"), (161280 + 333, 3072, 768, 0, "dgelu")])
+def test_gemm_at_the_benchmarked_row_counts(M, N, K, K2, epi):
+    """The five GEMM shapes of the C2 step at the benchmarked M = 645,120 (one 512-user pass: 2,520 256-row tiles = 34 tiles per
+    CTA pair, byte offsets past 2^31 in A and C), a strided sample of 4,099 rows (stride 157 + the first and last 256 rows)
+    against torch fp32 on the same operands, plus an all-rows finiteness / magnitude check."""
+    ops = _ops()
+    a, b = _rand((M, K), 1.0, 1), _rand((N, K), K ** -0.5, 2)
+    bias = _rand((N,), 0.5, 3, torch.float32)
+    rows = torch.cat([torch.arange(0, 256), torch.arange(256, M - 256, 157), torch.arange(M - 256, M)]).cuda()
+    kw, ref = {}, a[rows].float() @ b.float().t()
+    if K2:
+        a2, b2 = _rand((M, K2), 1.0, 4), _rand((N, K2), 0.1, 5)
+        kw.update(a2=a2, b2=b2)
+        ref = ref + a2[rows].float() @ b2.float().t()
+    if epi in ("res", "linear", "gelu"):
+        kw["bias"] = bias
+        ref = ref + bias
+    if epi == "res":
+        res = _rand((M, N), 1.0, 6)
+        kw["residual"] = res
+        ref = ref + res[rows].float()
+    aux = None
+    if epi == "gelu":
+        aux = torch.empty((M, N), dtype=BF16, device="cuda")
+        kw.update(epilogue=ops.EPI_GELU, aux=aux)
+    if epi == "dgelu":
+        aux = _rand((M, N), 1.5, 7)
+        kw.update(epilogue=ops.EPI_DGELU, aux=aux)
+        uf = aux[rows].float().requires_grad_(True)
+        torch.nn.functional.gelu(uf).sum().backward()
+        ref = ref * uf.grad
+    got = ops.gemm(a, b, **kw)
+    if epi == "gelu":
+        _close(aux[rows], ref, 2 ** -7, 1e-2, "pre-activation at M=%d" % M)
+        ref = torch.nn.functional.gelu(ref)
+    _close(got[rows], ref, 2 ** -6 if epi == "dgelu" else 2 ** -7, 2e-2, "gemm %s at M=%d N=%d K=%d" % (epi, M, N, K))
+    assert bool(torch.isfinite(got).all())
+    # every row block of 8,192 rows must carry the magnitude the sampled rows carry (a skipped or doubled tile would not)
+    blocks = got.float().pow(2).view(-1, N)[: (M // 8192) * 8192].view(-1, 8192 * N).mean(1).sqrt()
+    rms = float(ref.pow(2).mean().sqrt())
+    assert float(blocks.min()) > 0.8 * rms and float(blocks.max()) < 1.25 * rms, (float(blocks.min()), float(blocks.max()), rms)
