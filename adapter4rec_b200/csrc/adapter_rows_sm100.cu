@@ -75,6 +75,21 @@ A4R_DEVICE void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
                : "memory");
 }
 A4R_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Shared-memory loads must have RETURNED before their ring slot is handed back to the TMA producer.  `ld.shared; mbarrier.arrive`
+// only orders the ISSUE of the two: the arrive can reach the barrier while the load still sits in the shared-memory queue behind
+// tensor-core operand reads and TMA traffic, the producer refills the slot, and the load returns the NEXT box's bytes (measured:
+// 1-3 % of the launches at M = 161,280 returned `input` of chunk c + 2 in place of `h` of chunk c for a few rows of one warp).
+// A real instruction that reads one register of each load — and that ptxas may neither drop nor sink below the arrive, because it
+// is a (never-taken) shared-memory store — makes the warp wait for the data first.
+A4R_DEVICE void loads_returned(uint32_t scratch_saddr, uint32_t a, uint32_t b) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+      "xor.b32 t, %1, %2;\n\t"
+      "setp.eq.u32 p, t, 0x9E3779B9;\n\t"
+      "@p st.shared.b32 [%0], t;\n\t}" ::"r"(scratch_saddr),
+      "r"(a), "r"(b)
+      : "memory");
+}
 A4R_DEVICE void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -104,6 +119,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   uint64_t* in_full = u_empty + 2;                // [2][IN_BOXES]
   uint64_t* in_empty = in_full + 2 * IN_BOXES;    // [2][IN_BOXES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + 2 * IN_BOXES);
+  const uint32_t scratch = smem_u32(tmem_slot + 1);   // never-read word: target of the (practically never taken) store above
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.M + BM - 1) / BM;
@@ -346,6 +362,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           mbar_wait(&in_full[grp * IN_BOXES + b], (nb / IN_BOXES) & 1u);
           h0 = lds_v4(sin0 + b * IN_HALF + toff0);
           h1 = lds_v4(sin0 + b * IN_HALF + toff1);
+          loads_returned(scratch, h0.x, h1.x);
           __syncwarp();
           if (lane == 0) mbar_arrive(&in_empty[grp * IN_BOXES + b]);
           __syncwarp();
@@ -356,6 +373,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           mbar_wait(&in_full[grp * IN_BOXES + b], (nb / IN_BOXES) & 1u);
           i0 = lds_v4(sin0 + b * IN_HALF + toff0);
           i1 = lds_v4(sin0 + b * IN_HALF + toff1);
+          loads_returned(scratch, i0.x, i1.x);
           __syncwarp();
           if (lane == 0) mbar_arrive(&in_empty[grp * IN_BOXES + b]);
           __syncwarp();

@@ -26,13 +26,19 @@ def check(M, impl, wd, wu, bd, bu, g, b, tails=(0, 1, 2), acts=("relu", "gelu"),
                 torch.cuda.synchronize()
                 e = es = ez = em = 0.0
                 ones_ok = True
+                detail = []
                 for i in range(0, M, blk):          # torch fp32 reference in row blocks (every row is checked)
                     j = min(M, i + blk)
                     pre = h[i:j].float() @ wd.float().t() + bd
                     sr = torch.relu(pre) if act == "relu" else torch.nn.functional.gelu(pre)
                     zr = h[i:j].float() + sr.to(torch.bfloat16).float() @ wu.float().t() + bu + (inp[i:j].float() if tail != 2 else 0)
                     ref = torch.nn.functional.layer_norm(zr.to(torch.bfloat16).float(), (H,), g, b, 1e-12) if tail == 0 else zr
-                    e = max(e, float((out[i:j].float() - ref).abs().max()))
+                    err = (out[i:j].float() - ref).abs()
+                    e = max(e, float(err.max()))
+                    if float(err.max()) >= 0.08 and len(detail) < 12:      # where: (row, tile, first / last bad column, count)
+                        for rr in (err.max(1).values >= 0.08).nonzero().flatten()[:6].tolist():
+                            cols = (err[rr] >= 0.08).nonzero().flatten()
+                            detail.append((i + rr, (i + rr) // 128, int(cols.min()), int(cols.max()), int(cols.numel())))
                     if save:
                         es = max(es, float((s[i:j].float() - sr).abs().max()))
                         if tail == 0:
@@ -43,7 +49,7 @@ def check(M, impl, wd, wu, bd, bu, g, b, tails=(0, 1, 2), acts=("relu", "gelu"),
                 good = e < 0.08 and es < 0.03 and ez < 0.05 and em < 1e-3 and ones_ok
                 if not good:
                     ok = False
-                    print("BAD  M=%d tail=%d %s save=%d out err %.4f s %.4f z %.4f mean %.5f ones %s" % (M, tail, act, save, e, es, ez, em, ones_ok))
+                    print("BAD  M=%d tail=%d %s save=%d out err %.4f s %.4f z %.4f mean %.5f ones %s %s" % (M, tail, act, save, e, es, ez, em, ones_ok, detail))
     return ok
 
 
