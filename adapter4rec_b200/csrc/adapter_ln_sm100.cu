@@ -500,10 +500,10 @@ extern "C" int a4r_adapter_ln_fwd(const a4r_adapter_args* a, a4r_stream_t stream
   int rc = a4r_device_check();
   if (rc != A4R_OK) return rc;
   if (a->M == 0) return A4R_OK;
-  A4R_CHECK_ARG((a->impl & 255) == 0 || (a->impl & 255) == 2 || (a->impl & 255) == 3, "adapter_ln: impl must be 0 (default), 2 (staged) or 3 (rows)");
-  A4R_CHECK_ARG((a->impl & 255) != 3 || a4r_adapter_rows_supported(a->H, a->r), "adapter_ln: impl 3 does not support H=%lld r=%lld",
+  A4R_CHECK_ARG(a->impl == 0 || a->impl == 2 || a->impl == 3, "adapter_ln: impl must be 0 (default), 2 (staged) or 3 (rows)");
+  A4R_CHECK_ARG(a->impl != 3 || a4r_adapter_rows_supported(a->H, a->r), "adapter_ln: impl 3 does not support H=%lld r=%lld",
                 (long long)a->H, (long long)a->r);
-  if ((a->impl & 255) != 2 && a4r_adapter_rows_supported(a->H, a->r)) return a4r_adapter_rows_launch(a, static_cast<cudaStream_t>(stream_));
+  if (a->impl != 2 && a4r_adapter_rows_supported(a->H, a->r)) return a4r_adapter_rows_launch(a, static_cast<cudaStream_t>(stream_));
 
   AdParams p;
   p.h = static_cast<const __nv_bfloat16*>(a->h);

@@ -8,14 +8,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_train_entry_reduces_loss_and_evaluates():
+def test_train_entry_reduces_loss_and_evaluates(tmp_path):
     from adapter4rec_b200 import run
     from adapter4rec_b200.model import TextConfigLite
     from adapter4rec_b200.parameters import parse_args
     args = parse_args(["--embedding_dim", "64", "--batch_size", "32", "--epoch", "3", "--adapter_type", "houslby",
                        "--adding_adapter_to", "all", "--bert_model_load", "bert_tiny", "--word_embedding_dim", "128",
                        "--bert_adapter_down_size", "16", "--adapter_bert_lr", "5e-3", "--adapter_sasrec_lr", "5e-3",
-                       "--max_seq_len", "10", "--num_words_title", "12", "--drop_rate", "0.0"])
+                       "--max_seq_len", "10", "--num_words_title", "12", "--drop_rate", "0.0",
+                       "--pretrained_model_name", "None"])   # the reference default 'epoch-15' loads a checkpoint (run.py:374-381)
     run.setup_seed(123456)
     data = run.synthetic_data(item_num=300, users=96, num_words=12, max_seq_len=10, vocab=500)
     cfg = TextConfigLite(vocab_size=500, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
@@ -25,8 +26,20 @@ def test_train_entry_reduces_loss_and_evaluates():
     records = []
     log.addHandler(type("H", (logging.Handler,), {"emit": lambda self, r: records.append(r.getMessage())})())
     log.setLevel(logging.INFO)
-    model, trainer, hit10 = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16)
+    model, trainer, hit10 = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16,
+                                      model_dir=str(tmp_path))
     losses = [float(m.split(":")[-1]) for m in records if "mean batch loss" in m]
     assert len(losses) == 3 and losses[-1] < losses[0], losses
     assert 0.0 <= hit10 <= 1.0 and any("valid_results" in m for m in records)
     assert trainer.step_count == 9                                        # 96 users / 32 per batch x 3 epochs
+    # checkpoints in the reference's format (data_utils/utils.py:109-115) and the resume path (--load_ckpt_name, run.py:481-493)
+    import os
+    saved = sorted(f for f in os.listdir(tmp_path) if f.startswith("epoch-"))
+    assert saved, "an improving epoch must have written epoch-N.pt"
+    ckpt = torch.load(os.path.join(tmp_path, saved[-1]), weights_only=False)
+    assert set(ckpt) >= {"model_state_dict", "optimizer", "rng_state", "cuda_rng_state"}
+    assert set(ckpt["model_state_dict"]) == set(model.state_dict())
+    args.load_ckpt_name, args.epoch = saved[-1], 1
+    model2, trainer2, _ = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16, model_dir=str(tmp_path))
+    assert trainer2.step_count == ckpt["optimizer"]["step"] + 3
+    assert any("epoch %d mean batch loss" % (int(saved[-1].split("-")[1].split(".")[0]) + 1) in m for m in records)
