@@ -807,11 +807,14 @@ MidParams mid_params(const a4r_attn_args* a) {
 
 }  // namespace
 
+int a4r_attn_vit_tc_fwd(const a4r_attn_args* a, cudaStream_t stream);   // attention_tc_sm100.cu
+
 extern "C" int a4r_attn_mid_fwd(const a4r_attn_args* a, a4r_stream_t stream) {
   int rc = check_mid(a);
   if (rc != A4R_OK) return rc;
   if (a->N == 0) return A4R_OK;
-  if (a->mask_dtype == 0) {   // ViT: unmasked fast path, two CTAs per SM
+  if (a->mask_dtype == 0) return a4r_attn_vit_tc_fwd(a, static_cast<cudaStream_t>(stream));   // ViT: tcgen05 kernel
+  if (a->mask_dtype == 0) {   // (superseded) mma.sync unmasked path
     const VitParams v = vit_params(a);
     const int vsmem = 3 * v.Lr * 128;
     A4R_CUDA_OK(cudaFuncSetAttribute(attn_vit_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LMAX * 128));
