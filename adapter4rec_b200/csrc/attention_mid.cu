@@ -808,6 +808,7 @@ MidParams mid_params(const a4r_attn_args* a) {
 }  // namespace
 
 int a4r_attn_vit_tc_fwd(const a4r_attn_args* a, cudaStream_t stream);   // attention_tc_sm100.cu
+int a4r_attn_vit_tc_bwd(const a4r_attn_args* a, cudaStream_t stream);   // attention_tc_bwd_sm100.cu
 
 extern "C" int a4r_attn_mid_fwd(const a4r_attn_args* a, a4r_stream_t stream) {
   int rc = check_mid(a);
@@ -844,7 +845,8 @@ extern "C" int a4r_attn_mid_bwd(const a4r_attn_args* a, a4r_stream_t stream) {
   A4R_CHECK_ARG(a->dout != nullptr && a4r_aligned16(a->dout), "attention_mid bwd: dout missing or unaligned");
   A4R_CHECK_ARG(a->lse != nullptr && a->ctx != nullptr, "attention_mid bwd: needs the forward's lse and ctx outputs");
   if (a->N == 0) return A4R_OK;
-  if (a->mask_dtype == 0) {
+  if (a->mask_dtype == 0) return a4r_attn_vit_tc_bwd(a, static_cast<cudaStream_t>(stream));   // ViT: tcgen05 kernel
+  if (a->mask_dtype == 0) {   // (superseded) mma.sync unmasked path
     const VitParams v = vit_params(a);
     const int vsmem = 4 * v.Lr * 128;
     A4R_CUDA_OK(cudaFuncSetAttribute(attn_vit_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * LMAX * 128));

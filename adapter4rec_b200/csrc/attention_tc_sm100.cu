@@ -20,13 +20,10 @@
 //               (The row is consumed in 64-column register blocks, the next block in flight while the current one is exponentiated.)
 // The per-row log-sum-exp (natural log, scaled-score domain) is stored for the backward pass.
 // Tensor-memory map (512 columns): tile t owns [256 t, 256 t + 256): S = [0, Lk) fp32, P = [0, Lk/2) packed bf16, O = [128, 192).
-#include "a4r_common.cuh"
+#include "attn_tc_common.cuh"
 
 namespace {
 
-constexpr int DH = 64;
-constexpr int QT = 128;                  // query rows per tile
-constexpr int BOX = 16384;               // one [128 x 64] bf16 TMA box
 constexpr int STAGE = 6 * BOX;           // Q (2 boxes) | K (2) | V (2)
 constexpr int NSTAGE = 2;
 constexpr int THREADS = 384;
@@ -43,65 +40,6 @@ struct TcParams {
   int act[2];                            // active softmax warps per query tile
   float scale, c;                        // c = scale * log2(e)
 };
-
-A4R_DEVICE void tma_load_3d(const CUtensorMap* m, void* smem_dst, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 16 bf16 (8 packed columns per k-step)
-A4R_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// MN-major SW128 operand (a [rows = k][64 = mn] bf16 TMA box): 8 k-rows per 1,024-byte atom, one 64-wide mn chunk
-A4R_DEVICE uint64_t umma_desc_mn_sw128_1chunk(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(BOX >> 4) << 16;                   // LBO (next mn chunk): unused with N = 64
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // SBO: next group of 8 k-rows
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-A4R_DEVICE void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-A4R_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// 32 lanes x 64 consecutive fp32 columns in ONE instruction (a whole register block)
-A4R_DEVICE void tmem_ld64(uint32_t taddr, float* r) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(r);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
-      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]),
-        "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]),
-        "=r"(u[30]), "=r"(u[31]), "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]), "=r"(u[37]), "=r"(u[38]), "=r"(u[39]),
-        "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]), "=r"(u[46]), "=r"(u[47]), "=r"(u[48]), "=r"(u[49]),
-        "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]), "=r"(u[55]), "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]),
-        "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
-      : "r"(taddr)
-      : "memory");
-}
-A4R_DEVICE void tmem_ld16(uint32_t taddr, float* r) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(r);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-      : "r"(taddr)
-      : "memory");
-}
 
 #ifdef A4R_ATTN_TIMING
 __device__ long long g_attn_timing[2][8];
@@ -247,7 +185,7 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
     if (warp_on) {
       int it = 0;
 #ifdef A4R_ATTN_TIMING
-      long long acc_t[6] = {0, 0, 0, 0, 0, 0}, sub_t[3] = {0, 0, 0};
+      long long acc_t[6] = {0, 0, 0, 0, 0, 0};
 #endif
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
         const uint32_t tp = static_cast<uint32_t>(it) & 1u;
@@ -343,16 +281,9 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
         tmem_ld_wait();
         TSTAMP(ts2);
         for (int blk = 0; blk < nblk; blk += 2) {
-          TSTAMP(tb0);
           if (blk + 1 < nblk) load_block(blk + 1, sB);
-          TSTAMP(tb1);
           process(blk, sA);
-          TSTAMP(tb2);
           tmem_ld_wait();
-          TSTAMP(tb3);
-#ifdef A4R_ATTN_TIMING
-          sub_t[0] += tb1 - tb0; sub_t[1] += tb2 - tb1; sub_t[2] += tb3 - tb2;
-#endif
           if (blk + 1 < nblk) {
             if (blk + 2 < nblk) load_block(blk + 2, sA);
             process(blk + 1, sB);
@@ -401,7 +332,6 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
       if (blockIdx.x == 0 && lane == 0 && quad == 0) {
         for (int i = 0; i < 6; ++i) g_attn_timing[t][i] = acc_t[i];
         g_attn_timing[t][6] = it;
-        if (t == 0) for (int i = 0; i < 3; ++i) g_attn_timing[1][3 + i] = sub_t[i];   // (tile 1 slots 3..5 reused: sub-phases of tile 0)
       }
 #endif
     }
@@ -410,31 +340,6 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// [N images][L tokens][cols] bf16 view of a row-major [N*L, ld] activation: box = 64 columns x 128 tokens of ONE image, tokens
-// past L read as zeros (they belong to the next image in memory)
-int make_tmap_tokens(CUtensorMap* m, const void* base, int64_t N, int64_t L, int64_t cols, int64_t ld) {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  }
-  if (fn == nullptr) return a4r_set_error(A4R_ECUDA, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(N)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(L) * static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[3] = {64u, 128u, 1u};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return a4r_set_error(A4R_ECUDA, "cuTensorMapEncodeTiled (token view) failed (%d)", (int)r);
-  return A4R_OK;
 }
 
 }  // namespace

@@ -431,6 +431,14 @@ def test_adapter_block_at_the_benchmarked_row_counts():
     _run_tool("k5_check.py", "3", "--big", timeout=900)
 
 
+def test_vit_attention_tcgen05_forward_and_backward():
+    """attention_tc_sm100.cu / attention_tc_bwd_sm100.cu (a4r_attn_mid_fwd / _bwd, unmasked): L = 33 ... 256 incl. every tile
+    boundary (112 / 113 / 128 / 129), 197 and 207 at several batch sizes, inputs 6x larger (scores of +-100 nats), and rows
+    whose maximum sits 116 nats ahead in a LATER register block (the lazily raised softmax shift) — context, log-sum-exp and
+    dq | dk | dv against fp64 torch."""
+    _run_tool("attn_tc_check.py", "--bwd", timeout=600)
+
+
 def test_adapter_block_repeated_launches_are_bit_identical_and_correct():
     """900 launches of the default K5 kernel at M = 161,280 (300 per tail), each compared element-wise with one torch fp32
     reference and bit-wise with the first launch: the epilogue / TMA-refill race fixed in round 2 corrupted a few rows in 1-3 % of
