@@ -48,6 +48,10 @@ class ItemTable:
         return out
 
 
+def to_bf16_2d(x):
+    return x.to(BF16).reshape(x.shape[0], -1)
+
+
 def core_model(model):
     """The object that owns `bert_encoder` / `user_encoder`: strips DDP's `.module` and CompacterModel's `.model`
     (metrics.py:72-73,101-102 reach through `model.module.model` when 'compacter' is in args.adapter_type)."""
@@ -80,14 +84,17 @@ def get_item_embeddings(model, item_content, test_batch_size, args, use_modal, l
     module = core_model(model)
     module.eval()
     rank, world = _dist_info()
-    rows = torch.as_tensor(np.asarray(item_content) if not torch.is_tensor(item_content) else item_content).long()
+    rows = torch.as_tensor(np.asarray(item_content) if not torch.is_tensor(item_content) else item_content)
+    image_tree = hasattr(module, "cv_encoder")       # Downstream/CV: item_content = images [I+1, 3, R, R] float32
+    rows = rows.float() if image_tree else rows.long()
+    encoder = module.cv_encoder if image_tree else module.bert_encoder
     lo, hi = shard_range(rows.shape[0], rank, world)
     dev = next(module.parameters()).device
     outs = []
     with torch.no_grad():
         for i in range(lo, hi, test_batch_size):
             ids = rows[i:min(hi, i + test_batch_size)].to(dev, non_blocking=True)
-            outs.append(module.bert_encoder(ids))
+            outs.append(to_bf16_2d(encoder(ids)))
     emb = torch.cat(outs, 0) if outs else torch.zeros((0, args.embedding_dim), dtype=BF16, device=dev)
     return ItemTable(emb, lo, rows.shape[0], rank, world)
 

@@ -31,13 +31,13 @@ class FlatAdamTrainer:
     kernel launch per learning-rate group."""
 
     def __init__(self, model, lr, fine_tune_lr, adapter_bert_lr, adapter_sasrec_lr, betas=(0.9, 0.999), eps=1e-8,
-                 weight_decay=0.0, users_per_pass=128, process_group=None):
+                 weight_decay=0.0, users_per_pass=128, process_group=None, grouping=None):
         self.model = model
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.users_per_pass = users_per_pass
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        groups = group_parameters(model)
+        groups = (grouping or group_parameters)(model)      # the image tree groups by other names (cv/run_adapter.py)
         lrs = {"bert": fine_tune_lr, "recsys": lr, "adapter_bert": adapter_bert_lr, "adapter_recsys": adapter_sasrec_lr}
         plist = [(g, n, p) for g in ("bert", "recsys", "adapter_bert", "adapter_recsys") for n, p in groups[g]]
         if not plist:

@@ -79,3 +79,46 @@ def test_entry_script_flags_equal_the_reference():
     from adapter4rec_b200.parameters import parse_args
     ref = json.load(open(os.path.join(ROOT, "tests", "golden", "text_flags.json")))
     assert vars(parse_args([])) == ref
+
+
+def test_cv_entry_script_flags_equal_the_reference():
+    """adapter4rec_b200.cv.parameters.parse_args([]) == Downstream/CV/parameters.py parse_args() (names, types and defaults);
+    tests/golden/cv_flags.json is the reference parser's own dump (tests/golden/make_cv_flags.py)."""
+    import json
+    from adapter4rec_b200.cv.parameters import parse_args
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "cv_flags.json")))
+    got = vars(parse_args([]))
+    assert got == ref
+    assert {k: type(v) for k, v in got.items()} == {k: type(v) for k, v in ref.items()}
+
+
+def test_cv_parameter_groups_follow_the_reference_rules():
+    """run_adapter.py:487-510: names with 'image_net' go to the image group unless they are classifier-like ('fc' / 'classifier' /
+    'decoder_pred' in the name); 'adapter' (and only 'adapter': LoRA factors are NOT adapters here) selects the adapter groups.
+    A reference quirk the mirror keeps: the Houlsby bottleneck's parameters are called fc_down / fc_up, so the 'fc' test sends
+    the ViT's adapters to the adapter_recsys group (adapter_sasrec_lr); only adapters without 'fc' in their names (Compacter's
+    down_sampler / up_sampler) train with --adapter_cv_lr."""
+    import torch
+    from adapter4rec_b200.cv.run_adapter import group_parameters_cv
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.names = ["cv_encoder.image_net.vit.encoder.layer.0.output.adapter.fc_down.weight",
+                          "cv_encoder.image_net.vit.encoder.layer.0.output.adapter.down_sampler.W_left",
+                          "cv_encoder.image_net.vit.encoder.layer.0.attention.attention.query.lora_A",
+                          "cv_encoder.image_net.classifier.weight", "user_encoder.transformer_encoder.layer_norm.weight",
+                          "user_encoder.transformer_encoder.transformer_blocks.0.adapter1.fc_up.bias", "frozen.weight"]
+
+        def named_parameters(self, *a, **k):
+            for n in self.names:
+                p = torch.nn.Parameter(torch.zeros(1))
+                p.requires_grad = n != "frozen.weight"
+                yield n, p
+
+    g = {k: [n for n, _ in v] for k, v in group_parameters_cv(M()).items()}
+    assert g["adapter_bert"] == ["cv_encoder.image_net.vit.encoder.layer.0.output.adapter.down_sampler.W_left"]
+    assert g["bert"] == ["cv_encoder.image_net.vit.encoder.layer.0.attention.attention.query.lora_A"]
+    assert g["recsys"] == ["cv_encoder.image_net.classifier.weight", "user_encoder.transformer_encoder.layer_norm.weight"]
+    assert g["adapter_recsys"] == ["cv_encoder.image_net.vit.encoder.layer.0.output.adapter.fc_down.weight",
+                                   "user_encoder.transformer_encoder.transformer_blocks.0.adapter1.fc_up.bias"]

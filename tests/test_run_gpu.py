@@ -43,3 +43,36 @@ def test_train_entry_reduces_loss_and_evaluates(tmp_path):
     model2, trainer2, _ = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16, model_dir=str(tmp_path))
     assert trainer2.step_count == ckpt["optimizer"]["step"] + 3
     assert any("epoch %d mean batch loss" % (int(saved[-1].split("-")[1].split(".")[0]) + 1) in m for m in records)
+
+
+def test_cv_train_entry_reduces_loss_and_evaluates(tmp_path):
+    """adapter4rec_b200.cv.run_adapter.train (Downstream/CV/run_adapter.py:283-620) on synthetic images through the reference's
+    flags: ViT (2 layers, 48 x 48 images = 10 tokens) + serial Houlsby adapters + SASRec; loss goes down, both evaluations
+    run, a checkpoint in the reference's format is written."""
+    import os
+    from adapter4rec_b200.cv import ViTConfigLite
+    from adapter4rec_b200.cv import run_adapter as run
+    from adapter4rec_b200.cv.parameters import parse_args
+    args = parse_args(["--CV_model_load", "vit-base-patch16-224", "--CV_resize", "48", "--batch_size", "16", "--epoch", "3",
+                       "--adapter_type", "houslby", "--adding_adapter_to", "all", "--cv_adapter_down_size", "16",
+                       "--adapter_cv_lr", "5e-3", "--adapter_sasrec_lr", "5e-3", "--max_seq_len", "6", "--drop_rate", "0.0"])
+    run.setup_seed(12345)
+    data = run.synthetic_data(item_num=60, users=48, resize=48, max_seq_len=6)
+    cfg = ViTConfigLite(hidden_size=768, num_hidden_layers=2, num_attention_heads=12, intermediate_size=256, image_size=48,
+                        patch_size=16)
+    log = logging.getLogger("run_cv_test")
+    records = []
+    log.addHandler(type("H", (logging.Handler,), {"emit": lambda self, r: records.append(r.getMessage())})())
+    log.setLevel(logging.INFO)
+    model, trainer, hit10 = run.train(args, True, 0, data, Log_file=log, vit_config=cfg, users_per_pass=8, model_dir=str(tmp_path))
+    losses = [float(m.split(":")[-1]) for m in records if "mean batch loss" in m]
+    assert len(losses) == 3 and losses[-1] < losses[0], losses
+    assert 0.0 <= hit10 <= 1.0
+    assert sum("valid_results" in m for m in records) == 3 and sum("test_results" in m for m in records) == 3
+    assert trainer.step_count == 9
+    names = {n for n, _, _ in trainer.names}
+    assert names and all("adapter" in n for n in names)              # fine_tune_to None: only the adapters train
+    saved = sorted(f for f in os.listdir(tmp_path) if f.startswith("epoch-"))
+    assert saved
+    ckpt = torch.load(os.path.join(tmp_path, saved[-1]), weights_only=False)
+    assert set(ckpt["model_state_dict"]) == set(model.state_dict())
