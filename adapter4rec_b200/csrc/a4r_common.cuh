@@ -71,68 +71,49 @@ A4R_DEVICE float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// GELU pieces on ONE MUFU op.  With z = |x|/sqrt(2):  erfc(z) = exp(-z^2) * erfcx(z), and erfcx is smooth, so a
-// degree-8 polynomial Q (weighted minimax fit on [0, 4.25], fitted offline; |erfc error| <= 2.1e-6, i.e. far below
-// bf16 resolution) replaces erff's ~25-instruction branchy path — the GELU epilogues are the instruction-bound part
-// of the FFN GEMMs.  The same exponential e = exp(-x^2/2) serves the density term of GELU'.
+// erf-GELU for the GEMM / adapter epilogues, which are bound by the FMA pipe (measured: the packed FFMA2 form issues at half the
+// rate of FFMA, so an epilogue pays ~2 pipe cycles per packed operation and the degree-8 erfc polynomial of round 1 — 14 packed
+// operations per pair — made the FFN1 epilogue slower than the MMAs of its tile).  Phi(x) is approximated by
+//     Phi(x) ~= 1/2 + 1/2 tanh(x (c0 + c1 x^2 + c2 x^4)),   x^2 clamped at 64,
+// a three-coefficient minimax fit against the exact erf form (max |x dPhi| = 2.5e-5 over the real line, fitted offline) evaluated
+// with ONE MUFU.TANH (relative error 2^-11, i.e. |d gelu| <= 2.4e-4 |x|: an eighth of a bf16 ulp of the result) and 6 packed
+// operations per pair.  The density term of GELU' keeps the exact exponential (one more MUFU.EX2).
 A4R_DEVICE float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-A4R_DEVICE void gelu_parts(float x, float& cdf, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  e = ex2_approx(-1.44269504088896340736f * z * z);
-  const float zc = fminf(z, 4.25f);
-  float q = fmaf(0.00121288927f, zc, -0.013924433f);
-  q = fmaf(q, zc, 0.0703962739f);
-  q = fmaf(q, zc, -0.212979268f);
-  q = fmaf(q, zc, 0.449192171f);
-  q = fmaf(q, zc, -0.735232875f);
-  q = fmaf(q, zc, 0.997116424f);
-  q = fmaf(q, zc, -1.1281912f);
-  q = fmaf(q, zc, 0.999997987f);
-  const float half_erfc = 0.5f * q * e;                 // 0.5 * erfc(|x|/sqrt2) = 1 - Phi(|x|)
-  cdf = 0.5f + copysignf(0.5f - half_erfc, x);          // Phi(x)
+A4R_DEVICE float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
-A4R_DEVICE float gelu_fast(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return x * cdf;
+constexpr float kGeluC0 = 0.797507884f, kGeluC1 = 0.0370056460f, kGeluC2 = -3.51516783e-4f;
+A4R_DEVICE float gelu_cdf(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  const float u = x * fmaf(fmaf(x2, kGeluC2, kGeluC1), x2, kGeluC0);
+  return fmaf(0.5f, tanh_approx(u), 0.5f);
 }
+A4R_DEVICE float gelu_fast(float x) { return x * gelu_cdf(x); }
 A4R_DEVICE float gelu_grad_fast(float x) {
-  float cdf, e;
-  gelu_parts(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);
+  const float e = ex2_approx(-0.72134752044448170368f * x * x);          // exp(-x^2 / 2)
+  return fmaf(x * 0.39894228040143267794f, e, gelu_cdf(x));
 }
-// Two elements at a time on the packed fp32x2 pipe of sm_100 (FFMA2/FMUL2/FADD2): halves the instruction count of
-// the polynomial, which is what bounds the GELU epilogues.
+// Two elements at a time on the packed fp32x2 pipe of sm_100 (FFMA2 / FMUL2): half the issue slots of the scalar form.
 A4R_DEVICE float2 splat2(float c) { return make_float2(c, c); }
-A4R_DEVICE void gelu_parts2(float2 x, float2& cdf, float2& e) {
-  float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), splat2(0.70710678118654752440f));
-  const float2 t = __fmul2_rn(__fmul2_rn(z, splat2(-1.44269504088896340736f)), z);
-  e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-  const float2 zc = make_float2(fminf(z.x, 4.25f), fminf(z.y, 4.25f));
-  float2 q = __ffma2_rn(splat2(0.00121288927f), zc, splat2(-0.013924433f));
-  q = __ffma2_rn(q, zc, splat2(0.0703962739f));
-  q = __ffma2_rn(q, zc, splat2(-0.212979268f));
-  q = __ffma2_rn(q, zc, splat2(0.449192171f));
-  q = __ffma2_rn(q, zc, splat2(-0.735232875f));
-  q = __ffma2_rn(q, zc, splat2(0.997116424f));
-  q = __ffma2_rn(q, zc, splat2(-1.1281912f));
-  q = __ffma2_rn(q, zc, splat2(0.999997987f));
-  const float2 d = __ffma2_rn(__fmul2_rn(q, e), splat2(-0.5f), splat2(0.5f));   // 0.5 - 0.5 * erfc(|x|/sqrt2)
-  cdf = make_float2(0.5f + copysignf(d.x, x.x), 0.5f + copysignf(d.y, x.y));
+A4R_DEVICE float2 gelu_cdf2(float2 x) {
+  float2 x2 = __fmul2_rn(x, x);
+  x2 = make_float2(fminf(x2.x, 64.0f), fminf(x2.y, 64.0f));
+  float2 q = __ffma2_rn(x2, splat2(kGeluC2), splat2(kGeluC1));
+  q = __ffma2_rn(q, x2, splat2(kGeluC0));
+  const float2 u = __fmul2_rn(q, x);
+  return __ffma2_rn(make_float2(tanh_approx(u.x), tanh_approx(u.y)), splat2(0.5f), splat2(0.5f));
 }
-A4R_DEVICE float2 gelu_fast2(float2 x) {
-  float2 cdf, e;
-  gelu_parts2(x, cdf, e);
-  return __fmul2_rn(x, cdf);
-}
+A4R_DEVICE float2 gelu_fast2(float2 x) { return __fmul2_rn(x, gelu_cdf2(x)); }
 A4R_DEVICE float2 gelu_grad_fast2(float2 x) {
-  float2 cdf, e;
-  gelu_parts2(x, cdf, e);
-  return __ffma2_rn(__fmul2_rn(x, splat2(0.39894228040143267794f)), e, cdf);
+  const float2 t = __fmul2_rn(__fmul2_rn(x, splat2(-0.72134752044448170368f)), x);
+  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  return __ffma2_rn(__fmul2_rn(x, splat2(0.39894228040143267794f)), e, gelu_cdf2(x));
 }
 
 // 256-bit global access (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread per instruction

@@ -37,14 +37,21 @@ struct EpiGroups {
 // CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 the two SMs of a TPC own one 256 x BN tile, each CTA staging its own
 // 128 rows of A and HALF of the B rows (the pair's MMA reads both halves), which cuts shared-memory and L2->SM operand
 // traffic per CTA by a third — the energy that bounds this kernel under the 1 kW cap.
-template <int BN, int CG = 1>
+// BOXES: the epilogue hands its bf16 results to TMA through per-warp shared-memory boxes (the GELU epilogue, which writes TWO
+// tensors per chunk and was bound by the load/store unit: measured 630 -> 562 us at M = 161,280, N = 3072, K = 768); the
+// single-output epilogues keep direct 256-bit stores (the box hand-over adds ~350 cycles of latency per chunk, which their two
+// epilogue groups do not hide: measured 192 -> 225 us on attention.output) and the deeper operand ring.
+template <int BN, int CG = 1, bool BOXES = false>
 struct Cfg {
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = CG == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int kStages = BOXES ? (CG == 2 ? 5 : (BN == 256 ? 3 : (BN == 128 ? 6 : 8))) : (CG == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: power of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // every epilogue warp owns two 2 KB result boxes ([32 rows x 32 bf16], SWIZZLE_64B) that leave through TMA stores
+  static constexpr int kOutBoxBytes = 2048;
+  static constexpr int kMaxEpiWarps = !BOXES ? 0 : (BN == 256 ? 16 : 8);      // 4 epilogue groups at most on the 256-wide tiles
+  static constexpr int kSmemBytes = kStages * kStageBytes + kMaxEpiWarps * 2 * kOutBoxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -68,6 +75,15 @@ struct GemmParams {
 };
 
 // ---- epilogue helpers ---------------------------------------------------------------------------
+A4R_DEVICE void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+A4R_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+A4R_DEVICE void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+A4R_DEVICE void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // One 32-column chunk of one output row, as 64 bytes of bf16 = 16 x b32 (or 2 x 256-bit / 4 x 128-bit accesses).
 struct Row64 {
   uint32_t w[16];
@@ -109,16 +125,26 @@ A4R_DEVICE void store_row64(__nv_bfloat16* p, const float (&v)[32]) {
 
 // EPI: epilogue mode (compile time).  V32: every epilogue tensor is 32-byte aligned with ld % 16 == 0, so rows are
 // moved with 256-bit accesses; the tail chunk of a ragged N falls back to guarded 128-bit accesses.
+#ifdef A4R_GEMM_TIMING     // tools/micro/gemm_epi_timing.cu only
+__device__ long long g_gemm_timing[8];
+A4R_DEVICE long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
+#define GSTAMP(v) const long long v = clk()
+#else
+#define GSTAMP(v)
+#endif
+
 template <int BN, int EPI, bool V32, int CG>
 __global__ void __launch_bounds__(128 + 128 * EpiGroups<BN, EPI>::value, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-               const GemmParams p) {
-  using C = Cfg<BN, CG>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+  constexpr bool kBoxes = EPI == A4R_EPI_GELU;
+  using C = Cfg<BN, CG, kBoxes>;
   constexpr int NUM_EPI_GROUPS = EpiGroups<BN, EPI>::value;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* out_boxes = smem + C::kStages * C::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_boxes + C::kMaxEpiWarps * 2 * C::kOutBoxBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full_bar = empty_bar + C::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -139,6 +165,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.nk2 > 0) {
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmB2);
+    }
+    if constexpr (kBoxes) {
+      tma_prefetch_desc(&tmC);
+      tma_prefetch_desc(&tmAux);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -267,7 +297,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_in = kHasIn && in_ptr != nullptr;
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t nbox = 0;             // result boxes handed to TMA so far (the warp's two boxes alternate)
     const bool out_f32 = p.out_f32 != 0;
+#ifdef A4R_GEMM_TIMING
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    const long long gstart = clk();
+#endif
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m0 = (tile / p.tiles_n) * (BM * CG) + static_cast<int>(cta_rank) * BM;
       const int n0 = (tile % p.tiles_n) * BN;
@@ -286,6 +321,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) return;  // warp-uniform
         uint32_t acc[32];
+        GSTAMP(g0);
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(as * BN + c * 32),
                            acc);
@@ -302,7 +338,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tmem_ld_wait();
-        if (!row_ok) return;
+        GSTAMP(g1);
+#ifdef A4R_GEMM_TIMING
+        tacc[0] += g1 - g0;
+#endif
+        // (with result boxes rows past M are not skipped: their accumulators are zeros — A is zero-filled there — TMA clips
+        // their stores, and the whole warp has to reach the box hand-over below)
+        if constexpr (!kBoxes) {
+          if (!row_ok) return;
+        }
         float2 v[16];
         const float2 al = splat2(p.alpha);
         if (has_bias) {
@@ -320,7 +364,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // streamed input of this chunk: prefetched registers for full chunks, guarded loads for the ragged tail
         Row64 in = pre;
-        if (has_in && !full) {
+        if (has_in && !full && row_ok) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 t = make_uint4(0, 0, 0, 0);
@@ -328,24 +372,46 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             in.w[4 * j] = t.x; in.w[4 * j + 1] = t.y; in.w[4 * j + 2] = t.z; in.w[4 * j + 3] = t.w;
           }
         }
-        auto store_bf16 = [&](__nv_bfloat16* dst) {
+        // bf16 results leave through the warp's private [32 rows x 32 columns] SWIZZLE_64B box and ONE TMA store: a 32-byte
+        // st.global per lane touches 32 different lines per instruction (32 L1 wavefronts), and with two such tensors per chunk
+        // (residual / pre-activation + output) the K = 768 shapes were bound by the load/store unit, not by the MMAs.  The two
+        // boxes of a warp alternate, so a box is rewritten only after the store issued two hand-overs ago has read it.
+        auto store_bf16 = [&](const CUtensorMap* tm, __nv_bfloat16* dst) {
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[i].x, v[i].y);
-          if (full) {
-            if constexpr (V32) {
-              const uint32_t a8[8] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]};
-              const uint32_t b8[8] = {w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]};
-              st_na_v8(dst, a8);
-              st_na_v8(dst + 16, b8);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
-            }
-          } else {
+          if constexpr (kBoxes) {
+            const uint32_t box = smem_u32(out_boxes) + static_cast<uint32_t>((ew * 2 + (nbox & 1)) * C::kOutBoxBytes);
+            if (lane == 0) bulk_wait_read1();
+            __syncwarp();
+            const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (col0 + 8 * j < p.N) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+              sts_v4(box + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(tm, box, col0, m0 + quad * 32);      // columns past N and rows past M are clipped by the tensor map
+              bulk_commit();
+            }
+            ++nbox;
+          } else {
+            if (!row_ok) return;
+            if (full) {
+              if constexpr (V32) {
+                const uint32_t a8[8] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]};
+                const uint32_t b8[8] = {w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]};
+                st_na_v8(dst, a8);
+                st_na_v8(dst + 16, b8);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col0 + 8 * j < p.N) st_na_v4(dst + 8 * j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+            }
           }
         };
         auto drop_v = [&]() {
@@ -371,7 +437,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const __nv_bfloat16* r2 = reinterpret_cast<const __nv_bfloat16*>(p.residual2) + r64 * p.ldr2 + col0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (full || col0 + 8 * j < p.N) {
+              if (row_ok && (full || col0 + 8 * j < p.N)) {
                 const uint4 t = ld_nc_v4(r2 + 8 * j);
                 v[4 * j] = __fadd2_rn(v[4 * j], unpack_bf16x2(t.x));
                 v[4 * j + 1] = __fadd2_rn(v[4 * j + 1], unpack_bf16x2(t.y));
@@ -383,7 +449,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // gradient through a dropout whose input gradient is the sum formed above: mask the SUM
           if constexpr (EPI == EPI_LINEAR_DROPSUM) drop_v();
         } else if constexpr (EPI == A4R_EPI_GELU) {
-          if (p.aux != nullptr) store_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0);
+          if (p.aux != nullptr) store_bf16(&tmAux, reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = gelu_fast2(v[i]);
         } else if constexpr (EPI == A4R_EPI_RELU) {
@@ -403,17 +469,30 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float* cp = reinterpret_cast<float*>(p.C) + r64 * p.ldc + col0;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (full || col0 + 4 * j < p.N)
+            if (row_ok && (full || col0 + 4 * j < p.N))
               st_na_v4(cp + 4 * j, make_uint4(__float_as_uint(v[2 * j].x), __float_as_uint(v[2 * j].y),
                                               __float_as_uint(v[2 * j + 1].x), __float_as_uint(v[2 * j + 1].y)));
         } else {
-          store_bf16(reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col0);
+          GSTAMP(g2);
+          store_bf16(&tmC, reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col0);
+          GSTAMP(g3);
+#ifdef A4R_GEMM_TIMING
+          tacc[1] += g2 - g1;
+          tacc[2] += g3 - g2;
+          tacc[3] += 1;
+#endif
         }
       };
       Row64 pre0, pre1;
       prefetch(0, pre0);
       prefetch(1, pre1);
+      GSTAMP(g4);
       mbar_wait(&tmem_full_bar[as], aphase);
+      GSTAMP(g5);
+#ifdef A4R_GEMM_TIMING
+      tacc[4] += g5 - g4;
+      tacc[5] += 1;
+#endif
       tc_fence_after();
 #pragma unroll 1
       for (int cp = 0; cp < CHUNKS; cp += 2) {
@@ -436,6 +515,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         aphase ^= 1;
       }
     }
+    if constexpr (kBoxes) {
+      if (lane == 0) bulk_wait0();   // the last result boxes have been written out before the CTA retires
+    }
+#ifdef A4R_GEMM_TIMING
+    if (blockIdx.x == 0 && ew == 0 && lane == 0) {
+      for (int i = 0; i < 6; ++i) g_gemm_timing[i] = tacc[i];
+      g_gemm_timing[6] = clk() - gstart;
+    }
+#endif
   }
 
   tc_fence_before();
@@ -482,11 +570,34 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
   return A4R_OK;
 }
 
+// bf16 row-major [rows, cols] output (leading dimension ld): box = 32 columns x 32 rows, 64-byte swizzle — one epilogue warp's
+// chunk; elements outside [rows, cols] are not written
+int make_tmap_out(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return a4r_set_error(A4R_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return a4r_set_error(A4R_ECUDA, "cuTensorMapEncodeTiled (output box) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+                         (long long)rows, (long long)cols, (long long)ld);
+  return A4R_OK;
+}
+
 template <int BN, int EPI, bool V32, int CG>
 int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
-  using C = Cfg<BN, CG>;
-  CUtensorMap tmA, tmB, tmA2, tmB2;
+  constexpr bool kBoxes = EPI == A4R_EPI_GELU;
+  using C = Cfg<BN, CG, kBoxes>;
+  static_assert(!kBoxes || 4 * EpiGroups<BN, EPI>::value <= C::kMaxEpiWarps, "result boxes for every epilogue warp");
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmC, tmAux;
   int rc;
+  const bool box_c = kBoxes && !a->out_f32, box_aux = kBoxes && a->aux != nullptr;
+  if (box_c && (rc = make_tmap_out(&tmC, a->C, a->M, a->N, a->ldc)) != A4R_OK) return rc;
+  if (box_aux && (rc = make_tmap_out(&tmAux, a->aux, a->M, a->N, a->ldaux)) != A4R_OK) return rc;
   if ((rc = make_tmap(&tmA, a->A, a->M, a->K, a->lda, BM)) != A4R_OK) return rc;
   if ((rc = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, BN / CG)) != A4R_OK) return rc;
   if (a->K2 > 0) {
@@ -496,6 +607,8 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
     tmA2 = tmA;
     tmB2 = tmB;
   }
+  if (!box_c) tmC = tmA;        // (unused: stored directly)
+  if (!box_aux) tmAux = tmA;    // (unused)
   GemmParams p;
   p.C = a->C;
   p.aux = a->aux;
@@ -543,9 +656,9 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    A4R_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, EPI, V32, CG>, tmA, tmB, tmA2, tmB2, p));
+    A4R_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, EPI, V32, CG>, tmA, tmB, tmA2, tmB2, tmC, tmAux, p));
   } else {
-    gemm_tn_kernel<BN, EPI, V32, CG><<<grid, threads, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
+    gemm_tn_kernel<BN, EPI, V32, CG><<<grid, threads, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
   }
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
