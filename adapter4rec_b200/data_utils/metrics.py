@@ -139,8 +139,7 @@ def eval_arrays(model, tok, mask, tgt, hist, item_table, user_block, topk=10):
             lm = mask[b0:b1].to(dev, non_blocking=True)
             tg = tgt[b0:b1].to(dev, non_blocking=True).contiguous()
             hs = hist[b0:b1].to(dev, non_blocking=True).contiguous()
-            input_embs = item_table.gather(tk)                                        # K10
-            prec = module.user_encoder(input_embs, lm, dev)[:, -1].contiguous()       # K8 (+ last position)
+            prec = _user_vectors(module, item_table, tk, lm, dev)                      # K10 + K8 (+ last position)
             sc, ids = ops.score_topk(prec, item_table.shard, id_base=item_table.id_base, history=hs, k=topk)  # K11+K12
             if world > 1:
                 lsc, lid, _, _ = ops.topk_merge(sc, ids)                              # local merge of the item splits
@@ -154,6 +153,26 @@ def eval_arrays(model, tok, mask, tgt, hist, item_table, user_block, topk=10):
             ndcgs.append(ndcg)
             top_ids.append(mid)
     return torch.cat(hits), torch.cat(ndcgs), torch.cat(top_ids)
+
+
+def _user_vectors(module, item_table, tk, lm, dev):
+    """Last-position user vectors [U, D] (bf16) of one block (metrics.py:104: user_encoder(...)[:, -1]).  One rank: gather +
+    encode.  N ranks: the USERS of the block are split — rank r gathers (ownership-masked rows + one sum all-reduce over the
+    ranks, exact: a single non-zero term) and encodes only its U / N users, then the [U, D] vectors are all-gathered (1.5 KB
+    per user at D = 768) — instead of N redundant encoders over the whole block."""
+    world, rank = item_table.world, item_table.rank
+    if world == 1:
+        return module.user_encoder(item_table.gather(tk), lm, dev)[:, -1].contiguous()
+    U = tk.shape[0]
+    per = (U + world - 1) // world
+    input_embs = item_table.gather(tk)                       # every rank needs rows of every shard: masked gather + all-reduce
+    lo, hi = min(U, rank * per), min(U, rank * per + per)
+    mine = torch.zeros((per, input_embs.shape[-1]), dtype=input_embs.dtype, device=dev)
+    if hi > lo:
+        mine[:hi - lo] = module.user_encoder(input_embs[lo:hi].contiguous(), lm[lo:hi].contiguous(), dev)[:, -1]
+    allv = torch.empty((world * per, mine.shape[1]), dtype=mine.dtype, device=dev)
+    dist.all_gather_into_tensor(allv, mine)
+    return allv[:U].contiguous()
 
 
 def eval_model(model, user_history, eval_seq, item_embeddings, test_batch_size, args, item_num, Log_file, v_or_t,

@@ -204,3 +204,18 @@ def test_eval_model_matches_reference(kind):
     if all_decided:
         assert abs(hit10 - gold["eval_hit10_mean"]) < 1e-6
         assert abs(hit10 - sum(exp_hits) / len(exp_hits)) < 1e-6
+
+
+def test_sharded_evaluator_under_nccl_two_ranks():
+    """tools/dist_check_gpu.py under torchrun with 2 ranks (needs 2 visible GPUs, else skipped): the item-sharded evaluator
+    (per-rank item table, users of a block split across the ranks for the encoder, all-gather of the user vectors and of the
+    partial top-10 lists, merge) returns bit-identical ids / HR / NDCG to the unsharded run, and two data-parallel steps leave
+    bit-identical parameters on both ranks."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "dist_check_gpu.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
