@@ -1,4 +1,6 @@
-// attention_mid.cu — K3 for mid-length sequences (32 < L <= 256, head_dim 64): ViT-B/16 has L = 197 (+ n prompt tokens).
+// attention_mid.cu — K3 for MASKED mid-length sequences (32 < L <= 256, head_dim 64) + the dispatch of a4r_attn_mid_fwd / _bwd.
+// The unmasked case — ViT-B/16's L = 197 (+ n prompt tokens), i.e. every call the image tree makes — runs on tcgen05
+// (attention_tc_sm100.cu, attention_tc_bwd_sm100.cu); this file keeps the mma.sync formulation for sequences with a key mask.
 //
 // One CTA (4 warps) owns one (image, head): Q, K, V (and dO in the backward) of the whole sequence live in swizzled
 // shared memory (<= 32 KB each), so HBM sees q, k, v once and ctx once, exactly like the short-sequence kernel.
@@ -412,362 +414,6 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mid_bwd_kernel(const MidParam
 // =====================================================================================================================
 constexpr float LOG2E = 1.4426950408889634f;
 
-A4R_DEVICE float ex2f(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-struct VitParams {
-  const __nv_bfloat16* qkv;
-  __nv_bfloat16* out;         // fwd: ctx; bwd: dqkv
-  const __nv_bfloat16* dout;  // bwd
-  float* lse;                 // [N*L, heads] f32 (natural log, scaled-score domain)
-  const __nv_bfloat16* ctx;   // bwd: forward output
-  int64_t ld_qkv, ld_out;
-  int N, L, Lr, heads;        // Lr = L rounded up to 16
-  float scale, c;             // c = scale * log2(e)
-};
-
-A4R_DEVICE void load_rows_r(uint8_t* tile, const __nv_bfloat16* g, int64_t ld, int L, int Lr) {
-  const uint32_t base = smem_u32(tile);
-  for (int i = threadIdx.x; i < Lr * 8; i += WARPS * 32) {
-    const int row = i >> 3, ch = i & 7;
-    const bool ok = row < L;
-    const __nv_bfloat16* src = g + (ok ? static_cast<int64_t>(row) * ld + ch * 8 : 0);
-    const int sz = ok ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + toff(row, ch)), "l"(src), "r"(sz) : "memory");
-  }
-}
-
-// one block of NG 16-key groups of the forward: online softmax + O accumulation for a 16-query tile
-template <int NG, bool TAIL>
-A4R_DEVICE void vit_fwd_block(const uint32_t (&qa)[4][4], uint32_t sK, uint32_t sV, int key0, int L, int lane, float c,
-                              float (&o)[8][4], float (&mx)[2], float (&sum)[2]) {
-  const int t = lane & 3;
-  float s[2 * NG][4];
-#pragma unroll
-  for (int nt = 0; nt < 2 * NG; ++nt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) s[nt][e] = 0.0f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      uint32_t b[4];
-      ldb_nk(b, sK, key0 + g * 16, ks * 16, lane);
-      const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-      mma_bf16_16816(s[g * 2], qa[ks], b0);
-      mma_bf16_16816(s[g * 2 + 1], qa[ks], b1);
-    }
-  if (TAIL) {
-#pragma unroll
-    for (int nt = 0; nt < 2 * NG; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (key0 + nt * 8 + 2 * t + (e & 1) >= L) s[nt][e] = -INFINITY;
-  }
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    float bm = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 2 * NG; ++nt) bm = fmaxf(bm, fmaxf(s[nt][hh * 2], s[nt][hh * 2 + 1]));
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-    const float nm = fmaxf(mx[hh], bm);          // finite: every block holds at least one real key
-    const float corr = ex2f((mx[hh] - nm) * c);  // first block: ex2(-inf) = 0
-    const float nmc = nm * c;
-    mx[hh] = nm;
-    float bs = 0.0f;
-#pragma unroll
-    for (int nt = 0; nt < 2 * NG; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float ex = ex2f(fmaf(s[nt][hh * 2 + e], c, -nmc));
-        s[nt][hh * 2 + e] = ex;
-        bs += ex;
-      }
-    bs += __shfl_xor_sync(0xffffffffu, bs, 1);
-    bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-    sum[hh] = sum[hh] * corr + bs;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      o[nt][hh * 2] *= corr;
-      o[nt][hh * 2 + 1] *= corr;
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    uint32_t a[4];
-    c2a(a, s[2 * g], s[2 * g + 1]);
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t b[4];
-      ldb_kn(b, sV, np * 16, key0 + g * 16, lane);
-      const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-      mma_bf16_16816(o[np * 2], a, b0);
-      mma_bf16_16816(o[np * 2 + 1], a, b1);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(WARPS * 32, 2) attn_vit_fwd_kernel(const VitParams p) {
-  extern __shared__ __align__(128) uint8_t sm_mid[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int tile_bytes = p.Lr * 128;
-  uint8_t *tQ = sm_mid, *tK = sm_mid + tile_bytes, *tV = sm_mid + 2 * tile_bytes;
-  const uint32_t sQ = smem_u32(tQ), sK = smem_u32(tK), sV = smem_u32(tV);
-  const int64_t Hd = static_cast<int64_t>(p.heads) * DH;
-  const int ngroups = p.Lr >> 4;
-  const int nfull = (ngroups - 1) >> 2;            // full 64-key blocks before the last (tail) block
-  const int ntail = ngroups - nfull * 4;           // 1..4 groups in the last block
-  for (int w = blockIdx.x; w < p.N * p.heads; w += gridDim.x) {
-    const int n = w / p.heads, h = w % p.heads;
-    const __nv_bfloat16* q = p.qkv + static_cast<int64_t>(n) * p.L * p.ld_qkv + h * DH;
-    __syncthreads();  // previous iteration's readers are done
-    load_rows_r(tQ, q, p.ld_qkv, p.L, p.Lr);
-    load_rows_r(tK, q + Hd, p.ld_qkv, p.L, p.Lr);
-    load_rows_r(tV, q + 2 * Hd, p.ld_qkv, p.L, p.Lr);
-    cp_async_wait_all();
-    __syncthreads();
-    for (int m0 = warp * 16; m0 < p.Lr; m0 += WARPS * 16) {
-      uint32_t qa[4][4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) lda(qa[ks], sQ, m0, ks * 16, lane);
-      float o[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[nt][e] = 0.0f;
-      float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.0f, 0.0f};
-      for (int b = 0; b < nfull; ++b) vit_fwd_block<4, false>(qa, sK, sV, b * 64, p.L, lane, p.c, o, mx, sum);
-      const int key0 = nfull * 64;
-      if (ntail == 1) vit_fwd_block<1, true>(qa, sK, sV, key0, p.L, lane, p.c, o, mx, sum);
-      else if (ntail == 2) vit_fwd_block<2, true>(qa, sK, sV, key0, p.L, lane, p.c, o, mx, sum);
-      else if (ntail == 3) vit_fwd_block<3, true>(qa, sK, sV, key0, p.L, lane, p.c, o, mx, sum);
-      else vit_fwd_block<4, true>(qa, sK, sV, key0, p.L, lane, p.c, o, mx, sum);
-      const float inv0 = 1.0f / sum[0], inv1 = 1.0f / sum[1];
-      __nv_bfloat16* op = p.out + (static_cast<int64_t>(n) * p.L) * p.ld_out + h * DH;
-      const int r0 = m0 + g, r1 = m0 + g + 8;
-      if (p.lse != nullptr && t == 0) {
-        if (r0 < p.L) p.lse[(static_cast<int64_t>(n) * p.L + r0) * p.heads + h] = mx[0] * p.scale + __logf(sum[0]);
-        if (r1 < p.L) p.lse[(static_cast<int64_t>(n) * p.L + r1) * p.heads + h] = mx[1] * p.scale + __logf(sum[1]);
-      }
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * t;
-        if (r0 < p.L) *reinterpret_cast<uint32_t*>(op + static_cast<int64_t>(r0) * p.ld_out + col) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
-        if (r1 < p.L) *reinterpret_cast<uint32_t*>(op + static_cast<int64_t>(r1) * p.ld_out + col) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
-      }
-    }
-  }
-}
-
-// dQ phase: one block of NG (1 or 2) 16-key groups for a 16-query tile
-template <int NG>
-A4R_DEVICE void vit_dq_block(const uint32_t (&qa)[4][4], const uint32_t (&da)[4][4], uint32_t sK, uint32_t sV, int key0, int lane,
-                             float c, float scale, const float (&lse2)[2], const float (&delta)[2], float (&acc)[8][4]) {
-  float s[2 * NG][4], dp[2 * NG][4];
-#pragma unroll
-  for (int nt = 0; nt < 2 * NG; ++nt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.0f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      uint32_t b[4], v[4];
-      ldb_nk(b, sK, key0 + g * 16, ks * 16, lane);
-      ldb_nk(v, sV, key0 + g * 16, ks * 16, lane);
-      const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]}, v0[2] = {v[0], v[1]}, v1[2] = {v[2], v[3]};
-      mma_bf16_16816(s[g * 2], qa[ks], b0);
-      mma_bf16_16816(s[g * 2 + 1], qa[ks], b1);
-      mma_bf16_16816(dp[g * 2], da[ks], v0);      // dP = dO·Vᵀ has the same operand structure
-      mma_bf16_16816(dp[g * 2 + 1], da[ks], v1);
-    }
-#pragma unroll
-  for (int nt = 0; nt < 2 * NG; ++nt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      s[nt][e] = ex2f(fmaf(s[nt][e], c, -lse2[e >> 1])) * (dp[nt][e] - delta[e >> 1]) * scale;   // dS (padded keys: K = 0 below)
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    uint32_t a[4];
-    c2a(a, s[2 * g], s[2 * g + 1]);
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t b[4];
-      ldb_kn(b, sK, np * 16, key0 + g * 16, lane);
-      const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-      mma_bf16_16816(acc[np * 2], a, b0);
-      mma_bf16_16816(acc[np * 2 + 1], a, b1);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(WARPS * 32, 2) attn_vit_bwd_kernel(const VitParams p) {
-  extern __shared__ __align__(128) uint8_t sm_mid[];
-  __shared__ __align__(8) float s_lse2[LMAX], s_delta[LMAX];   // lse * log2(e), <dO, O>; zero past L
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int tile_bytes = p.Lr * 128;
-  uint8_t *tQ = sm_mid, *tK = tQ + tile_bytes, *tV = tK + tile_bytes, *tdO = tV + tile_bytes;
-  const uint32_t sQ = smem_u32(tQ), sK = smem_u32(tK), sV = smem_u32(tV), sdO = smem_u32(tdO);
-  const int64_t Hd = static_cast<int64_t>(p.heads) * DH;
-  const int ngroups = p.Lr >> 4;
-  for (int w = blockIdx.x; w < p.N * p.heads; w += gridDim.x) {
-    const int n = w / p.heads, h = w % p.heads;
-    const __nv_bfloat16* q = p.qkv + static_cast<int64_t>(n) * p.L * p.ld_qkv + h * DH;
-    __nv_bfloat16* dq = p.out + static_cast<int64_t>(n) * p.L * p.ld_qkv + h * DH;
-    __syncthreads();
-    load_rows_r(tQ, q, p.ld_qkv, p.L, p.Lr);
-    load_rows_r(tK, q + Hd, p.ld_qkv, p.L, p.Lr);
-    load_rows_r(tV, q + 2 * Hd, p.ld_qkv, p.L, p.Lr);
-    load_rows_r(tdO, p.dout + static_cast<int64_t>(n) * p.L * p.ld_out + h * DH, p.ld_out, p.L, p.Lr);
-    for (int r = threadIdx.x; r < p.Lr; r += WARPS * 32)
-      s_lse2[r] = r < p.L ? p.lse[(static_cast<int64_t>(n) * p.L + r) * p.heads + h] * LOG2E : 0.0f;
-    cp_async_wait_all();
-    __syncthreads();
-    // delta_i = <dO_i, O_i>: 8 lanes per row, one 16-byte chunk each (Lr * 8 is a multiple of 32: whole warps stay together)
-    for (int i = threadIdx.x; i < p.Lr * 8; i += WARPS * 32) {
-      const int r = i >> 3, ch = i & 7;
-      float d = 0.0f;
-      if (r < p.L) {
-        const int64_t grow = static_cast<int64_t>(n) * p.L + r;
-        const uint4 ov = ld_nc_v4(p.ctx + grow * p.ld_out + h * DH + ch * 8);
-        const uint4 dv4 = *reinterpret_cast<const uint4*>(tdO + toff(r, ch));
-        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 a = unpack_bf16x2(ow[e]), b = unpack_bf16x2(dw[e]);
-          d += a.x * b.x + a.y * b.y;
-        }
-      }
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      if (ch == 0) s_delta[r] = d;
-    }
-    __syncthreads();
-    // ---------------- phase A: per query tile -> dQ ----------------
-    for (int m0 = warp * 16; m0 < p.Lr; m0 += WARPS * 16) {
-      uint32_t qa[4][4], da[4][4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        lda(qa[ks], sQ, m0, ks * 16, lane);
-        lda(da[ks], sdO, m0, ks * 16, lane);
-      }
-      const float lse2[2] = {s_lse2[m0 + g], s_lse2[m0 + g + 8]};
-      const float delta[2] = {s_delta[m0 + g], s_delta[m0 + g + 8]};
-      float acc[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
-      int grp = 0;
-      for (; grp + 2 <= ngroups; grp += 2) vit_dq_block<2>(qa, da, sK, sV, grp * 16, lane, p.c, p.scale, lse2, delta, acc);
-      if (grp < ngroups) vit_dq_block<1>(qa, da, sK, sV, grp * 16, lane, p.c, p.scale, lse2, delta, acc);
-      const int r0 = m0 + g, r1 = m0 + g + 8;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * t;
-        if (r0 < p.L) *reinterpret_cast<uint32_t*>(dq + static_cast<int64_t>(r0) * p.ld_qkv + col) = pack_bf16x2(acc[nt][0], acc[nt][1]);
-        if (r1 < p.L) *reinterpret_cast<uint32_t*>(dq + static_cast<int64_t>(r1) * p.ld_qkv + col) = pack_bf16x2(acc[nt][2], acc[nt][3]);
-      }
-    }
-    // ---------------- phase B: per key tile -> dK, dV (reads only shared tiles and s_lse2 / s_delta) ----------------
-    for (int j0 = warp * 16; j0 < p.Lr; j0 += WARPS * 16) {
-      uint32_t ka[4][4], va[4][4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        lda(ka[ks], sK, j0, ks * 16, lane);
-        lda(va[ks], sV, j0, ks * 16, lane);
-      }
-      float dk[8][4], dv[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dk[nt][e] = dv[nt][e] = 0.0f;
-      for (int i0 = 0; i0 < p.Lr; i0 += 16) {  // 16 queries at a time (columns of Sᵀ)
-        float st[2][4], dpt[2][4];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) st[nt][e] = dpt[nt][e] = 0.0f;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t b[4], c4[4];
-          ldb_nk(b, sQ, i0, ks * 16, lane);
-          ldb_nk(c4, sdO, i0, ks * 16, lane);
-          const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]}, c0[2] = {c4[0], c4[1]}, c1[2] = {c4[2], c4[3]};
-          mma_bf16_16816(st[0], ka[ks], b0);     // Sᵀ = K·Qᵀ
-          mma_bf16_16816(st[1], ka[ks], b1);
-          mma_bf16_16816(dpt[0], va[ks], c0);    // dPᵀ = V·dOᵀ
-          mma_bf16_16816(dpt[1], va[ks], c1);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const int i = i0 + nt * 8 + 2 * t;     // query index of elements e = 0, 2 (e = 1, 3: i + 1)
-          const float2 l2 = *reinterpret_cast<const float2*>(&s_lse2[i]);
-          const float2 dl = *reinterpret_cast<const float2*>(&s_delta[i]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float pr = ex2f(fmaf(st[nt][e], p.c, -((e & 1) ? l2.y : l2.x)));    // padded query: Q = dO = 0 below
-            dpt[nt][e] = pr * (dpt[nt][e] - ((e & 1) ? dl.y : dl.x)) * p.scale;      // dSᵀ
-            st[nt][e] = pr;                                                            // Pᵀ
-          }
-        }
-        uint32_t pa[4], sa[4];
-        c2a(pa, st[0], st[1]);
-        c2a(sa, dpt[0], dpt[1]);
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          uint32_t b[4], c4[4];
-          ldb_kn(b, sQ, np * 16, i0, lane);
-          ldb_kn(c4, sdO, np * 16, i0, lane);
-          const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-          const uint32_t c0[2] = {c4[0], c4[1]}, c1[2] = {c4[2], c4[3]};
-          mma_bf16_16816(dk[np * 2], sa, b0);
-          mma_bf16_16816(dk[np * 2 + 1], sa, b1);
-          mma_bf16_16816(dv[np * 2], pa, c0);
-          mma_bf16_16816(dv[np * 2 + 1], pa, c1);
-        }
-      }
-      const int jr[2] = {j0 + g, j0 + g + 8};
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * t;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (jr[hh] < p.L) {
-            __nv_bfloat16* row = dq + static_cast<int64_t>(jr[hh]) * p.ld_qkv + col;
-            *reinterpret_cast<uint32_t*>(row + Hd) = pack_bf16x2(dk[nt][hh * 2], dk[nt][hh * 2 + 1]);
-            *reinterpret_cast<uint32_t*>(row + 2 * Hd) = pack_bf16x2(dv[nt][hh * 2], dv[nt][hh * 2 + 1]);
-          }
-        }
-      }
-    }
-  }
-}
-
-VitParams vit_params(const a4r_attn_args* a) {
-  VitParams p;
-  p.qkv = static_cast<const __nv_bfloat16*>(a->qkv);
-  p.out = static_cast<__nv_bfloat16*>(a->out);
-  p.dout = static_cast<const __nv_bfloat16*>(a->dout);
-  p.lse = a->lse;
-  p.ctx = static_cast<const __nv_bfloat16*>(a->ctx);
-  p.ld_qkv = a->ld_qkv;
-  p.ld_out = a->ld_out;
-  p.N = static_cast<int>(a->N);
-  p.L = static_cast<int>(a->L);
-  p.Lr = (p.L + 15) & ~15;
-  p.heads = static_cast<int>(a->heads);
-  p.scale = a->scale;
-  p.c = a->scale * LOG2E;
-  return p;
-}
 
 int check_mid(const a4r_attn_args* a) {
   A4R_CHECK_ARG(a != nullptr && a->qkv && a->out, "attention_mid: NULL pointer");
@@ -815,18 +461,6 @@ extern "C" int a4r_attn_mid_fwd(const a4r_attn_args* a, a4r_stream_t stream) {
   if (rc != A4R_OK) return rc;
   if (a->N == 0) return A4R_OK;
   if (a->mask_dtype == 0) return a4r_attn_vit_tc_fwd(a, static_cast<cudaStream_t>(stream));   // ViT: tcgen05 kernel
-  if (a->mask_dtype == 0) {   // (superseded) mma.sync unmasked path
-    const VitParams v = vit_params(a);
-    const int vsmem = 3 * v.Lr * 128;
-    A4R_CUDA_OK(cudaFuncSetAttribute(attn_vit_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LMAX * 128));
-    int64_t vblocks = static_cast<int64_t>(v.N) * v.heads;
-    const int64_t vcap = static_cast<int64_t>(a4r_num_sms()) * 2;
-    if (vblocks > vcap) vblocks = vcap;
-    attn_vit_fwd_kernel<<<static_cast<int>(vblocks), WARPS * 32, vsmem, static_cast<cudaStream_t>(stream)>>>(v);
-    A4R_LAUNCH_OK();
-    a4r_count_launch(1);
-    return A4R_OK;
-  }
   const MidParams p = mid_params(a);
   const int smem = 3 * p.Lp * 128;
   A4R_CUDA_OK(cudaFuncSetAttribute(attn_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LMAX * 128));
@@ -846,18 +480,6 @@ extern "C" int a4r_attn_mid_bwd(const a4r_attn_args* a, a4r_stream_t stream) {
   A4R_CHECK_ARG(a->lse != nullptr && a->ctx != nullptr, "attention_mid bwd: needs the forward's lse and ctx outputs");
   if (a->N == 0) return A4R_OK;
   if (a->mask_dtype == 0) return a4r_attn_vit_tc_bwd(a, static_cast<cudaStream_t>(stream));   // ViT: tcgen05 kernel
-  if (a->mask_dtype == 0) {   // (superseded) mma.sync unmasked path
-    const VitParams v = vit_params(a);
-    const int vsmem = 4 * v.Lr * 128;
-    A4R_CUDA_OK(cudaFuncSetAttribute(attn_vit_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * LMAX * 128));
-    int64_t vblocks = static_cast<int64_t>(v.N) * v.heads;
-    const int64_t vcap = static_cast<int64_t>(a4r_num_sms()) * 2;
-    if (vblocks > vcap) vblocks = vcap;
-    attn_vit_bwd_kernel<<<static_cast<int>(vblocks), WARPS * 32, vsmem, static_cast<cudaStream_t>(stream)>>>(v);
-    A4R_LAUNCH_OK();
-    a4r_count_launch(1);
-    return A4R_OK;
-  }
   const MidParams p = mid_params(a);
   const int smem = 4 * p.Lp * 128;
   A4R_CUDA_OK(cudaFuncSetAttribute(attn_mid_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * LMAX * 128));
