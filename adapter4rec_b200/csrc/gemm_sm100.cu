@@ -37,21 +37,34 @@ struct EpiGroups {
 // CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 the two SMs of a TPC own one 256 x BN tile, each CTA staging its own
 // 128 rows of A and HALF of the B rows (the pair's MMA reads both halves), which cuts shared-memory and L2->SM operand
 // traffic per CTA by a third — the energy that bounds this kernel under the 1 kW cap.
-// BOXES: the epilogue hands its bf16 results to TMA through per-warp shared-memory boxes (the GELU epilogue, which writes TWO
-// tensors per chunk and was bound by the load/store unit: measured 630 -> 562 us at M = 161,280, N = 3072, K = 768); the
-// single-output epilogues keep direct 256-bit stores (the box hand-over adds ~350 cycles of latency per chunk, which their two
-// epilogue groups do not hide: measured 192 -> 225 us on attention.output) and the deeper operand ring.
-template <int BN, int CG = 1, bool BOXES = false>
+// Epilogue boxes: every epilogue warp owns two 2 KB shared-memory boxes ([32 rows x 32 bf16], SWIZZLE_64B) that TMA fills or
+// drains, because a 32-byte global access per lane touches 32 different lines per instruction (32 L1 wavefronts) and the
+// K = 768 shapes — one 32-column chunk of a 256 x 256 tile every ~190 cycles per SM — were bound by the load/store unit:
+//   * GELU (two OUTPUT tensors per chunk, pre-activation + activation): both leave through the boxes + TMA stores
+//     (measured at M = 161,280, N = 3072, K = 768: 630 -> 562 us);
+//   * LINEAR / LINEAR_DROPSUM / GELU' / RELU' (one streamed INPUT tensor — residual or pre-activation): the chunk is prefetched
+//     two chunks ahead by a TMA load into the boxes instead of into registers; the single output keeps its direct 256-bit
+//     stores (a box hand-over adds ~350 cycles of latency per chunk, which two epilogue groups do not hide: measured 192 ->
+//     225 us on attention.output when the output went through boxes as well).
+template <int BN, int EPI>
+struct EpiBoxes {
+  static constexpr bool kOut = EPI == A4R_EPI_GELU;
+  static constexpr bool kIn = EPI == A4R_EPI_LINEAR || EPI == EPI_LINEAR_DROPSUM || EPI == A4R_EPI_DGELU || EPI == A4R_EPI_DRELU;
+  static constexpr int kWarps = (kOut || kIn) ? 4 * EpiGroups<BN, EPI>::value : 0;
+  static constexpr int kBytes = kWarps * 2 * 2048;
+};
+template <int BN, int CG, int EPI>
 struct Cfg {
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = BOXES ? (CG == 2 ? 5 : (BN == 256 ? 3 : (BN == 128 ? 6 : 8))) : (CG == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+  static constexpr int kBoxBytes = EpiBoxes<BN, EPI>::kBytes;
+  static constexpr int kWantStages = CG == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int kFitStages = (232448 - 1024 - 512 - kBoxBytes) / kStageBytes;      // 227 KB per CTA
+  static constexpr int kStages = kFitStages < kWantStages ? kFitStages : kWantStages;
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: power of two >= 32
-  // every epilogue warp owns two 2 KB result boxes ([32 rows x 32 bf16], SWIZZLE_64B) that leave through TMA stores
-  static constexpr int kOutBoxBytes = 2048;
-  static constexpr int kMaxEpiWarps = !BOXES ? 0 : (BN == 256 ? 16 : 8);      // 4 epilogue groups at most on the 256-wide tiles
-  static constexpr int kSmemBytes = kStages * kStageBytes + kMaxEpiWarps * 2 * kOutBoxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBoxBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(kStages >= 3, "operand ring too shallow");
 };
 
 struct GemmParams {
@@ -137,18 +150,21 @@ template <int BN, int EPI, bool V32, int CG>
 __global__ void __launch_bounds__(128 + 128 * EpiGroups<BN, EPI>::value, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
-  constexpr bool kBoxes = EPI == A4R_EPI_GELU;
-  using C = Cfg<BN, CG, kBoxes>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+               const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
+  constexpr bool kBoxes = EpiBoxes<BN, EPI>::kOut;       // results through boxes + TMA stores
+  constexpr bool kInBoxes = EpiBoxes<BN, EPI>::kIn;      // streamed input through TMA loads + boxes
+  using C = Cfg<BN, CG, EPI>;
   constexpr int NUM_EPI_GROUPS = EpiGroups<BN, EPI>::value;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_boxes = smem + C::kStages * C::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_boxes + C::kMaxEpiWarps * 2 * C::kOutBoxBytes);
+  uint8_t* out_boxes = smem + C::kStages * C::kStageBytes;      // (input boxes for the kInBoxes epilogues)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_boxes + C::kBoxBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tmem_full_bar = empty_bar + C::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* in_bar = tmem_empty_bar + 3;                         // [epilogue warp][2]: a streamed-input box has landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -170,6 +186,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmC);
       tma_prefetch_desc(&tmAux);
     }
+    if constexpr (kInBoxes) tma_prefetch_desc(&tmIn);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -179,6 +196,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 4 * NUM_EPI_GROUPS * CG);  // one arrive per epilogue warp of every CTA of the pair
+    }
+    if constexpr (kInBoxes) {
+      for (int s = 0; s < 8 * NUM_EPI_GROUPS; ++s) mbar_init(&in_bar[s], 1);
     }
     mbar_fence_init();
   }
@@ -298,6 +318,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aphase = 0;
     uint32_t nbox = 0;             // result boxes handed to TMA so far (the warp's two boxes alternate)
+    uint32_t n_in[2] = {0u, 0u};   // input boxes consumed per slot (mbarrier phase)
     const bool out_f32 = p.out_f32 != 0;
 #ifdef A4R_GEMM_TIMING
     long long tacc[6] = {0, 0, 0, 0, 0, 0};
@@ -310,12 +331,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const int64_t r64 = row;
       auto chunk_col = [&](int ci) { return n0 + (group + ci * NUM_EPI_GROUPS) * 32; };
-      auto prefetch = [&](int ci, Row64& dst) {
-        if (has_in && row_ok && ci < CHUNKS && (group + ci * NUM_EPI_GROUPS) < BN / 32 && chunk_col(ci) + 32 <= p.N)
-          load_row64<V32>(in_ptr + r64 * in_ld + chunk_col(ci), dst);
+      // the streamed input of chunk ci: one TMA load of the warp's [32 rows x 32 columns] box into slot `slot` (rows past M and
+      // columns past N arrive as zeros); issued two chunks ahead, after the slot's previous contents have been consumed
+      auto prefetch = [&](int ci, int slot) {
+        if constexpr (kInBoxes) {
+          if (!has_in || ci >= CHUNKS || (group + ci * NUM_EPI_GROUPS) >= BN / 32 || chunk_col(ci) >= p.N) return;   // warp-uniform
+          __syncwarp();
+          if (lane == 0) {
+            uint64_t* bar = &in_bar[ew * 2 + slot];
+            mbar_expect_tx(bar, 2048);
+            tma_load_2d(&tmIn, out_boxes + (ew * 2 + slot) * 2048, bar, chunk_col(ci), m0 + quad * 32);
+          }
+        }
       };
       // one 32-column chunk: TMEM -> registers -> fused op -> global
-      auto body = [&](int ci, const Row64& pre) {
+      auto body = [&](int ci, int slot) {
         const int c = group + ci * NUM_EPI_GROUPS;
         if (c >= BN / 32) return;
         const int col0 = n0 + c * 32;
@@ -344,9 +374,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         // (with result boxes rows past M are not skipped: their accumulators are zeros — A is zero-filled there — TMA clips
         // their stores, and the whole warp has to reach the box hand-over below)
-        if constexpr (!kBoxes) {
-          if (!row_ok) return;
-        }
         float2 v[16];
         const float2 al = splat2(p.alpha);
         if (has_bias) {
@@ -362,15 +389,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 16; ++i)
             v[i] = __fmul2_rn(al, make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])));
         }
-        // streamed input of this chunk: prefetched registers for full chunks, guarded loads for the ragged tail
-        Row64 in = pre;
-        if (has_in && !full && row_ok) {
+        // streamed input of this chunk: this lane's row of the prefetched box (64 bytes, 64-byte swizzle)
+        Row64 in;
+        if constexpr (kInBoxes) {
+          if (has_in) {
+            mbar_wait(&in_bar[ew * 2 + slot], n_in[slot] & 1u);
+            ++n_in[slot];
+            const uint32_t box = smem_u32(out_boxes) + static_cast<uint32_t>((ew * 2 + slot) * 2048) + lane * 64;
+            const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (col0 + 8 * j < p.N) t = ld_nc_v4(in_ptr + r64 * in_ld + col0 + 8 * j);
-            in.w[4 * j] = t.x; in.w[4 * j + 1] = t.y; in.w[4 * j + 2] = t.z; in.w[4 * j + 3] = t.w;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = lds_v4(box + ((static_cast<uint32_t>(j) ^ sw) << 4));
+              in.w[4 * j] = t.x; in.w[4 * j + 1] = t.y; in.w[4 * j + 2] = t.z; in.w[4 * j + 3] = t.w;
+            }
           }
+        }
+        if constexpr (!kBoxes) {
+          if (!row_ok) return;      // (after the box wait: every lane keeps the slot's phase count)
         }
         // bf16 results leave through the warp's private [32 rows x 32 columns] SWIZZLE_64B box and ONE TMA store: a 32-byte
         // st.global per lane touches 32 different lines per instruction (32 L1 wavefronts), and with two such tensors per chunk
@@ -381,7 +416,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[i].x, v[i].y);
           if constexpr (kBoxes) {
-            const uint32_t box = smem_u32(out_boxes) + static_cast<uint32_t>((ew * 2 + (nbox & 1)) * C::kOutBoxBytes);
+            const uint32_t box = smem_u32(out_boxes) + static_cast<uint32_t>((ew * 2 + (nbox & 1)) * 2048);
             if (lane == 0) bulk_wait_read1();
             __syncwarp();
             const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
@@ -483,9 +518,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         }
       };
-      Row64 pre0, pre1;
-      prefetch(0, pre0);
-      prefetch(1, pre1);
+      prefetch(0, 0);
+      prefetch(1, 1);
       GSTAMP(g4);
       mbar_wait(&tmem_full_bar[as], aphase);
       GSTAMP(g5);
@@ -496,11 +530,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll 1
       for (int cp = 0; cp < CHUNKS; cp += 2) {
-        body(cp, pre0);
-        prefetch(cp + 2, pre0);
+        body(cp, 0);
+        prefetch(cp + 2, 0);
         if (cp + 1 < CHUNKS) {
-          body(cp + 1, pre1);
-          prefetch(cp + 3, pre1);
+          body(cp + 1, 1);
+          prefetch(cp + 3, 1);
         }
       }
       // all of this warp's TMEM reads for this stage are complete (wait::ld in body): release it
@@ -590,11 +624,19 @@ int make_tmap_out(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, 
 
 template <int BN, int EPI, bool V32, int CG>
 int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
-  constexpr bool kBoxes = EPI == A4R_EPI_GELU;
-  using C = Cfg<BN, CG, kBoxes>;
-  static_assert(!kBoxes || 4 * EpiGroups<BN, EPI>::value <= C::kMaxEpiWarps, "result boxes for every epilogue warp");
-  CUtensorMap tmA, tmB, tmA2, tmB2, tmC, tmAux;
+  constexpr bool kBoxes = EpiBoxes<BN, EPI>::kOut;
+  constexpr bool kInBoxes = EpiBoxes<BN, EPI>::kIn;
+  using C = Cfg<BN, CG, EPI>;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmC, tmAux, tmIn;
   int rc;
+  {
+    // the streamed epilogue input: residual (LINEAR) or aux (GELU' / RELU')
+    const void* in_ptr = (EPI == A4R_EPI_LINEAR || EPI == EPI_LINEAR_DROPSUM) ? a->residual : a->aux;
+    const int64_t in_ld = (EPI == A4R_EPI_LINEAR || EPI == EPI_LINEAR_DROPSUM) ? a->ldr : a->ldaux;
+    if (kInBoxes && in_ptr != nullptr) {
+      if ((rc = make_tmap_out(&tmIn, in_ptr, a->M, a->N, in_ld)) != A4R_OK) return rc;
+    }
+  }
   const bool box_c = kBoxes && !a->out_f32, box_aux = kBoxes && a->aux != nullptr;
   if (box_c && (rc = make_tmap_out(&tmC, a->C, a->M, a->N, a->ldc)) != A4R_OK) return rc;
   if (box_aux && (rc = make_tmap_out(&tmAux, a->aux, a->M, a->N, a->ldaux)) != A4R_OK) return rc;
@@ -609,6 +651,7 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
   }
   if (!box_c) tmC = tmA;        // (unused: stored directly)
   if (!box_aux) tmAux = tmA;    // (unused)
+  if (!(kInBoxes && ((EPI == A4R_EPI_LINEAR || EPI == EPI_LINEAR_DROPSUM) ? a->residual : a->aux) != nullptr)) tmIn = tmA;   // (unused)
   GemmParams p;
   p.C = a->C;
   p.aux = a->aux;
@@ -656,9 +699,9 @@ int launch_gemm(const a4r_gemm_args* a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    A4R_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, EPI, V32, CG>, tmA, tmB, tmA2, tmB2, tmC, tmAux, p));
+    A4R_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, EPI, V32, CG>, tmA, tmB, tmA2, tmB2, tmC, tmAux, tmIn, p));
   } else {
-    gemm_tn_kernel<BN, EPI, V32, CG><<<grid, threads, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, p);
+    gemm_tn_kernel<BN, EPI, V32, CG><<<grid, threads, C::kSmemBytes, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmAux, tmIn, p);
   }
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
