@@ -122,6 +122,10 @@ class BertAdaptedSelfOutput(nn.Module):
         mods = (d,) if intermediate is None else (d, intermediate)
         if any(m.weight.requires_grad or m.bias.requires_grad for m in mods):
             return None
+        if inp is not x2 and not inp.is_contiguous():
+            # the [CLS]-only tail of the padded layout hands in a strided [N, H] view of the skip rows: one small copy keeps
+            # it on the fused kernel, i.e. on the same instruction sequence as the unpadded layout (bit-equal results)
+            inp = inp.contiguous()
         if not (ops.adapter_ln_supported(self.adapter.fc_down.in_features, self.adapter.fc_down.out_features)
                 and inp.is_contiguous() and x2.shape[0] == inp.shape[0]):
             return None
