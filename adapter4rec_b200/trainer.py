@@ -1,7 +1,8 @@
-"""Data-parallel adapter-tuning step: forward + backward through the sm_100a kernels, ONE all-reduce of the flat
-trainable-gradient buffer over NCCL, fused flat Adam.  Mirrors the optimisation set-up of
-Downstream/Text/run.py:503-529,595-600 (4 learning-rate groups chosen by parameter NAME, torch.optim.Adam defaults,
-DistributedDataParallel's gradient averaging)."""
+"""Data-parallel adapter-tuning step: forward + backward through the sm_100a kernels, sum all-reduce of the flat
+trainable-gradient buffer over NCCL — one collective for adapter tuning (<= 10 MB), `bucket_bytes` slices issued from
+gradient hooks while the backward is still running for full fine-tuning (440 MB) — and fused flat Adam.  Mirrors the
+optimisation set-up of Downstream/Text/run.py:503-529,595-600 (4 learning-rate groups chosen by parameter NAME,
+torch.optim.Adam defaults, DistributedDataParallel's gradient averaging and bucketed overlap)."""
 import torch
 import torch.distributed as dist
 
@@ -31,7 +32,8 @@ class FlatAdamTrainer:
     kernel launch per learning-rate group."""
 
     def __init__(self, model, lr, fine_tune_lr, adapter_bert_lr, adapter_sasrec_lr, betas=(0.9, 0.999), eps=1e-8,
-                 weight_decay=0.0, users_per_pass=128, process_group=None, grouping=None):
+                 weight_decay=0.0, users_per_pass=128, process_group=None, grouping=None, bucket_bytes=25 << 20,
+                 overlap=True):
         self.model = model
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.users_per_pass = users_per_pass
@@ -64,6 +66,49 @@ class FlatAdamTrainer:
                 self.segments.append((g, lrs[g], start, off - start))
         self.step_count = 0
         self.num_trainable = total
+        # Backward-overlapped reduction (DistributedDataParallel's bucket hooks, run.py:503): the flat buffer is cut into
+        # contiguous buckets of <= bucket_bytes; a bucket's all-reduce is issued (async: NCCL runs it on its own stream
+        # behind everything the current stream has enqueued so far) as soon as every gradient in it has been accumulated
+        # in the LAST pass of the step.  Buckets are issued in one fixed order on every rank — from the end of the buffer
+        # (the last layers, whose gradients come first) to the start — whatever order they complete in.
+        self.buckets = []            # [offset, numel, number of parameters]
+        self._works, self._live, self._next = [], False, -1
+        if self.world > 1 and overlap:
+            cap = max(1, int(bucket_bytes) // 4)
+            for (g, n, p), (_, off, k) in zip(plist, self.names):
+                if not self.buckets or self.buckets[-1][1] + k > cap:
+                    self.buckets.append([off, 0, 0])
+                b = self.buckets[-1]
+                b[1] += k
+                b[2] += 1
+                p.register_post_accumulate_grad_hook(self._make_hook(len(self.buckets) - 1))
+        self._pending = [b[2] for b in self.buckets]
+        self._ready = [False] * len(self.buckets)
+
+    def _make_hook(self, b):
+        def hook(_param):
+            if not self._live:
+                return
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._ready[b] = True
+                self._issue_ready()
+        return hook
+
+    def _issue_ready(self, force=False):
+        """issue the all-reduces of the completed buckets, strictly in descending bucket order (same on every rank);
+        force: issue the rest too (parameters that received no gradient this step never fire their hook)"""
+        while self._next >= 0 and (force or self._ready[self._next]):
+            off, n, _ = self.buckets[self._next]
+            self._works.append(dist.all_reduce(self.flat_grad[off:off + n], op=dist.ReduceOp.SUM, group=self.pg,
+                                               async_op=True))
+            self._next -= 1
+
+    def _arm(self):
+        self._pending = [b[2] for b in self.buckets]
+        self._ready = [False] * len(self.buckets)
+        self._next = len(self.buckets) - 1
+        self._live = bool(self.buckets)
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -86,13 +131,24 @@ class FlatAdamTrainer:
             loss_c = model(sample_items[b0 * rows_per_user:b1 * rows_per_user], lm, sample_items.device)
             w = (float(b1 - b0) / B) if cpc else (lm != 0).sum().float() / count_all
             weighted = loss_c * w
+            if b1 == B:
+                self._arm()      # gradients are final after this pass: buckets may leave while it is running
             weighted.backward()
             total = weighted.detach() if total is None else total + weighted.detach()
         return total
 
     def reduce_gradients(self):
-        """The ONE collective of a training step: sum all-reduce of the flat gradient buffer (NCCL on GPUs)."""
-        if self.world > 1:
+        """Sum all-reduce of the flat gradient buffer (NCCL on GPUs): whatever the backward hooks have not issued yet is
+        issued here, then the current stream waits for all of it.  Without hooks (overlap=False, or gradients written
+        outside forward_backward) this is the ONE collective of the step."""
+        if self.world <= 1:
+            return
+        if self._live:
+            self._issue_ready(force=True)
+            for w in self._works:
+                w.wait()
+            self._works, self._live = [], False
+        else:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
 
     def optimizer_step(self):

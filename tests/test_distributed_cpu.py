@@ -74,6 +74,34 @@ def _worker(rank, world, port, ret):
         tr.reduce_gradients()
         assert torch.all(lin.weight.grad == 3.0) and torch.all(lin.bias.grad == 30.0)
         assert float(tr.flat_grad.sum()) == 12 * 3.0 + 3 * 30.0
+        # (5) bucketed reduction issued from gradient hooks during the LAST pass of a multi-pass step: every bucket (incl.
+        # one whose parameter receives no gradient) ends up holding the sum over ranks of the accumulated local gradients
+        class Toy(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                torch.manual_seed(3)
+                self.unused, self.a, self.b = torch.nn.Linear(2, 2), torch.nn.Linear(6, 5), torch.nn.Linear(5, 1)
+
+            def forward(self, rows, log_mask, dev):
+                return (self.b(torch.tanh(self.a(rows))).view(log_mask.shape[0], -1).mean(1) * log_mask.sum(1)).sum() / 7.0
+        toy = Toy()
+        tr2 = FlatAdamTrainer(toy, 1e-3, 1e-3, 1e-3, 1e-3, users_per_pass=3, bucket_bytes=64)
+        assert len(tr2.buckets) >= 3 and sum(b[1] for b in tr2.buckets) == tr2.num_trainable
+        gen = torch.Generator().manual_seed(100 + rank)
+        rows, lm = torch.randn(8 * 2, 6, generator=gen), (torch.rand(8, 4, generator=gen) < 0.7).float()
+        tr2.zero_grad()
+        tr2.forward_backward(rows, lm)
+        assert tr2._live and len(tr2._works) > 0      # some buckets left while the backward was running
+        tr2.reduce_gradients()
+        got = tr2.flat_grad.clone()
+        ref_model = Toy()
+        tr3 = FlatAdamTrainer(ref_model, 1e-3, 1e-3, 1e-3, 1e-3, users_per_pass=3, overlap=False)
+        tr3.zero_grad()
+        tr3.forward_backward(rows, lm)
+        want = tr3.flat_grad.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        assert torch.allclose(got, want, rtol=0, atol=1e-6), float((got - want).abs().max())
+        assert float(got.abs().sum()) > 0 and not tr2._live and not tr2._works
         ret[rank] = "ok"
     except Exception as e:  # noqa: BLE001
         import traceback

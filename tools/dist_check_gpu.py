@@ -3,7 +3,9 @@
 (1) full-ranking eval with the item table sharded by item id (all-gather of partial top-10 lists + merge) gives the SAME
     top-10 ids / HR / NDCG as the unsharded evaluation of the gathered table;
 (2) data-parallel training: after two steps on different per-rank batches every rank holds bit-identical parameters
-    (one flat-gradient all-reduce per step) and the loss is finite.
+    (one flat-gradient all-reduce per step) and the loss is finite;
+(3) full fine-tuning with the backward-overlapped bucketed reduction (64 KB buckets issued from gradient hooks) gives the
+    gradients of the single blocking all-reduce.
 Prints one line per check; exit code 0 iff all pass."""
 import os
 import sys
@@ -65,10 +67,39 @@ ref = flat.clone()
 dist.broadcast(ref, 0)
 same = torch.equal(flat, ref) and bool(torch.isfinite(torch.as_tensor(float(loss))))
 ok &= same
+if rank == 0:
+    print("parameters bit-identical on all ranks after 2 DP steps:", same, "| loss %.5f" % float(loss))
+
+# ---- (3) bucketed, backward-overlapped reduction == one blocking all-reduce (full fine-tuning: every tensor trainable)
+cf = cases.tiny_case("full_ft")
+sdf = cases.build_state_dict(cf)
+itf = cases.build_item_content(cf)
+sif, lmf, _ = cases.build_batch(cf, itf)
+Bf = sif.shape[0]
+halff = slice(rank * (Bf // world), (rank + 1) * (Bf // world))
+xf, lf = sif[halff].reshape(-1, 2 * cf.L).to(dev), lmf[halff].to(dev)
+grads = []
+for overlap in (True, False):
+    mf, _ = build_gpu_model(cf, sdf)
+    mf.eval()                                  # no dropout: both runs see the same arithmetic
+    tf = FlatAdamTrainer(mf, 1e-3, 1e-4, 1e-3, 1e-3, users_per_pass=4, bucket_bytes=64 << 10, overlap=overlap)
+    tf.zero_grad()
+    tf.forward_backward(xf, lf)
+    issued_early = len(tf._works)
+    tf.reduce_gradients()
+    torch.cuda.synchronize()
+    grads.append(tf.flat_grad.clone())
+    if overlap:
+        nb, early = len(tf.buckets), issued_early
+err = float((grads[0] - grads[1]).abs().max() / grads[1].abs().max())
+same3 = (torch.equal(grads[0], grads[1]) if world == 2 else err < 1e-6) and nb > 1 and early > 0
+ok &= same3
+if rank == 0:
+    print("bucketed overlapped reduction == blocking all-reduce (full fine-tuning, %d buckets, %d issued during the backward):"
+          % (nb, early), same3, "| max rel diff %.2e" % err)
 flags = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("parameters bit-identical on all ranks after 2 DP steps:", same, "| loss %.5f" % float(loss))
     print("ALL OK" if int(flags) else "FAILED")
 dist.destroy_process_group()
 sys.exit(0 if int(flags) else 1)
