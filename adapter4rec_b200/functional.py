@@ -522,7 +522,18 @@ class QKVFunction(torch.autograd.Function):
                 b_ext_t, a_cat_t = b_ext.t().contiguous(), a_cat.t().contiguous()
                 if cache.get("b_ext") is b_ext:
                     cache["b_ext_t"], cache["a_cat_t"] = b_ext_t, a_cat_t
-            dT = ops.gemm(dqkv, b_ext_t)
+            # only the projections that carry a LoRA pair have non-zero rows in B_ext: with q|k|v fused and LoRA on q and v
+            # (run.py:414-428) the key third of dqkv is skipped — its products are exact zeros — so this HBM-bound skinny
+            # GEMM reads 2/3 of dqkv (two K-segments through the GEMM's second operand pair)
+            lj = [j for j, _, _ in ctx.slots]
+            if n == 3 and len(lj) == 2:
+                (ja, jb) = lj
+                dT = ops.gemm(dqkv[:, ja * H:(ja + 1) * H], b_ext_t[:, ja * H:(ja + 1) * H],
+                              a2=dqkv[:, jb * H:(jb + 1) * H], b2=b_ext_t[:, jb * H:(jb + 1) * H])
+            elif n == 3 and len(lj) == 1:
+                dT = ops.gemm(dqkv[:, lj[0] * H:(lj[0] + 1) * H], b_ext_t[:, lj[0] * H:(lj[0] + 1) * H])
+            else:
+                dT = ops.gemm(dqkv, b_ext_t)
             dx = ops.gemm(dqkv, cache["wt"], a2=dT, b2=a_cat_t, residual=dskip) if ctx.needs_input_grad[0] else None
         else:
             dx = ops.gemm(dqkv, cache["wt"], residual=dskip) if ctx.needs_input_grad[0] else None
@@ -532,18 +543,28 @@ class QKVFunction(torch.autograd.Function):
             # runs only if one of its results is wanted (x is saved only when a lora_A or a weight trains).
             want_g1 = any(ctx.param_needs[4 * j + 1] for j in range(n)) or any(ctx.param_needs[4 * j + 3] for j, _, _ in ctx.slots)
             want_g2 = any(ctx.param_needs[4 * j + 2] for j, _, _ in ctx.slots)
-            g1 = ops.wgrad(dqkv, T) if want_g1 else None            # [n*H, 64] = dqkvᵀ · [T | 1]
+            # g1 rows of projection j are wanted for its bias or its lora_B; a projection that needs neither (the frozen key
+            # projection under LoRA on q and v) is not read: one weight-gradient launch per wanted third of dqkv
+            g1_rows = [ctx.param_needs[4 * j + 1] or any(jj == j and ctx.param_needs[4 * j + 3] for jj, _, _ in ctx.slots)
+                       for j in range(n)]
+            g1 = [None] * n
+            if want_g1:
+                if all(g1_rows):
+                    full = ops.wgrad(dqkv, T)                       # [n*H, 64] = dqkvᵀ · [T | 1]
+                    g1 = [full[j * H:(j + 1) * H] for j in range(n)]
+                else:
+                    g1 = [ops.wgrad(dqkv[:, j * H:(j + 1) * H], T) if g1_rows[j] else None for j in range(n)]
             g2 = ops.wgrad(dT, x) if want_g2 else None              # [64, K]   = dTᵀ · x
         for j in range(n):
             dq = dqkv[:, j * H:(j + 1) * H]
             if ctx.param_needs[4 * j]:
                 grads[4 * j] = ops.wgrad(dq, x)
             if ctx.param_needs[4 * j + 1]:
-                grads[4 * j + 1] = g1[j * H:(j + 1) * H, LORA_PAD - 1].contiguous() if fused else ops.colsum(dq)
+                grads[4 * j + 1] = g1[j][:, LORA_PAD - 1].contiguous() if fused else ops.colsum(dq)
         for j, o, r in ctx.slots:
             dq = dqkv[:, j * H:(j + 1) * H]
             if ctx.param_needs[4 * j + 3]:   # lora_B [H, r] = (1/r) dqᵀ · T_j
-                grads[4 * j + 3] = (g1[j * H:(j + 1) * H, o:o + r] * (1.0 / r)) if fused else \
+                grads[4 * j + 3] = (g1[j][:, o:o + r] * (1.0 / r)) if fused else \
                     _pad_cols_wgrad(dq, T, o, r, 1.0 / r, transpose=False)
             if ctx.param_needs[4 * j + 2]:   # lora_A [r, K] = dT_jᵀ · x   (dT already carries the 1/r of B_ext)
                 grads[4 * j + 2] = g2[o:o + r].contiguous() if fused else _pad_cols_wgrad(dT, x, o, r, 1.0, transpose=True)

@@ -2,6 +2,11 @@
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+if "--lib" in sys.argv:      # A/B against a variant build of the library (tools/variants/*.so)
+    import adapter4rec_b200.lib as _lib
+    i = sys.argv.index("--lib")
+    _lib.LIB_PATH = os.path.abspath(sys.argv[i + 1])
+    del sys.argv[i:i + 2]
 from adapter4rec_b200 import ops
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 161280
