@@ -4,7 +4,7 @@
 O=gpurun_out
 T=${1:-420}
 SEL="gemm or adapter or layernorm or attn or score or wgrad or embed or topk"
-for tool in memcheck synccheck racecheck; do
+for tool in ${TOOLS:-memcheck synccheck racecheck}; do
   timeout $T compute-sanitizer --tool $tool --print-limit 20 --log-file $O/r02_sanitizer_$tool.log \
     python -m pytest tests/test_kernels_gpu.py -x -q -k "$SEL" -p no:cacheprovider > $O/r02_sanitizer_${tool}_pytest.log 2>&1
   echo "== $tool: exit $?"; tail -3 $O/r02_sanitizer_${tool}_pytest.log; grep -c "=========" $O/r02_sanitizer_$tool.log; grep "SUMMARY" $O/r02_sanitizer_$tool.log | tail -2

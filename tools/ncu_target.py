@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 M = 161280
 SHAPES = [(M, 64, 768, 0), (M, 2304, 832, 0), (M, 768, 768, 0), (M, 3072, 768, 1), (M, 768, 3072, 0), (M, 3072, 768, 3),
-          (M, 64, 2304, 0), (M, 768, 2368, 0)]
+          (M, 64, 1536, 0), (M, 768, 2368, 0)]
 if __name__ == "__main__":
     import torch
     from adapter4rec_b200 import ops
@@ -20,7 +20,8 @@ if __name__ == "__main__":
         f = ops.gemm(y, w1, bias=b1, epilogue=ops.EPI_GELU, aux=u)              # FFN1 + GELU (+ pre-activation)
         h = ops.gemm(f, w2, bias=b2, residual=y)                                # FFN2 + residual
         du = ops.gemm(h, w2.t().contiguous(), epilogue=ops.EPI_DGELU, aux=u)    # dFFN2 with fused GELU'
-        dt = ops.gemm(qkv, bext.t().contiguous())                               # dT = dqkv B_ext
+        bt = bext.t().contiguous()
+        dt = ops.gemm(qkv[:, :768], bt[:, :768], a2=qkv[:, 1536:], b2=bt[:, 1536:])    # dT = dq B_q + dv B_v (key third skipped)
         dx = ops.gemm(qkv, w_qkv.t().contiguous(), a2=dt, b2=acat.t().contiguous())   # dx = [dqkv | dT] [W ; A_cat]
     torch.cuda.synchronize()
     print("done")
