@@ -8,7 +8,12 @@
 // epilogue threads can touch global memory in a coalesced (row-distributed) layout; measured, that skeleton alone costs
 // 20.6 us per 128-token tile against 13.4 us of HBM time.  Here every epilogue thread keeps the TMEM-native
 // layout (one token row per thread) from the accumulator to the result and ALL global traffic is TMA:
-//   warp 0   TMA producer of the down-projection operands (h k-blocks + W_d k-blocks, 2-stage ring), W_u resident;
+//   warp 0   TMA producer of the down-projection operands (h k-blocks + W_d k-blocks, NSTAGE-deep ring);
+//   warp 20  TMA producer of W_u: 4 KB chunks ([32 output columns x 64] bf16) re-streamed from L2 for every tile through a ring
+//            of NWU slots.  (W_u used to be resident: 96 KB of the 227 KB, which left a 2-stage operand ring — a third of the
+//            tile time was the epilogue waiting for the NEXT tile's down-projection, 12 k-blocks at two DRAM round trips in
+//            flight.  Re-reading 96 KB per tile from L2 costs 1/8 more L2->SM traffic and frees the room for a 4-stage ring,
+//            a fourth residual box per group and double result boxes.)
 //   warp 1   tcgen05 issuer: S1 = h · W_dᵀ, then U = s · W_uᵀ in 32-column chunks, chunk c into TMEM stage c & 1;
 //   warps 2, 3  TMA producers of the RESIDUALS, one per epilogue group: [128 x 32] boxes of h and input (SWIZZLE_64B) through a
 //            ring of three single boxes per group (each ring has ONE consumer group: no cross-group barrier phases);
@@ -29,18 +34,26 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int RP = 64;
 constexpr int CC = 32;                        // columns per up-projection chunk
-constexpr int NSTAGE = 2;
+#ifndef A4R_K5_NSTAGE          // (tuning builds only: tools/k5_variants.sh)
+#define A4R_K5_NSTAGE 4
+#define A4R_K5_NWU 4
+#define A4R_K5_INBOXES 4
+#endif
+constexpr int NSTAGE = A4R_K5_NSTAGE;
+constexpr int NWU = A4R_K5_NWU;               // W_u chunk ring (4 KB slots)
+constexpr int WU_CHUNK = CC * 128;            // 32 rows of W_u x 64 bf16 (SW128, K-major)
 constexpr int STAGE_A = BM * BK * 2;          // 16 KB of h
 constexpr int STAGE_B = RP * BK * 2;          // 8 KB of W_d
 constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
 constexpr int S_TILE = BM * RP * 2;           // 16 KB operand tile of the up-projection (also: row-statistics exchange)
 constexpr int IN_HALF = BM * CC * 2;          // 8 KB: one [128 x 32] bf16 box
-constexpr int OUT_STAGE = IN_HALF;          // 16 per-warp result boxes of 1 KB = two of these
-constexpr int IN_BOXES = 3;                   // residual boxes per group: a ring of single [128 x 32] boxes (h, input, h, ...), so
+constexpr int OUT_STAGE = IN_HALF;          // 16 per-warp result boxes of 1 KB = two of these; every warp owns TWO boxes
+constexpr int IN_BOXES = A4R_K5_INBOXES;                   // residual boxes per group: a ring of single [128 x 32] boxes (h, input, h, ...), so
                                               // a group's next chunk is in flight while it works on the current one
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = 128 + EPI_THREADS;
+constexpr int WU_WARP = 4 + EPI_WARPS;         // warp 20: W_u chunk producer
+constexpr int THREADS = 128 + EPI_THREADS + 32;
 constexpr int TMEM_COLS = 512;
 constexpr int U_COL = 0;                      // two 32-column U stages
 constexpr int S1_COL = 64;                    // 64 columns
@@ -68,6 +81,7 @@ A4R_DEVICE void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, in
 }
 A4R_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 A4R_DEVICE void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+A4R_DEVICE void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 A4R_DEVICE void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 A4R_DEVICE void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
@@ -104,15 +118,16 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
                     const __grid_constant__ CUtensorMap tmZ, const RowParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_wu = smem;                                          // [H][64] bf16, SW128
-  uint8_t* s_ring = s_wu + static_cast<size_t>(p.H) * 128;
+  uint8_t* s_wu = smem;                                          // NWU x [32][64] bf16, SW128
+  uint8_t* s_ring = s_wu + NWU * WU_CHUNK;
   uint8_t* s_act = s_ring + NSTAGE * STAGE_BYTES;                // [128][64] bf16, SW128
   uint8_t* s_in = s_act + S_TILE;                                // 2 groups x IN_BOXES residual boxes, SW64
-  uint8_t* s_o = s_in + 2 * IN_BOXES * IN_HALF;                  // 16 x 1 KB: one result box per epilogue warp (out and z_out)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_o + 2 * OUT_STAGE);
+  uint8_t* s_o = s_in + 2 * IN_BOXES * IN_HALF;                  // 16 x 2 x 1 KB: two result boxes per epilogue warp
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_o + 4 * OUT_STAGE);
   uint64_t* empty_bar = full_bar + NSTAGE;
-  uint64_t* wu_bar = empty_bar + NSTAGE;
-  uint64_t* s1_full = wu_bar + 1;
+  uint64_t* wu_full = empty_bar + NSTAGE;         // [NWU]
+  uint64_t* wu_empty = wu_full + NWU;             // [NWU]
+  uint64_t* s1_full = wu_empty + NWU;
   uint64_t* s_ready = s1_full + 1;
   uint64_t* u_full = s_ready + 1;     // [2]
   uint64_t* u_empty = u_full + 2;     // [2]
@@ -140,7 +155,10 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(wu_bar, 1);
+    for (int s = 0; s < NWU; ++s) {
+      mbar_init(&wu_full[s], 1);
+      mbar_init(&wu_empty[s], 1);
+    }
     mbar_init(s1_full, 1);
     mbar_init(s_ready, EPI_WARPS);
     for (int s = 0; s < 2; ++s) {
@@ -165,8 +183,6 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   if (warp == 0) {
     // ============================== TMA producer: down-projection operands ==============================
     if (lane == 0) {
-      mbar_expect_tx(wu_bar, static_cast<uint32_t>(p.H) * 128u);
-      for (int c = 0; c < nch; ++c) tma_load_2d(&tmWu, s_wu + static_cast<size_t>(c) * CC * 128, wu_bar, 0, c * CC);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -180,6 +196,19 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
             stage = 0;
             phase ^= 1;
           }
+        }
+      }
+    }
+  } else if (warp == WU_WARP) {
+    // ============================== TMA producer of the W_u chunks (L2-resident: 96 KB re-streamed per tile) ==============
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nch; ++c, ++n) {
+          const uint32_t slot = n % NWU;
+          mbar_wait(&wu_empty[slot], ((n / NWU) & 1u) ^ 1u);
+          mbar_expect_tx(&wu_full[slot], WU_CHUNK);
+          tma_load_2d(&tmWu, s_wu + slot * WU_CHUNK, &wu_full[slot], 0, c * CC);
         }
       }
     }
@@ -212,7 +241,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cu[2] = {0u, 0u};
-      uint32_t it = 0;
+      uint32_t it = 0, nwu = 0;                        // nwu: running W_u chunk number (ring slot nwu % NWU)
       auto down_kb = [&](int kb) {
         tc_fence_after();
         const uint32_t sa = smem_u32(s_ring + stage * STAGE_BYTES);
@@ -228,7 +257,6 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         }
         if (kb == nkb - 1) umma_commit(s1_full);
       };
-      mbar_wait(wu_bar, 0);
       if (static_cast<int>(blockIdx.x) < num_tiles) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -244,15 +272,18 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         while (c < nch || kb < nkb) {
           if (c < nch) {
             const int g = c & 1;
-            if (mbar_try_wait(&u_empty[g], (cu[g] & 1u) ^ 1u)) {
+            const uint32_t slot = nwu % NWU;
+            if (mbar_try_wait(&u_empty[g], (cu[g] & 1u) ^ 1u) && mbar_try_wait(&wu_full[slot], (nwu / NWU) & 1u)) {
               tc_fence_after();
-              const uint64_t bdesc = umma_desc_k_sw128(smem_u32(s_wu + static_cast<size_t>(c) * CC * 128));
+              const uint64_t bdesc = umma_desc_k_sw128(smem_u32(s_wu + slot * WU_CHUNK));
 #pragma unroll
               for (int k = 0; k < RP / 16; ++k)
                 umma_bf16_ss(tmem_base + U_COL + g * CC, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
                              idesc_up, k != 0 ? 1u : 0u);
               umma_commit(&u_full[g]);
+              umma_commit(&wu_empty[slot]);                    // the W_u slot is free once these MMAs have read it
               ++cu[g];
+              ++nwu;
               ++c;
               continue;
             }
@@ -264,7 +295,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < WU_WARP) {
     // ============================== epilogue: one token row per thread, start to end ==============================
     const int ew = warp - 4;
     const int quad = warp & 3, cs = ew >> 2;             // TMEM lane quadrant; 16-column slice of S1
@@ -277,21 +308,24 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     const uint32_t toff0 = rl * 64 + (((2u * hf) ^ sw) << 4), toff1 = rl * 64 + (((2u * hf + 1u) ^ sw) << 4);
     const uint32_t sin0 = smem_u32(s_in) + grp * IN_BOXES * IN_HALF;
     uint32_t nb = 0;                                     // running residual-box number of this group (as in its producer)
-    const uint32_t so_w = smem_u32(s_o) + ew * 1024;     // this warp's private out box
+    const uint32_t so_w = smem_u32(s_o) + ew * 2048;     // this warp's two private out boxes (they alternate)
+    uint32_t n_out = 0;
     float* stats = reinterpret_cast<float*>(s_act);      // [128][4][2] after the tile's last up-projection has retired
     uint32_t n_u = 0, it = 0;
 
     // Results leave per WARP: its 32 rows x 16 columns form a private 1 KB box (row pitch 32 B, no swizzle) that lane 0 hands to
     // TMA — no barrier wider than the warp, so the 16 warps drift freely instead of waiting for the slowest of a group.
     auto emit = [&](const CUtensorMap* tm, const uint32_t (&w)[8], int c, int row0) {
-      if (lane == 0) bulk_wait_read0();                  // this warp's previous store has read its bytes
+      const uint32_t box = so_w + (n_out & 1u) * 1024;
+      ++n_out;
+      if (lane == 0) bulk_wait_read1();                  // the store issued from THIS box two hand-overs ago has read its bytes
       __syncwarp();                                      // (tcgen05.* / bar.sync are .aligned: keep the warp converged)
-      sts_v4(so_w + lane * 32, w[0], w[1], w[2], w[3]);
-      sts_v4(so_w + lane * 32 + 16, w[4], w[5], w[6], w[7]);
+      sts_v4(box + lane * 32, w[0], w[1], w[2], w[3]);
+      sts_v4(box + lane * 32 + 16, w[4], w[5], w[6], w[7]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tm, so_w, c * CC + hf * 16, row0 + quad * 32);   // rows past M are clipped by the tensor map
+        tma_store_2d(tm, box, c * CC + hf * 16, row0 + quad * 32);   // rows past M are clipped by the tensor map
         bulk_commit();
       }
       __syncwarp();
@@ -541,8 +575,10 @@ int a4r_adapter_rows_launch(const a4r_adapter_args* a, cudaStream_t stream) {
   } else {
     tmZ = tmOut;
   }
-  const size_t smem = static_cast<size_t>(a->H) * 128 + NSTAGE * STAGE_BYTES + S_TILE + 2 * IN_BOXES * IN_HALF + 2 * OUT_STAGE +
-                      32 * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = static_cast<size_t>(NWU) * WU_CHUNK + NSTAGE * STAGE_BYTES + S_TILE + 2 * IN_BOXES * IN_HALF + 4 * OUT_STAGE +
+                      48 * sizeof(uint64_t) + 16 + 1024;
+  static_assert(NWU * WU_CHUNK + NSTAGE * STAGE_BYTES + S_TILE + 2 * IN_BOXES * IN_HALF + 4 * OUT_STAGE + 48 * 8 + 16 + 1024 <= 232448,
+                "shared-memory plan exceeds 227 KB");
   A4R_CUDA_OK(cudaFuncSetAttribute(adapter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int tiles = (p.M + BM - 1) / BM;
   const int grid = tiles < a4r_num_sms() ? tiles : a4r_num_sms();

@@ -4,6 +4,11 @@ persistent CTA and M = 645,120 = 34 tiles per CTA: the multi-tile ring / phase p
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+if "--lib" in sys.argv:      # A/B against a variant build of the library (tools/variants/*.so)
+    import adapter4rec_b200.lib as _lib
+    _i = sys.argv.index("--lib")
+    _lib.LIB_PATH = os.path.abspath(sys.argv[_i + 1])
+    del sys.argv[_i:_i + 2]
 from adapter4rec_b200 import ops
 
 H, r = 768, 64

@@ -2,6 +2,11 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+if "--lib" in sys.argv:      # A/B against a variant build of the library (tools/variants/*.so)
+    import adapter4rec_b200.lib as _lib
+    _i = sys.argv.index("--lib")
+    _lib.LIB_PATH = os.path.abspath(sys.argv[_i + 1])
+    del sys.argv[_i:_i + 2]
 from adapter4rec_b200 import ops
 M, H = int(os.environ.get('K5_M', '161280')), 768
 def r(*s, sc=1.0): return (torch.randn(*s, device="cuda") * sc).to(torch.bfloat16)
