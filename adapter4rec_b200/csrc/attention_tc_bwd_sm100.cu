@@ -116,7 +116,7 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   uint64_t* dq_free = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // (warp-uniform for the compiler)
   const int units = p.N * p.heads;
   const int H = p.heads * DH;
   const int my_units = (units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -181,8 +181,8 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         if (p.nq > 1) load_qd(img, head, 1);
         if (p.nkj > 1) load_kv(img, head, 1);
       }
-    } else if (warp == 1 && lane == 0) {
-      // ============================== MMA issuer ==============================
+    } else if (warp == 1) {
+      // ============================== MMA issuer: the WHOLE warp, converged (see umma_*_elect) ==============================
       // steps of a unit: (j, i) lexicographic; global step index g; M12(g + 1) is issued before M345(g)
       const int steps_per_unit = p.nq * p.nkj;
       const int total_steps = my_units * steps_per_unit;
@@ -201,6 +201,7 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         if (j == 0) mbar_wait(&qd_full[nqd % QD_SLOTS], (nqd / QD_SLOTS) & 1u);       // first use of the (Q_i | dO_i) pair
         if (i == 0) mbar_wait(&kv_full[nkv % KV_SLOTS], (nkv / KV_SLOTS) & 1u);       // first use of the (K_j | V_j) pair
         if (g > 0) mbar_wait(sdp_free, static_cast<uint32_t>(g - 1) & 1u);            // S, dP of the previous step were read
+        __syncwarp();
         tc_fence_after();
         const uint32_t qd = smem_u32(s_qd + (nqd % QD_SLOTS) * PAIR), kv = smem_u32(s_kv + (nkv % KV_SLOTS) * PAIR);
         const int ncols = min(128, p.Lk - j * QT);
@@ -209,11 +210,11 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const uint64_t ado = umma_desc_k_sw128(qd + BOX), bv = umma_desc_k_sw128(kv + BOX);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_bf16_ss(tmem_base + COL_S, aq + static_cast<uint64_t>(2 * k), bk + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
+          umma_bf16_ss_elect(tmem_base + COL_S, aq + static_cast<uint64_t>(2 * k), bk + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_bf16_ss(tmem_base + COL_DP, ado + static_cast<uint64_t>(2 * k), bv + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
-        umma_commit(sdp_full);
+          umma_bf16_ss_elect(tmem_base + COL_DP, ado + static_cast<uint64_t>(2 * k), bv + static_cast<uint64_t>(2 * k), idesc, k != 0 ? 1u : 0u);
+        umma_commit_elect(sdp_full);
       };
       auto issue_m345 = [&](int g) {
         int it, i, j;
@@ -223,6 +224,7 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const int jg = it * p.nkj + j;                      // global key-group index: dV_j / dK_j accumulators
         if (i == 0 && jg > 0) mbar_wait(dvk_free, static_cast<uint32_t>(jg - 1) & 1u);
         if (j == 0 && i == 0 && it > 0) mbar_wait(dq_free, static_cast<uint32_t>(it - 1) & 1u);
+        __syncwarp();
         tc_fence_after();
         const uint32_t qd = smem_u32(s_qd + (nqd % QD_SLOTS) * PAIR), kv = smem_u32(s_kv + (nkv % KV_SLOTS) * PAIR);
         const int rows = min(128, p.L - i * QT), ncols = min(128, p.Lk - j * QT);
@@ -233,25 +235,25 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const uint64_t ap = umma_desc_mn_sw128_2chunk(smem_u32(s_p)), ads = umma_desc_mn_sw128_2chunk(smem_u32(s_ds));
         const uint64_t bdo = umma_desc_mn_sw128_1chunk(qd + BOX), bq = umma_desc_mn_sw128_1chunk(qd);
         for (int k = 0; k < kq; ++k)
-          umma_bf16_ss(tmem_base + COL_DV, ap + static_cast<uint64_t>(128 * k), bdo + static_cast<uint64_t>(128 * k), idesc_t,
-                       (i | k) != 0 ? 1u : 0u);
+          umma_bf16_ss_elect(tmem_base + COL_DV, ap + static_cast<uint64_t>(128 * k), bdo + static_cast<uint64_t>(128 * k), idesc_t,
+                             (i | k) != 0 ? 1u : 0u);
         for (int k = 0; k < kq; ++k)
-          umma_bf16_ss(tmem_base + COL_DK, ads + static_cast<uint64_t>(128 * k), bq + static_cast<uint64_t>(128 * k), idesc_t,
-                       (i | k) != 0 ? 1u : 0u);
+          umma_bf16_ss_elect(tmem_base + COL_DK, ads + static_cast<uint64_t>(128 * k), bq + static_cast<uint64_t>(128 * k), idesc_t,
+                             (i | k) != 0 ? 1u : 0u);
         // M5: dQ_i += dS K_j        (A K-major: two 64-key chunks; B = K_j MN-major)
         const uint32_t idesc_q = idesc_o | (1u << 16);
         const uint64_t bkm = umma_desc_mn_sw128_1chunk(kv);
         for (int k = 0; k < kk; ++k) {
           const uint64_t a = umma_desc_k_sw128(smem_u32(s_ds) + (k >> 2) * BOX) + static_cast<uint64_t>(2 * (k & 3));
-          umma_bf16_ss(tmem_base + COL_DQ + i * DH, a, bkm + static_cast<uint64_t>(128 * k), idesc_q, (j | k) != 0 ? 1u : 0u);
+          umma_bf16_ss_elect(tmem_base + COL_DQ + i * DH, a, bkm + static_cast<uint64_t>(128 * k), idesc_q, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(pds_free);
+        umma_commit_elect(pds_free);
         if (i == p.nq - 1) {                                 // last query tile of this key group
-          umma_commit(dvk_full);
-          umma_commit(&kv_empty[nkv % KV_SLOTS]);
+          umma_commit_elect(dvk_full);
+          umma_commit_elect(&kv_empty[nkv % KV_SLOTS]);
         }
-        if (j == p.nkj - 1) umma_commit(&qd_empty[nqd % QD_SLOTS]);   // last key group: the (Q_i | dO_i) pair is dead
-        if (j == p.nkj - 1 && i == p.nq - 1) umma_commit(dq_full);
+        if (j == p.nkj - 1) umma_commit_elect(&qd_empty[nqd % QD_SLOTS]);   // last key group: the (Q_i | dO_i) pair is dead
+        if (j == p.nkj - 1 && i == p.nq - 1) umma_commit_elect(dq_full);
       };
       if (total_steps > 0) issue_m12(0);
       for (int g = 0; g < total_steps; ++g) {
@@ -328,6 +330,32 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       }
     };
 
+    // dQ_0 (warps 0-3) / dQ_1 (warps 4-7) of a finished unit
+    auto read_dq = [&](int img, int head, int itq) {
+      mbar_wait(dq_full, static_cast<uint32_t>(itq) & 1u);
+      __syncwarp();
+      tc_fence_after();
+      float o[64];
+      const bool tile_on = half < p.nq;
+      if (tile_on) tmem_ld64(tmem_base + lane_addr + COL_DQ + half * DH, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      __syncwarp();
+      const int qrow = half * QT + rl;
+      if (tile_on && qrow < p.L) {
+        __nv_bfloat16* dst = p.dqkv + (static_cast<int64_t>(img) * p.L + qrow) * p.ld_qkv + head * DH;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(o[c8 * 16 + 2 * e], o[c8 * 16 + 2 * e + 1]);
+          st_na_v8(dst + c8 * 16, w);
+        }
+      }
+    };
+
     float2 info0 = make_float2(INFINITY, 0.0f), info1 = info0, next0 = info0, next1 = info0;
     if (my_units > 0) {
       info0 = row_info(blockIdx.x, 0);
@@ -335,6 +363,7 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     }
     int g = 0, jg = 0, it = 0;
     int pend_img = -1, pend_head = 0, pend_j = 0, pend_jg = 0;      // a finished key group whose dV / dK are still in tensor memory
+    int pend_dq_img = -1, pend_dq_head = 0, pend_dq_it = 0;         // a finished unit whose dQ is still in tensor memory
 #ifdef A4R_ATTN_TIMING
     long long acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -409,6 +438,10 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             read_dvk(pend_img, pend_head, pend_j, pend_jg);
             pend_img = -1;
           }
+          if (pend_dq_img >= 0) {
+            read_dq(pend_dq_img, pend_dq_head, pend_dq_it);
+            pend_dq_img = -1;
+          }
           BSTAMP(b5);
           BACC(4, b4, b5);
           if (i == p.nq - 1) {
@@ -420,40 +453,16 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           }
         }
       }
-      // ---- dQ_0 (warps 0-3) / dQ_1 (warps 4-7) ----
-      BSTAMP(b8);
-      mbar_wait(dq_full, static_cast<uint32_t>(it) & 1u);
-      BSTAMP(b9);
-      BACC(7, b8, b9);
-      __syncwarp();
-      tc_fence_after();
-      {
-        float o[64];
-        const bool tile_on = half < p.nq;
-        if (tile_on) tmem_ld64(tmem_base + lane_addr + COL_DQ + half * DH, o);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dq_free);
-        __syncwarp();
-        const int qrow = half * QT + rl;
-        if (tile_on && qrow < p.L) {
-          __nv_bfloat16* dst = p.dqkv + (static_cast<int64_t>(img) * p.L + qrow) * p.ld_qkv + head * DH;
-#pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            uint32_t w[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(o[c8 * 16 + 2 * e], o[c8 * 16 + 2 * e + 1]);
-            st_na_v8(dst + c8 * 16, w);
-          }
-        }
-      }
-      BSTAMP(b10);
-      BACC(5, b9, b10);
+      // dQ of this unit is read out during the NEXT unit's first step (like dV / dK): its last M5 retires while the compute warps
+      // already exponentiate that step, instead of the whole CTA draining its pipeline at every unit boundary.
+      pend_dq_img = img;
+      pend_dq_head = head;
+      pend_dq_it = it;
       info0 = next0;
       info1 = next1;
     }
     if (pend_img >= 0) read_dvk(pend_img, pend_head, pend_j, pend_jg);
+    if (pend_dq_img >= 0) read_dq(pend_dq_img, pend_dq_head, pend_dq_it);
 #ifdef A4R_ATTN_TIMING
     if (blockIdx.x == 0 && cw == 0 && lane == 0) {
       for (int i = 0; i < 8; ++i) g_attn_bwd_timing[i] = acc_t[i];

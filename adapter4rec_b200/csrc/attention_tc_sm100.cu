@@ -30,7 +30,18 @@ constexpr int THREADS = 384;
 constexpr int BLK_CH = 4;                 // score chunks of 16 columns per register block (two blocks in flight)
 constexpr int TILE_COLS = 256;
 constexpr int O_COL = 128;
+constexpr int OUT_BOX = 32 * 128;           // one warp's result box
 constexpr float LOG2E = 1.4426950408889634f;
+#ifdef A4R_ATTN_POLL_TRY            // (A/B build of tools/micro only: the blocking probe this kernel used to poll with)
+#define A4R_POLL mbar_try_wait
+#else
+#define A4R_POLL mbar_test_wait
+#endif
+
+template <bool B>
+struct FullBlock {
+  static constexpr bool value = B;
+};
 
 struct TcParams {
   __nv_bfloat16* out;
@@ -42,17 +53,19 @@ struct TcParams {
 };
 
 #ifdef A4R_ATTN_TIMING
-__device__ long long g_attn_timing[2][8];
+__device__ long long g_attn_timing[8][8];      // [tile * 4 + quad][phase]; [0][7], [1][7]: issuer
 #define TSTAMP(var) const long long var = clock64()
+__device__ long long g_attn_trace[16][10][6];   // [unit][0-7: tile*4+quad, 8: issuer scores, 9: issuer P V][event]
 #else
 #define TSTAMP(var)
 #endif
 
 __global__ void __launch_bounds__(THREADS, 1)
-attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams p) {
+attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE);
+  uint8_t* s_out = smem + NSTAGE * STAGE;            // 8 softmax warps x [32 rows x 128 B] result boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 8 * OUT_BOX);
   uint64_t* qk_full = bars;            // [2] stage
   uint64_t* v_full = bars + 2;         // [2]
   uint64_t* qk_free = bars + 4;        // [2]
@@ -63,11 +76,14 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
   uint64_t* s_free = bars + 14;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // (warp-uniform for the compiler)
   const int units = p.N * p.heads;
   const int H = p.heads * DH;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmOut);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&qk_full[s], 1);
@@ -108,39 +124,35 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
         mbar_expect_tx(&v_full[st], static_cast<uint32_t>(p.nk * BOX));
         for (int j = 0; j < p.nk; ++j) tma_load_3d(&tmQKV, sq + (4 + j) * BOX, &v_full[st], 2 * H + head * DH, j * QT, img);
       }
-    } else if (warp == 1 && lane == 0) {
-      // ============================== MMA issuer ==============================
+    } else if (warp == 1) {
+      // ============================== MMA issuer: the WHOLE warp, converged (see umma_*_elect) ==============================
       const uint32_t idesc_s = umma_idesc_bf16(QT, static_cast<uint32_t>(p.Lk));
       const uint32_t idesc_o = umma_idesc_bf16(QT, DH) | (1u << 16);      // B (= V) MN-major
       const int ksteps = p.Lk / 16;
       const int my_units = (units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
       // Two in-order queues — score MMAs (unit i, tile t) and P V MMAs (unit j, tile t') — merged by readiness: the scores of the
       // next unit are issued as soon as their tile's tensor-memory region has been read out, without waiting for the other
-      // tile's P V of the current unit.
+      // tile's P V of the current unit.  Probes are non-blocking and made warp-uniform by a vote.
       int si = 0, st_ = 0, pj = 0, pt = 0;
       while (pj < my_units) {
         bool progressed = false;
         if (si < my_units) {
           const int stg = si & 1;
-          if (mbar_try_wait(&qk_full[stg], static_cast<uint32_t>(si >> 1) & 1u) &&
-              mbar_try_wait(&s_free[st_], (static_cast<uint32_t>(si) & 1u) ^ 1u)) {
+          if (__all_sync(0xffffffffu, A4R_POLL(&qk_full[stg], static_cast<uint32_t>(si >> 1) & 1u) &&
+                                          A4R_POLL(&s_free[st_], (static_cast<uint32_t>(si) & 1u) ^ 1u))) {
             tc_fence_after();
             const uint32_t sq = smem_u32(smem + stg * STAGE);
             const uint64_t adesc = umma_desc_k_sw128(sq + st_ * BOX), bdesc = umma_desc_k_sw128(sq + 2 * BOX);
 #pragma unroll
             for (int k = 0; k < DH / 16; ++k)
-              umma_bf16_ss(tmem_base + st_ * TILE_COLS, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
-                           idesc_s, k != 0 ? 1u : 0u);
-            umma_commit(&s_full[st_]);
+              umma_bf16_ss_elect(tmem_base + st_ * TILE_COLS, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                 idesc_s, k != 0 ? 1u : 0u);
+            umma_commit_elect(&s_full[st_]);
 #ifdef A4R_ATTN_TIMING
-            if (blockIdx.x == 0) {
-              const long long q0 = clock64();
-              mbar_wait(&s_full[st_], static_cast<uint32_t>(si) & 1u);
-              g_attn_timing[0][7] += clock64() - q0;
-            }
+            if (blockIdx.x == 0 && si < 16 && lane == 0) g_attn_trace[si][8][st_] = clock64();
 #endif
             if (++st_ == p.nq) {
-              umma_commit(&qk_free[stg]);                  // Q and K of this stage are dead once the score MMAs retire
+              umma_commit_elect(&qk_free[stg]);            // Q and K of this stage are dead once the score MMAs retire
               st_ = 0;
               ++si;
             }
@@ -149,23 +161,24 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
         }
         if (!progressed && pj < si + (st_ > pt ? 1 : 0)) {   // the P V of (pj, pt) follows the scores of (pj, pt)
           const int stg = pj & 1;
-          if (mbar_try_wait(&v_full[stg], static_cast<uint32_t>(pj >> 1) & 1u) && mbar_try_wait(&p_ready[pt], static_cast<uint32_t>(pj) & 1u)) {
+          if (__all_sync(0xffffffffu, A4R_POLL(&v_full[stg], static_cast<uint32_t>(pj >> 1) & 1u) &&
+                                          A4R_POLL(&p_ready[pt], static_cast<uint32_t>(pj) & 1u))) {
+#ifdef A4R_ATTN_TIMING
+            if (blockIdx.x == 0 && pj < 16 && lane == 0) g_attn_trace[pj][9][2 + pt] = clock64();
+#endif
             tc_fence_after();
             const uint32_t sq = smem_u32(smem + stg * STAGE);
             const uint64_t vdesc = umma_desc_mn_sw128_1chunk(sq + 4 * BOX);
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16_ts(tmem_base + pt * TILE_COLS + O_COL, tmem_base + pt * TILE_COLS + 8 * k, vdesc + static_cast<uint64_t>(128 * k),
-                           idesc_o, k != 0 ? 1u : 0u);
-            umma_commit(&o_full[pt]);
+            const uint32_t ts = tmem_base + pt * TILE_COLS;
+            umma_bf16_ts_elect<0>(ts + O_COL, ts, vdesc, idesc_o);
+#pragma unroll 4
+            for (int k = 1; k < ksteps; ++k) umma_bf16_ts_elect<1>(ts + O_COL, ts + 8 * k, vdesc + static_cast<uint64_t>(128 * k), idesc_o);
+            umma_commit_elect(&o_full[pt]);
 #ifdef A4R_ATTN_TIMING
-            if (blockIdx.x == 0) {
-              const long long q0 = clock64();
-              mbar_wait(&o_full[pt], static_cast<uint32_t>(pj) & 1u);
-              g_attn_timing[1][7] += clock64() - q0;
-            }
+            if (blockIdx.x == 0 && pj < 16 && lane == 0) g_attn_trace[pj][9][pt] = clock64();
 #endif
             if (++pt == p.nq) {
-              umma_commit(&v_free[stg]);
+              umma_commit_elect(&v_free[stg]);
               pt = 0;
               ++pj;
             }
@@ -181,7 +194,9 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
     const bool warp_on = t * QT + quad * 32 < p.L;
     const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + t * TILE_COLS;
     const int nch = p.Lk / 16;
+    const uint32_t obox = smem_u32(s_out) + (warp - 4) * OUT_BOX;
     const int nblk = (nch + BLK_CH - 1) / BLK_CH;
+    const int ltail = p.L & 15;              // valid keys in a partial last chunk (0: the chunk is whole)
     if (warp_on) {
       int it = 0;
 #ifdef A4R_ATTN_TIMING
@@ -214,27 +229,73 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
               if (blk * BLK_CH + i < nch) tmem_ld16(tbase + (blk * BLK_CH + i) * 16, dst + i * 16);
           }
         };
-        auto process = [&](int blk, float* sv) {
-          if (blk == nblk - 1 && (p.L & 15) != 0) {          // the partial last chunk: keys >= L must not count (exp2(-inf) = 0)
+        // `full` blocks (all BLK_CH chunks valid, no key past L) run as ONE branch-free basic block: with a branch per chunk the
+        // compiler schedules 16 exponentials at a time and a warp sits out the MUFU latency 13 times per row (measured: a warp
+        // ALONE on its scheduler needed 23 cycles per score against the 8 the MUFU pipe takes).
+        // Only block 0 takes a maximum (it sets the shift).  Later blocks exponentiate under the running shift straight away and
+        // look at their own SUM: a block sum below 2^20 proves every term is (no overflow anywhere, P exact in bf16's range); a
+        // larger one (or inf / NaN) sends the warp through the rare path — raise the shift of the rows that need it, rescale the
+        // P columns written so far and the running sum, and exponentiate the block (still in registers) again.
+        auto block_max = [&](int blk, const float* sv, bool full) {
+          float bm4[BLK_CH];
+#pragma unroll
+          for (int i = 0; i < BLK_CH; ++i) {
+            bm4[i] = -INFINITY;
+            if (full || blk * BLK_CH + i < nch) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) bm4[i] = fmaxf(bm4[i], sv[i * 16 + e]);
+            }
+          }
+          return fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
+        };
+        auto process = [&](int blk, float* sv, auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
+          if (!FULL && ltail != 0) {                     // the partial last chunk: keys >= L must not count (exp2(-inf) = 0)
 #pragma unroll
             for (int i = 0; i < BLK_CH; ++i)
+              if (blk * BLK_CH + i == nch - 1) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if ((blk * BLK_CH + i) * 16 + e >= p.L) sv[i * 16 + e] = -INFINITY;
+                for (int e = 0; e < 16; ++e)
+                  if (e >= ltail) sv[i * 16 + e] = -INFINITY;
+              }
           }
-          float bm = -INFINITY;
+          if (blk == 0) mc = block_max(0, sv, FULL) * p.c;
+          auto exponentiate = [&]() {
+            // packed fp32 pairs (FFMA2 / FADD2): the shift-and-scale and the row sum cost half an instruction per score each
+            float2 cs2[BLK_CH];                           // one partial sum pair per chunk: four independent chains
+            const float2 c2 = make_float2(p.c, p.c), m2 = make_float2(-mc, -mc);
 #pragma unroll
-          for (int i = 0; i < BLK_CH; ++i)
-            if (blk * BLK_CH + i < nch) {
+            for (int i = 0; i < BLK_CH; ++i) {
+              const int ch = blk * BLK_CH + i;
+              cs2[i] = make_float2(0.0f, 0.0f);
+              if (FULL || ch < nch) {
+                uint32_t w[8];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) bm = fmaxf(bm, sv[i * 16 + e]);
+                for (int e = 0; e < 8; ++e) {
+                  const float2 x = __ffma2_rn(make_float2(sv[i * 16 + 2 * e], sv[i * 16 + 2 * e + 1]), c2, m2);
+#ifdef A4R_ATTN_EXP_OFF      // timing experiment only (tools/micro/attn_tc_timing.cu)
+                  const float2 pp = x;
+#else
+                  const float2 pp = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+#endif
+                  cs2[i] = __fadd2_rn(cs2[i], pp);
+                  w[e] = pack_bf16x2(pp.x, pp.y);
+                }
+#ifdef A4R_ATTN_STTM_OFF
+                if (w[0] == 0x12345678u)
+#endif
+                tmem_st_32x32b_x8(tbase + ch * 8, w);   // P chunk ch lands on score columns of chunk ch / 2: already in registers
+              }
             }
-          const float bmc = bm * p.c;
-          if (blk == 0) {
-            mc = bmc;
-          } else if (__any_sync(0xffffffffu, bmc > mc + 20.0f)) {
+            const float2 s01 = __fadd2_rn(cs2[0], cs2[1]), s23 = __fadd2_rn(cs2[2], cs2[3]);
+            const float2 s4 = __fadd2_rn(s01, s23);
+            return s4.x + s4.y;
+          };
+          float bs = exponentiate();
+          if (blk != 0 && __any_sync(0xffffffffu, !(bs < 1048576.0f))) {
             // rare: raise the shift of the rows that need it; rescale their P columns [0, 8 * BLK_CH * blk) and running sums
-            const float nmc = bmc > mc + 20.0f ? bmc : mc;
+            const float bmc = block_max(blk, sv, FULL) * p.c;
+            const float nmc = !(bs < 1048576.0f) && bmc > mc ? bmc : mc;
             const float f = ex2_approx(mc - nmc);
             mc = nmc;
             sum *= f;
@@ -253,40 +314,24 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
               }
               tmem_st_32x32b_x8(tbase + cc * 8, w);
             }
+            bs = exponentiate();
           }
-#pragma unroll
-          for (int i = 0; i < BLK_CH; ++i) {
-            const int ch = blk * BLK_CH + i;
-            if (ch < nch) {
-              uint32_t w[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-#ifdef A4R_ATTN_EXP_OFF      // timing experiment only (tools/micro/attn_tc_timing.cu)
-                const float p0 = fmaf(sv[i * 16 + 2 * e], p.c, -mc), p1 = fmaf(sv[i * 16 + 2 * e + 1], p.c, -mc);
-#else
-                const float p0 = ex2_approx(fmaf(sv[i * 16 + 2 * e], p.c, -mc));
-                const float p1 = ex2_approx(fmaf(sv[i * 16 + 2 * e + 1], p.c, -mc));
-#endif
-                sum += p0 + p1;
-                w[e] = pack_bf16x2(p0, p1);
-              }
-#ifdef A4R_ATTN_STTM_OFF
-              if (w[0] == 0x12345678u)
-#endif
-              tmem_st_32x32b_x8(tbase + ch * 8, w);     // P chunk ch lands on score columns of chunk ch / 2: already in registers
-            }
-          }
+          sum += bs;
+        };
+        auto process_block = [&](int blk, float* sv) {
+          if (blk * BLK_CH + BLK_CH <= nch && (blk * BLK_CH + BLK_CH < nch || ltail == 0)) process(blk, sv, FullBlock<true>{});
+          else process(blk, sv, FullBlock<false>{});
         };
         load_block(0, sA);
         tmem_ld_wait();
         TSTAMP(ts2);
         for (int blk = 0; blk < nblk; blk += 2) {
           if (blk + 1 < nblk) load_block(blk + 1, sB);
-          process(blk, sA);
+          process_block(blk, sA);
           tmem_ld_wait();
           if (blk + 1 < nblk) {
             if (blk + 2 < nblk) load_block(blk + 2, sA);
-            process(blk + 1, sB);
+            process_block(blk + 1, sB);
             tmem_ld_wait();
           }
         }
@@ -310,28 +355,43 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TcParams
         if (lane == 0) mbar_arrive(&s_free[t]);
         __syncwarp();
         TSTAMP(ts5);
-        if (row < p.L) {
+        // The warp's 32 rows x 64 columns leave as ONE TMA store from its private 4 KB box (SWIZZLE_128B: the 16-byte row-per-thread
+        // writes are conflict-free); rows >= L are clipped by the tensor map.  (32-byte-per-lane global stores touched 32 lines
+        // per instruction and kept the warp ~950 cycles.)
+        {
           const float inv = 1.0f / sum;
-          __nv_bfloat16* dst = p.out + (static_cast<int64_t>(img) * p.L + row) * p.ld_out + head * DH;
+          if (lane == 0) bulk_wait_read0();             // this box's previous store (one unit ago) has read its bytes
+          __syncwarp();
 #pragma unroll
-          for (int c8 = 0; c8 < DH / 16; ++c8) {
-            uint32_t w[8];
+          for (int c8 = 0; c8 < DH / 8; ++c8) {
+            uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(o[c8 * 16 + 2 * e] * inv, o[c8 * 16 + 2 * e + 1] * inv);
-            st_na_v8(dst + c8 * 16, w);
+            for (int e = 0; e < 4; ++e) w[e] = pack_bf16x2(o[c8 * 8 + 2 * e] * inv, o[c8 * 8 + 2 * e + 1] * inv);
+            sts_v4(obox + lane * 128 + ((c8 ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
           }
-          if (p.lse != nullptr)
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmOut, obox, head * DH, t * QT + quad * 32, img);
+            bulk_commit();
+          }
+          if (row < p.L && p.lse != nullptr)
             p.lse[(static_cast<int64_t>(img) * p.L + row) * p.heads + head] = mc * 0.6931471805599453f + __logf(sum);   // mc = shift * scale * log2(e)
         }
 #ifdef A4R_ATTN_TIMING
         const long long ts6 = clock64();
+        if (blockIdx.x == 0 && lane == 0 && it < 16) {
+          long long* tr = g_attn_trace[it][t * 4 + quad];
+          tr[0] = ts0; tr[1] = ts1; tr[2] = ts3; tr[3] = ts4; tr[4] = ts5; tr[5] = ts6;
+        }
         acc_t[0] += ts1 - ts0; acc_t[1] += ts2 - ts1; acc_t[2] += ts3 - ts2; acc_t[3] += ts4 - ts3; acc_t[4] += ts5 - ts4; acc_t[5] += ts6 - ts5;
 #endif
       }
+      if (lane == 0) bulk_wait_read0();                 // the last store still reads this CTA's shared memory
 #ifdef A4R_ATTN_TIMING
-      if (blockIdx.x == 0 && lane == 0 && quad == 0) {
-        for (int i = 0; i < 6; ++i) g_attn_timing[t][i] = acc_t[i];
-        g_attn_timing[t][6] = it;
+      if (blockIdx.x == 0 && lane == 0) {
+        for (int i = 0; i < 6; ++i) g_attn_timing[t * 4 + quad][i] = acc_t[i];
+        g_attn_timing[t * 4 + quad][6] = it;
       }
 #endif
     }
@@ -365,11 +425,14 @@ int a4r_attn_vit_tc_fwd(const a4r_attn_args* a, cudaStream_t stream) {
   CUtensorMap tm;
   int rc = make_tmap_tokens(&tm, a->qkv, a->N, a->L, 3 * a->heads * DH, a->ld_qkv);
   if (rc != A4R_OK) return rc;
-  const size_t smem = static_cast<size_t>(NSTAGE) * STAGE + 16 * sizeof(uint64_t) + 16 + 1024;
+  CUtensorMap tmo;
+  if ((rc = make_tmap_tokens(&tmo, a->out, a->N, a->L, a->heads * DH, a->ld_out, 32)) != A4R_OK) return rc;
+  const size_t smem = static_cast<size_t>(NSTAGE) * STAGE + 8 * OUT_BOX + 16 * sizeof(uint64_t) + 16 + 1024;
+  static_assert(NSTAGE * STAGE + 8 * OUT_BOX + 16 * 8 + 16 + 1024 <= 232448, "shared-memory plan exceeds 227 KB");
   const int64_t units = a->N * a->heads;
   const int grid = static_cast<int>(units < a4r_num_sms() ? units : a4r_num_sms());
   A4R_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  attn_vit_tc_fwd_kernel<<<grid, THREADS, smem, stream>>>(tm, p);
+  attn_vit_tc_fwd_kernel<<<grid, THREADS, smem, stream>>>(tm, tmo, p);
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;
