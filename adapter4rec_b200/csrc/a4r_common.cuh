@@ -358,6 +358,106 @@ A4R_DEVICE bool rng_keep(uint64_t bits, int lane4, uint32_t thr16) {
   return ((static_cast<uint32_t>(bits >> (16 * lane4))) & 0xFFFFu) >= thr16;
 }
 
+// Non-blocking probe of an mbarrier phase.  (mbarrier.try_wait may SUSPEND the thread for a system-dependent time when the phase is
+// not complete: in a loop that polls two queues, a probe of the queue that cannot advance then hides the other queue's event.)
+A4R_DEVICE bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// ---- tcgen05 issue from WARP-UNIFORM code ----------------------------------------------------------------------------------
+// `if (lane == 0) { tcgen05.mma ... }` puts the instruction in a divergent region: ptxas then wraps EVERY UTCHMMA in an
+// ELECT / BRA.U.ANY loop and rebuilds its uniform-register operands inside it — about ten dependent uniform-datapath
+// instructions, measured at 77-87 cycles per MMA on the issuing thread (clock64 traces of the attention forward: 13 P V
+// instructions of N = 64 took 1.0-1.1 k cycles to ISSUE, 32 cycles each to execute).  Executed by all 32 lanes of a converged warp
+// with the election inside the PTX, the same instructions compile to back-to-back UTCHMMAs.  The callers keep every operand
+// warp-uniform (loop counters, kernel parameters, shared-memory addresses) and make poll results uniform with a vote.
+A4R_DEVICE void umma_bf16_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// expect_tx + one / two 2-D TMA loads on the same mbarrier, from a converged warp (one elected lane arms and issues)
+A4R_DEVICE void tma_load_2d_elect(const CUtensorMap* m, void* smem_dst, uint64_t* bar, int c0, int c1, uint32_t expect_bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%2], %5;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(expect_bytes)
+      : "memory");
+}
+A4R_DEVICE void tma_load_2d_elect_noarm(const CUtensorMap* m, void* smem_dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// the same store issued by a converged warp with the election inside the PTX (no ELECT / BRA.U.ANY loop around the UTMASTG); the
+// elected lane of a full, converged warp is always the same one, so its bulk groups can be waited on the same way
+A4R_DEVICE void tma_store_2d_commit_elect(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
+      "@q cp.async.bulk.commit_group;\n\t}"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+      : "memory");
+}
+A4R_DEVICE void bulk_wait_read1_elect() {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group.read 1;\n\t}" ::: "memory");
+}
+A4R_DEVICE void bulk_wait0_elect() {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group 0;\n\t}" ::: "memory");
+}
+A4R_DEVICE void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+               ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+A4R_DEVICE void umma_bf16_ss_2cta_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+A4R_DEVICE void umma_commit_2cta_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+A4R_DEVICE void tma_load_2d_2cta_elect(const CUtensorMap* m, void* smem_dst, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+A4R_DEVICE void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 A4R_DEVICE bool elect_one() {
   uint32_t pred;
   asm volatile(

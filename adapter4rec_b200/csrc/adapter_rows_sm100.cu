@@ -136,7 +136,7 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + 2 * IN_BOXES);
   const uint32_t scratch = smem_u32(tmem_slot + 1);   // never-read word: target of the (practically never taken) store above
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // (warp-uniform for the compiler)
   const int num_tiles = (p.M + BM - 1) / BM;
   const int nkb = p.H / BK;
   const int nch = p.H / CC;
@@ -182,16 +182,16 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
 
   if (warp == 0) {
     // ============================== TMA producer: down-projection operands ==============================
-    if (lane == 0) {
+    {                                                    // (whole warp, converged: tma_load_2d_elect)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          __syncwarp();
           uint8_t* sa = s_ring + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(&tmH, sa, &full_bar[stage], kb * BK, tile * BM);
-          tma_load_2d(&tmWd, sa + STAGE_A, &full_bar[stage], kb * BK, 0);
+          tma_load_2d_elect(&tmH, sa, &full_bar[stage], kb * BK, tile * BM, STAGE_BYTES);
+          tma_load_2d_elect_noarm(&tmWd, sa + STAGE_A, &full_bar[stage], kb * BK, 0);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -201,29 +201,29 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     }
   } else if (warp == WU_WARP) {
     // ============================== TMA producer of the W_u chunks (L2-resident: 96 KB re-streamed per tile) ==============
-    if (lane == 0) {
+    {
       uint32_t n = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int c = 0; c < nch; ++c, ++n) {
           const uint32_t slot = n % NWU;
           mbar_wait(&wu_empty[slot], ((n / NWU) & 1u) ^ 1u);
-          mbar_expect_tx(&wu_full[slot], WU_CHUNK);
-          tma_load_2d(&tmWu, s_wu + slot * WU_CHUNK, &wu_full[slot], 0, c * CC);
+          __syncwarp();
+          tma_load_2d_elect(&tmWu, s_wu + slot * WU_CHUNK, &wu_full[slot], 0, c * CC, WU_CHUNK);
         }
       }
     }
   } else if (warp == 2 || warp == 3) {
     // ============================== TMA producers of the residual boxes: warp 2 feeds group 0, warp 3 group 1 ==============
     // (each ring belongs to ONE group, so a consumer is never more than one phase away from its barrier)
-    if (lane == 0) {
+    {
       const int g = warp - 2;
       uint32_t nb = 0;                                  // running box number of this group: ring slot nb % IN_BOXES
       auto load_box = [&](const CUtensorMap* tm, int c, int tile) {
         const uint32_t b = nb % IN_BOXES;
         uint64_t* full = &in_full[g * IN_BOXES + b];
         mbar_wait(&in_empty[g * IN_BOXES + b], ((nb / IN_BOXES) & 1u) ^ 1u);
-        mbar_expect_tx(full, IN_HALF);
-        tma_load_2d(tm, s_in + (g * IN_BOXES + b) * IN_HALF, full, c * CC, tile * BM);
+        __syncwarp();
+        tma_load_2d_elect(tm, s_in + (g * IN_BOXES + b) * IN_HALF, full, c * CC, tile * BM, IN_HALF);
         ++nb;
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -234,8 +234,10 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer: the WHOLE warp, converged ==============================
+    // (issued under `if (lane == 0)` every UTCHMMA sat in an ELECT / BRA.U.ANY loop — ~80 cycles per instruction on the issuing
+    //  thread, 144 small MMAs per tile; see a4r_common.cuh: umma_bf16_ss_elect.  Probes are made warp-uniform by a vote.)
+    {
       const uint32_t idesc_down = umma_idesc_bf16(BM, RP);
       const uint32_t idesc_up = umma_idesc_bf16(BM, CC);
       int stage = 0;
@@ -248,24 +250,26 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         const uint64_t adesc = umma_desc_k_sw128(sa), bdesc = umma_desc_k_sw128(sa + STAGE_A);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
-          umma_bf16_ss(tmem_base + S1_COL, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc_down,
-                       (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
+          umma_bf16_ss_elect(tmem_base + S1_COL, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc_down,
+                             (kb | k) != 0 ? 1u : 0u);
+        umma_commit_elect(&empty_bar[stage]);
         if (++stage == NSTAGE) {
           stage = 0;
           phase ^= 1;
         }
-        if (kb == nkb - 1) umma_commit(s1_full);
+        if (kb == nkb - 1) umma_commit_elect(s1_full);
       };
       if (static_cast<int>(blockIdx.x) < num_tiles) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          __syncwarp();
           down_kb(kb);
         }
       }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const bool has_next = tile + static_cast<int>(gridDim.x) < num_tiles;
         mbar_wait(s_ready, it & 1);
+        __syncwarp();
         tc_fence_after();
         const uint64_t adesc = umma_desc_k_sw128(smem_u32(s_act));
         int c = 0, kb = has_next ? 0 : nkb;
@@ -273,22 +277,22 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           if (c < nch) {
             const int g = c & 1;
             const uint32_t slot = nwu % NWU;
-            if (mbar_try_wait(&u_empty[g], (cu[g] & 1u) ^ 1u) && mbar_try_wait(&wu_full[slot], (nwu / NWU) & 1u)) {
+            if (__all_sync(0xffffffffu, mbar_test_wait(&u_empty[g], (cu[g] & 1u) ^ 1u) && mbar_test_wait(&wu_full[slot], (nwu / NWU) & 1u))) {
               tc_fence_after();
               const uint64_t bdesc = umma_desc_k_sw128(smem_u32(s_wu + slot * WU_CHUNK));
 #pragma unroll
               for (int k = 0; k < RP / 16; ++k)
-                umma_bf16_ss(tmem_base + U_COL + g * CC, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
-                             idesc_up, k != 0 ? 1u : 0u);
-              umma_commit(&u_full[g]);
-              umma_commit(&wu_empty[slot]);                    // the W_u slot is free once these MMAs have read it
+                umma_bf16_ss_elect(tmem_base + U_COL + g * CC, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                                   idesc_up, k != 0 ? 1u : 0u);
+              umma_commit_elect(&u_full[g]);
+              umma_commit_elect(&wu_empty[slot]);              // the W_u slot is free once these MMAs have read it
               ++cu[g];
               ++nwu;
               ++c;
               continue;
             }
           }
-          if (kb < nkb && mbar_try_wait(&full_bar[stage], phase)) {
+          if (kb < nkb && __all_sync(0xffffffffu, mbar_test_wait(&full_bar[stage], phase))) {
             down_kb(kb);
             ++kb;
           }
@@ -318,16 +322,14 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     auto emit = [&](const CUtensorMap* tm, const uint32_t (&w)[8], int c, int row0) {
       const uint32_t box = so_w + (n_out & 1u) * 1024;
       ++n_out;
-      if (lane == 0) bulk_wait_read1();                  // the store issued from THIS box two hand-overs ago has read its bytes
-      __syncwarp();                                      // (tcgen05.* / bar.sync are .aligned: keep the warp converged)
+      __syncwarp();                                      // (elect.sync / tcgen05.* / bar.sync are .aligned: keep the warp converged)
+      bulk_wait_read1_elect();                           // the store issued from THIS box two hand-overs ago has read its bytes
+      __syncwarp();
       sts_v4(box + lane * 32, w[0], w[1], w[2], w[3]);
       sts_v4(box + lane * 32 + 16, w[4], w[5], w[6], w[7]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(tm, box, c * CC + hf * 16, row0 + quad * 32);   // rows past M are clipped by the tensor map
-        bulk_commit();
-      }
+      tma_store_2d_commit_elect(tm, box, c * CC + hf * 16, row0 + quad * 32);   // rows past M are clipped by the tensor map
       __syncwarp();
     };
 
@@ -494,7 +496,8 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         emit(&tmOut, w, c, row0);
       }
     }
-    if (lane == 0) bulk_wait0();   // the last stores have left shared memory (and are complete) before the CTA retires
+    __syncwarp();
+    bulk_wait0_elect();            // the last stores have left shared memory (and are complete) before the CTA retires
   }
 
   tc_fence_before();

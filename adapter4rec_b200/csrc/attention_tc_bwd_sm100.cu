@@ -155,23 +155,25 @@ attn_vit_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane == 0) {
-      // ============================== TMA producer: pairs in the order the steps consume them ==============================
+    if (warp == 0) {
+      // ============================== TMA producer (whole warp, converged): pairs in the order the steps consume them ==============================
       uint32_t nqd = 0, nkv = 0;
       auto load_qd = [&](int img, int head, int i) {
         const uint32_t slot = nqd % QD_SLOTS;
         mbar_wait(&qd_empty[slot], ((nqd / QD_SLOTS) & 1u) ^ 1u);
-        mbar_expect_tx(&qd_full[slot], PAIR);
-        tma_load_3d(&tmQKV, s_qd + slot * PAIR, &qd_full[slot], head * DH, i * QT, img);
-        tma_load_3d(&tmDO, s_qd + slot * PAIR + BOX, &qd_full[slot], head * DH, i * QT, img);
+        __syncwarp();
+        mbar_expect_tx_elect(&qd_full[slot], PAIR);
+        tma_load_3d_elect(&tmQKV, s_qd + slot * PAIR, &qd_full[slot], head * DH, i * QT, img);
+        tma_load_3d_elect(&tmDO, s_qd + slot * PAIR + BOX, &qd_full[slot], head * DH, i * QT, img);
         ++nqd;
       };
       auto load_kv = [&](int img, int head, int j) {
         const uint32_t slot = nkv % KV_SLOTS;
         mbar_wait(&kv_empty[slot], ((nkv / KV_SLOTS) & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full[slot], PAIR);
-        tma_load_3d(&tmQKV, s_kv + slot * PAIR, &kv_full[slot], H + head * DH, j * QT, img);
-        tma_load_3d(&tmQKV, s_kv + slot * PAIR + BOX, &kv_full[slot], 2 * H + head * DH, j * QT, img);
+        __syncwarp();
+        mbar_expect_tx_elect(&kv_full[slot], PAIR);
+        tma_load_3d_elect(&tmQKV, s_kv + slot * PAIR, &kv_full[slot], H + head * DH, j * QT, img);
+        tma_load_3d_elect(&tmQKV, s_kv + slot * PAIR + BOX, &kv_full[slot], 2 * H + head * DH, j * QT, img);
         ++nkv;
       };
       for (int u = blockIdx.x; u < units; u += gridDim.x) {

@@ -108,8 +108,8 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane == 0) {
-      // ============================== TMA producer ==============================
+    if (warp == 0) {
+      // ============================== TMA producer (whole warp, converged) ==============================
       int it = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
         const int st = it & 1;
@@ -117,12 +117,14 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const int img = u / p.heads, head = u - img * p.heads;
         uint8_t* sq = smem + st * STAGE;
         mbar_wait(&qk_free[st], ph ^ 1u);
-        mbar_expect_tx(&qk_full[st], static_cast<uint32_t>((p.nq + p.nk) * BOX));
-        for (int t = 0; t < p.nq; ++t) tma_load_3d(&tmQKV, sq + t * BOX, &qk_full[st], head * DH, t * QT, img);
-        for (int j = 0; j < p.nk; ++j) tma_load_3d(&tmQKV, sq + (2 + j) * BOX, &qk_full[st], H + head * DH, j * QT, img);
+        __syncwarp();
+        mbar_expect_tx_elect(&qk_full[st], static_cast<uint32_t>((p.nq + p.nk) * BOX));
+        for (int t = 0; t < p.nq; ++t) tma_load_3d_elect(&tmQKV, sq + t * BOX, &qk_full[st], head * DH, t * QT, img);
+        for (int j = 0; j < p.nk; ++j) tma_load_3d_elect(&tmQKV, sq + (2 + j) * BOX, &qk_full[st], H + head * DH, j * QT, img);
         mbar_wait(&v_free[st], ph ^ 1u);
-        mbar_expect_tx(&v_full[st], static_cast<uint32_t>(p.nk * BOX));
-        for (int j = 0; j < p.nk; ++j) tma_load_3d(&tmQKV, sq + (4 + j) * BOX, &v_full[st], 2 * H + head * DH, j * QT, img);
+        __syncwarp();
+        mbar_expect_tx_elect(&v_full[st], static_cast<uint32_t>(p.nk * BOX));
+        for (int j = 0; j < p.nk; ++j) tma_load_3d_elect(&tmQKV, sq + (4 + j) * BOX, &v_full[st], 2 * H + head * DH, j * QT, img);
       }
     } else if (warp == 1) {
       // ============================== MMA issuer: the WHOLE warp, converged (see umma_*_elect) ==============================
@@ -360,7 +362,8 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         // per instruction and kept the warp ~950 cycles.)
         {
           const float inv = 1.0f / sum;
-          if (lane == 0) bulk_wait_read0();             // this box's previous store (one unit ago) has read its bytes
+          __syncwarp();
+          bulk_wait_read0_elect();                      // this box's previous store (one unit ago) has read its bytes
           __syncwarp();
 #pragma unroll
           for (int c8 = 0; c8 < DH / 8; ++c8) {
@@ -371,10 +374,7 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tmOut, obox, head * DH, t * QT + quad * 32, img);
-            bulk_commit();
-          }
+          tma_store_3d_commit_elect(&tmOut, obox, head * DH, t * QT + quad * 32, img);
           if (row < p.L && p.lse != nullptr)
             p.lse[(static_cast<int64_t>(img) * p.L + row) * p.heads + head] = mc * 0.6931471805599453f + __logf(sum);   // mc = shift * scale * log2(e)
         }
@@ -387,7 +387,8 @@ attn_vit_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         acc_t[0] += ts1 - ts0; acc_t[1] += ts2 - ts1; acc_t[2] += ts3 - ts2; acc_t[3] += ts4 - ts3; acc_t[4] += ts5 - ts4; acc_t[5] += ts6 - ts5;
 #endif
       }
-      if (lane == 0) bulk_wait_read0();                 // the last store still reads this CTA's shared memory
+      __syncwarp();
+      bulk_wait_read0_elect();                          // the last store still reads this CTA's shared memory
 #ifdef A4R_ATTN_TIMING
       if (blockIdx.x == 0 && lane == 0) {
         for (int i = 0; i < 6; ++i) g_attn_timing[t * 4 + quad][i] = acc_t[i];

@@ -15,6 +15,27 @@ A4R_DEVICE void tma_load_3d(const CUtensorMap* m, void* smem_dst, uint64_t* bar,
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// the same load issued by a converged warp (election inside the PTX: a4r_common.cuh)
+A4R_DEVICE void tma_load_3d_elect(const CUtensorMap* m, void* smem_dst, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+A4R_DEVICE void tma_store_3d_commit_elect(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n\t"
+      "@q cp.async.bulk.commit_group;\n\t}"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+A4R_DEVICE void bulk_wait_read0_elect() {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group.read 0;\n\t}" ::: "memory");
+}
 // shared memory -> global store of one box (rows / columns outside the tensor are clipped)
 A4R_DEVICE void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -32,13 +53,7 @@ A4R_DEVICE void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// ---- tcgen05 issue from WARP-UNIFORM code ----------------------------------------------------------------------------------
-// `if (lane == 0) { tcgen05.mma ... }` puts the instruction in a divergent region: ptxas then wraps EVERY UTCHMMA in an
-// ELECT / BRA.U.ANY loop and rebuilds its uniform-register operands inside it — about ten dependent uniform-datapath
-// instructions, measured at 77-87 cycles per MMA on the issuing thread (clock64 traces of the attention forward: 13 P V
-// instructions of N = 64 took 1.0-1.1 k cycles to ISSUE, 32 cycles each to execute).  Executed by all 32 lanes of a converged warp
-// with the election inside the PTX, the same instructions compile to back-to-back UTCHMMAs.  The callers keep every operand
-// warp-uniform (loop counters, kernel parameters, shared-memory addresses) and make poll results uniform with a vote.
+// A in tensor memory; issued from warp-uniform code (see a4r_common.cuh: umma_bf16_ss_elect)
 template <int ACC>
 A4R_DEVICE void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
   asm volatile(
@@ -47,22 +62,6 @@ A4R_DEVICE void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bd
       "setp.ne.b32 p, %4, 0;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "n"(ACC)
-      : "memory");
-}
-A4R_DEVICE void umma_bf16_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-A4R_DEVICE void umma_commit_elect(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
 // MN-major SW128 operand (a [rows = k][64 = mn] bf16 TMA box): 8 k-rows per 1,024-byte atom, one 64-wide mn chunk
@@ -74,19 +73,6 @@ A4R_DEVICE uint64_t umma_desc_mn_sw128_1chunk(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
-}
-// Non-blocking probe of an mbarrier phase.  (mbarrier.try_wait may SUSPEND the thread for a system-dependent time when the phase is
-// not complete: in a loop that polls two queues, a probe of the queue that cannot advance then hides the other queue's event.)
-A4R_DEVICE bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 A4R_DEVICE void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),

@@ -166,7 +166,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint64_t* in_bar = tmem_empty_bar + 3;                         // [epilogue warp][2]: a streamed-input box has landed
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // (warp-uniform for the compiler)
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;   // tiles of (128*CG) x BN
   const int nk = p.nk1 + p.nk2;
@@ -217,8 +217,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // ============================== TMA producer: the WHOLE warp, converged (a4r_common.cuh: *_elect) ==============================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -226,6 +226,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(cta_rank) * (BN / CG) * (CG - 1);
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          __syncwarp();
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kStageBytesA;
           const CUtensorMap* ma = kb < p.nk1 ? &tmA : &tmA2;
@@ -233,14 +234,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kc = (kb < p.nk1 ? kb : kb - p.nk1) * BK;
           if constexpr (CG == 2) {
             // both CTAs' bytes are credited to the LEADER's full barrier
-            if (leader) mbar_expect_tx(&full_bar[stage], C::kStageBytes * 2);
+            if (leader) mbar_expect_tx_elect(&full_bar[stage], C::kStageBytes * 2);
             const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_2cta(ma, sa, bar, kc, m0);
-            tma_load_2d_2cta(mb, sb, bar, kc, n0);
+            tma_load_2d_2cta_elect(ma, sa, bar, kc, m0);
+            tma_load_2d_2cta_elect(mb, sb, bar, kc, n0);
           } else {
-            mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-            tma_load_2d(ma, sa, &full_bar[stage], kc, m0);
-            tma_load_2d(mb, sb, &full_bar[stage], kc, n0);
+            tma_load_2d_elect(ma, sa, &full_bar[stage], kc, m0, C::kStageBytes);
+            tma_load_2d_elect_noarm(mb, sb, &full_bar[stage], kc, n0);
           }
           if (++stage == C::kStages) {
             stage = 0;
@@ -250,8 +250,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer (leader CTA only when CG = 2) ==============================
-    if (lane == 0 && leader) {
+    // ============================== MMA issuer (leader CTA only when CG = 2): the WHOLE warp, converged ==============================
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -259,10 +259,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t aphase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        __syncwarp();
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          __syncwarp();
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
@@ -271,21 +273,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance the start address by k*16 elements (32 B) inside the 128 B swizzle row
             if constexpr (CG == 2)
-              umma_bf16_ss_2cta(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                                (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss_2cta_elect(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                      (kb | k) != 0 ? 1u : 0u);
             else
-              umma_bf16_ss(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss_elect(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of the pair) when these MMAs retire
-          if constexpr (CG == 2) umma_commit_2cta(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+          if constexpr (CG == 2) umma_commit_2cta_elect(&empty_bar[stage], 3); else umma_commit_elect(&empty_bar[stage]);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator ready for the epilogue warps (of both CTAs)
-        if constexpr (CG == 2) umma_commit_2cta(&tmem_full_bar[as], 3); else umma_commit(&tmem_full_bar[as]);
+        if constexpr (CG == 2) umma_commit_2cta_elect(&tmem_full_bar[as], 3); else umma_commit_elect(&tmem_full_bar[as]);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -337,11 +339,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (kInBoxes) {
           if (!has_in || ci >= CHUNKS || (group + ci * NUM_EPI_GROUPS) >= BN / 32 || chunk_col(ci) >= p.N) return;   // warp-uniform
           __syncwarp();
-          if (lane == 0) {
-            uint64_t* bar = &in_bar[ew * 2 + slot];
-            mbar_expect_tx(bar, 2048);
-            tma_load_2d(&tmIn, out_boxes + (ew * 2 + slot) * 2048, bar, chunk_col(ci), m0 + quad * 32);
-          }
+          tma_load_2d_elect(&tmIn, out_boxes + (ew * 2 + slot) * 2048, &in_bar[ew * 2 + slot], chunk_col(ci), m0 + quad * 32, 2048);
         }
       };
       // one 32-column chunk: TMEM -> registers -> fused op -> global
@@ -417,7 +415,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[i].x, v[i].y);
           if constexpr (kBoxes) {
             const uint32_t box = smem_u32(out_boxes) + static_cast<uint32_t>((ew * 2 + (nbox & 1)) * 2048);
-            if (lane == 0) bulk_wait_read1();
+            __syncwarp();
+            bulk_wait_read1_elect();
             __syncwarp();
             const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
 #pragma unroll
@@ -425,10 +424,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               sts_v4(box + lane * 64 + ((static_cast<uint32_t>(j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(tm, box, col0, m0 + quad * 32);      // columns past N and rows past M are clipped by the tensor map
-              bulk_commit();
-            }
+            tma_store_2d_commit_elect(tm, box, col0, m0 + quad * 32);   // columns past N and rows past M are clipped by the tensor map
             ++nbox;
           } else {
             if (!row_ok) return;
@@ -550,7 +546,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if constexpr (kBoxes) {
-      if (lane == 0) bulk_wait0();   // the last result boxes have been written out before the CTA retires
+      __syncwarp();
+      bulk_wait0_elect();            // the last result boxes have been written out before the CTA retires
     }
 #ifdef A4R_GEMM_TIMING
     if (blockIdx.x == 0 && ew == 0 && lane == 0) {

@@ -50,7 +50,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // (warp-uniform for the compiler)
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
   const int pair = static_cast<int>(blockIdx.x >> 1);
@@ -87,18 +87,19 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                                   // the WHOLE warp, converged: TMA / tcgen05 issue with the election inside the PTX (a4r_common.cuh)
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         for (int kb = 0; kb < p.nk; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          __syncwarp();
           uint8_t* sa = smem + stage * STAGE_BYTES;
           // both CTAs' bytes are credited to the LEADER's full barrier
-          if (leader) mbar_expect_tx(&full_bar[stage], STAGE_BYTES * CG);
+          if (leader) mbar_expect_tx_elect(&full_bar[stage], STAGE_BYTES * CG);
           const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_2cta(&tmU, sa, bar, kb * BK, m0);
-          tma_load_2d_2cta(&tmE, sa + STAGE_A, bar, kb * BK, t * BN + static_cast<int>(cta_rank) * (BN / CG));
+          tma_load_2d_2cta_elect(&tmU, sa, bar, kb * BK, m0);
+          tma_load_2d_2cta_elect(&tmE, sa + STAGE_A, bar, kb * BK, t * BN + static_cast<int>(cta_rank) * (BN / CG));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -107,30 +108,32 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        __syncwarp();
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
         for (int kb = 0; kb < p.nk; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          __syncwarp();
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = umma_desc_k_sw128(sa), bdesc = umma_desc_k_sw128(sa + STAGE_A);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_ss_2cta(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2cta(&empty_bar[stage], 3);   // frees the slot in both CTAs of the pair
+            umma_bf16_ss_2cta_elect(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta_elect(&empty_bar[stage], 3);   // frees the slot in both CTAs of the pair
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2cta(&tmem_full_bar[as], 3);
+        umma_commit_2cta_elect(&tmem_full_bar[as], 3);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;

@@ -65,7 +65,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full_bar = empty_bar + C::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // (warp-uniform for the compiler)
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x % (p.tiles_n * p.tiles_k);
   const int split = blockIdx.x / (p.tiles_n * p.tiles_k);
@@ -97,19 +97,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {                                   // the WHOLE warp, converged: TMA / tcgen05 issue with the election inside the PTX (a4r_common.cuh)
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
         const int t0 = (kb_begin + i) * BT;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        __syncwarp();
         uint8_t* sa = smem + stage * C::kStage;
         uint8_t* sb = sa + C::kStageA;
-        mbar_expect_tx(&full_bar[stage], C::kStage);
+        mbar_expect_tx_elect(&full_bar[stage], C::kStage);
 #pragma unroll
-        for (int j = 0; j < TILE_N / 64; ++j) tma_load_2d(&tmA, sa + j * CHUNK_BYTES, &full_bar[stage], n0 + 64 * j, t0);
+        for (int j = 0; j < TILE_N / 64; ++j) tma_load_2d_elect_noarm(&tmA, sa + j * CHUNK_BYTES, &full_bar[stage], n0 + 64 * j, t0);
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmB, sb + j * CHUNK_BYTES, &full_bar[stage], k0 + 64 * j, t0);
+        for (int j = 0; j < BN / 64; ++j) tma_load_2d_elect_noarm(&tmB, sb + j * CHUNK_BYTES, &full_bar[stage], k0 + 64 * j, t0);
         if (++stage == C::kStages) {
           stage = 0;
           phase ^= 1;
@@ -117,28 +118,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // both operands MN-major: bits 15 (A) and 16 (B) of the instruction descriptor
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_N, BN) | (1u << 15) | (1u << 16);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&full_bar[stage], phase);
+        __syncwarp();
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * C::kStage);
         const uint64_t adesc = umma_desc_mn_sw128(sa);
         const uint64_t bdesc = umma_desc_mn_sw128(sa + C::kStageA);
 #pragma unroll
         for (int k = 0; k < BT / 16; ++k)   // 16 token rows = 2048 B = 128 descriptor units
-          umma_bf16_ss(tmem_base, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc,
-                       (i | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
+          umma_bf16_ss_elect(tmem_base, adesc + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc,
+                             (i | k) != 0 ? 1u : 0u);
+        umma_commit_elect(&empty_bar[stage]);
         if (++stage == C::kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(tmem_full_bar);
+      umma_commit_elect(tmem_full_bar);
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;
