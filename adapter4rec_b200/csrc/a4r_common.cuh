@@ -451,6 +451,48 @@ A4R_DEVICE void tma_load_2d_2cta_elect(const CUtensorMap* m, void* smem_dst, uin
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies for streams whose reuse distance is known (createpolicy; 64-bit opaque operand of .L2::cache_hint)
+A4R_DEVICE uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+A4R_DEVICE uint64_t l2_evict_normal_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+A4R_DEVICE uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+A4R_DEVICE void tma_load_2d_elect_hint(const CUtensorMap* m, void* smem_dst, uint64_t* bar, int c0, int c1, uint32_t expect_bytes, uint64_t pol) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%2], %5;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %6;\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(expect_bytes), "l"(pol)
+      : "memory");
+}
+A4R_DEVICE void tma_load_2d_elect_noarm_hint(const CUtensorMap* m, void* smem_dst, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+A4R_DEVICE void tma_store_2d_commit_elect_hint(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;\n\t"
+      "@q cp.async.bulk.commit_group;\n\t}"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
 A4R_DEVICE void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

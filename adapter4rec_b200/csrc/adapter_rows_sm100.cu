@@ -34,6 +34,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int RP = 64;
 constexpr int CC = 32;                        // columns per up-projection chunk
+#ifndef A4R_K5_L2HINT
+#define A4R_K5_L2HINT 1
+#endif
 #ifndef A4R_K5_NSTAGE          // (tuning builds only: tools/k5_variants.sh)
 #define A4R_K5_NSTAGE 4
 #define A4R_K5_NWU 4
@@ -74,15 +77,6 @@ struct RowParams {
 };
 
 A4R_DEVICE void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-A4R_DEVICE void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(smem_src), "r"(c0), "r"(c1)
-               : "memory");
-}
-A4R_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-A4R_DEVICE void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-A4R_DEVICE void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-A4R_DEVICE void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 A4R_DEVICE void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -179,10 +173,17 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#if A4R_K5_L2HINT
+  const bool saves = p.store_z != 0 || p.s_out != nullptr || p.u_out != nullptr;
+  const uint64_t single_use = saves ? l2_evict_normal_policy() : l2_evict_first_policy();
+#endif
 
   if (warp == 0) {
     // ============================== TMA producer: down-projection operands ==============================
     {                                                    // (whole warp, converged: tma_load_2d_elect)
+#if A4R_K5_L2HINT
+      const uint64_t keep = l2_evict_last_policy();
+#endif
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -190,8 +191,15 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           __syncwarp();
           uint8_t* sa = s_ring + stage * STAGE_BYTES;
+#if A4R_K5_L2HINT
+          // h is read again as the residual one tile time later (148 SMs x 0.8 MB of streams in between = the L2 capacity: half of
+          // the re-reads missed): it enters L2 as evict_last, its second read and every single-use stream are evict_first
+          tma_load_2d_elect_hint(&tmH, sa, &full_bar[stage], kb * BK, tile * BM, STAGE_BYTES, keep);
+          tma_load_2d_elect_noarm_hint(&tmWd, sa + STAGE_A, &full_bar[stage], kb * BK, 0, keep);
+#else
           tma_load_2d_elect(&tmH, sa, &full_bar[stage], kb * BK, tile * BM, STAGE_BYTES);
           tma_load_2d_elect_noarm(&tmWd, sa + STAGE_A, &full_bar[stage], kb * BK, 0);
+#endif
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -202,13 +210,20 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   } else if (warp == WU_WARP) {
     // ============================== TMA producer of the W_u chunks (L2-resident: 96 KB re-streamed per tile) ==============
     {
+#if A4R_K5_L2HINT
+      const uint64_t keep = l2_evict_last_policy();
+#endif
       uint32_t n = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int c = 0; c < nch; ++c, ++n) {
           const uint32_t slot = n % NWU;
           mbar_wait(&wu_empty[slot], ((n / NWU) & 1u) ^ 1u);
           __syncwarp();
+#if A4R_K5_L2HINT
+          tma_load_2d_elect_hint(&tmWu, s_wu + slot * WU_CHUNK, &wu_full[slot], 0, c * CC, WU_CHUNK, keep);
+#else
           tma_load_2d_elect(&tmWu, s_wu + slot * WU_CHUNK, &wu_full[slot], 0, c * CC, WU_CHUNK);
+#endif
         }
       }
     }
@@ -217,13 +232,22 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     // (each ring belongs to ONE group, so a consumer is never more than one phase away from its barrier)
     {
       const int g = warp - 2;
+#if A4R_K5_L2HINT
+      // (measured A/B, M = 161,280: evict_first on the single-use streams helps the inference variant, 191 -> 182 us, and costs the
+      //  training variants 2-4 %, whose z / s stores compete for the same L2 ways: training leaves them at the default priority)
+      const uint64_t drop = single_use;
+#endif
       uint32_t nb = 0;                                  // running box number of this group: ring slot nb % IN_BOXES
       auto load_box = [&](const CUtensorMap* tm, int c, int tile) {
         const uint32_t b = nb % IN_BOXES;
         uint64_t* full = &in_full[g * IN_BOXES + b];
         mbar_wait(&in_empty[g * IN_BOXES + b], ((nb / IN_BOXES) & 1u) ^ 1u);
         __syncwarp();
+#if A4R_K5_L2HINT
+        tma_load_2d_elect_hint(tm, s_in + (g * IN_BOXES + b) * IN_HALF, full, c * CC, tile * BM, IN_HALF, drop);
+#else
         tma_load_2d_elect(tm, s_in + (g * IN_BOXES + b) * IN_HALF, full, c * CC, tile * BM, IN_HALF);
+#endif
         ++nb;
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -314,6 +338,9 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     uint32_t nb = 0;                                     // running residual-box number of this group (as in its producer)
     const uint32_t so_w = smem_u32(s_o) + ew * 2048;     // this warp's two private out boxes (they alternate)
     uint32_t n_out = 0;
+#if A4R_K5_L2HINT
+    const uint64_t drop_out = single_use;
+#endif
     float* stats = reinterpret_cast<float*>(s_act);      // [128][4][2] after the tile's last up-projection has retired
     uint32_t n_u = 0, it = 0;
 
@@ -329,7 +356,11 @@ adapter_rows_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       sts_v4(box + lane * 32 + 16, w[4], w[5], w[6], w[7]);
       fence_proxy_async_smem();
       __syncwarp();
+#if A4R_K5_L2HINT
+      tma_store_2d_commit_elect_hint(tm, box, c * CC + hf * 16, row0 + quad * 32, drop_out);   // rows past M are clipped by the tensor map
+#else
       tma_store_2d_commit_elect(tm, box, c * CC + hf * 16, row0 + quad * 32);   // rows past M are clipped by the tensor map
+#endif
       __syncwarp();
     };
 
