@@ -88,11 +88,17 @@ class VITAdaptedSelfOutput(nn.Module):
         self.self_output = self_output
         self.adapter = AdapterBlock(args, 768, args.cv_adapter_down_size, args.adapter_dropout_rate)
 
+    def _dense(self, hidden_states):
+        """dense + the wrapped module's nn.Dropout (model.py:191-193; ViT's default probability is 0: then nothing is launched)"""
+        h = self.self_output.dense(hidden_states)
+        p = self.self_output.dropout.p if self.training else 0.0
+        return Fn.dropout_add(to_2d_bf16(h), None, p).view(h.shape) if p > 0 else h
+
     def forward(self, hidden_states, input_tensor=None):
-        return self.adapter(self.self_output.dense(hidden_states))
+        return self.adapter(self._dense(hidden_states))
 
     def forward_fused(self, hidden_states, residual):
-        h = self.self_output.dense(to_2d_bf16(hidden_states))
+        h = self._dense(to_2d_bf16(hidden_states))
         return to_2d_bf16(self.adapter(h, extra_residual=to_2d_bf16(residual)))
 
 
@@ -108,7 +114,11 @@ class VITAdaptedOutput(nn.Module):
         return self.forward_from_dense(self.self_output.dense(to_2d_bf16(hidden_states)), input_tensor)
 
     def forward_from_dense(self, h, input_tensor):
-        return self.adapter(to_2d_bf16(h), extra_residual=to_2d_bf16(input_tensor)).view(input_tensor.shape)
+        h = to_2d_bf16(h)
+        p = self.self_output.dropout.p if self.training else 0.0     # model.py:207-209: dropout sits between dense and the adapter
+        if p > 0:
+            h = Fn.dropout_add(h, None, p)
+        return self.adapter(h, extra_residual=to_2d_bf16(input_tensor)).view(input_tensor.shape)
 
 
 class VITAdaptedParallelSelfOutput(nn.Module):

@@ -12,6 +12,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if "--lib" in sys.argv:      # A/B against a variant build of the library (tools/variants/*.so)
+    import adapter4rec_b200.lib as _lib
+    _i = sys.argv.index("--lib")
+    _lib.LIB_PATH = os.path.abspath(sys.argv[_i + 1])
+    del sys.argv[_i:_i + 2]
 import torch  # noqa: E402
 
 from adapter4rec_b200 import ops  # noqa: E402
