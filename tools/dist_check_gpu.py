@@ -79,7 +79,8 @@ Bf = sif.shape[0]
 halff = slice(rank * (Bf // world), (rank + 1) * (Bf // world))
 xf, lf = sif[halff].reshape(-1, 2 * cf.L).to(dev), lmf[halff].to(dev)
 grads = []
-for overlap in (True, False):
+names3 = None
+for overlap in (True, False, False):
     mf, _ = build_gpu_model(cf, sdf)
     mf.eval()                                  # no dropout: both runs see the same arithmetic
     tf = FlatAdamTrainer(mf, 1e-3, 1e-4, 1e-3, 1e-3, users_per_pass=4, bucket_bytes=64 << 10, overlap=overlap)
@@ -89,14 +90,21 @@ for overlap in (True, False):
     tf.reduce_gradients()
     torch.cuda.synchronize()
     grads.append(tf.flat_grad.clone())
+    names3 = tf.names
     if overlap:
         nb, early = len(tf.buckets), issued_early
 err = float((grads[0] - grads[1]).abs().max() / grads[1].abs().max())
-same3 = (torch.equal(grads[0], grads[1]) if world == 2 else err < 1e-6) and nb > 1 and early > 0
+# Two blocking runs differ from each other by the same amount: the embedding-table gradients are fp32 atomics
+# (a4r_scatter_add_rows: red.global.add, the order of the adds of a repeated token is not fixed), everything else is bit-equal.
+run_to_run = float((grads[1] - grads[2]).abs().max() / grads[1].abs().max())
+atomic = ("word_embeddings", "position_embeddings", "token_type_embeddings")
+exact = all(torch.equal(grads[0][off:off + k], grads[1][off:off + k]) for n, off, k in names3 if not any(a in n for a in atomic))
+differing = [n for n, off, k in names3 if not torch.equal(grads[0][off:off + k], grads[1][off:off + k])]
+same3 = exact and err < 1e-6 and nb > 1 and early > 0
 ok &= same3
 if rank == 0:
     print("bucketed overlapped reduction == blocking all-reduce (full fine-tuning, %d buckets, %d issued during the backward):"
-          % (nb, early), same3, "| max rel diff %.2e" % err)
+          % (nb, early), same3, "| max rel diff %.2e (two blocking runs: %.2e; tensors that differ: %s)" % (err, run_to_run, differing))
 flags = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
