@@ -439,6 +439,13 @@ def test_vit_attention_tcgen05_forward_and_backward():
     _run_tool("attn_tc_check.py", "--bwd", timeout=600)
 
 
+def test_vit_attention_tcgen05_repeated_launches_are_bit_identical():
+    """The tcgen05 attention forward and backward use no atomics: ~1,000 launches over five shapes (197 / 207 / 256 / 129 / 64
+    tokens) must each reproduce the first launch bit for bit — the check for hand-over races (per-warp TMA result boxes,
+    tensor-memory column reuse, mbarrier phases, converged-warp issue) that a single launch cannot be relied on to show."""
+    _run_tool("attn_stress.py", "60", timeout=600)
+
+
 def test_adapter_block_repeated_launches_are_bit_identical_and_correct():
     """900 launches of the default K5 kernel at M = 161,280 (300 per tail), each compared element-wise with one torch fp32
     reference and bit-wise with the first launch: the epilogue / TMA-refill race fixed in round 2 corrupted a few rows in 1-3 % of
