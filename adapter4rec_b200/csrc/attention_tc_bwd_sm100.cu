@@ -55,31 +55,44 @@ A4R_DEVICE uint64_t umma_desc_mn_sw128_2chunk(uint32_t smem_addr) {
 // {lse * log2(e), scale * sum_d dO[r, d] O[r, d]} per (token row, head), written as one float2 into the first 8 bytes of the row's
 // dq slot of dqkv (which the main kernel reads before it overwrites the slot with dQ): no workspace, 8 bytes per (row, head).
 // One warp per token row; 8 lanes share a head (64 columns = 8 chunks of 8).
+template <int ITERS>
 __global__ void __launch_bounds__(256)
 attn_row_info_kernel(const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                      __nv_bfloat16* __restrict__ dqkv, int64_t rows, int heads, int64_t ld_out, int64_t ld_qkv, float scale) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nchunk = heads * 8;
   for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
-    for (int c0 = 0; c0 < heads * 8; c0 += 32) {
-      const int c = c0 + lane;                       // 8-column chunk of the row; head = c / 8
-      float acc = 0.0f;
-      if (c < heads * 8) {
-        const uint4 a = ld_nc_v4(ctx + row * ld_out + c * 8), b = ld_nc_v4(dout + row * ld_out + c * 8);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    // every load of the row is issued before the first use (the kernel is one pass over two [rows, H] tensors: HBM-bound, and
+    // with a load-use-store chain per 32-chunk group it kept too few bytes in flight: 0.61 of the HBM peak)
+    uint4 a[ITERS], b[ITERS];
+    float l[ITERS];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 x = bf16x2_to_f2(aw[e]), y = bf16x2_to_f2(bw[e]);
-          acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
-        }
+    for (int i = 0; i < ITERS; ++i) {
+      const int c = i * 32 + lane;                   // 8-column chunk of the row; head = c / 8
+      a[i] = b[i] = make_uint4(0u, 0u, 0u, 0u);
+      l[i] = 0.0f;
+      if (c < nchunk) {
+        a[i] = ld_nc_v4(ctx + row * ld_out + c * 8);
+        b[i] = ld_nc_v4(dout + row * ld_out + c * 8);
+        if ((lane & 7) == 0) l[i] = __ldg(lse + row * heads + (c >> 3));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int c = i * 32 + lane;
+      const uint32_t aw[4] = {a[i].x, a[i].y, a[i].z, a[i].w}, bw[4] = {b[i].x, b[i].y, b[i].z, b[i].w};
+      float acc = 0.0f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = bf16x2_to_f2(aw[e]), y = bf16x2_to_f2(bw[e]);
+        acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      if ((lane & 7) == 0 && c < heads * 8) {
-        const int head = c >> 3;
-        *reinterpret_cast<float2*>(dqkv + row * ld_qkv + head * DH) = make_float2(lse[row * heads + head] * LOG2E_F, acc * scale);
-      }
+      if ((lane & 7) == 0 && c < nchunk)
+        *reinterpret_cast<float2*>(dqkv + row * ld_qkv + (c >> 3) * DH) = make_float2(l[i] * LOG2E_F, acc * scale);
     }
   }
 }
@@ -512,7 +525,15 @@ int a4r_attn_vit_tc_bwd(const a4r_attn_args* a, cudaStream_t stream) {
   A4R_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t rows = a->N * a->L;
   const int info_blocks = static_cast<int>(rows < 8 * 8 * a4r_num_sms() ? (rows + 7) / 8 : 8 * a4r_num_sms());
-  attn_row_info_kernel<<<info_blocks, 256, 0, stream>>>(p.ctx, p.dout, p.lse, p.dqkv, rows, p.heads, p.ld_out, p.ld_qkv, p.scale);
+  const int info_iters = (p.heads * 8 + 31) / 32;                 // 32 eight-column chunks per warp pass
+  if (info_iters <= 1)
+    attn_row_info_kernel<1><<<info_blocks, 256, 0, stream>>>(p.ctx, p.dout, p.lse, p.dqkv, rows, p.heads, p.ld_out, p.ld_qkv, p.scale);
+  else if (info_iters <= 3)
+    attn_row_info_kernel<3><<<info_blocks, 256, 0, stream>>>(p.ctx, p.dout, p.lse, p.dqkv, rows, p.heads, p.ld_out, p.ld_qkv, p.scale);
+  else if (info_iters <= 8)
+    attn_row_info_kernel<8><<<info_blocks, 256, 0, stream>>>(p.ctx, p.dout, p.lse, p.dqkv, rows, p.heads, p.ld_out, p.ld_qkv, p.scale);
+  else
+    return a4r_set_error(A4R_EINVAL, "attention backward: more than 32 heads are not supported by the row-information kernel");
   A4R_LAUNCH_OK();
   attn_vit_tc_bwd_kernel<<<grid, BWD_THREADS, smem, stream>>>(tmQKV, tmDO, p);
   A4R_LAUNCH_OK();
