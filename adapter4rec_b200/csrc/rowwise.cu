@@ -701,6 +701,53 @@ extern "C" int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, 
   return A4R_OK;
 }
 
+// ---- weight caches: fp32 master -> bf16 copy and / or bf16 transpose in ONE pass --------------------------------------------
+namespace {
+// 32 x 32 tiles through shared memory (+1 padding): both outputs are written with contiguous rows
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
+                                                             __nv_bfloat16* __restrict__ dst_t, int64_t rows, int64_t cols) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+  const int64_t tiles_c = (cols + 31) / 32, tiles = ((rows + 31) / 32) * tiles_c;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int64_t r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+      const float v = (r < rows && c < cols) ? src[r * ld_src + c] : 0.0f;
+      tile[ty + 8 * i][tx] = v;
+      if (dst != nullptr && r < rows && c < cols) dst[r * cols + c] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    if (dst_t != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t c = c0 + ty + 8 * i, r = r0 + tx;         // row of the transpose = column of the source
+        if (c < cols && r < rows) dst_t[c * rows + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+      }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+
+extern "C" int a4r_cast_transpose_f32_bf16(const float* src, int64_t ld_src, void* dst, void* dst_t, int64_t rows, int64_t cols,
+                                           a4r_stream_t stream_) {
+  A4R_CHECK_ARG(rows >= 0 && cols >= 0 && ld_src >= cols, "cast_transpose: bad shape");
+  A4R_CHECK_ARG(dst != nullptr || dst_t != nullptr, "cast_transpose: no output requested");
+  if (rows == 0 || cols == 0) return A4R_OK;
+  A4R_CHECK_ARG(src != nullptr, "cast_transpose: src is NULL");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  const int64_t tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 8;
+  cast_transpose_kernel<<<static_cast<int>(tiles < cap ? tiles : cap), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      src, ld_src, static_cast<__nv_bfloat16*>(dst), static_cast<__nv_bfloat16*>(dst_t), rows, cols);
+  A4R_LAUNCH_OK();
+  a4r_count_launch(1);
+  return A4R_OK;
+}
+
 extern "C" int a4r_act_fwd(const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream_) {
   A4R_CHECK_ARG(u && out, "act_fwd: NULL pointer");
   A4R_CHECK_ARG(n >= 0 && n % 8 == 0, "act_fwd: n must be a multiple of 8");

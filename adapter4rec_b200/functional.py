@@ -25,6 +25,7 @@ class WeightCache:
 
     def __init__(self):
         self.key = None
+        self.master = None
         self.w = None
         self.wt = None
 
@@ -32,11 +33,21 @@ class WeightCache:
         key = (weight.data_ptr(), weight._version, weight.device, PARAM_EPOCH[0] if weight.requires_grad else -1)
         if key != self.key:
             self.key = key
-            self.w = weight.detach().to(BF16).contiguous()
-            self.wt = None
+            self.master = weight.detach()
+            if self._fusable(self.master):
+                self.w, self.wt = ops.cast_transpose(self.master, True, need_t)   # one pass: bf16 copy (+ transpose)
+            else:
+                self.w, self.wt = self.master.to(BF16).contiguous(), None
         if need_t and self.wt is None:
-            self.wt = self.w.t().contiguous()
+            if self._fusable(self.master):
+                _, self.wt = ops.cast_transpose(self.master, False, True)
+            else:
+                self.wt = self.w.t().contiguous()
         return self.w, self.wt
+
+    @staticmethod
+    def _fusable(w):
+        return w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.stride(1) == 1
 
 
 def _as2d(x):

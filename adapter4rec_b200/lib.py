@@ -100,6 +100,7 @@ PROTOTYPES = {
     "a4r_act_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "a4r_act_fwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "a4r_scatter_add_rows": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "a4r_cast_transpose_f32_bf16": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "a4r_dropout": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p]),
     "a4r_colsum_workspace_bytes": (c_size_t, [c_int64]),
     "a4r_colsum": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),

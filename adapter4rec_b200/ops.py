@@ -280,6 +280,17 @@ def act_bwd(dy, u, kind):
     return out
 
 
+def cast_transpose(w, want=True, want_t=False):
+    """bf16 copy and / or bf16 transpose of an fp32 2-D weight in one kernel (the weight caches of functional.WeightCache)"""
+    assert w.dtype == torch.float32 and w.dim() == 2 and w.stride(1) == 1
+    rows, cols = w.shape
+    out = torch.empty((rows, cols), dtype=BF16, device=w.device) if want else None
+    out_t = torch.empty((cols, rows), dtype=BF16, device=w.device) if want_t else None
+    _l.check(_l.get_lib().a4r_cast_transpose_f32_bf16(_p(w), w.stride(0), _p(out), _p(out_t), rows, cols, _stream()),
+             "a4r_cast_transpose_f32_bf16")
+    return out, out_t
+
+
 def act_fwd(u, kind):
     """act(u) stand-alone (activations that have no GEMM-epilogue mode: leaky_relu, gelu_new)."""
     assert u.dtype == BF16 and u.is_contiguous()

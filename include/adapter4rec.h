@@ -299,6 +299,13 @@ A4R_API int a4r_scatter_add_rows(const void* src, int64_t ld, const int64_t* idx
 A4R_API int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
 A4R_API int a4r_act_fwd(const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
 
+/* Weight caches: dst [rows, cols] = bf16(src) and / or dst_t [cols, rows] = bf16(src)^T from an fp32 master [rows, cols] (row
+ * stride ld_src) in one pass; either output may be NULL.  Replaces the per-forward half-precision weight copies that
+ * torch.cuda.amp.autocast makes in the reference (Downstream/CV/run_adapter.py:588, Downstream/CV/run.py:261; the text tree
+ * trains in fp32) and the explicit transposes of the data-gradient GEMMs: the copies are cached per parameter version. */
+A4R_API int a4r_cast_transpose_f32_bf16(const float* src, int64_t ld_src, void* dst, void* dst_t, int64_t rows, int64_t cols,
+                                        a4r_stream_t stream);
+
 /* Dropout (+ residual): out = x * mask / (1 - p) (+ res), n bf16 elements (n %% 8 == 0).  Replaces nn.Dropout on the
  * hidden states (BertSelfOutput.dropout / BertOutput.dropout / BertEmbeddings.dropout, SASRec modules.py:27,72,107)
  * fused with the residual add that follows it.  Counter-based RNG: element i is decided by (seed, offset + i / 4), so

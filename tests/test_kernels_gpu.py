@@ -439,6 +439,22 @@ def test_vit_attention_tcgen05_forward_and_backward():
     _run_tool("attn_tc_check.py", "--bwd", timeout=600)
 
 
+@pytest.mark.parametrize("rows,cols", [(768, 768), (3072, 768), (64, 768), (768, 64), (30522, 768), (37, 101), (1, 8)])
+def test_cast_transpose_matches_torch(rows, cols):
+    """a4r_cast_transpose_f32_bf16 (the weight caches): bf16 copy and bf16 transpose of an fp32 matrix, bit-equal to torch's
+    round-to-nearest-even cast, incl. ragged tiles, a row-strided source and either output alone."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + cols)
+    base = torch.randn(rows, cols + 8, generator=g, device="cuda")
+    for w in (base[:, :cols].contiguous(), base[:, :cols]):
+        ref = w.to(torch.bfloat16)
+        a, at = ops.cast_transpose(w, True, True)
+        assert torch.equal(a, ref) and torch.equal(at, ref.t().contiguous())
+        a2, none_t = ops.cast_transpose(w, True, False)
+        none_a, at2 = ops.cast_transpose(w, False, True)
+        assert none_t is None and none_a is None and torch.equal(a2, ref) and torch.equal(at2, ref.t().contiguous())
+
+
 def test_vit_attention_tcgen05_repeated_launches_are_bit_identical():
     """The tcgen05 attention forward and backward use no atomics: ~1,000 launches over five shapes (197 / 207 / 256 / 129 / 64
     tokens) must each reproduce the first launch bit for bit — the check for hand-over races (per-warp TMA result boxes,
