@@ -3,6 +3,8 @@ trainable-gradient buffer over NCCL — one collective for adapter tuning (<= 10
 gradient hooks while the backward is still running for full fine-tuning (440 MB) — and fused flat Adam.  Mirrors the
 optimisation set-up of Downstream/Text/run.py:503-529,595-600 (4 learning-rate groups chosen by parameter NAME,
 torch.optim.Adam defaults, DistributedDataParallel's gradient averaging and bucketed overlap)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -33,7 +35,7 @@ class FlatAdamTrainer:
 
     def __init__(self, model, lr, fine_tune_lr, adapter_bert_lr, adapter_sasrec_lr, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=0.0, users_per_pass=128, process_group=None, grouping=None, bucket_bytes=25 << 20,
-                 overlap=True):
+                 overlap=None):
         self.model = model
         self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.users_per_pass = users_per_pass
@@ -71,6 +73,12 @@ class FlatAdamTrainer:
         # behind everything the current stream has enqueued so far) as soon as every gradient in it has been accumulated
         # in the LAST pass of the step.  Buckets are issued in one fixed order on every rank — from the end of the buffer
         # (the last layers, whose gradients come first) to the start — whatever order they complete in.
+        # overlap=None (default): overlapped only when the job spans more than one node.  Inside one NVSwitch node the blocking
+        # all-reduce of the whole 440 MB full-fine-tuning buffer costs ~1.5 ms, less than the SMs the NCCL kernels take from
+        # the backward when they run beside it (8 x B200, tools/bench_full_ft.py: 107.2 ms blocking, 109.3 ms overlapped).
+        if overlap is None:
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", self.world))
+            overlap = self.world > max(local, 1)
         self.buckets = []            # [offset, numel, number of parameters]
         self._works, self._live, self._next = [], False, -1
         if self.world > 1 and overlap:

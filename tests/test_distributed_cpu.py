@@ -85,7 +85,7 @@ def _worker(rank, world, port, ret):
             def forward(self, rows, log_mask, dev):
                 return (self.b(torch.tanh(self.a(rows))).view(log_mask.shape[0], -1).mean(1) * log_mask.sum(1)).sum() / 7.0
         toy = Toy()
-        tr2 = FlatAdamTrainer(toy, 1e-3, 1e-3, 1e-3, 1e-3, users_per_pass=3, bucket_bytes=64)
+        tr2 = FlatAdamTrainer(toy, 1e-3, 1e-3, 1e-3, 1e-3, users_per_pass=3, bucket_bytes=64, overlap=True)
         assert len(tr2.buckets) >= 3 and sum(b[1] for b in tr2.buckets) == tr2.num_trainable
         gen = torch.Generator().manual_seed(100 + rank)
         rows, lm = torch.randn(8 * 2, 6, generator=gen), (torch.rand(8, 4, generator=gen) < 0.7).float()
@@ -102,6 +102,12 @@ def _worker(rank, world, port, ret):
         dist.all_reduce(want, op=dist.ReduceOp.SUM)
         assert torch.allclose(got, want, rtol=0, atol=1e-6), float((got - want).abs().max())
         assert float(got.abs().sum()) > 0 and not tr2._live and not tr2._works
+        # overlap=None: blocking inside one node, bucketed when the job spans several (LOCAL_WORLD_SIZE < WORLD_SIZE)
+        os.environ["LOCAL_WORLD_SIZE"] = str(world)
+        assert len(FlatAdamTrainer(Toy(), 1e-3, 1e-3, 1e-3, 1e-3, bucket_bytes=64).buckets) == 0
+        os.environ["LOCAL_WORLD_SIZE"] = "1"
+        assert len(FlatAdamTrainer(Toy(), 1e-3, 1e-3, 1e-3, 1e-3, bucket_bytes=64).buckets) >= 3
+        os.environ.pop("LOCAL_WORLD_SIZE")
         ret[rank] = "ok"
     except Exception as e:  # noqa: BLE001
         import traceback
