@@ -46,6 +46,16 @@ struct EpiGroups {
 //     two chunks ahead by a TMA load into the boxes instead of into registers; the single output keeps its direct 256-bit
 //     stores (a box hand-over adds ~350 cycles of latency per chunk, which two epilogue groups do not hide: measured 192 ->
 //     225 us on attention.output when the output went through boxes as well).
+#ifndef A4R_GELU_AUX_BOX      // (A/B builds: which of the GELU forward's two outputs leave through the shared-memory boxes)
+#define A4R_GELU_AUX_BOX 1
+#endif
+#ifndef A4R_GELU_C_BOX
+#define A4R_GELU_C_BOX 1
+#endif
+template <bool B>
+struct BoxTag {
+  static constexpr bool value = B;
+};
 template <int BN, int EPI>
 struct EpiBoxes {
   static constexpr bool kOut = EPI == A4R_EPI_GELU;
@@ -409,11 +419,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // st.global per lane touches 32 different lines per instruction (32 L1 wavefronts), and with two such tensors per chunk
         // (residual / pre-activation + output) the K = 768 shapes were bound by the load/store unit, not by the MMAs.  The two
         // boxes of a warp alternate, so a box is rewritten only after the store issued two hand-overs ago has read it.
-        auto store_bf16 = [&](const CUtensorMap* tm, __nv_bfloat16* dst) {
+        auto store_bf16 = [&](const CUtensorMap* tm, __nv_bfloat16* dst, auto box_tag) {
+          constexpr bool kUseBox = kBoxes && decltype(box_tag)::value;
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[i].x, v[i].y);
-          if constexpr (kBoxes) {
+          if constexpr (kUseBox) {
             const uint32_t box = smem_u32(out_boxes) + static_cast<uint32_t>((ew * 2 + (nbox & 1)) * 2048);
             __syncwarp();
             bulk_wait_read1_elect();
@@ -480,7 +491,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // gradient through a dropout whose input gradient is the sum formed above: mask the SUM
           if constexpr (EPI == EPI_LINEAR_DROPSUM) drop_v();
         } else if constexpr (EPI == A4R_EPI_GELU) {
-          if (p.aux != nullptr) store_bf16(&tmAux, reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0);
+          if (p.aux != nullptr) store_bf16(&tmAux, reinterpret_cast<__nv_bfloat16*>(p.aux) + r64 * p.ldaux + col0, BoxTag<A4R_GELU_AUX_BOX != 0>{});
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = gelu_fast2(v[i]);
         } else if constexpr (EPI == A4R_EPI_RELU) {
@@ -505,7 +516,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                               __float_as_uint(v[2 * j + 1].x), __float_as_uint(v[2 * j + 1].y)));
         } else {
           GSTAMP(g2);
-          store_bf16(&tmC, reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col0);
+          store_bf16(&tmC, reinterpret_cast<__nv_bfloat16*>(p.C) + r64 * p.ldc + col0, BoxTag<A4R_GELU_C_BOX != 0>{});
           GSTAMP(g3);
 #ifdef A4R_GEMM_TIMING
           tacc[1] += g2 - g1;
