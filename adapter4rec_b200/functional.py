@@ -464,10 +464,11 @@ class QKVFunction(torch.autograd.Function):
         if reuse:
             bias = cache["bias"]
         else:
-            bias = torch.zeros(n * H, dtype=torch.float32, device=dev)
-            for j in range(n):
-                if params[4 * j + 1] is not None:
-                    bias[j * H:(j + 1) * H] = params[4 * j + 1].detach()
+            # one concatenation (a missing bias contributes a cached block of zeros)
+            zero_h = cache.get("zero_h")
+            if zero_h is None or zero_h.device != dev or zero_h.numel() != H:
+                zero_h = cache["zero_h"] = torch.zeros(H, dtype=torch.float32, device=dev)
+            bias = torch.cat([zero_h if params[4 * j + 1] is None else params[4 * j + 1].detach().float() for j in range(n)])
             cache["small_key"], cache["bias"] = skey, bias
         # LoRA bookkeeping: slot j occupies columns [off_j, off_j + r_j) of the 64-wide T
         slots, off = [], 0
@@ -484,18 +485,34 @@ class QKVFunction(torch.autograd.Function):
             if reuse and "a_cat" in cache:
                 a_cat, b_ext, t_bias = cache["a_cat"], cache["b_ext"], cache["t_bias"]
             else:
-                a_cat = torch.zeros((LORA_PAD, K), dtype=BF16, device=dev)
-                b_ext = torch.zeros((n * H, LORA_PAD), dtype=BF16, device=dev)
+                # Rebuilt once per optimizer step: the operands are assembled in two persistent fp32 staging matrices (the
+                # LoRA tensors are written straight into their slots, the padding stays zero) and every bf16 operand of the step
+                # — A_cat, A_catᵀ, B_ext, B_extᵀ — comes out of two a4r_cast_transpose_f32_bf16 launches.
+                st = cache.get("lora_stage")
+                if st is None or st[0].device != dev or st[0].shape != (LORA_PAD, K) or st[1].shape != (n * H, LORA_PAD):
+                    st = cache["lora_stage"] = (torch.zeros((LORA_PAD, K), dtype=torch.float32, device=dev),
+                                                torch.zeros((n * H, LORA_PAD), dtype=torch.float32, device=dev))
+                    cache["lora_slots"] = None
+                if cache.get("lora_slots") != slots:               # a different slot layout: clear what the old one wrote
+                    st[0].zero_()
+                    st[1].zero_()
+                    cache["lora_slots"] = list(slots)
                 for j, o, r in slots:
-                    a_cat[o:o + r] = params[4 * j + 2].detach().to(BF16)
-                    b_ext[j * H:(j + 1) * H, o:o + r] = (params[4 * j + 3].detach() * (1.0 / r)).to(BF16)
+                    st[0][o:o + r].copy_(params[4 * j + 2].detach())
+                    torch.mul(params[4 * j + 3].detach(), 1.0 / r, out=st[1][j * H:(j + 1) * H, o:o + r])
+                a_cat, a_cat_t = ops.cast_transpose(st[0], True, True)
+                b_ext, b_ext_t = ops.cast_transpose(st[1], True, True)
                 # column 63 of T is a constant 1 (zero weight row + bias 1): it contributes nothing to qkv (B_ext[:, 63] = 0)
                 # and turns the bias gradients into one more column of the fused dqkvᵀ·T weight-gradient below
-                t_bias = torch.zeros(LORA_PAD, dtype=torch.float32, device=dev)
-                if ctx.ones_col:
-                    t_bias[LORA_PAD - 1] = 1.0
+                tb = cache.get("t_bias_const")                      # (ones_col, tensor): a constant, built once
+                if tb is None or tb[0] != ctx.ones_col or tb[1].device != dev:
+                    t_bias = torch.zeros(LORA_PAD, dtype=torch.float32, device=dev)
+                    if ctx.ones_col:
+                        t_bias[LORA_PAD - 1] = 1.0
+                    tb = cache["t_bias_const"] = (ctx.ones_col, t_bias)
+                t_bias = tb[1]
                 cache["a_cat"], cache["b_ext"], cache["t_bias"] = a_cat, b_ext, t_bias
-                cache["a_cat_t"] = cache["b_ext_t"] = None
+                cache["a_cat_t"], cache["b_ext_t"] = a_cat_t, b_ext_t
             T = ops.gemm(x, a_cat, bias=t_bias)
             qkv = ops.gemm(x, w, bias=bias, a2=T, b2=b_ext)
         else:
