@@ -520,6 +520,41 @@ def bench_c1_houlsby(dev, world, rank, steps, users=256):
             "note": "C1 shapes (Houlsby r=64, S=20, 30 tokens) at %d users per GPU per step, dropout on; NOT the headline value" % users}
 
 
+def bench_c4_roberta_prompt_cpc(dev, world, rank, steps, users=256):
+    """BASELINE.json configs[3] ("C4") as a throughput leg: ModelCPC (the last position predicts the target,
+    Downstream/Text/model/model.py:73-135) over RoBERTa-base (vocabulary 50,265, position ids from the padding index 1) with a
+    SoftEmbedding prefix of 10 learned tokens (model.py:586-630; run.py:429-434) — the configuration whose PARITY is pinned at
+    full size in tests/test_fullsize_gpu.py.  Synthetic Adressa-shape titles: 30 token slots, S = 20.  Non-headline figure."""
+    import torch
+    from adapter4rec_b200 import surgery
+    from adapter4rec_b200.model import ModelCPC, RobertaModel, TextConfigLite
+    from adapter4rec_b200.trainer import FlatAdamTrainer
+    args = make_args()
+    args.adapter_type, args.n_tokens, args.bert_model_load = "prompt", 10, "roberta-base"
+    torch.manual_seed(123456)
+    cfg = TextConfigLite(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, pad_token_id=1, layer_norm_eps=1e-5)
+    model = ModelCPC(args, ITEMS, True, RobertaModel(cfg)).to(dev)
+    surgery.freeze_all(model)
+    model = surgery.insert_adapters(model, args)
+    model.train()
+    trainer = FlatAdamTrainer(model, args.lr, args.fine_tune_lr, args.adapter_bert_lr, args.adapter_sasrec_lr,
+                              users_per_pass=min(users, 128))
+    gen = torch.Generator().manual_seed(777 + rank)
+    cat = synth_catalogue(gen)
+    ids, mask = cat[:, :L].clone(), cat[:, L:]
+    ids[:, 0] = torch.where(mask[:, 0] > 0, torch.zeros_like(ids[:, 0]), ids[:, 0])        # <s> = 0
+    ids = torch.where(mask > 0, torch.where(ids == 102, torch.full_like(ids, 2), ids), torch.ones_like(ids))   # </s> = 2, <pad> = 1
+    cat = torch.cat([ids, mask], 1)
+    batches = [tuple(t.to(dev) for t in synth_batch(cat, users, gen)) for _ in range(2)]
+    ms, loss = _time_steps(trainer, batches, steps, 2, dev, world)
+    return {"value": users * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "users_per_gpu_per_step": users,
+            "users_per_pass": min(users, 128), "trainable_params": trainer.num_trainable, "loss": loss,
+            "token_slots_per_item": L + args.n_tokens,
+            "note": "C4 shapes (CPC + RoBERTa-base + 10 soft-prompt tokens, S=20, 30 + 10 token slots per item) at %d users per GPU "
+                    "per step, dropout on; the frozen backbone still needs its data gradients down to the prompt; NOT the headline "
+                    "value" % users}
+
+
 def bench_c3_vit(dev, world, rank, steps, users=64):
     """BASELINE.json configs[2] ("C3"): SASRec + ViT-B/16-224 with Houlsby adapters (r = 64), S=10 => 22 images per user,
     synthetic images in (-1, 1) (the post-Normalize(0.5, 0.5) range), bf16.  Non-headline figure."""
@@ -720,6 +755,8 @@ def main():
         variants["c1_bert_houlsby"] = bench_c1_houlsby(dev, world, rank, max(2, min(a.steps, 3)))
         torch.cuda.empty_cache()
         variants["c3_vit_houlsby"] = bench_c3_vit(dev, world, rank, max(2, min(a.steps, 3)))
+        torch.cuda.empty_cache()
+        variants["c4_roberta_prompt_cpc"] = bench_c4_roberta_prompt_cpc(dev, world, rank, max(2, min(a.steps, 3)))
         torch.cuda.empty_cache()
 
     if rank != 0:

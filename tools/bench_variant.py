@@ -13,13 +13,15 @@ import torch
 import bench
 
 ap = argparse.ArgumentParser()
-ap.add_argument("which", choices=["c1", "c3"])
+ap.add_argument("which", choices=["c1", "c3", "c4"])
 ap.add_argument("--users", type=int, default=0)
 ap.add_argument("--steps", type=int, default=2)
 a = ap.parse_args()
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
-if a.which == "c1":
+if a.which == "c4":
+    out = bench.bench_c4_roberta_prompt_cpc(dev, 1, 0, a.steps, users=a.users or 256)
+elif a.which == "c1":
     out = bench.bench_c1_houlsby(dev, 1, 0, a.steps, users=a.users or 256)
 else:
     out = bench.bench_c3_vit(dev, 1, 0, a.steps, users=a.users or 64)
