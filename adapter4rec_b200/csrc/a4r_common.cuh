@@ -354,6 +354,14 @@ A4R_DEVICE uint64_t rng64(uint64_t seed, uint64_t counter) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+// A seed argument with bit 63 set (A4R_SEED_INDIRECT, adapter4rec.h) is the device address of the 64-bit seed: a step
+// recorded in a CUDA graph bakes its kernel arguments, so the seed that must change between replays lives in device
+// memory.  Resolved once per thread, next to the draws, only on paths that have dropout switched on.
+A4R_DEVICE uint64_t rng_seed(uint64_t s) {
+  if (static_cast<int64_t>(s) < 0)
+    s = __ldg(reinterpret_cast<const unsigned long long*>(s & 0x7FFFFFFFFFFFFFFFull));
+  return s;
+}
 A4R_DEVICE bool rng_keep(uint64_t bits, int lane4, uint32_t thr16) {
   return ((static_cast<uint32_t>(bits >> (16 * lane4))) & 0xFFFFu) >= thr16;
 }

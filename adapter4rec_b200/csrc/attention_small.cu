@@ -45,6 +45,7 @@ struct AttnParams {
 A4R_DEVICE void prob_dropout(float (&s)[2][4][4], const AttnParams& p, int n, int h, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const uint64_t base = p.drop_offset + (static_cast<uint64_t>(n) * p.heads + h) * (32 * 8);
+  const uint64_t seed = rng_seed(p.drop_seed);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -52,7 +53,7 @@ A4R_DEVICE void prob_dropout(float (&s)[2][4][4], const AttnParams& p, int n, in
       const int i = mt * 16 + hh * 8 + g;
 #pragma unroll
       for (int np = 0; np < 2; ++np) {
-        const uint64_t r = rng64(p.drop_seed, base + static_cast<uint64_t>(i) * 8 + np * 4 + t);
+        const uint64_t r = rng64(seed, base + static_cast<uint64_t>(i) * 8 + np * 4 + t);
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll

@@ -458,9 +458,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         auto drop_v = [&]() {
           const uint64_t ctr = p.drop_offset + ((static_cast<uint64_t>(r64) * static_cast<uint64_t>(p.N) + col0) >> 2);
+          const uint64_t seed = rng_seed(p.drop_seed);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {   // 4 consecutive columns per counter
-              const uint64_t r = rng64(p.drop_seed, ctr + q);
+              const uint64_t r = rng64(seed, ctr + q);
               v[2 * q].x = rng_keep(r, 0, p.drop_thr16) ? v[2 * q].x * p.drop_scale : 0.0f;
               v[2 * q].y = rng_keep(r, 1, p.drop_thr16) ? v[2 * q].y * p.drop_scale : 0.0f;
               v[2 * q + 1].x = rng_keep(r, 2, p.drop_thr16) ? v[2 * q + 1].x * p.drop_scale : 0.0f;

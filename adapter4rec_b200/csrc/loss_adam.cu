@@ -133,7 +133,12 @@ __global__ void __launch_bounds__(LOSS_THREADS) bce_bwd_kernel(const a4r_bce_arg
 // torch.optim.Adam (no amsgrad, no weight decay unless given):  one flat fp32 segment per launch
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
-                            float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
+                            float weight_decay, float bc1, float bc2_sqrt, float grad_scale,
+                            const float* __restrict__ bias_corr) {
+  if (bias_corr != nullptr) {   // step recorded in a CUDA graph: the step-dependent factors come from device memory
+    bc1 = bias_corr[0];
+    bc2_sqrt = bias_corr[1];
+  }
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float grad = g[i] * grad_scale;
@@ -210,7 +215,25 @@ extern "C" int a4r_adam_step(float* p, const float* g, float* m, float* v, int64
   if (blocks > cap) blocks = cap;
   adam_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
-      grad_scale);
+      grad_scale, nullptr);
+  A4R_LAUNCH_OK();
+  a4r_count_launch(1);
+  return A4R_OK;
+}
+
+extern "C" int a4r_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, const float* bias_corr, float grad_scale,
+                                 a4r_stream_t stream_) {
+  A4R_CHECK_ARG(p && g && m && v && bias_corr, "adam: NULL pointer");
+  A4R_CHECK_ARG(n >= 0, "adam: bad n");
+  int rc = a4r_device_check();
+  if (rc != A4R_OK) return rc;
+  if (n == 0) return A4R_OK;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(a4r_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  adam_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.0f, 1.0f, grad_scale, bias_corr);
   A4R_LAUNCH_OK();
   a4r_count_launch(1);
   return A4R_OK;

@@ -242,7 +242,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         if (dz_masked != nullptr && valid) {
           // the gradient that flows back through the dropout in front of this LayerNorm's residual add
           const uint64_t ctr = offset + ((static_cast<uint64_t>(row) * H + ch * 8) >> 2);
-          const uint64_t r0 = rng64(seed, ctr), r1 = rng64(seed, ctr + 1);
+          const uint64_t sd = rng_seed(seed);
+          const uint64_t r0 = rng64(sd, ctr), r1 = rng64(sd, ctr + 1);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             o[e] = rng_keep(r0, e, thr16) ? o[e] * dscale : 0.0f;
@@ -486,6 +487,7 @@ __global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, i
 __global__ void dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                __nv_bfloat16* __restrict__ out, int64_t nvec, uint32_t thr16, float scale, uint64_t seed,
                                uint64_t offset) {
+  seed = rng_seed(seed);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float a[8], o[8];

@@ -276,6 +276,8 @@ class DropoutState:
     the (seed, offset) its forward drew."""
     seed = 0x5EEDA4D2
     counter = 0
+    seed_address = None      # set while a step is being recorded in a CUDA graph: device address of the seed of each replay
+    SEED_INDIRECT = 1 << 63  # A4R_SEED_INDIRECT (include/adapter4rec.h)
 
     @classmethod
     def manual_seed(cls, seed):
@@ -285,7 +287,18 @@ class DropoutState:
     def draw(cls, n_counters):
         off = cls.counter
         cls.counter += int(n_counters)
+        if cls.seed_address is not None:
+            return cls.SEED_INDIRECT | int(cls.seed_address), off
         return cls.seed, off
+
+    @classmethod
+    def replay_seed(cls, step, base=None):
+        """seed of replay number `step` of a recorded step: the counter offsets are baked into the graph, so successive replays
+        differ by their seed (splitmix64 of the base seed and the step number: unrelated streams, below bit 63)"""
+        z = ((cls.seed if base is None else int(base)) + 0x9E3779B97F4A7C15 * (int(step) + 1)) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return (z ^ (z >> 31)) & 0x7FFFFFFFFFFFFFFF
 
 
 class DropoutAddFunction(torch.autograd.Function):

@@ -118,6 +118,8 @@ PROTOTYPES = {
     "a4r_inbatch_ce_bwd": (c_int32, [POINTER(InbatchCeArgs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "a4r_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                 c_float, c_int64, c_float, c_void_p]),
+    "a4r_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                                    c_float, c_void_p, c_float, c_void_p]),
     "a4r_patchify": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "a4r_vit_assemble": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                    c_void_p]),

@@ -504,6 +504,25 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
              "a4r_adam_step")
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, bias_corr, grad_scale=1.0):
+    """adam_step with (1 - beta1^t, sqrt(1 - beta2^t)) read from the device tensor bias_corr (f32 [2]): the form a CUDA-graph
+    replay needs, bit-identical to adam_step for the same t."""
+    for t in (p, g, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    assert bias_corr.dtype == torch.float32 and bias_corr.numel() == 2 and bias_corr.is_cuda
+    _l.check(_l.get_lib().a4r_adam_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+                                            float(eps), float(weight_decay), _p(bias_corr), float(grad_scale), _stream()),
+             "a4r_adam_step_dev")
+
+
+def adam_bias_corrections(beta1, beta2, step):
+    """the two factors a4r_adam_step derives from the step number (in double, as the library does)"""
+    import math
+    import struct
+    b1, b2 = (struct.unpack("f", struct.pack("f", float(b)))[0] for b in (beta1, beta2))   # the ABI takes the betas as float
+    return 1.0 - math.pow(b1, int(step)), math.sqrt(1.0 - math.pow(b2, int(step)))
+
+
 def gather_rows(table, ids):
     """out[..., :] = table[ids[...], :]  (bf16 table [R, D], int64 ids of any shape)."""
     assert table.dtype == BF16 and table.is_contiguous() and ids.dtype == torch.int64

@@ -169,10 +169,112 @@ class FlatAdamTrainer:
         Fn.bump_param_epoch()
 
     def train_step(self, sample_items, log_mask):
+        self._eager_steps = getattr(self, "_eager_steps", 0) + 1
         self.zero_grad()
         loss = self.forward_backward(sample_items, log_mask)
         self.optimizer_step()
         return loss
+
+    # ---- the step under a CUDA graph (SURVEY.md 8e "capture the step in a CUDA graph per rank", 8f-2) --------------------
+    # One rank records zero_grad + every pass of forward/backward + Adam ONCE and replays it per step: ~1,800 launches
+    # become one cudaGraphLaunch.  What a recording would bake but must change between steps lives in 16 bytes of device
+    # memory the host refreshes before each replay: the dropout seed (A4R_SEED_INDIRECT: the kernels read it through a
+    # pointer; the counter offsets stay those of the recording) and Adam's two bias-correction factors
+    # (a4r_adam_step_dev).  With more than one rank the all-reduce stays OUTSIDE the recording (two graphs around one
+    # eager NCCL call), so nothing of NCCL's is captured.  Learning rates, shapes and users_per_pass are baked: a step
+    # with other shapes is recorded again.
+    _GRAPH_SLOTS = 64
+
+    def _graph_body_backward(self):
+        self.zero_grad()
+        return self.forward_backward(self._g_items, self._g_mask)
+
+    def _graph_body_adam(self):
+        for _, lr, off, n in self.segments:
+            ops.adam_step_dev(self.flat_param[off:off + n], self.flat_grad[off:off + n], self.exp_avg[off:off + n],
+                              self.exp_avg_sq[off:off + n], lr, self.betas[0], self.betas[1], self.eps,
+                              self.weight_decay, self._g_state.view(torch.float32)[2:4], grad_scale=1.0 / self.world)
+
+    def _record(self, sample_items, log_mask):
+        if self.buckets:
+            raise RuntimeError("graphed steps keep the gradient all-reduce outside the recording: build the trainer with "
+                               "overlap=False")
+        dev = sample_items.device
+        self._g_items, self._g_mask = sample_items.clone(), log_mask.clone()
+        self._g_state = torch.zeros(2, dtype=torch.int64, device=dev)      # [seed | bc1 f32, bc2_sqrt f32]
+        self._g_host = torch.zeros(self._GRAPH_SLOTS, 2, dtype=torch.int64).pin_memory()
+        self._g_events = [None] * self._GRAPH_SLOTS
+        self._g_replays = 0
+        Fn.bump_param_epoch()        # whatever built the weight caches last: the recording must contain their rebuild
+        Fn.DropoutState.seed_address = self._g_state.data_ptr()
+        self._g_counter0, self._g_base_seed = Fn.DropoutState.counter, Fn.DropoutState.seed
+        torch.cuda.synchronize(dev)
+        try:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._g_loss = self._graph_body_backward()
+                if self.world <= 1:
+                    self._graph_body_adam()
+            graphs = [g1]
+            if self.world > 1:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g1.pool()):
+                    self._graph_body_adam()
+                graphs.append(g2)
+        finally:
+            Fn.DropoutState.seed_address = None
+        self._g_counter1 = Fn.DropoutState.counter
+        self._graphs = graphs
+        self._g_shapes = (tuple(sample_items.shape), tuple(log_mask.shape), self.users_per_pass)
+
+    def graph_seed(self, step):
+        """the dropout seed replay `step` (= step_count after the step) runs with — an eager step given this seed and the
+        recording's first counter (graph_counter0) draws the same masks (tests/test_graph_step_gpu.py)"""
+        return Fn.DropoutState.replay_seed(step, self._g_base_seed)
+
+    @property
+    def graph_counter0(self):
+        return self._g_counter0
+
+    def release_graph(self):
+        """drop the recording and its private memory pool"""
+        self._graphs = None
+        self._g_loss = self._g_items = self._g_mask = None
+
+    def train_step_graphed(self, sample_items, log_mask):
+        """train_step replayed from a recording (CUDA only).  The first call of a trainer runs eagerly (it loads every
+        kernel and builds the frozen-weight caches, neither of which may happen inside a recording); the next call
+        records; every call after that is: two small copies into the static inputs, 16 bytes of per-step state, one
+        graph launch (two around the all-reduce when world > 1).  Returns the loss tensor of the recording (overwritten
+        by the next replay)."""
+        if not getattr(self, "_eager_steps", 0):
+            return self.train_step(sample_items, log_mask)
+        shapes = (tuple(sample_items.shape), tuple(log_mask.shape), self.users_per_pass)
+        if getattr(self, "_graphs", None) is None or self._g_shapes != shapes:
+            self.release_graph()
+            self._record(sample_items, log_mask)
+        self._g_items.copy_(sample_items, non_blocking=True)
+        self._g_mask.copy_(log_mask, non_blocking=True)
+        self.step_count += 1
+        slot = self._g_replays % self._GRAPH_SLOTS
+        self._g_replays += 1
+        if self._g_events[slot] is not None:
+            self._g_events[slot].synchronize()       # the copy that last read this pinned slot has run
+        bc1, bc2s = ops.adam_bias_corrections(self.betas[0], self.betas[1], self.step_count)
+        host = self._g_host[slot]
+        host[0] = self.graph_seed(self.step_count)
+        host.view(torch.float32)[2] = bc1
+        host.view(torch.float32)[3] = bc2s
+        self._g_state.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._g_events[slot] = ev
+        self._graphs[0].replay()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+            self._graphs[1].replay()
+        Fn.bump_param_epoch()        # eager consumers (the evaluator) rebuild their weight caches from the new parameters
+        return self._g_loss
 
     def state_dict(self):
         """optimizer state + the dropout RNG position (the reference checkpoints torch's RNG states for the same purpose:

@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra (non-headline) unpadded-token measurement")
+    ap.add_argument("--variants", default="all",
+                    help="comma list of the non-headline variants to run: layouts (unpadded / dedup), graphed_step, c1, c3, c4")
     return ap.parse_args()
 
 
@@ -491,6 +493,57 @@ def _time_steps(trainer, batches, steps, warmup, dev, world):
     return float(t) / steps, float(loss)
 
 
+def bench_graphed(trainer, a, host, resident, dev, world):
+    """zero_grad + every pass of forward / backward + Adam recorded ONCE in a CUDA graph (the all-reduce
+    stays an eager NCCL call between two graphs when world > 1) and replayed per step — same kernels, same arithmetic
+    (tests/test_graph_step_gpu.py: bit-identical to the eager step), one cudaGraphLaunch instead of ~1,800 launches.
+    Timed like the headline: resident batches, then end to end with the pinned-host batch copy and the loss read-back."""
+    import torch
+    import torch.distributed as dist
+    n_pool = len(resident)
+    torch.cuda.empty_cache()            # the recording allocates one step's activations in its own pool
+    from adapter4rec_b200 import lib
+    lib_launches0 = lib.launch_count()
+    for i in range(2):                  # call 1 records (the trainer has run eager steps already), call 2 replays
+        trainer.train_step_graphed(*resident[i % n_pool])
+    recorded_launches = lib.launch_count() - lib_launches0
+    torch.cuda.synchronize()
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            out = fn(i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) / a.steps, out
+
+    gms, gloss = timed(lambda i: trainer.train_step_graphed(*resident[i % n_pool]))
+
+    def e2e_step(i):
+        x, m = host[i % n_pool]
+        return trainer.train_step_graphed(x.to(dev, non_blocking=True), m.to(dev, non_blocking=True)).item()
+
+    ems, eloss = timed(e2e_step)
+    mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    trainer.release_graph()
+    torch.cuda.empty_cache()
+    return {"value": a.users * world / (gms / 1e3), "unit": UNIT, "ms_per_step": gms,
+            "e2e": {"value": a.users * world / (ems / 1e3), "ms_per_step": ems},
+            "kernels_in_the_recording": recorded_launches, "graph_launches_per_step": 1 if world <= 1 else 2,
+            "loss_after_these_steps": float(gloss), "max_mem_gb": mem,
+            "note": "trainer.train_step_graphed: the headline step (same batches, dropout on, fresh masks per replay through the "
+                    "indirect seed) replayed from one recording; training simply continues; NOT the headline value"}
+
+
 def bench_c1_houlsby(dev, world, rank, steps, users=256):
     """BASELINE.json configs[0] ("C1") on the GPU: SASRec + BERT-base with serial Houlsby adapters (r = 64 in BERT, 16 in
     SASRec: parameters.py:55,62), S=20, 30 tokens — the configuration that runs the fused adapter block (K5) 24 times per
@@ -698,7 +751,11 @@ def main():
     # (tests/test_model_gpu.py::test_unpadded_token_layout_gives_the_same_step).  Reported NEXT TO the headline, which
     # executes every padded token exactly as the reference does.
     variants = {}
-    if not a.no_variants:
+
+    def want(name):
+        return not a.no_variants and (a.variants == "all" or name in a.variants.split(","))
+
+    if want("layouts"):
         bert = model.bert_encoder.text_encoders.title.bert_model
         bert.unpad = True
         for i in range(2):
@@ -739,6 +796,14 @@ def main():
         bert.unpad = False
         model.dedup_items = False
 
+    # ---------------- variant: the same step replayed from a CUDA graph (trainer.train_step_graphed) ----------------
+    if want("graphed_step"):
+        try:
+            variants["graphed_step"] = bench_graphed(trainer, a, host, resident, dev, world)
+        except Exception as exc:  # noqa: BLE001 — a failed recording must not take the headline line with it
+            variants["graphed_step"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+            trainer.release_graph()
+
     # ---------------- second half of the metric: full-ranking eval users/s ----------------
     del trainer, resident
     model.zero_grad(set_to_none=True)
@@ -750,14 +815,16 @@ def main():
         eval_out["eval_model_d64"] = bench_eval_full(model, args, dev, world, rank, a.steps)
         eval_out["item_table_build"] = bench_item_table(model, args, cat, dev, world, rank)
     # ---------------- the other two training configurations of BASELINE.json (non-headline) ----------------
-    if not a.no_variants:
+    if want("c1"):
         torch.cuda.empty_cache()
         variants["c1_bert_houlsby"] = bench_c1_houlsby(dev, world, rank, max(2, min(a.steps, 3)))
+    if want("c3"):
         torch.cuda.empty_cache()
         variants["c3_vit_houlsby"] = bench_c3_vit(dev, world, rank, max(2, min(a.steps, 3)))
+    if want("c4"):
         torch.cuda.empty_cache()
         variants["c4_roberta_prompt_cpc"] = bench_c4_roberta_prompt_cpc(dev, world, rank, max(2, min(a.steps, 3)))
-        torch.cuda.empty_cache()
+    torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
