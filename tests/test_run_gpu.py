@@ -76,3 +76,83 @@ def test_cv_train_entry_reduces_loss_and_evaluates(tmp_path):
     assert saved
     ckpt = torch.load(os.path.join(tmp_path, saved[-1]), weights_only=False)
     assert set(ckpt["model_state_dict"]) == set(model.state_dict())
+
+
+def _capture(name):
+    log = logging.getLogger(name)
+    records = []
+    log.addHandler(type("H", (logging.Handler,), {"emit": lambda self, r: records.append(r.getMessage())})())
+    log.setLevel(logging.INFO)
+    return log, records
+
+
+def test_text_pretraining_entry_trains_the_unfrozen_tail_and_resumes(tmp_path):
+    """adapter4rec_b200.pretraining.text_run.train (Pretraining/Text/run.py:127-352): no adapters, embeddings + encoder layer 0
+    frozen by --freeze_paras_before, layer 1 + projection + user encoder trained in two learning-rate groups; loss goes down,
+    a checkpoint is written EVERY epoch and --load_ckpt_name continues from it."""
+    import os
+    from adapter4rec_b200.model import TextConfigLite
+    from adapter4rec_b200.pretraining import text_run as run
+    from adapter4rec_b200.pretraining.text_parameters import parse_args
+    args = parse_args(["--embedding_dim", "64", "--batch_size", "32", "--epoch", "3", "--bert_model_load", "bert_tiny",
+                       "--freeze_paras_before", "21", "--lr", "2e-3", "--fine_tune_lr", "5e-4", "--max_seq_len", "10",
+                       "--num_words_title", "12", "--drop_rate", "0.0"])
+    run.setup_seed(123456)
+    data = run.synthetic_data(item_num=300, users=96, num_words=12, max_seq_len=10, vocab=500)
+    cfg = TextConfigLite(vocab_size=500, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                         intermediate_size=512, max_position_embeddings=32, hidden_dropout_prob=0.0,
+                         attention_probs_dropout_prob=0.0)
+    log, records = _capture("pretrain_text_test")
+    model, trainer, hit10 = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16,
+                                      model_dir=str(tmp_path))
+    losses = [float(m.split(":")[-1]) for m in records if "mean batch loss" in m]
+    assert len(losses) == 3 and losses[-1] < losses[0], losses
+    assert 0.0 <= hit10 <= 1.0 and sum("valid_results" in m for m in records) == 3
+    names = [n for n, _, _ in trainer.names]
+    assert any("bert_model.encoder.layer.1." in n for n in names) and not any("bert_model.encoder.layer.0." in n for n in names)
+    assert not any("bert_model.embeddings" in n or "pooler" in n for n in names)
+    assert sorted(f for f in os.listdir(tmp_path)) == ["epoch-1.pt", "epoch-2.pt", "epoch-3.pt"]
+    frozen = model.bert_encoder.text_encoders.title.bert_model.encoder.layer[0].output.dense.weight
+    ckpt = torch.load(os.path.join(tmp_path, "epoch-3.pt"), weights_only=False)
+    assert set(ckpt["model_state_dict"]) == set(model.state_dict())
+    assert torch.equal(ckpt["model_state_dict"]["bert_encoder.text_encoders.title.bert_model.encoder.layer.0.output.dense.weight"]
+                       .cpu(), frozen.detach().cpu()) and frozen.grad is None
+    args.load_ckpt_name, args.epoch = "epoch-3.pt", 1
+    _, trainer2, _ = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16, model_dir=str(tmp_path))
+    assert trainer2.step_count == 12 and os.path.exists(os.path.join(tmp_path, "epoch-4.pt"))
+    assert 0.0 <= run.test(args, True, 0, data, Log_file=log, bert_config=cfg, model_dir=str(tmp_path)) <= 1.0
+    assert any("test_results" in m for m in records)
+
+
+@pytest.mark.parametrize("downstream", [False, True])
+def test_cv_full_finetuning_entries_train_and_evaluate(tmp_path, downstream):
+    """Pretraining/CV/run.py (downstream=False) and Downstream/CV/run.py (True) mirrors: ViT with its embeddings + layer 0 frozen
+    by --freeze_paras_before, the rest fine-tuned without adapters; the downstream script also ranks the test users every
+    epoch and starts from the pre-training checkpoint's format."""
+    import os
+    from adapter4rec_b200.cv import ViTConfigLite
+    if downstream:
+        from adapter4rec_b200.cv import run
+        from adapter4rec_b200.cv.parameters import parse_args
+    else:
+        from adapter4rec_b200.pretraining import cv_run as run
+        from adapter4rec_b200.pretraining.cv_parameters import parse_args
+    args = parse_args(["--CV_model_load", "vit-base-patch16-224", "--CV_resize", "48", "--batch_size", "16", "--epoch", "2",
+                       "--freeze_paras_before", "20", "--lr", "2e-3", "--fine_tune_lr", "2e-4", "--max_seq_len", "6",
+                       "--drop_rate", "0.0"])
+    run.setup_seed(12345)
+    data = run.synthetic_data(item_num=60, users=48, resize=48, max_seq_len=6)
+    cfg = ViTConfigLite(hidden_size=768, num_hidden_layers=2, num_attention_heads=12, intermediate_size=256, image_size=48,
+                        patch_size=16)
+    log, records = _capture("cv_full_ft_test_%d" % downstream)
+    model, trainer, hit10 = run.train(args, True, 0, data, Log_file=log, vit_config=cfg, users_per_pass=8, model_dir=str(tmp_path))
+    losses = [float(m.split(":")[-1]) for m in records if "mean batch loss" in m]
+    assert len(losses) == 2 and losses[-1] < losses[0], losses
+    assert 0.0 <= hit10 <= 1.0 and sum("valid_results" in m for m in records) == 2
+    assert sum("test_results" in m for m in records) == (2 if downstream else 0)
+    names = [n for n, _, _ in trainer.names]
+    assert any("vit.encoder.layer.1." in n for n in names) and any("classifier" in n for n in names)
+    assert not any("vit.encoder.layer.0." in n or "vit.embeddings" in n for n in names)
+    assert sorted(os.listdir(tmp_path)) == ["epoch-1.pt", "epoch-2.pt"]
+    ckpt = torch.load(os.path.join(tmp_path, "epoch-2.pt"), weights_only=False)
+    assert set(ckpt["model_state_dict"]) == set(model.state_dict())
