@@ -65,11 +65,12 @@ def build_model(args, item_num, local_rank, bert_config=None, bert_state_dict=No
     return (Model if 'sasrec' in args.arch else ModelCPC)(args, item_num, True, bert_model).to(local_rank)
 
 
-def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, users_per_pass=128, model_dir=None):
+def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, users_per_pass=128, model_dir=None,
+          bert_state_dict=None):
     if not use_modal:
         raise NotImplementedError("item_tower='id' is outside the modality-encoder hot path")
     Log_file = Log_file or logging.getLogger("adapter4rec_b200.pretraining")
-    model = build_model(args, data.item_num, local_rank, bert_config)
+    model = build_model(args, data.item_num, local_rank, bert_config, bert_state_dict)
     trainer = FlatAdamTrainer(model, args.lr, args.fine_tune_lr, args.lr, args.lr, users_per_pass=users_per_pass,
                               grouping=group_parameters_pretrain)
     Log_file.info("##### trainable_num {} #####".format(trainer.num_trainable))
@@ -112,11 +113,47 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
     return model, trainer, max_hit10
 
 
-def test(args, use_modal, local_rank, data, Log_file=None, bert_config=None, model_dir=None):
+def test(args, use_modal, local_rank, data, Log_file=None, bert_config=None, model_dir=None, bert_state_dict=None):
     """run.py:32-118: build, load --load_ckpt_name, rank the TEST users."""
     Log_file = Log_file or logging.getLogger("adapter4rec_b200.pretraining")
-    model = build_model(args, data.item_num, local_rank, bert_config)
+    model = build_model(args, data.item_num, local_rank, bert_config, bert_state_dict)
     if 'None' not in args.load_ckpt_name:
         ckpt = torch.load(_checkpoint_path(model_dir, args.load_ckpt_name), map_location="cpu", weights_only=False)
         model.load_state_dict(ckpt['model_state_dict'])
     return run_eval(model, data, args, Log_file, "test", local_rank)
+
+
+def main(argv=None, pretrained_root="../pretrained_models", users_per_pass=128):
+    """`python -m adapter4rec_b200.pretraining.text_run <flags of Pretraining/Text/run.py>`: run.py:393-431 — device, process
+    group, seed 123456, the reference's checkpoint directory name, then train or test from the TSV files."""
+    import os
+    from ..data_utils.preprocess import load_text_data
+    from ..run import _file_logger, load_body
+    from .text_parameters import parse_args
+    args = parse_args(argv)
+    if 'modal' not in args.item_tower:
+        raise NotImplementedError("item_tower='id' is outside the modality-encoder hot path")
+    local_rank = int(os.environ.get("LOCAL_RANK", max(args.local_rank, 0)))
+    torch.cuda.set_device(local_rank)
+    if "RANK" in os.environ and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend='nccl', init_method="env://")
+    setup_seed(123456)
+    dir_label = str(args.item_tower) + f'_{args.bert_model_load}_freeze_{args.freeze_paras_before}'
+    log_paras = (f'{args.arch}_{args.bert_model_load}_bs_{args.batch_size}_ed_{args.embedding_dim}_lr_{args.lr}'
+                 f'_L2_{args.l2_weight}_dp_{args.drop_rate}_Flr_{args.fine_tune_lr}')
+    model_dir = os.path.join('./checkpoint_' + dir_label, 'cpt_' + log_paras)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    Log_file = _file_logger("Log_file", './logs_' + dir_label + ('_test' if 'test' in args.mode else '_train'), rank)
+    Log_file.info(args)
+    os.makedirs(model_dir, exist_ok=True)
+    tokenizer, cfg, state = load_body(args, pretrained_root)
+    data = load_text_data(args, tokenizer, Log_file)
+    if 'train' in args.mode:
+        return train(args, True, local_rank, data, Log_file, cfg, users_per_pass, model_dir, bert_state_dict=state)
+    if 'test' in args.mode:
+        return test(args, True, local_rank, data, Log_file, cfg, model_dir, bert_state_dict=state)
+
+
+if __name__ == "__main__":
+    main()

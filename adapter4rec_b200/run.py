@@ -148,9 +148,10 @@ def save_model(now_epoch, model, model_dir, trainer, Log_file):
     return ckpt_path
 
 
-def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, users_per_pass=128, model_dir=None):
+def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, users_per_pass=128, model_dir=None,
+          bert_state_dict=None):
     Log_file = Log_file or logging.getLogger("adapter4rec_b200")
-    model = build_model(args, data.item_num, local_rank, bert_config)
+    model = build_model(args, data.item_num, local_rank, bert_config, bert_state_dict)
     trainer = FlatAdamTrainer(model, args.lr, args.fine_tune_lr, args.adapter_bert_lr, args.adapter_sasrec_lr,
                               users_per_pass=users_per_pass)
     Log_file.info("##### trainable_num {} #####".format(trainer.num_trainable))
@@ -200,3 +201,80 @@ def run_eval(model, data, args, Log_file, v_or_t, local_rank, batch_size=512):
     hist, seqs = (data.users_history_for_valid, data.users_valid) if v_or_t == "valid" else \
         (data.users_history_for_test, data.users_test)
     return eval_model(model, hist, seqs, table, batch_size, args, data.item_num, Log_file, v_or_t, local_rank)
+
+
+def test(args, use_modal, local_rank, data, Log_file=None, bert_config=None, bert_state_dict=None, model_dir=None):
+    """run.py:86-275 (--mode test): the model built as for training, --load_ckpt_name from model_dir (a missing file is an
+    error), then the TEST users ranked."""
+    Log_file = Log_file or logging.getLogger("adapter4rec_b200")
+    model = build_model(args, data.item_num, local_rank, bert_config, bert_state_dict)
+    if 'None' not in args.load_ckpt_name:
+        ckpt = torch.load(_checkpoint_path(model_dir, args.load_ckpt_name), map_location="cpu", weights_only=False)
+        model.load_state_dict(ckpt['model_state_dict'])
+    return run_eval(model, data, args, Log_file, "test", local_rank)
+
+
+def load_body(args, pretrained_root="../pretrained_models"):
+    """run.py:288-300: tokenizer, config and (when the file is there) weights of the body named by --bert_model_load, from
+    the directory layout the reference uses.  Tokenisation is transformers' (host-side, as in the reference); the body itself
+    is this package's BertModel / RobertaModel, which takes the checkpoint's tensors by name."""
+    import json
+    from transformers import BertTokenizer, RobertaTokenizer
+    roberta = 'roberta' in args.bert_model_load
+    path = os.path.join(pretrained_root, 'roberta' if roberta else 'bert', args.bert_model_load)
+    tokenizer = (RobertaTokenizer if roberta else BertTokenizer).from_pretrained(path)
+    cfg = TextConfigLite(**json.load(open(os.path.join(path, "config.json"))))
+    weights = os.path.join(path, "pytorch_model.bin")
+    state = None
+    if os.path.exists(weights):
+        state = torch.load(weights, map_location="cpu", weights_only=True)
+        state = {re.sub(r'^(bert|roberta)\.', '', k): v for k, v in state.items()}
+    return tokenizer, cfg, state
+
+
+def _file_logger(name, directory, rank):
+    log = logging.getLogger(name)
+    log.setLevel(logging.INFO if rank in (-1, 0) else logging.ERROR)
+    if rank in (-1, 0) and not log.handlers:
+        os.makedirs(directory, exist_ok=True)
+        for h in (logging.FileHandler(os.path.join(directory, "log.log"), encoding="utf-8"), logging.StreamHandler()):
+            h.setFormatter(logging.Formatter("[%(levelname)s %(asctime)s] %(message)s"))
+            log.addHandler(h)
+    return log
+
+
+def main(argv=None, pretrained_root="../pretrained_models", users_per_pass=128):
+    """`python -m adapter4rec_b200.run <flags of Downstream/Text/run.py>` under torchrun (or alone on one GPU): run.py:681-711
+    — device, process group, seed 123456, the reference's checkpoint directory name, then train or test from the TSV files
+    named by --root_data_dir / --dataset / --news / --behaviors."""
+    from .data_utils.preprocess import load_text_data
+    from .parameters import parse_args
+    args = parse_args(argv)
+    local_rank = int(os.environ.get("LOCAL_RANK", max(args.local_rank, 0)))
+    torch.cuda.set_device(local_rank)
+    if "RANK" in os.environ and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend='nccl', init_method="env://")
+    setup_seed(123456)
+    dir_label = (f'{args.arch}_{args.bert_model_load}_freeze_{args.freeze_paras_before}_{args.pretrained_model_name}'
+                 f'_add_adapter_to_{args.adding_adapter_to}_adapter_bert_lr_{args.adapter_bert_lr}'
+                 f'_adapter_sasrec_lr_{args.adapter_sasrec_lr}_adapter_down_size_{args.adapter_down_size}'
+                 f'_bert_adapter_down_size_{args.bert_adapter_down_size}__serial_{args.is_serial}'
+                 f'_layernorm_{args.finetune_layernorm}_{args.adapter_type}_adam')
+    log_paras = (f'{args.bert_model_load}_bs_{args.batch_size}_ed_{args.embedding_dim}_lr_{args.lr}_L2_{args.l2_weight}'
+                 f'_dp_{args.drop_rate}_Flr_{args.fine_tune_lr}_SASAlr_{args.adapter_sasrec_lr}_BAlr_{args.adapter_bert_lr}')
+    model_dir = os.path.join('./checkpoint_' + dir_label, 'cpt_' + log_paras + args.pretrained_model_name + args.behaviors)
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    Log_file = _file_logger("Log_file", './logs_' + dir_label + ('_test' if 'test' in args.mode else '_train'), rank)
+    Log_file.info(args)
+    os.makedirs(model_dir, exist_ok=True)
+    tokenizer, cfg, state = load_body(args, pretrained_root)
+    data = load_text_data(args, tokenizer, Log_file)
+    if 'train' in args.mode:
+        return train(args, True, local_rank, data, Log_file, cfg, users_per_pass, model_dir, bert_state_dict=state)
+    if 'test' in args.mode:
+        return test(args, True, local_rank, data, Log_file, cfg, state, model_dir)
+
+
+if __name__ == "__main__":
+    main()

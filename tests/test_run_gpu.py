@@ -156,3 +156,55 @@ def test_cv_full_finetuning_entries_train_and_evaluate(tmp_path, downstream):
     assert sorted(os.listdir(tmp_path)) == ["epoch-1.pt", "epoch-2.pt"]
     ckpt = torch.load(os.path.join(tmp_path, "epoch-2.pt"), weights_only=False)
     assert set(ckpt["model_state_dict"]) == set(model.state_dict())
+
+
+def test_two_stage_workflow_from_tsv_files(tmp_path, monkeypatch):
+    """The reference's whole workflow through the launchable mains, from files: (1) `pretraining.text_run.main` — Pretraining/
+    Text/run.py's flags — reads the news / behaviours TSVs with the real BertTokenizer, fine-tunes the unfrozen tail and writes
+    epoch-N.pt under the reference's checkpoint directory name; (2) `run.main` — Downstream/Text/run.py's flags — loads that
+    file through --pretrained_model_dir / --pretrained_model_name BEFORE inserting Houlsby adapters (run.py:374-381), trains
+    only the adapters and evaluates; (3) --mode test ranks the test users from the saved adapter checkpoint."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import preprocess_fixture as F
+    from adapter4rec_b200 import run
+    from adapter4rec_b200.pretraining import text_run
+    monkeypatch.chdir(tmp_path)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    logging.getLogger("Log_file").handlers.clear()
+    name = F.write_tiny_body(str(tmp_path / "pretrained_models"))
+    data_flags = ["--root_data_dir", os.path.dirname(F.DIR), "--dataset", os.path.basename(F.DIR), "--news", "news.tsv",
+                  "--behaviors", "behaviors.tsv", "--max_seq_len", str(F.MAX_SEQ_LEN), "--min_seq_len", str(F.MIN_SEQ_LEN),
+                  "--num_words_title", str(F.NUM_WORDS), "--bert_model_load", name, "--embedding_dim", "64",
+                  "--batch_size", "16", "--drop_rate", "0.0", "--local_rank", "0"]
+    root = str(tmp_path / "pretrained_models")
+    model, trainer, _ = text_run.main(data_flags + ["--epoch", "2", "--freeze_paras_before", "21", "--lr", "1e-3",
+                                                     "--fine_tune_lr", "1e-4"], pretrained_root=root, users_per_pass=8)
+    assert trainer.step_count == 2 * 4                                # 53 users / 16 per batch, 2 epochs
+    stage1 = [os.path.join(d, f) for d, _, fs in os.walk(tmp_path) for f in fs if f == "epoch-2.pt"]
+    assert len(stage1) == 1 and "checkpoint_modal_%s_freeze_21" % name in stage1[0]
+    body_after_stage1 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model2, trainer2, hit10 = run.main(
+        data_flags + ["--epoch", "2", "--adapter_type", "houslby", "--adding_adapter_to", "all", "--bert_adapter_down_size", "16",
+                      "--adapter_bert_lr", "5e-3", "--adapter_sasrec_lr", "5e-3", "--pretrained_model_dir",
+                      os.path.dirname(stage1[0]), "--pretrained_model_name", "epoch-2"], pretrained_root=root, users_per_pass=8)
+    assert 0.0 <= hit10 <= 1.0 and all("adapter" in n for n, _, _ in trainer2.names)
+    sd2 = model2.state_dict()
+    for k, v in body_after_stage1.items():                            # the frozen backbone IS the pre-trained one
+        k2 = k if k in sd2 else None
+        if k2 is not None:
+            assert torch.equal(sd2[k2], v), k
+    shared = [k for k in body_after_stage1 if k in sd2]          # the wrapped sub-layers carry other key names
+    assert len(shared) >= 20 and "bert_encoder.text_encoders.title.bert_model.embeddings.word_embeddings.weight" in shared
+    assert any(k.startswith("user_encoder.") for k in shared)
+    stage2 = sorted(os.path.join(d, f) for d, _, fs in os.walk(tmp_path) for f in fs
+                    if f.startswith("epoch-") and "add_adapter_to_all" in d)
+    assert stage2
+    hit_test = run.main(data_flags + ["--mode", "test", "--adapter_type", "houslby", "--adding_adapter_to", "all",
+                                      "--bert_adapter_down_size", "16", "--adapter_bert_lr", "5e-3", "--adapter_sasrec_lr", "5e-3",
+                                      "--pretrained_model_dir", os.path.dirname(stage1[0]), "--pretrained_model_name", "epoch-2",
+                                      "--load_ckpt_name", os.path.basename(stage2[-1])], pretrained_root=root)
+    assert 0.0 <= hit_test <= 1.0
+    logging.getLogger("Log_file").handlers.clear()
