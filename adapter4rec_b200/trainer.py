@@ -44,6 +44,7 @@ class FlatAdamTrainer:
         groups = (grouping or group_parameters)(model)      # the image tree groups by other names (cv/run_adapter.py)
         lrs = {"bert": fine_tune_lr, "recsys": lr, "adapter_bert": adapter_bert_lr, "adapter_recsys": adapter_sasrec_lr}
         plist = [(g, n, p) for g in ("bert", "recsys", "adapter_bert", "adapter_recsys") for n, p in groups[g]]
+        self._plist, self._lrs, self._group_order = plist, lrs, ("bert", "recsys", "adapter_bert", "adapter_recsys")
         if not plist:
             raise ValueError("no trainable parameters")
         dev = plist[0][2].device
@@ -277,16 +278,71 @@ class FlatAdamTrainer:
         return self._g_loss
 
     def state_dict(self):
-        """optimizer state + the dropout RNG position (the reference checkpoints torch's RNG states for the same purpose:
-        a resumed run draws the masks the uninterrupted run would have drawn)"""
-        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "names": list(self.names), "dropout_seed": Fn.DropoutState.seed, "dropout_counter": Fn.DropoutState.counter}
+        """The optimizer entry of a checkpoint (data_utils/utils.py:109-115 stores `optimizer.state_dict()`), in
+        torch.optim.Adam's OWN format — `state` {index: step, exp_avg, exp_avg_sq} per parameter, `param_groups` with the four
+        groups of run.py:524-529 in the reference's order (bert, recsys, adapter_bert, adapter_recsys; an empty group stays in
+        the list) and consecutive parameter indices — so that a checkpoint written here resumes under the reference's
+        `optimizer.load_state_dict` and one written by the reference resumes here.  The extra key `a4r` carries what torch has no
+        slot for: the parameter names (checked on load) and the dropout RNG position (the reference checkpoints torch's RNG
+        states for the same purpose: a resumed run draws the masks the uninterrupted run would have drawn)."""
+        template = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1.0, betas=self.betas, eps=self.eps,
+                                    weight_decay=self.weight_decay).state_dict()['param_groups'][0]
+        lr_of = {g: lr for g, lr, _, _ in self.segments}
+        state, groups, index = {}, [], 0
+        by_group = {g: [] for g in self._group_order}
+        for (g, _n, p), (_name, off, k) in zip(self._plist, self.names):
+            by_group[g].append(index)
+            if self.step_count > 0:
+                state[index] = {"step": torch.tensor(float(self.step_count)),
+                                "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
+                                "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
+            index += 1
+        for g in self._group_order:
+            entry = dict(template)
+            entry["lr"] = lr_of.get(g, self._lrs[g])
+            entry["params"] = by_group[g]
+            groups.append(entry)
+        return {"state": state, "param_groups": groups,
+                "a4r": {"names": list(self.names), "dropout_seed": Fn.DropoutState.seed,
+                        "dropout_counter": Fn.DropoutState.counter}}
 
     def load_state_dict(self, sd):
-        if [tuple(x) for x in sd["names"]] != [tuple(x) for x in self.names]:
-            raise ValueError("optimizer state was saved for a different set of trainable parameters")
-        self.step_count = sd["step"]
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        if "dropout_seed" in sd:
-            Fn.DropoutState.seed, Fn.DropoutState.counter = int(sd["dropout_seed"]), int(sd["dropout_counter"])
+        """Accepts (a) state_dict() above, (b) the state_dict of the reference's torch.optim.Adam over the same trainable set
+        (same four groups; checked by count and shape — torch's format carries no names), (c) the flat format this package
+        wrote before (keys step / exp_avg / exp_avg_sq / names)."""
+        if "param_groups" not in sd:                                                   # (c)
+            if [tuple(x) for x in sd["names"]] != [tuple(x) for x in self.names]:
+                raise ValueError("optimizer state was saved for a different set of trainable parameters")
+            self.step_count = sd["step"]
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            extra = sd
+        else:
+            extra = sd.get("a4r", {})
+            if "names" in extra and [tuple(x) for x in extra["names"]] != [tuple(x) for x in self.names]:
+                raise ValueError("optimizer state was saved for a different set of trainable parameters")
+            sizes = [len(g["params"]) for g in sd["param_groups"]]
+            mine = [sum(1 for g, _, _ in self._plist if g == name) for name in self._group_order]
+            if sizes != mine:
+                raise ValueError("optimizer state has parameter groups of sizes %r, this trainer's are %r (bert, recsys, "
+                                 "adapter_bert, adapter_recsys)" % (sizes, mine))
+            order = [i for g in sd["param_groups"] for i in g["params"]]
+            steps = set()
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            for idx, (g, _n, p), (_name, off, k) in zip(order, self._plist, self.names):
+                st = sd["state"].get(idx)
+                if st is None:                     # a parameter that never received a gradient has no state in torch
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError("optimizer state of parameter %d has shape %r, %s has %r"
+                                     % (idx, tuple(st["exp_avg"].shape), _name, tuple(p.shape)))
+                self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(st["step"]))
+            if len(steps) > 1:
+                raise ValueError("parameters with different step counts (%r): one flat Adam step count cannot represent them"
+                                 % sorted(steps))
+            self.step_count = steps.pop() if steps else 0
+        if "dropout_seed" in extra:
+            Fn.DropoutState.seed, Fn.DropoutState.counter = int(extra["dropout_seed"]), int(extra["dropout_counter"])

@@ -198,3 +198,87 @@ def test_build_model_applies_the_reference_freeze_and_refuses_missing_checkpoint
     args3 = parse_args(base + ["--pretrained_model_dir", str(tmp_path), "--pretrained_model_name", "epoch-15"])
     with pytest.raises(FileNotFoundError):
         run.build_model(args3, 50, "cpu", cfg)
+
+
+def _four_group_module():
+    torch.manual_seed(3)
+    return torch.nn.ModuleDict({
+        "bert_encoder": torch.nn.ModuleDict({"adapter": torch.nn.Linear(3, 2), "query": torch.nn.Linear(3, 4)}),
+        "user_encoder": torch.nn.ModuleDict({"lora_x": torch.nn.Linear(2, 2, bias=False), "fc": torch.nn.Linear(4, 3)})})
+
+
+def _reference_optimizer(m, lr, fine_tune_lr, adapter_bert_lr, adapter_sasrec_lr):
+    """the optimizer Downstream/Text/run.py:505-529 builds (same name tests, same group order)"""
+    g = {"bert": [], "recsys": [], "adapter_bert": [], "adapter_recsys": []}
+    for name, p in m.named_parameters():
+        if p.requires_grad:
+            ad = "adapter" in name or "lora" in name
+            g[("adapter_bert" if ad else "bert") if 'bert_encoder' in name else ("adapter_recsys" if ad else "recsys")].append(p)
+    return torch.optim.Adam([{'params': g["bert"], 'lr': fine_tune_lr}, {'params': g["recsys"], 'lr': lr},
+                             {'params': g["adapter_bert"], 'lr': adapter_bert_lr},
+                             {'params': g["adapter_recsys"], 'lr': adapter_sasrec_lr}])
+
+
+def test_optimizer_state_is_interchangeable_with_the_reference_checkpoint_format(tmp_path):
+    """SURVEY.md 8f-4 "checkpoint I/O compatibility": data_utils/utils.py:109-115 stores torch.optim.Adam's state_dict under
+    'optimizer'.  (1) a state written by the reference's optimizer loads into FlatAdamTrainer (moments land at the right
+    offsets of the flat buffers, the step count carries over); (2) FlatAdamTrainer.state_dict() loads into the reference's
+    optimizer through torch's own load_state_dict and the two then take the same next step; (3) both directions survive
+    torch.save / torch.load; (4) mismatched trainable sets are refused."""
+    from adapter4rec_b200 import functional as Fn
+    from adapter4rec_b200.trainer import FlatAdamTrainer
+    lrs = dict(lr=1e-3, fine_tune_lr=2e-3, adapter_bert_lr=3e-3, adapter_sasrec_lr=4e-3)
+    ref_model = _four_group_module()
+    opt = _reference_optimizer(ref_model, **lrs)
+    g = torch.Generator().manual_seed(9)
+    for _ in range(3):
+        for p in ref_model.parameters():
+            p.grad = torch.randn(p.shape, generator=g)
+        opt.step()
+    torch.save({"optimizer": opt.state_dict()}, tmp_path / "ref.pt")
+    mine = _four_group_module()
+    mine.load_state_dict(ref_model.state_dict())
+    tr = FlatAdamTrainer(mine, lrs["lr"], lrs["fine_tune_lr"], lrs["adapter_bert_lr"], lrs["adapter_sasrec_lr"])
+    tr.load_state_dict(torch.load(tmp_path / "ref.pt", weights_only=False)["optimizer"])                      # (1)
+    assert tr.step_count == 3
+    ref_params = [p for grp in opt.param_groups for p in grp["params"]]
+    by_name = dict(mine.named_parameters())
+    assert [tuple(by_name[n].shape) for n, _, _ in tr.names] == [tuple(p.shape) for p in ref_params]     # same order
+    for (n, off, k), p in zip(tr.names, ref_params):
+        assert torch.equal(tr.exp_avg[off:off + k], opt.state[p]["exp_avg"].reshape(-1)), n
+        assert torch.equal(tr.exp_avg_sq[off:off + k], opt.state[p]["exp_avg_sq"].reshape(-1)), n
+    Fn.DropoutState.seed, Fn.DropoutState.counter = 4242, 17
+    torch.save({"optimizer": tr.state_dict()}, tmp_path / "mine.pt")                                     # (2) + (3)
+    sd = torch.load(tmp_path / "mine.pt", weights_only=False)["optimizer"]
+    assert [grp["lr"] for grp in sd["param_groups"]] == [2e-3, 1e-3, 3e-3, 4e-3]
+    assert [len(grp["params"]) for grp in sd["param_groups"]] == [2, 2, 2, 1]
+    other = _four_group_module()
+    other.load_state_dict(ref_model.state_dict())
+    opt2 = _reference_optimizer(other, **lrs)
+    opt2.load_state_dict(sd)                                                  # torch's own loader takes it
+    g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+    for p in ref_model.parameters():
+        p.grad = torch.randn(p.shape, generator=g1)
+    for p in other.parameters():
+        p.grad = torch.randn(p.shape, generator=g2)
+    opt.step(), opt2.step()
+    for a, b in zip(ref_model.parameters(), other.parameters()):
+        assert torch.equal(a, b)
+    Fn.DropoutState.seed, Fn.DropoutState.counter = 1, 1
+    sd = torch.load(tmp_path / "mine.pt", weights_only=False)["optimizer"]    # (opt2 adopted and advanced sd's step tensors)
+    tr.load_state_dict(sd)
+    assert (Fn.DropoutState.seed, Fn.DropoutState.counter) == (4242, 17) and tr.step_count == 3
+    # a fresh trainer writes an empty state (torch does the same before the first step) and reads it back
+    fresh = FlatAdamTrainer(_four_group_module(), 1e-3, 1e-3, 1e-3, 1e-3)
+    assert fresh.state_dict()["state"] == {}
+    fresh.load_state_dict(fresh.state_dict())
+    assert fresh.step_count == 0
+    # (4) another trainable set
+    small = _four_group_module()
+    small["user_encoder"]["fc"].weight.requires_grad = False
+    with pytest.raises(ValueError):
+        FlatAdamTrainer(small, 1e-3, 1e-3, 1e-3, 1e-3).load_state_dict(opt.state_dict())
+    # the flat format this package wrote before still loads
+    legacy = {"step": 7, "exp_avg": tr.exp_avg.clone() * 2, "exp_avg_sq": tr.exp_avg_sq.clone(), "names": list(tr.names)}
+    tr.load_state_dict(legacy)
+    assert tr.step_count == 7

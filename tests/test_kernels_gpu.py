@@ -285,6 +285,73 @@ def test_adam_matches_torch():
     _close(p, ref.detach(), 1e-6, 1e-6, "adam")
 
 
+def test_adam_dev_is_bit_identical_to_adam_step():
+    """a4r_adam_step_dev (bias corrections read from device memory: the form a CUDA-graph replay needs) against a4r_adam_step
+    for the same step numbers: bit-identical parameters and moments."""
+    ops = _ops()
+    n = 70001
+    p0 = _rand((n,), 1, 1, torch.float32)
+    pa, pb = p0.clone(), p0.clone()
+    ma, va, mb, vb = (torch.zeros_like(p0) for _ in range(4))
+    bc = torch.zeros(2, dtype=torch.float32, device="cuda")
+    for step in (1, 2, 3, 1000, 123456):
+        g = _rand((n,), 1, 20 + step % 97, torch.float32)
+        ops.adam_step(pa, g, ma, va, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, grad_scale=0.5)
+        bc.copy_(torch.tensor(ops.adam_bias_corrections(0.9, 0.999, step), dtype=torch.float32))
+        ops.adam_step_dev(pb, g, mb, vb, 1e-3, 0.9, 0.999, 1e-8, 0.01, bc, grad_scale=0.5)
+        assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb), step
+
+
+def test_trainer_resumes_from_a_reference_format_optimizer_checkpoint():
+    """SURVEY.md 8f-4 "checkpoint I/O compatibility", the GPU half: moments + step written by torch.optim.Adam (the format
+    data_utils/utils.py:109-115 stores) are loaded into FlatAdamTrainer, then both take two more steps on the same gradients:
+    the flat fused Adam continues exactly where torch's left off (fp32 rounding: 1e-6)."""
+    from adapter4rec_b200.trainer import FlatAdamTrainer
+    torch.manual_seed(11)
+
+    def make():
+        torch.manual_seed(11)
+        return torch.nn.ModuleDict({
+            "bert_encoder": torch.nn.ModuleDict({"adapter": torch.nn.Linear(96, 64), "query": torch.nn.Linear(96, 128)}),
+            "user_encoder": torch.nn.ModuleDict({"lora_x": torch.nn.Linear(64, 8, bias=False), "fc": torch.nn.Linear(128, 96)})
+        }).cuda()
+
+    ref, mine = make(), make()
+    groups = {"bert": [], "recsys": [], "adapter_bert": [], "adapter_recsys": []}
+    for name, p in ref.named_parameters():
+        ad = "adapter" in name or "lora" in name
+        groups[("adapter_bert" if ad else "bert") if 'bert_encoder' in name else ("adapter_recsys" if ad else "recsys")].append(p)
+    opt = torch.optim.Adam([{'params': groups["bert"], 'lr': 2e-3}, {'params': groups["recsys"], 'lr': 1e-3},
+                            {'params': groups["adapter_bert"], 'lr': 3e-3}, {'params': groups["adapter_recsys"], 'lr': 4e-3}])
+    g = torch.Generator(device="cuda").manual_seed(3)
+
+    def grads():
+        return [torch.randn(p.shape, generator=g, device="cuda") for p in ref.parameters()]
+
+    for _ in range(3):
+        for p, gr in zip(ref.parameters(), grads()):
+            p.grad = gr
+        opt.step()
+    mine.load_state_dict(ref.state_dict())
+    tr = FlatAdamTrainer(mine, 1e-3, 2e-3, 3e-3, 4e-3)
+    tr.load_state_dict(opt.state_dict())
+    assert tr.step_count == 3
+    for _ in range(2):
+        gs = grads()
+        for p, q, gr in zip(ref.parameters(), mine.parameters(), gs):
+            p.grad = gr
+            q.grad.copy_(gr)                       # .grad of a trainer parameter is a view of the flat gradient buffer
+        opt.step()
+        tr.optimizer_step()
+    assert tr.step_count == 5
+    for (n, a), b in zip(ref.named_parameters(), mine.parameters()):
+        _close(b.detach(), a.detach(), 1e-6, 1e-6, n)
+    back = tr.state_dict()
+    for i, p in enumerate(q for grp in opt.param_groups for q in grp["params"]):
+        _close(back["state"][i]["exp_avg"], opt.state[p]["exp_avg"], 1e-6, 1e-7, "exp_avg %d" % i)
+        assert float(back["state"][i]["step"]) == 5.0
+
+
 @pytest.mark.parametrize("M,H,r,act,tail", [
     (128, 768, 64, "relu", 0), (1000, 768, 64, "gelu", 0), (148 * 128 + 77, 768, 64, "relu", 0),
     (300, 128, 16, "relu", 0), (300, 128, 16, "gelu", 0), (515, 256, 8, "relu", 0), (70, 64, 16, "relu", 0),
