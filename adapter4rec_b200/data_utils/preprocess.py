@@ -30,6 +30,17 @@ def read_news(news_path):
     return item_id_to_dic, item_name_to_id
 
 
+def read_images(images_path):
+    """Downstream/CV/data_utils/preprocess.py:71-83 (the image tree's catalogue reader): 1-based ids in file order, the LMDB key
+    of an item is its name in ASCII.  The image tree's `read_behaviors` (same file, :5-68) applies the rules of the text
+    tree's to these dictionaries — it is the function below; only its log lines differ."""
+    item_id_to_keys, item_name_to_id = {}, {}
+    for index, fields in enumerate(_rows(images_path), start=1):
+        item_name_to_id[fields[0]] = index
+        item_id_to_keys[index] = fields[0].encode('ascii')
+    return item_id_to_keys, item_name_to_id
+
+
 def read_news_bert(news_path, args, tokenizer):
     """preprocess.py:78-106.  Ids are 1-based in file order (a repeated doc_name keeps its LAST id, every line still takes an
     id); the title is lower-cased and tokenised to exactly --num_words_title entries.  Only the `title` attribute is
