@@ -41,7 +41,8 @@ def test_train_entry_reduces_loss_and_evaluates(tmp_path):
     assert set(ckpt["model_state_dict"]) == set(model.state_dict())
     args.load_ckpt_name, args.epoch = saved[-1], 1
     model2, trainer2, _ = run.train(args, True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=16, model_dir=str(tmp_path))
-    assert trainer2.step_count == ckpt["optimizer"]["step"] + 3
+    assert {"state", "param_groups"} <= set(ckpt["optimizer"])         # torch.optim.Adam's own format (utils.py:109-115)
+    assert trainer2.step_count == int(ckpt["optimizer"]["state"][0]["step"]) + 3
     assert any("epoch %d mean batch loss" % (int(saved[-1].split("-")[1].split(".")[0]) + 1) in m for m in records)
 
 
