@@ -5,7 +5,9 @@
 (2) data-parallel training: after two steps on different per-rank batches every rank holds bit-identical parameters
     (one flat-gradient all-reduce per step) and the loss is finite;
 (3) full fine-tuning with the backward-overlapped bucketed reduction (64 KB buckets issued from gradient hooks) gives the
-    gradients of the single blocking all-reduce.
+    gradients of the single blocking all-reduce;
+(4) the train step replayed from CUDA graphs (trainer.train_step_graphed: two recordings around one eager NCCL all-reduce) is
+    bit-identical to the eager data-parallel step on every rank, dropout on.
 Prints one line per check; exit code 0 iff all pass."""
 import os
 import sys
@@ -105,6 +107,34 @@ ok &= same3
 if rank == 0:
     print("bucketed overlapped reduction == blocking all-reduce (full fine-tuning, %d buckets, %d issued during the backward):"
           % (nb, early), same3, "| max rel diff %.2e (two blocking runs: %.2e; tensors that differ: %s)" % (err, run_to_run, differing))
+# ---- (4) the step replayed from CUDA graphs (two recordings around ONE eager NCCL all-reduce) == the eager DP step
+from adapter4rec_b200 import functional as Fn  # noqa: E402
+pair = []
+for _ in range(2):
+    mg, _ = build_gpu_model(c, sd)
+    mg.train()                                 # dropout on: the replay reads its seed through the pointer
+    pair.append(FlatAdamTrainer(mg, 1e-3, 1e-4, 1e-3, 1e-3, users_per_pass=max(1, x.shape[0] // (2 * (c.S + 1) * 2)),
+                                overlap=False))
+tg, te = pair
+Fn.DropoutState.manual_seed(31 + rank)
+tg.train_step_graphed(x, lm)                   # first call: eager
+Fn.DropoutState.manual_seed(31 + rank)
+te.train_step(x, lm)
+same4 = torch.equal(tg.flat_param, te.flat_param)
+for t in range(3):
+    Fn.DropoutState.manual_seed(31 + rank)
+    lg = tg.train_step_graphed(x, lm).clone()
+    Fn.DropoutState.seed, Fn.DropoutState.counter = tg.graph_seed(tg.step_count), tg.graph_counter0
+    le = te.train_step(x, lm).clone()
+    same4 &= torch.equal(lg, le) and torch.equal(tg.flat_param, te.flat_param) and torch.equal(tg.exp_avg, te.exp_avg)
+ref4 = tg.flat_param.detach().clone()
+dist.broadcast(ref4, 0)
+same4 &= torch.equal(ref4, tg.flat_param) and len(tg._graphs) == 2
+tg.release_graph()
+ok &= same4
+if rank == 0:
+    print("graphed DP step (2 recordings + 1 eager all-reduce per step) bit-identical to the eager DP step, 3 replays:", same4)
+
 flags = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -18,6 +18,8 @@ shapes = [
     ("QKV+lora ext  ", 2304, 768, {"ext": 64, "bias": True}),
     ("QKV plain     ", 2304, 768, {"bias": True}),
     ("out-proj+res  ", 768, 768, {"bias": True, "res": True}),
+    ("out-proj+res+drop", 768, 768, {"bias": True, "res": True, "drop": True}),
+    ("FFN2+res+drop ", 768, 3072, {"bias": True, "res": True, "drop": True}),
     ("FFN1 gelu+aux ", 3072, 768, {"bias": True, "epi": ops.EPI_GELU, "aux": True}),
     ("FFN1 gelu     ", 3072, 768, {"bias": True, "epi": ops.EPI_GELU}),
     ("FFN1 linear   ", 3072, 768, {"bias": True}),
@@ -37,6 +39,7 @@ for name, N, K, o in shapes:
     if o.get("res"): kw["residual"] = r(M, N)
     if o.get("epi") is not None: kw["epilogue"] = o["epi"]
     if o.get("aux"): kw["aux"] = r(M, N)
+    if o.get("drop"): kw["dropout"] = (0.1, 0x5EED, 1234)
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     for _ in range(3): ops.gemm(a, b, out=out, **kw)
     ts = []
