@@ -196,10 +196,22 @@ class FlatAdamTrainer:
                               self.exp_avg_sq[off:off + n], lr, self.betas[0], self.betas[1], self.eps,
                               self.weight_decay, self._g_state.view(torch.float32)[2:4], grad_scale=1.0 / self.world)
 
-    def _record(self, sample_items, log_mask):
+    def graph_unsafe_reason(self):
+        """why this trainer's step cannot be recorded (None if it can): a recording needs shapes and launch sequences that do
+        not depend on the batch's VALUES"""
         if self.buckets:
-            raise RuntimeError("graphed steps keep the gradient all-reduce outside the recording: build the trainer with "
-                               "overlap=False")
+            return ("graphed steps keep the gradient all-reduce outside the recording: build the trainer with overlap=False")
+        for name, m in self.model.named_modules():
+            if getattr(m, "unpad", False):
+                return "%s.unpad = True executes only the kept tokens: the token count is read back from the batch" % (name or "model")
+            if getattr(m, "dedup_items", False):
+                return "%s.dedup_items = True encodes the distinct items: their number is read back from the batch" % (name or "model")
+        return None
+
+    def _record(self, sample_items, log_mask):
+        reason = self.graph_unsafe_reason()
+        if reason is not None:
+            raise RuntimeError("train_step_graphed: " + reason)
         dev = sample_items.device
         self._g_items, self._g_mask = sample_items.clone(), log_mask.clone()
         self._g_state = torch.zeros(2, dtype=torch.int64, device=dev)      # [seed | bc1 f32, bc2_sqrt f32]

@@ -48,3 +48,22 @@ def test_bias_corrections_follow_the_library_arithmetic():
         assert bc1 == 1.0 - math.pow(b1, step)
         assert bc2s == math.sqrt(1.0 - math.pow(b2, step))
     assert ops.adam_bias_corrections(0.9, 0.999, 1)[0] == 1.0 - b1
+
+
+def test_recording_is_refused_for_value_dependent_steps():
+    """unpadded-token and dedup layouts read counts back from the batch (host syncs, data-dependent shapes); bucketed overlap
+    issues NCCL from gradient hooks: none of them can be baked into a recording — refused with the reason, never mis-recorded"""
+    import torch
+    from adapter4rec_b200.trainer import FlatAdamTrainer
+    m = torch.nn.ModuleDict({"bert_encoder": torch.nn.ModuleDict({"adapter": torch.nn.Linear(2, 2)}),
+                             "user_encoder": torch.nn.Linear(2, 2)})
+    tr = FlatAdamTrainer(m, 1e-3, 1e-3, 1e-3, 1e-3)
+    assert tr.graph_unsafe_reason() is None
+    m["bert_encoder"].unpad = True
+    assert "unpad" in tr.graph_unsafe_reason()
+    m["bert_encoder"].unpad = False
+    m.dedup_items = True
+    assert "dedup_items" in tr.graph_unsafe_reason()
+    m.dedup_items = False
+    tr.buckets = [[0, 1, 1]]
+    assert "overlap=False" in tr.graph_unsafe_reason()
