@@ -797,7 +797,9 @@ def main():
         model.dedup_items = False
 
     # ---------------- variant: the same step replayed from a CUDA graph (trainer.train_step_graphed) ----------------
-    if want("graphed_step"):
+    # (default run: one GPU only — a rank-local failure while recording would leave the other ranks inside a collective;
+    # `--variants graphed_step` runs it at any N: profiles/r02_bench_graphed_step_n2.json)
+    if want("graphed_step") and (world == 1 or a.variants != "all"):
         try:
             variants["graphed_step"] = bench_graphed(trainer, a, host, resident, dev, world)
         except Exception as exc:  # noqa: BLE001 — a failed recording must not take the headline line with it
