@@ -171,7 +171,10 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
     users = sorted(data.users_train.keys())
     train_ds = BuildTrainDataset(data.users_train, data.item_content, data.item_num, args.max_seq_len, True,
                                  device=next(model.parameters()).device, seed=123456 + rank)   # run.py:686 seed; per-rank stream
-    max_hit10 = 0.0
+    max_hit10, max_eval, max_epoch, now_epoch = 0.0, 0.0, 0, start_epoch
+    # utils.py:90-102 (para_and_log): --logging_num progress lines per epoch
+    steps_per_epoch = -(-((len(users) + world - 1) // world) // args.batch_size)
+    steps_for_log = max(1, int(steps_per_epoch / max(1, args.logging_num)))
     for ep in range(args.epoch):
         now_epoch = start_epoch + ep + 1
         model.train()
@@ -186,13 +189,22 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
             loss_sum, batches = loss_sum + float(loss), batches + 1
             if loss != loss:                                        # NaN guard of run.py:602-604
                 raise FloatingPointError("loss is NaN")
+            if batches % steps_for_log == 0:                        # run.py:606-608
+                Log_file.info('cnt: {}, Ed: {}, batch loss: {:.5f}, sum loss: {:.5f}'.format(
+                    batches, batches * args.batch_size, loss_sum / batches, loss_sum))
         Log_file.info('epoch {} mean batch loss: {:.5f}'.format(now_epoch, loss_sum / max(1, batches)))
         hit10 = run_eval(model, data, args, Log_file, "valid", local_rank)
-        if hit10 > max_hit10 or max_hit10 == 0:                     # run.py:620-626: test + checkpoint on improvement
-            max_hit10 = hit10
+        if hit10 > max_eval:                                        # run.py:660-663
+            max_eval, max_epoch = hit10, now_epoch
+        if max_eval > max_hit10 or max_hit10 == 0 or ep % 10 == 0:  # run.py:618-630: rank the TEST users and checkpoint on a
+            max_hit10 = max(max_hit10, max_eval)                    # better validation HR@10, and every tenth epoch
+            run_eval(model, data, args, Log_file, "test", local_rank)
             if model_dir is not None and rank == 0:
                 save_model(now_epoch, model, model_dir, trainer, Log_file)
-    return model, trainer, max_hit10
+    if model_dir is not None and rank == 0 and args.epoch > 0:      # run.py:637-638: the last state is always kept
+        save_model(now_epoch, model, model_dir, trainer, Log_file)
+    Log_file.info(' max eval Hit10 {:0.5f}  in epoch {}'.format(max_eval * 100, max_epoch))
+    return model, trainer, max_eval
 
 
 def run_eval(model, data, args, Log_file, v_or_t, local_rank, batch_size=512):

@@ -35,7 +35,9 @@ def test_train_entry_reduces_loss_and_evaluates(tmp_path):
     # checkpoints in the reference's format (data_utils/utils.py:109-115) and the resume path (--load_ckpt_name, run.py:481-493)
     import os
     saved = sorted(f for f in os.listdir(tmp_path) if f.startswith("epoch-"))
-    assert saved, "an improving epoch must have written epoch-N.pt"
+    assert "epoch-1.pt" in saved and "epoch-3.pt" in saved      # first evaluation (run.py:618) and the final state (:637-638)
+    assert any("test_results" in m for m in records)             # the test users are ranked when the validation HR@10 improves
+    assert any(m.startswith("cnt: ") for m in records)           # --logging_num progress lines (run.py:606-608)
     ckpt = torch.load(os.path.join(tmp_path, saved[-1]), weights_only=False)
     assert set(ckpt) >= {"model_state_dict", "optimizer", "rng_state", "cuda_rng_state"}
     assert set(ckpt["model_state_dict"]) == set(model.state_dict())
