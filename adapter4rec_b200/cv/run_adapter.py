@@ -159,6 +159,8 @@ def train(args, use_modal, local_rank, data, Log_file=None, vit_config=None, use
             max_hit10 = max(max_hit10, hit10)
             if model_dir is not None and rank == 0:
                 save_model(now_epoch, model, model_dir, trainer, Log_file)
+    if model_dir is not None and rank == 0 and args.epoch > 0:                         # :629-630: the last state is always kept
+        save_model(start_epoch + args.epoch, model, model_dir, trainer, Log_file)
     return model, trainer, max_hit10
 
 

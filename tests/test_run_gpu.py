@@ -76,7 +76,7 @@ def test_cv_train_entry_reduces_loss_and_evaluates(tmp_path):
     names = {n for n, _, _ in trainer.names}
     assert names and all("adapter" in n for n in names)              # fine_tune_to None: only the adapters train
     saved = sorted(f for f in os.listdir(tmp_path) if f.startswith("epoch-"))
-    assert saved
+    assert "epoch-1.pt" in saved and "epoch-3.pt" in saved               # first evaluation and the final state (:629-630)
     ckpt = torch.load(os.path.join(tmp_path, saved[-1]), weights_only=False)
     assert set(ckpt["model_state_dict"]) == set(model.state_dict())
 
