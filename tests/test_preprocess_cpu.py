@@ -134,3 +134,20 @@ def test_image_tree_readers_on_the_reference_dataset():
     out = P.read_behaviors(G.USERS, keys, name_to_id, ref["max_seq_len"], ref["min_seq_len"], logging.getLogger("preprocess_test"))
     assert out[0] == ref["item_num"] and len(out[2]) == ref["users"]
     assert G.digest(*out) == ref["sha256"]
+
+
+def test_text_readers_on_the_reference_catalogue_with_the_real_tokenizer():
+    """read_news_bert + get_doc_input_bert on the REAL Adressa catalogue the reference ships (20,373 titles) with transformers'
+    BertTokenizer on the reference's own vocab.txt: the [I+1, 60] token matrix equals, byte for byte, what the unmodified
+    readers produced (tests/golden/make_golden_preprocess_adressa.py) — the item side of BASELINE.json configs[0]'s plumbing
+    run.  Skipped where the reference's files are absent."""
+    import make_golden_preprocess_adressa as G
+    if not (os.path.exists(G.NEWS) and os.path.exists(G.BODY)):
+        pytest.skip("the reference's dataset / vocabulary files are not on this machine")
+    from transformers import BertTokenizer
+    from adapter4rec_b200.data_utils import preprocess as P
+    ref = json.load(open(os.path.join(F.DIR, "adressa_digest.json")))
+    content, name_to_id = G.token_matrix(P, BertTokenizer.from_pretrained(G.BODY))
+    assert content.shape == (ref["rows"], ref["cols"]) and len(name_to_id) == ref["names"]
+    assert abs(float(content[1:, 30:].sum(1).mean()) - ref["mean_tokens"]) < 1e-9
+    assert G.digest(content, name_to_id) == ref["sha256"]
