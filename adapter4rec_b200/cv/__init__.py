@@ -2,5 +2,6 @@
 from .model import (CompacterModel, Model, ModelCPC, SASRecAdaptedSelfOutput, SASRecCompacterAdaptedSelfOutput,
                     SASRecParallelAdaptedSelfOutput, SASRecPfeifferV2AdaptedSelfOutput, SoftPrompt, VITAdaptedOutput,
                     VITAdaptedParallelOutput, VITAdaptedParallelSelfOutput, VITAdaptedSelfOutput, VITCompacterAdaptedOutput,
-                    VITCompacterAdaptedSelfOutput, Vit_Encoder)
+                    VITCompacterAdaptedSelfOutput, VITKAdaptedCVModel, VITPfeifferAdaptedSelfOutput, Vit_Encoder)
+from ..model import PHMLinear, SASRecKAdaptedTransformerBlocks  # noqa: F401  (names of run_adapter.py's import line)
 from .vit import ViTConfigLite, ViTForImageClassification, ViTModel

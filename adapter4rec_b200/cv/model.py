@@ -220,3 +220,26 @@ class SoftPrompt(nn.Module):
     def forward(self, pixel_values, bool_masked_pos=None, interpolate_pos_encoding=None):
         x, L = self.tokens(pixel_values)
         return x.view(pixel_values.shape[0], L, -1)
+
+
+class VITKAdaptedCVModel(nn.Module):
+    """Name kept so that run_adapter.py's import line (Downstream/CV/run_adapter.py:17-22) resolves.  The reference's own class
+    (Downstream/CV/model/model.py:374-404) does not run under the installed transformers (its wrapped encoder is called with a
+    signature that library no longer accepts; SURVEY.md §8c, probe p4), so there is nothing to pin an implementation to:
+    constructing it says so, exactly as `surgery.insert_adapters_cv` does for --adapter_type kadapter."""
+
+    def __init__(self, cv_model=None, args=None):
+        super().__init__()
+        raise NotImplementedError("VITKAdaptedCVModel: the reference's own class does not run under the installed "
+                                  "transformers; the text tree's K-Adapter (BertKAdaptedBertModel) is implemented")
+
+
+class VITPfeifferAdaptedSelfOutput(nn.Module):
+    """Name kept for the same import line.  In the reference (model.py:215-232) the class is only reached through
+    `add_pfeiffer_adapter_to_vit` (run_adapter.py:44-45), which no branch of the adapter dispatch calls (:367-445 has
+    pfeiffer_ver2 / kadapter / lora / compacter / prompt / houslby): dead code there, not built here."""
+
+    def __init__(self, self_output=None, args=None):
+        super().__init__()
+        raise NotImplementedError("VITPfeifferAdaptedSelfOutput is unreachable from run_adapter.py's dispatch "
+                                  "(--adapter_type pfeiffer_ver2 uses VITAdaptedSelfOutput + SASRecPfeifferV2AdaptedSelfOutput)")
