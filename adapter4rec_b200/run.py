@@ -149,7 +149,9 @@ def save_model(now_epoch, model, model_dir, trainer, Log_file):
 
 
 def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, users_per_pass=128, model_dir=None,
-          bert_state_dict=None):
+          bert_state_dict=None, graphed=False):
+    """graphed=True replays each step from a CUDA graph per rank (trainer.train_step_graphed: bit-identical arithmetic, one
+    recording per batch shape); the default is the eager step."""
     Log_file = Log_file or logging.getLogger("adapter4rec_b200")
     model = build_model(args, data.item_num, local_rank, bert_config, bert_state_dict)
     trainer = FlatAdamTrainer(model, args.lr, args.fine_tune_lr, args.adapter_bert_lr, args.adapter_sasrec_lr,
@@ -185,7 +187,7 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
             # negatives + token-row gather on the device (only the user indices cross PCIe); the host restatement
             # build_train_batch above stays as the reference-order implementation for CPU-side tools
             items, log_mask = train_ds.batch(mine[b0:b0 + args.batch_size])
-            loss = trainer.train_step(items.view(-1, items.size(-1)), log_mask)
+            loss = (trainer.train_step_graphed if graphed else trainer.train_step)(items.view(-1, items.size(-1)), log_mask)
             loss_sum, batches = loss_sum + float(loss), batches + 1
             if loss != loss:                                        # NaN guard of run.py:602-604
                 raise FloatingPointError("loss is NaN")
@@ -204,6 +206,8 @@ def train(args, use_modal, local_rank, data, Log_file=None, bert_config=None, us
     if model_dir is not None and rank == 0 and args.epoch > 0:      # run.py:637-638: the last state is always kept
         save_model(now_epoch, model, model_dir, trainer, Log_file)
     Log_file.info(' max eval Hit10 {:0.5f}  in epoch {}'.format(max_eval * 100, max_epoch))
+    if graphed:
+        trainer.release_graph()
     return model, trainer, max_eval
 
 

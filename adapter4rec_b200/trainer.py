@@ -183,7 +183,7 @@ class FlatAdamTrainer:
     # pointer; the counter offsets stay those of the recording) and Adam's two bias-correction factors
     # (a4r_adam_step_dev).  With more than one rank the all-reduce stays OUTSIDE the recording (two graphs around one
     # eager NCCL call), so nothing of NCCL's is captured.  Learning rates, shapes and users_per_pass are baked: a step
-    # with other shapes is recorded again.
+    # with other shapes gets its own recording (the two most recently used are kept).
     _GRAPH_SLOTS = 64
 
     def _graph_body_backward(self):
@@ -208,16 +208,19 @@ class FlatAdamTrainer:
                 return "%s.dedup_items = True encodes the distinct items: their number is read back from the batch" % (name or "model")
         return None
 
+    _MAX_RECORDINGS = 2      # an epoch has two batch shapes: the full batches and the last, shorter one
+
     def _record(self, sample_items, log_mask):
         reason = self.graph_unsafe_reason()
         if reason is not None:
             raise RuntimeError("train_step_graphed: " + reason)
         dev = sample_items.device
+        if getattr(self, "_g_state", None) is None:      # shared by every recording of this trainer
+            self._g_state = torch.zeros(2, dtype=torch.int64, device=dev)      # [seed | bc1 f32, bc2_sqrt f32]
+            self._g_host = torch.zeros(self._GRAPH_SLOTS, 2, dtype=torch.int64).pin_memory()
+            self._g_events = [None] * self._GRAPH_SLOTS
+            self._g_replays = 0
         self._g_items, self._g_mask = sample_items.clone(), log_mask.clone()
-        self._g_state = torch.zeros(2, dtype=torch.int64, device=dev)      # [seed | bc1 f32, bc2_sqrt f32]
-        self._g_host = torch.zeros(self._GRAPH_SLOTS, 2, dtype=torch.int64).pin_memory()
-        self._g_events = [None] * self._GRAPH_SLOTS
-        self._g_replays = 0
         Fn.bump_param_epoch()        # whatever built the weight caches last: the recording must contain their rebuild
         Fn.DropoutState.seed_address = self._g_state.data_ptr()
         self._g_counter0, self._g_base_seed = Fn.DropoutState.counter, Fn.DropoutState.seed
@@ -236,9 +239,23 @@ class FlatAdamTrainer:
                 graphs.append(g2)
         finally:
             Fn.DropoutState.seed_address = None
-        self._g_counter1 = Fn.DropoutState.counter
-        self._graphs = graphs
-        self._g_shapes = (tuple(sample_items.shape), tuple(log_mask.shape), self.users_per_pass)
+        return {"graphs": graphs, "items": self._g_items, "mask": self._g_mask, "loss": self._g_loss,
+                "counter0": self._g_counter0, "base_seed": self._g_base_seed}
+
+    def _select_recording(self, sample_items, log_mask):
+        """the recording for these shapes becomes the current one (recorded now if there is none; the least recently used of
+        more than _MAX_RECORDINGS is dropped with its memory pool)"""
+        shapes = (tuple(sample_items.shape), tuple(log_mask.shape), self.users_per_pass)
+        recs = self.__dict__.setdefault("_recordings", {})
+        rec = recs.pop(shapes, None)
+        if rec is None:
+            while len(recs) >= self._MAX_RECORDINGS:
+                recs.pop(next(iter(recs)))
+            self._graphs = self._g_loss = self._g_items = self._g_mask = None
+            rec = self._record(sample_items, log_mask)
+        recs[shapes] = rec                                # most recently used last
+        self._graphs, self._g_items, self._g_mask, self._g_loss = rec["graphs"], rec["items"], rec["mask"], rec["loss"]
+        self._g_counter0, self._g_base_seed, self._g_shapes = rec["counter0"], rec["base_seed"], shapes
 
     def graph_seed(self, step):
         """the dropout seed replay `step` (= step_count after the step) runs with — an eager step given this seed and the
@@ -250,7 +267,8 @@ class FlatAdamTrainer:
         return self._g_counter0
 
     def release_graph(self):
-        """drop the recording and its private memory pool"""
+        """drop every recording and its private memory pool"""
+        self._recordings = {}
         self._graphs = None
         self._g_loss = self._g_items = self._g_mask = None
 
@@ -258,14 +276,12 @@ class FlatAdamTrainer:
         """train_step replayed from a recording (CUDA only).  The first call of a trainer runs eagerly (it loads every
         kernel and builds the frozen-weight caches, neither of which may happen inside a recording); the next call
         records; every call after that is: two small copies into the static inputs, 16 bytes of per-step state, one
-        graph launch (two around the all-reduce when world > 1).  Returns the loss tensor of the recording (overwritten
-        by the next replay)."""
+        graph launch (two around the all-reduce when world > 1).  One recording per batch shape, the two most recently
+        used are kept (an epoch alternates between its full batches and the last, shorter one).  Returns the loss tensor
+        of the recording (overwritten by its next replay)."""
         if not getattr(self, "_eager_steps", 0):
             return self.train_step(sample_items, log_mask)
-        shapes = (tuple(sample_items.shape), tuple(log_mask.shape), self.users_per_pass)
-        if getattr(self, "_graphs", None) is None or self._g_shapes != shapes:
-            self.release_graph()
-            self._record(sample_items, log_mask)
+        self._select_recording(sample_items, log_mask)
         self._g_items.copy_(sample_items, non_blocking=True)
         self._g_mask.copy_(log_mask, non_blocking=True)
         self.step_count += 1

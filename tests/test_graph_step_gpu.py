@@ -88,5 +88,45 @@ def test_graphed_step_records_again_for_new_shapes():
     first = tr_g._graphs[0]
     half = c.B // 2
     loss = tr_g.train_step_graphed(si[:half * rows_per_user], lm[:half])
-    assert tr_g._graphs[0] is not first and torch.isfinite(loss).all() and tr_g.step_count == 3
+    second = tr_g._graphs[0]
+    assert second is not first and torch.isfinite(loss).all() and tr_g.step_count == 3
+    # back to the first shape: its recording is still there (an epoch alternates full batches and the last, shorter one)
+    tr_g.train_step_graphed(si, lm)
+    assert tr_g._graphs[0] is first and len(tr_g._recordings) == 2
+    # a third shape drops the least recently used recording (the half batch), never the one just replayed
+    one = rows_per_user
+    loss = tr_g.train_step_graphed(si[:one], lm[:1])
+    assert len(tr_g._recordings) == 2 and tr_g._graphs[0] not in (first, second) and torch.isfinite(loss).all()
+    tr_g.train_step_graphed(si, lm)
+    assert tr_g._graphs[0] is first and tr_g.step_count == 6
     tr_g.release_graph()
+    assert tr_g._recordings == {} and tr_g._graphs is None
+
+
+def test_entry_script_loop_with_graphed_steps(tmp_path):
+    """run.train(graphed=True): the training loop of Downstream/Text/run.py with every step replayed from a CUDA graph — 96
+    users at batch 40 give two full batches and a 16-user tail per epoch, i.e. two recordings that alternate; same losses as
+    the eager loop (no dropout in this configuration: the two runs are the same arithmetic)."""
+    import logging
+    from adapter4rec_b200 import run
+    from adapter4rec_b200.model import TextConfigLite
+    from adapter4rec_b200.parameters import parse_args
+    flags = ["--embedding_dim", "64", "--batch_size", "40", "--epoch", "2", "--adapter_type", "houslby",
+             "--adding_adapter_to", "all", "--bert_model_load", "bert_tiny", "--bert_adapter_down_size", "16",
+             "--adapter_bert_lr", "5e-3", "--adapter_sasrec_lr", "5e-3", "--max_seq_len", "10", "--num_words_title", "12",
+             "--drop_rate", "0.0", "--adapter_dropout_rate", "0.0", "--pretrained_model_name", "None"]
+    cfg = TextConfigLite(vocab_size=500, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
+                         max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    losses = {}
+    for graphed in (False, True):
+        run.setup_seed(123456)
+        data = run.synthetic_data(item_num=300, users=96, num_words=12, max_seq_len=10, vocab=500)
+        log = logging.getLogger("graphed_loop_%d" % graphed)
+        records = []
+        log.addHandler(type("H", (logging.Handler,), {"emit": lambda self, r, rec=records: rec.append(r.getMessage())})())
+        log.setLevel(logging.INFO)
+        _, trainer, _ = run.train(parse_args(flags), True, 0, data, Log_file=log, bert_config=cfg, users_per_pass=8,
+                                  graphed=graphed)
+        assert trainer.step_count == 6
+        losses[graphed] = [float(m.split(":")[-1]) for m in records if "mean batch loss" in m]
+    assert len(losses[True]) == 2 and losses[True] == losses[False], losses
