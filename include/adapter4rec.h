@@ -297,7 +297,8 @@ A4R_API int a4r_scatter_add_rows(const void* src, int64_t ld, const int64_t* idx
  * a4r_act_fwd: out = act(u) for the same kinds (the activations without a GEMM-epilogue mode run stand-alone on the
  * r-wide bottleneck). */
 A4R_API int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
-/* The same update with the two step-dependent factors read from device memory: bias_corr[0] = 1 - beta1^step,
+/* The same update (optim.Adam(...).step(), Downstream/Text/run.py:524-529,600) with the two step-dependent factors read from
+ * device memory: bias_corr[0] = 1 - beta1^step,
  * bias_corr[1] = sqrt(1 - beta2^step).  For a train step recorded in a CUDA graph ("the step under one
  * CUDA graph"): kernel arguments are baked at capture, so what changes between replays is uploaded before each replay.
  * Given the factors a4r_adam_step computes for the same step the result is bit-identical. */
@@ -319,7 +320,9 @@ A4R_API int a4r_cast_transpose_f32_bf16(const float* src, int64_t ld_src, void* 
  * the backward regenerates the mask by calling the same function on the gradient with the same (seed, offset). */
 A4R_API int a4r_dropout(const void* x, const void* res, void* out, int64_t n, float p, uint64_t seed, uint64_t offset,
                         a4r_stream_t stream);
-/* Every dropout seed of this header (a4r_dropout, a4r_gemm_args.dropout_seed, a4r_attention_args.dropout_seed, the
+/* (nn.Dropout draws from torch's global generator, advanced by every call: BertSelfOutput.dropout etc. as above, SASRec
+ * modules.py:27,72,107; the reference checkpoints that generator's state, Downstream/Text/data_utils/utils.py:109-115.)
+ * Every dropout seed of this header (a4r_dropout, a4r_gemm_args.dropout_seed, a4r_attention_args.dropout_seed, the
  * dropout_seed of a4r_layernorm_bwd) may be given indirectly: with bit 63 set, the low 63 bits are the DEVICE address of
  * the 64-bit seed (8-byte aligned), read when the kernel runs.  A step recorded in a CUDA graph keeps its (baked)
  * counter offsets and draws fresh masks on every replay from the seed the host stores there before the replay. */
