@@ -297,14 +297,6 @@ A4R_API int a4r_scatter_add_rows(const void* src, int64_t ld, const int64_t* idx
  * a4r_act_fwd: out = act(u) for the same kinds (the activations without a GEMM-epilogue mode run stand-alone on the
  * r-wide bottleneck). */
 A4R_API int a4r_act_bwd(const void* dy, const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
-/* The same update (optim.Adam(...).step(), Downstream/Text/run.py:524-529,600) with the two step-dependent factors read from
- * device memory: bias_corr[0] = 1 - beta1^step,
- * bias_corr[1] = sqrt(1 - beta2^step).  For a train step recorded in a CUDA graph ("the step under one
- * CUDA graph"): kernel arguments are baked at capture, so what changes between replays is uploaded before each replay.
- * Given the factors a4r_adam_step computes for the same step the result is bit-identical. */
-A4R_API int a4r_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                              float eps, float weight_decay, const float* bias_corr, float grad_scale, a4r_stream_t stream);
-
 A4R_API int a4r_act_fwd(const void* u, void* out, int64_t n, int32_t kind, a4r_stream_t stream);
 
 /* Weight caches: dst [rows, cols] = bf16(src) and / or dst_t [cols, rows] = bf16(src)^T from an fp32 master [rows, cols] (row
@@ -329,7 +321,7 @@ A4R_API int a4r_dropout(const void* x, const void* res, void* out, int64_t n, fl
 #define A4R_SEED_INDIRECT (1ull << 63)
 
 /* out[j] (+)= sum_m x[m, j] for a bf16 [M, ld] matrix, j < width: bias gradients of trainable biases
- * (lora.Linear bias, AdapterBlock biases).  Deterministic two-stage reduction through `workspace`. */
+ * (lora.Linear bias, Downstream/Text/run.py:414-428; AdapterBlock biases, Downstream/Text/model/modules.py:117-127).  Deterministic two-stage reduction through `workspace`. */
 A4R_API size_t a4r_colsum_workspace_bytes(int64_t width);
 A4R_API int a4r_colsum(const void* x, int64_t ld, int64_t M, int64_t width, float* out, int32_t accumulate,
                void* workspace, size_t workspace_bytes, a4r_stream_t stream);
@@ -421,6 +413,13 @@ A4R_API int a4r_inbatch_ce_bwd(const a4r_inbatch_ce_args* args, const float* gra
  * step is 1-based; the gradient is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
 A4R_API int a4r_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int64_t step, float grad_scale, a4r_stream_t stream);
+/* The same update (optim.Adam(...).step(), Downstream/Text/run.py:524-529,600) with the two step-dependent factors read from
+ * device memory: bias_corr[0] = 1 - beta1^step, bias_corr[1] = sqrt(1 - beta2^step).  For a train step recorded in a CUDA
+ * graph ("the step under one CUDA graph"): kernel arguments are baked at capture, so what changes
+ * between replays is uploaded before each replay.
+ * Given the factors a4r_adam_step computes for the same step the result is bit-identical. */
+A4R_API int a4r_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, const float* bias_corr, float grad_scale, a4r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10: item-ID gather  out[r,:] = table[ids[r],:]  (bf16 rows of D elements).  Replaces the CPU fancy-index
